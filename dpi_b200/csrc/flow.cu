@@ -1,0 +1,488 @@
+// flow.cu - host side of the RealNVP phase program: parameter layout, fused permutation maps,
+// phase planning, launches. Mirrors generative_model/realnvpfc_model.py RealNVP :562-603.
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "flow.cuh"
+
+namespace dpi {
+void* flow_kernel_ptr();
+
+namespace {
+
+inline long long pad32(long long n) { return (n + 31) / 32 * 32; }
+
+struct Program {
+  Phase* d_phases = nullptr;
+  int n_phases = 0;
+  int max_tiles = 0;
+  std::vector<int> phase_tiles;
+};
+
+struct BatchPlan {
+  int B = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
+  long long oY, oL1, oL2, oO, oST, oLDP, oGY, oGPRE, oGN, oGP1, oGP2, oPART, oRED, total_floats;
+  // [dir][train] forward programs, and the backward program
+  Program fwd[2][2];
+  Program bwd;
+};
+
+}  // namespace
+}  // namespace dpi
+
+struct dpi_flow_s {
+  int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
+  int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1;
+  long long n_params = 0, n_bn = 0;
+  std::vector<dpi::StageTab> stages;          // reverse execution order
+  std::vector<long long> act_off;             // [n_flow][4]
+  std::vector<long long> cpl_off;             // [n_flow][2][P_COUNT]
+  std::vector<long long> bn_off;              // [n_flow][2][4]
+  std::vector<int32_t> h_gmaps;               // [2][S][D] + trailing [D]
+  dpi::StageTab* d_stages = nullptr;
+  int* d_gmaps = nullptr;
+  std::mutex mu;
+  std::map<int, std::unique_ptr<dpi::BatchPlan>> plans;
+};
+
+namespace dpi {
+namespace {
+
+struct GemmPlan { int bn, tiles_n, splits, kchunk; };
+
+// Pick the column tile and split-K factor so a phase offers about `target` tiles.
+GemmPlan plan_gemm(int tiles_m, int N, int K, int target, bool allow_split, int min_bn = 16) {
+  GemmPlan g{};
+  const int cands[3] = {64, 32, 16};
+  g.bn = min_bn;
+  for (int c = 0; c < 3; ++c) {
+    const int bn = cands[c];
+    if (bn < min_bn) break;
+    g.bn = bn;
+    if ((long long)tiles_m * ((N + bn - 1) / bn) >= target) break;
+  }
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  g.splits = 1;
+  g.kchunk = (K + kBK - 1) / kBK * kBK;
+  if (allow_split) {
+    const int mn = tiles_m * g.tiles_n;
+    int want = std::max(1, target / std::max(1, mn));
+    const int max_splits = std::max(1, K / (2 * kBK));  // at least two k-tiles per split
+    want = std::min(std::min(want, max_splits), 32);
+    if (want > 1) {
+      int chunk = (K + want - 1) / want;
+      chunk = (chunk + kBK - 1) / kBK * kBK;
+      g.kchunk = chunk;
+      g.splits = (K + chunk - 1) / chunk;
+    }
+  }
+  return g;
+}
+
+SubOp gemm_subop(int op, int which, int tiles_m, const GemmPlan& g) {
+  SubOp s{};
+  s.op = op; s.which = which; s.tiles_m = tiles_m; s.tiles_n = g.tiles_n; s.splits = g.splits;
+  s.bn = g.bn; s.kchunk = g.kchunk; s.ntiles = tiles_m * g.tiles_n * g.splits;
+  return s;
+}
+SubOp strip_subop(int op, int which, int ntiles) {
+  SubOp s{};
+  s.op = op; s.which = which; s.ntiles = ntiles; s.tiles_m = 1; s.tiles_n = ntiles; s.splits = 1; s.bn = 0;
+  return s;
+}
+
+struct Builder {
+  std::vector<Phase> phases;
+  long long max_part = 0;
+  void add(int stage, SubOp a) {
+    Phase p{};
+    p.stage = stage; p.nsub = 1; p.sub[0] = a;
+    finish(p);
+  }
+  void add(int stage, SubOp a, SubOp b) {
+    Phase p{};
+    p.stage = stage; p.nsub = 2; p.sub[0] = a; p.sub[1] = b;
+    finish(p);
+  }
+  void finish(Phase& p) {
+    long long part = 0;
+    int ctr = 16;
+    for (int i = 0; i < p.nsub; ++i) {
+      SubOp& s = p.sub[i];
+      s.ctr_off = ctr;
+      s.part_off = part;
+      if (s.splits > 1) {
+        ctr += s.tiles_m * s.tiles_n;
+        part += (long long)s.tiles_m * s.tiles_n * s.splits * kBM * s.bn;
+      }
+    }
+    max_part = std::max(max_part, part);
+    phases.push_back(p);
+  }
+};
+
+int upload(Builder& b, Program& prog) {
+  prog.n_phases = (int)b.phases.size();
+  prog.max_tiles = 1;
+  prog.phase_tiles.clear();
+  for (auto& p : b.phases) {
+    int t = p.sub[0].ntiles + (p.nsub > 1 ? p.sub[1].ntiles : 0);
+    prog.phase_tiles.push_back(t);
+    prog.max_tiles = std::max(prog.max_tiles, t);
+    for (int i = 0; i < p.nsub; ++i)
+      if (p.sub[i].splits > 1 && p.sub[i].ctr_off + p.sub[i].tiles_m * p.sub[i].tiles_n > kCtrlWords) {
+        set_error("flow planner: too many split-K tiles");
+        return DPI_ERR_UNSUPPORTED;
+      }
+  }
+  DPI_CUDA(cudaMalloc(&prog.d_phases, sizeof(Phase) * b.phases.size()));
+  DPI_CUDA(cudaMemcpy(prog.d_phases, b.phases.data(), sizeof(Phase) * b.phases.size(), cudaMemcpyHostToDevice));
+  return DPI_OK;
+}
+
+int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
+  const int D = h->D, Da = h->Da, Db = h->Db, Dout = h->Dout, H = h->H, S = h->S;
+  const int target = h->n_sm * std::max(1, h->ctas_per_sm);
+  bp.B = B;
+  bp.tiles_m = (B + kBM - 1) / kBM;
+  const int tm = bp.tiles_m;
+  const bool sep_stats = tm > 1;
+
+  // output layer: BJ = 32 (BN 64) when that still fills the grid, else BJ = 16
+  int bj = 32;
+  if ((long long)tm * ((Db + 31) / 32) < target) bj = 16;
+  const int tiles_j = (Db + bj - 1) / bj;
+  bp.ldp_tiles = tiles_j;
+  bp.red_tiles = (Db + 31) / 32;
+
+  long long max_part = 0;
+  for (int dir = 0; dir < 2; ++dir)
+    for (int train = 0; train < 2; ++train) {
+      Builder b;
+      for (int e = 0; e < S; ++e) {
+        b.add(e, gemm_subop(OP_FWD_HID, 1, tm, plan_gemm(tm, H, Da, target, true)));
+        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 1, (H + 31) / 32));
+        b.add(e, gemm_subop(OP_FWD_HID, 2, tm, plan_gemm(tm, H, H, target, true)));
+        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 2, (H + 31) / 32));
+        SubOp o{};
+        o.op = OP_FWD_OUT; o.which = 3; o.tiles_m = tm; o.tiles_n = tiles_j; o.splits = 1; o.bn = 2 * bj;
+        o.kchunk = H; o.ntiles = tm * tiles_j;
+        b.add(e, o);
+      }
+      SubOp fin = strip_subop(OP_LOGDET_FINAL, 0, (B + kThreads - 1) / kThreads);
+      if (dir == 1) {
+        long long n = ((long long)B * D + kThreads - 1) / kThreads;
+        b.add(S - 1, fin, strip_subop(OP_GATHER_OUT, 0, (int)n));
+      } else {
+        b.add(S - 1, fin);
+      }
+      max_part = std::max(max_part, b.max_part);
+      int rc = upload(b, bp.fwd[dir][train]);
+      if (rc) return rc;
+    }
+  {
+    Builder b;
+    for (int e = S - 1; e >= 0; --e) {
+      b.add(e, strip_subop(OP_B0, 0, bp.red_tiles));
+      b.add(e, gemm_subop(OP_DGRAD_HID, 2, tm, plan_gemm(tm, H, Dout, target, true)),
+            gemm_subop(OP_WGRAD, 3, (Dout + kBM - 1) / kBM, plan_gemm((Dout + kBM - 1) / kBM, H, B, target, false)));
+      if (sep_stats) {
+        if (h->has_bn) b.add(e, strip_subop(OP_BNBWD_STATS, 2, (H + 31) / 32));
+        b.add(e, strip_subop(OP_BNBWD_APPLY, 2, (H + 31) / 32));
+      }
+      b.add(e, gemm_subop(OP_DGRAD_HID, 1, tm, plan_gemm(tm, H, H, target, true)),
+            gemm_subop(OP_WGRAD, 2, (H + kBM - 1) / kBM, plan_gemm((H + kBM - 1) / kBM, H, B, target, false)));
+      if (sep_stats) {
+        if (h->has_bn) b.add(e, strip_subop(OP_BNBWD_STATS, 1, (H + 31) / 32));
+        b.add(e, strip_subop(OP_BNBWD_APPLY, 1, (H + 31) / 32));
+      }
+      b.add(e, gemm_subop(OP_DGRAD_IN, 1, tm, plan_gemm(tm, Da, H, target, false)),
+            gemm_subop(OP_WGRAD, 1, (H + kBM - 1) / kBM, plan_gemm((H + kBM - 1) / kBM, Da, B, target, false)));
+    }
+    b.add(0, strip_subop(OP_BWD_FINAL, 0, 1));
+    max_part = std::max(max_part, b.max_part);
+    int rc = upload(b, bp.bwd);
+    if (rc) return rc;
+  }
+
+  long long o = 0;
+  auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
+  bp.oY = take((long long)S * B * D);
+  bp.oL1 = take((long long)S * B * H);
+  bp.oL2 = take((long long)S * B * H);
+  bp.oO = take((long long)S * B * Dout);
+  bp.oST = take((long long)S * 4 * H);
+  bp.oLDP = take((long long)S * bp.ldp_tiles * B);
+  bp.oGY = take(2LL * B * D);
+  bp.oGPRE = take((long long)B * Dout);
+  bp.oGN = take((long long)B * H);
+  bp.oGP1 = take((long long)B * H);
+  bp.oGP2 = take((long long)B * H);
+  bp.oPART = take(std::max(32LL, max_part));
+  bp.oRED = take((long long)S * bp.red_tiles * 2);
+  bp.total_floats = o;
+  return DPI_OK;
+}
+
+int get_plan(dpi_flow_s* h, int B, BatchPlan** out) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  auto it = h->plans.find(B);
+  if (it == h->plans.end()) {
+    std::unique_ptr<BatchPlan> bp(new BatchPlan());
+    int rc = build_plan(h, B, *bp);
+    if (rc) return rc;
+    it = h->plans.emplace(B, std::move(bp)).first;
+  }
+  *out = it->second.get();
+  return DPI_OK;
+}
+
+void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
+  a.st = h->d_stages; a.gmaps = h->d_gmaps;
+  a.D = h->D; a.Da = h->Da; a.Db = h->Db; a.Dout = h->Dout; a.H = h->H; a.S = h->S; a.has_bn = h->has_bn;
+  a.B = bp.B; a.tiles_m = bp.tiles_m; a.ldp_tiles = bp.ldp_tiles; a.red_tiles = bp.red_tiles;
+  a.oY = bp.oY; a.oL1 = bp.oL1; a.oL2 = bp.oL2; a.oO = bp.oO; a.oST = bp.oST; a.oLDP = bp.oLDP; a.oGY = bp.oGY;
+  a.oGPRE = bp.oGPRE; a.oGN = bp.oGN; a.oGP1 = bp.oGP1; a.oGP2 = bp.oGP2; a.oPART = bp.oPART; a.oRED = bp.oRED;
+  a.ctrl = (unsigned*)workspace;
+  a.W = (float*)((char*)workspace + kCtrlWords * sizeof(unsigned));
+}
+
+int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t stream) {
+  a.phases = prog.d_phases;
+  DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), stream));
+  if (h->persistent) {
+    int grid = std::min(prog.max_tiles, h->n_sm * std::min(h->ctas_per_sm, h->coop_max_per_sm));
+    grid = std::max(grid, 1);
+    a.phase_begin = 0; a.phase_end = prog.n_phases; a.persistent = 1;
+    void* params[] = {&a};
+    DPI_CUDA(cudaLaunchCooperativeKernel(flow_kernel_ptr(), dim3(grid), dim3(kThreads), params, 0, stream));
+    count_launch();
+  } else {
+    a.persistent = 0;
+    void* params[] = {&a};
+    for (int p = 0; p < prog.n_phases; ++p) {
+      a.phase_begin = p; a.phase_end = p + 1;
+      DPI_CUDA(cudaLaunchKernel(flow_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, 0, stream));
+      count_launch();
+    }
+  }
+  return DPI_OK;
+}
+
+}  // namespace
+}  // namespace dpi
+
+using namespace dpi;
+
+extern "C" {
+
+int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidden, int batch_norm,
+                    const int32_t* orders) {
+  DPI_REQUIRE(out && orders, "dpi_flow_create: null argument");
+  DPI_REQUIRE(ndim >= 2 && n_flow >= 1 && hidden >= 1, "dpi_flow_create: bad dims ndim=%d n_flow=%d hidden=%d", ndim, n_flow, hidden);
+  DeviceGuard g(device);
+  DPI_REQUIRE(g.ok, "dpi_flow_create: cannot select device %d", device);
+  std::unique_ptr<dpi_flow_s> h(new dpi_flow_s());
+  h->device = device; h->D = ndim; h->Db = ndim / 2; h->Da = ndim - ndim / 2; h->Dout = 2 * (ndim / 2);
+  h->H = hidden; h->n_flow = n_flow; h->S = 2 * n_flow; h->has_bn = batch_norm ? 1 : 0;
+  h->n_sm = sm_count(device);
+  DPI_REQUIRE(h->n_sm > 0, "dpi_flow_create: no CUDA device %d", device);
+  int nb = 0;
+  DPI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)flow_kernel_ptr(), kThreads, 0));
+  h->coop_max_per_sm = std::max(1, nb);
+  const char* mode = getenv("DPI_B200_FLOW_MODE");
+  h->persistent = (mode && mode[0] == 's') ? 0 : 1;
+  const char* cps = getenv("DPI_B200_CTAS_PER_SM");
+  h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
+
+  const int D = h->D, Da = h->Da, Dout = h->Dout, H = h->H;
+  for (int i = 0; i < n_flow; ++i)
+    for (int j = 0; j < ndim; ++j) DPI_REQUIRE(orders[(size_t)i * ndim + j] >= 0 && orders[(size_t)i * ndim + j] < ndim, "dpi_flow_create: orders[%d][%d] out of range", i, j);
+
+  // ---- flat parameter layout: nn.Module.parameters() order, tensor starts padded to 32 floats
+  long long o = 0, ob = 0;
+  auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
+  h->act_off.assign((size_t)n_flow * 4, 0);
+  h->cpl_off.assign((size_t)n_flow * 2 * P_COUNT, -1);
+  h->bn_off.assign((size_t)n_flow * 2 * 4, -1);
+  for (int i = 0; i < n_flow; ++i) {
+    for (int k = 0; k < 4; ++k) h->act_off[(size_t)i * 4 + k] = take(1);
+    for (int c = 0; c < 2; ++c) {
+      long long* p = &h->cpl_off[((size_t)i * 2 + c) * P_COUNT];
+      p[P_W1] = take((long long)H * Da); p[P_B1] = take(H);
+      if (h->has_bn) { p[P_G1] = take(H); p[P_BE1] = take(H); }
+      p[P_W2] = take((long long)H * H); p[P_B2] = take(H);
+      if (h->has_bn) { p[P_G2] = take(H); p[P_BE2] = take(H); }
+      p[P_SCALE] = take(Dout); p[P_W3] = take((long long)Dout * H); p[P_B3] = take(Dout);
+      if (h->has_bn)
+        for (int k = 0; k < 4; ++k) { h->bn_off[((size_t)i * 2 + c) * 4 + k] = ob; ob += pad32(H); }
+    }
+  }
+  h->n_params = o;
+  h->n_bn = std::max(32LL, ob);
+
+  // ---- stage table in reverse execution order
+  h->stages.resize(h->S);
+  for (int s = 0; s < h->S; ++s) {
+    const int i = n_flow - 1 - s / 2, c = (s % 2 == 0) ? 1 : 0;  // coupling2 first (:459-464)
+    StageTab& st = h->stages[s];
+    for (int k = 0; k < P_COUNT; ++k) st.p[k] = h->cpl_off[((size_t)i * 2 + c) * P_COUNT + k];
+    st.loc = h->act_off[(size_t)i * 4 + (c ? 2 : 0)];
+    st.lsi = h->act_off[(size_t)i * 4 + (c ? 3 : 1)];
+    for (int k = 0; k < 4; ++k) st.r[k] = h->bn_off[((size_t)i * 2 + c) * 4 + k];
+  }
+
+  // ---- fused gather maps
+  h->h_gmaps.assign((size_t)(2 * h->S + 1) * D, 0);
+  std::vector<int32_t> inv(D);
+  for (int e = 0; e < h->S; ++e) {
+    int32_t* g0 = &h->h_gmaps[((size_t)0 * h->S + e) * D];
+    const int i0 = n_flow - 1 - e / 2;
+    if (e % 2 == 0) {
+      const int32_t* ord = orders + (size_t)i0 * D;
+      for (int j = 0; j < D; ++j) inv[ord[j]] = j;            // Order_inverse (:553-559)
+      for (int j = 0; j < D; ++j) g0[j] = inv[D - 1 - j];      // x[:, inv][:, flip]
+    } else {
+      for (int j = 0; j < D; ++j) g0[j] = D - 1 - j;
+    }
+    int32_t* g1 = &h->h_gmaps[((size_t)1 * h->S + e) * D];
+    const int i1 = e / 2;
+    if (e % 2 == 0) {
+      if (i1 == 0) for (int j = 0; j < D; ++j) g1[j] = j;
+      else {
+        const int32_t* ord = orders + (size_t)(i1 - 1) * D;
+        for (int j = 0; j < D; ++j) g1[j] = D - 1 - ord[j];   // y[:, flip][:, order]
+      }
+    } else {
+      for (int j = 0; j < D; ++j) g1[j] = D - 1 - j;
+    }
+  }
+  {
+    int32_t* gf = &h->h_gmaps[(size_t)2 * h->S * D];
+    const int32_t* ord = orders + (size_t)(n_flow - 1) * D;
+    for (int j = 0; j < D; ++j) gf[j] = D - 1 - ord[j];
+  }
+  DPI_CUDA(cudaMalloc(&h->d_stages, sizeof(StageTab) * h->S));
+  DPI_CUDA(cudaMemcpy(h->d_stages, h->stages.data(), sizeof(StageTab) * h->S, cudaMemcpyHostToDevice));
+  DPI_CUDA(cudaMalloc(&h->d_gmaps, sizeof(int32_t) * h->h_gmaps.size()));
+  DPI_CUDA(cudaMemcpy(h->d_gmaps, h->h_gmaps.data(), sizeof(int32_t) * h->h_gmaps.size(), cudaMemcpyHostToDevice));
+  *out = h.release();
+  return DPI_OK;
+}
+
+int dpi_flow_destroy(dpi_flow_t h) {
+  if (!h) return DPI_OK;
+  DeviceGuard g(h->device);
+  for (auto& kv : h->plans) {
+    for (int d = 0; d < 2; ++d)
+      for (int t = 0; t < 2; ++t) cudaFree(kv.second->fwd[d][t].d_phases);
+    cudaFree(kv.second->bwd.d_phases);
+  }
+  cudaFree(h->d_stages);
+  cudaFree(h->d_gmaps);
+  delete h;
+  return DPI_OK;
+}
+
+int64_t dpi_flow_param_count(dpi_flow_t h) { return h ? h->n_params : -1; }
+int64_t dpi_flow_bn_count(dpi_flow_t h) { return h ? h->n_bn : -1; }
+
+int64_t dpi_flow_param_offset(dpi_flow_t h, int flow, int tensor_id) {
+  if (!h || flow < 0 || flow >= h->n_flow || tensor_id < 0 || tensor_id >= 4 + 2 * P_COUNT) return -1;
+  if (tensor_id < 4) return h->act_off[(size_t)flow * 4 + tensor_id];
+  const int c = (tensor_id - 4) / P_COUNT, k = (tensor_id - 4) % P_COUNT;
+  return h->cpl_off[((size_t)flow * 2 + c) * P_COUNT + k];
+}
+
+int64_t dpi_flow_bn_offset(dpi_flow_t h, int flow, int coupling, int stat_id) {
+  if (!h || flow < 0 || flow >= h->n_flow || coupling < 0 || coupling > 1 || stat_id < 0 || stat_id > 3) return -1;
+  return h->bn_off[((size_t)flow * 2 + coupling) * 4 + stat_id];
+}
+
+int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out) {
+  DPI_REQUIRE(h && out, "dpi_flow_gather_map: null argument");
+  DPI_REQUIRE(direction >= 0 && direction <= 2 && stage >= 0 && (direction == 2 ? stage == 0 : stage < h->S),
+              "dpi_flow_gather_map: bad direction/stage");
+  const int32_t* src = &h->h_gmaps[((size_t)direction * h->S + stage) * h->D];
+  std::copy(src, src + h->D, out);
+  return DPI_OK;
+}
+
+size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch) {
+  if (!h || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  return kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
+}
+
+int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {
+  DPI_REQUIRE(h, "dpi_flow_set_mode: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->persistent = persistent ? 1 : 0;
+  if (ctas_per_sm > 0 && ctas_per_sm != h->ctas_per_sm) {
+    h->ctas_per_sm = ctas_per_sm;
+    // tile plans depend on the grid size: drop cached plans (their device tables stay alive for
+    // any launch already enqueued; freed at destroy time would leak, so free them now after a sync)
+    cudaDeviceSynchronize();
+    for (auto& kv : h->plans) {
+      for (int d = 0; d < 2; ++d)
+        for (int t = 0; t < 2; ++t) cudaFree(kv.second->fwd[d][t].d_phases);
+      cudaFree(kv.second->bwd.d_phases);
+    }
+    h->plans.clear();
+  }
+  return DPI_OK;
+}
+
+int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float* params, float* bn_running,
+                 const float* in, float* out, float* logdet, void* workspace, size_t workspace_bytes,
+                 dpi_stream_t stream) {
+  DPI_REQUIRE(h && params && in && out && logdet && workspace, "dpi_flow_run: null argument");
+  DPI_REQUIRE(direction == 0 || direction == 1, "dpi_flow_run: direction must be 0 (reverse) or 1 (forward)");
+  DPI_REQUIRE(batch >= 1, "dpi_flow_run: batch must be >= 1");
+  DPI_REQUIRE(!(h->has_bn && !bn_running), "dpi_flow_run: bn_running required for a BatchNorm flow");
+  DPI_REQUIRE(!(h->has_bn && train && batch < 2),
+              "dpi_flow_run: Expected more than 1 value per channel when training (batch=%d)", batch);
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  int rc = get_plan(h, batch, &bp);
+  if (rc) return rc;
+  const size_t need = kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
+  if (workspace_bytes < need) {
+    set_error("dpi_flow_run: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DPI_ERR_WORKSPACE;
+  }
+  KArgs a{};
+  fill_args(h, *bp, a, workspace);
+  a.dir = direction; a.train = train ? 1 : 0;
+  a.P = params; a.G = nullptr; a.R = bn_running; a.in = in; a.out = out; a.logdet = logdet;
+  a.g_out = nullptr; a.g_ld = nullptr; a.g_in = nullptr;
+  return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
+}
+
+int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
+                      const float* g_out, const float* g_logdet, float* g_in, void* workspace,
+                      size_t workspace_bytes, dpi_stream_t stream) {
+  DPI_REQUIRE(h && params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward: null argument");
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  int rc = get_plan(h, batch, &bp);
+  if (rc) return rc;
+  const size_t need = kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
+  if (workspace_bytes < need) {
+    set_error("dpi_flow_backward: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DPI_ERR_WORKSPACE;
+  }
+  KArgs a{};
+  fill_args(h, *bp, a, workspace);
+  a.dir = 0; a.train = 1;
+  a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
+  a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
+  return launch_program(h, bp->bwd, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

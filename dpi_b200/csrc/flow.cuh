@@ -1,0 +1,70 @@
+// flow.cuh - tables shared by the flow planner (host) and the phase-program kernel (device).
+//
+// The RealNVP flow (generative_model/realnvpfc_model.py:562-603) is executed as a *phase
+// program*: a host-planned list of phases, each a set of independent tiles, with a grid-wide
+// dependency between consecutive phases. The same device code runs either as one persistent
+// cooperative kernel (grid barrier between phases) or as one launch per phase.
+#pragma once
+#include "common.cuh"
+#include "gemm_tile.cuh"
+
+namespace dpi {
+
+constexpr int kCtrlWords = 4096;  // barrier + error flag + split-K tile counters (uint32)
+
+// indices into StageTab::p - order == registration order of one AffineCoupling
+enum { P_W1 = 0, P_B1, P_G1, P_BE1, P_W2, P_B2, P_G2, P_BE2, P_SCALE, P_W3, P_B3, P_COUNT };
+
+// One coupling stage = (AffineCoupling, ActNorm) pair. Index 0 is the stage RealNVP.reverse
+// runs first: blocks[n_flow-1].coupling2/actnorm2 (:599-600, :459-461).
+struct StageTab {
+  long long p[P_COUNT];  // float offsets into the flat parameter / gradient buffers
+  long long loc, lsi;    // ActNorm.loc / .log_scale_inv
+  long long r[4];        // running_mean1, running_var1, running_mean2, running_var2 (flat bn buffer)
+};
+
+enum Op : int {
+  OP_FWD_HID = 1,    // Linear + LeakyReLU (+ BatchNorm batch statistics)  net.0-2 / net.3-5
+  OP_FWD_OUT,        // ZeroFC + tanh/exp affine coupling + ActNorm + logdet partials
+  OP_BN_STATS,       // batch statistics when the batch spans several row tiles
+  OP_LOGDET_FINAL,   // deterministic reduction of logdet partials
+  OP_GATHER_OUT,     // trailing permutation of RealNVP.forward
+  OP_B0,             // backward of ActNorm + coupling elementwise part
+  OP_DGRAD_HID,      // dgrad through W3 / W2 (+ fused BatchNorm/LeakyReLU backward)
+  OP_WGRAD,          // weight gradients
+  OP_DGRAD_IN,       // dgrad through W1 + scatter through the fused permutation
+  OP_BNBWD_STATS,    // BatchNorm backward column sums (large batch)
+  OP_BNBWD_APPLY,    // BatchNorm/LeakyReLU backward elementwise (large batch)
+  OP_BWD_FINAL       // ActNorm gradients from per-tile partials
+};
+
+struct SubOp {
+  int op, which;              // which: layer selector (1,2 hidden; 3 output)
+  int ntiles;                 // tiles_m * tiles_n * splits (GEMM ops) or strips
+  int tiles_m, tiles_n, splits, bn, kchunk;
+  int ctr_off;                // first split-K counter (ctrl words)
+  long long part_off;         // split-K partial area (floats, relative to oPART)
+};
+struct Phase {
+  int stage;                  // execution position e in [0, S)
+  int nsub;
+  SubOp sub[2];
+};
+
+struct KArgs {
+  const StageTab* st;
+  const int* gmaps;           // [2][S][D] fused gather maps, by direction and execution position
+  const Phase* phases;
+  int D, Da, Db, Dout, H, S, has_bn, B, tiles_m, dir, train;
+  int ldp_tiles, red_tiles;
+  // workspace layout (float offsets from W)
+  long long oY, oL1, oL2, oO, oST, oLDP, oGY, oGPRE, oGN, oGP1, oGP2, oPART, oRED;
+  // bases
+  const float* P; float* G; float* R; float* W;
+  const float* in; float* out; float* logdet;
+  const float* g_out; const float* g_ld; float* g_in;
+  unsigned* ctrl;
+  int phase_begin, phase_end, persistent;
+};
+
+}  // namespace dpi

@@ -1,0 +1,194 @@
+/*
+ * dpi_b200.h - C ABI of libdpi_b200.so: the sm_100a implementation of the DPI
+ * variational-posterior training step (RealNVP flow run in reverse with log|det J|,
+ * measurement operators, data/prior/entropy losses, their backward pass, clip + Adam).
+ *
+ * The reference (HeSunPU/DPI) is pure Python/PyTorch and has no FFI layer of its own; the
+ * Python callables listed below are what this library stands behind. Every entry point
+ *   - takes raw device pointers into caller-owned (torch) memory, explicit sizes, a
+ *     caller-supplied workspace and a cudaStream_t;
+ *   - is asynchronous on that stream: no internal device synchronisation, no host read of
+ *     device data (unlike the reference's ActNorm `.item()`, realnvpfc_model.py:33,52);
+ *   - is safe to call from any host thread (PyTorch calls backward from its autograd thread);
+ *     the device is taken from the handle, not from thread-local state;
+ *   - returns 0 on success or a negative code; `dpi_last_error()` (thread-local) explains.
+ * Handles own only immutable device tables built at create time.
+ *
+ * Paths are relative to /root/reference/DPItorch.
+ */
+#ifndef DPI_B200_H
+#define DPI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dpi_stream_t; /* cudaStream_t */
+
+#define DPI_OK 0
+#define DPI_ERR_INVALID (-1)
+#define DPI_ERR_CUDA (-2)
+#define DPI_ERR_UNSUPPORTED (-3)
+#define DPI_ERR_WORKSPACE (-4)
+
+const char* dpi_last_error(void);
+int dpi_version(void);
+/* Number of kernel launches issued by this library in this process (for bench.py's gpu_launches). */
+long long dpi_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * RealNVP flow: generative_model/realnvpfc_model.py  RealNVP :562-603, Flow :427-474,
+ * AffineCoupling :143-257, ZeroFC :128-141, ActNorm :8-66.
+ * All trainable tensors live in ONE flat fp32 buffer (same order as nn.Module.parameters(),
+ * each tensor start padded to 32 floats); BatchNorm running statistics in a second flat buffer.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dpi_flow_s* dpi_flow_t;
+
+/* tensor ids for dpi_flow_param_offset: per flow block */
+enum {
+  DPI_T_ACT1_LOC = 0, DPI_T_ACT1_LSI = 1, DPI_T_ACT2_LOC = 2, DPI_T_ACT2_LSI = 3,
+  /* per coupling (add DPI_T_COUPLING_STRIDE for coupling2) */
+  DPI_T_W1 = 4, DPI_T_B1 = 5, DPI_T_G1 = 6, DPI_T_BE1 = 7, DPI_T_W2 = 8, DPI_T_B2 = 9,
+  DPI_T_G2 = 10, DPI_T_BE2 = 11, DPI_T_SCALE = 12, DPI_T_W3 = 13, DPI_T_B3 = 14,
+  DPI_T_COUPLING_STRIDE = 11
+};
+/* running-stat ids for dpi_flow_bn_offset: per coupling */
+enum { DPI_R_MEAN1 = 0, DPI_R_VAR1 = 1, DPI_R_MEAN2 = 2, DPI_R_VAR2 = 3 };
+
+/* orders: host int32 [n_flow * ndim], orders[i] = the permutation applied after block i in
+ * forward (RealNVP.__init__ :568-577). hidden = int(ndim / (2*seqfrac)). */
+int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidden, int batch_norm,
+                    const int32_t* orders);
+int dpi_flow_destroy(dpi_flow_t h);
+int64_t dpi_flow_param_count(dpi_flow_t h); /* floats in the flat parameter buffer */
+int64_t dpi_flow_bn_count(dpi_flow_t h);    /* floats in the flat running-stat buffer */
+int64_t dpi_flow_param_offset(dpi_flow_t h, int flow, int tensor_id);
+int64_t dpi_flow_bn_offset(dpi_flow_t h, int flow, int coupling /*0|1*/, int stat_id);
+/* the fused gather map of stage s (reverse direction), int32[ndim] copied to host `out` */
+int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out);
+
+size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch);
+
+/* RealNVP.reverse (direction 0, :594-603) / RealNVP.forward (direction 1, :583-592).
+ * in/out [batch, ndim], logdet [batch]. train!=0: BatchNorm batch statistics, running stats in
+ * `bn_running` updated (momentum 0.1, unbiased variance); train==0: running stats used.
+ * The workspace keeps every activation dpi_flow_backward needs. */
+int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float* params,
+                 float* bn_running, const float* in, float* out, float* logdet, void* workspace,
+                 size_t workspace_bytes, dpi_stream_t stream);
+
+/* Backward of a train-mode dpi_flow_run(direction=0): given dL/dout [batch, ndim] and
+ * dL/dlogdet [batch], writes dL/din [batch, ndim] (may be NULL) and OVERWRITES the flat
+ * gradient buffer `grads` (same layout as params; padding untouched). */
+int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
+                      const float* g_out, const float* g_logdet, float* g_in, void* workspace,
+                      size_t workspace_bytes, dpi_stream_t stream);
+
+/* 0: one launch per phase; 1: one persistent cooperative launch with grid barriers */
+int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm);
+
+/* ------------------------------------------------------------------------------------------
+ * Image head: positivity + scale (DPI_interferometry.py:205-211, DPI_MRI.py:174-179) fused
+ * with the image priors (interferometry_helpers.py Loss_l1 :349, Loss_TSV :354, Loss_TV :358,
+ * Loss_flux :363, Loss_center :369-382, Loss_cross_entropy :384-387; MRI_helpers.py:28-38).
+ * ------------------------------------------------------------------------------------------ */
+enum { DPI_PRIOR_L1 = 0, DPI_PRIOR_TSV = 1, DPI_PRIOR_TV = 2, DPI_PRIOR_FLUX = 3,
+       DPI_PRIOR_CENTER = 4, DPI_PRIOR_MEM = 5, DPI_PRIOR_COUNT = 6 };
+
+/* img = softplus(x) * exp(*log_scale); det[b] = sum(x - softplus(x)) + *log_scale * npix^2 */
+int dpi_positivity_forward(int batch, int npix, const float* x, const float* log_scale, float* img,
+                           float* det, dpi_stream_t stream);
+/* g_x = (g_img + g_img2) * exp(ls) * sigmoid(x) + g_det[b] * (1 - sigmoid(x));
+ * g_log_scale_partial[b] = sum_p (g_img + g_img2)*img + npix^2 * g_det[b]  (caller sums over b).
+ * g_img, g_img2, g_det, g_log_scale_partial may each be NULL. */
+int dpi_positivity_backward(int batch, int npix, const float* x, const float* log_scale,
+                            const float* img, const float* g_img, const float* g_img2,
+                            const float* g_det, float* g_x, float* g_log_scale_partial,
+                            dpi_stream_t stream);
+
+/* All six priors of each image in one pass: values[b, DPI_PRIOR_COUNT]. `prior_img` (may be NULL
+ * unless MEM is wanted) is the y_true of Loss_cross_entropy; `flux`/`center` as in the factories.
+ * If g_img != NULL also writes g_img[b,:] = sum_t gw[b,t] * d values[b,t] / d img (gw [batch, 6]). */
+int dpi_image_priors(int batch, int npix, const float* img, const float* prior_img, float flux,
+                     float center, float* values, const float* gw, float* g_img, dpi_stream_t stream);
+/* Fused positivity + priors: reads x, writes img and det, then as dpi_image_priors. */
+int dpi_image_head(int batch, int npix, const float* x, const float* log_scale, float* img, float* det,
+                   const float* prior_img, float flux, float center, float* values, const float* gw,
+                   float* g_img, dpi_stream_t stream);
+/* out[0] = sum(in[0..n)); sq_out[0] = out[0]^2 (either may be NULL). Deterministic, one CTA. */
+int dpi_reduce_sum(int n, const float* in, float* out, double* sq_out, dpi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Interferometry operator: interferometry_helpers.py eht_observation_pytorch :235-292
+ * (ttype='direct': torch_complex_matmul :36-39) and the chi^2 terms :299-347.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dpi_eht_s* dpi_eht_t;
+/* dft_mat host fp32 [npix*npix, n_vis, 2]; index/sign tables host, as Obs_params_torch returns. */
+int dpi_eht_create(dpi_eht_t* out, int device, int npix, int n_vis, const float* dft_mat, int n_cp,
+                   const int64_t* cp_ind /*[3*n_cp]*/, const double* cp_sign /*[3*n_cp]*/, int n_ca,
+                   const int64_t* ca_ind /*[4*n_ca]*/);
+int dpi_eht_destroy(dpi_eht_t h);
+size_t dpi_eht_workspace_bytes(dpi_eht_t h, int batch);
+/* vis [B,2,n_vis] fp32, visamp [B,n_vis] fp32, cphase [B,n_cp] fp64 (degrees), logcamp [B,n_ca] */
+int dpi_eht_forward(dpi_eht_t h, int batch, const float* img, float* vis, float* visamp,
+                    double* cphase, float* logcamp, void* workspace, size_t workspace_bytes,
+                    dpi_stream_t stream);
+/* any upstream gradient may be NULL; g_img [B, npix*npix] is overwritten */
+int dpi_eht_backward(dpi_eht_t h, int batch, const float* vis, const float* g_vis,
+                     const float* g_visamp, const double* g_cphase, const float* g_logcamp,
+                     float* g_img, void* workspace, size_t workspace_bytes, dpi_stream_t stream);
+
+/* Fused data term of DPI_interferometry.py:221-229. Given vis from dpi_eht_forward:
+ * loss_cp[b] (fp64) = Loss_angle_diff, loss_ca[b] = Loss_logca_diff2, and
+ * g_img = d(w_cp * sum_b loss_cp[b] + w_ca * sum_b loss_ca[b]) / d img. */
+int dpi_eht_data_grad(dpi_eht_t h, int batch, const float* vis, const float* cphase_true,
+                      const float* sigma_cp, const float* logcamp_true, const float* sigma_ca,
+                      float w_cp, float w_ca, double* loss_cp, float* loss_ca, float* g_img,
+                      void* workspace, size_t workspace_bytes, dpi_stream_t stream);
+
+/* chi^2 data terms. mode: */
+enum { DPI_CHI2_ANGLE = 0,   /* Loss_angle_diff :299 (y in degrees, pred fp64) */
+       DPI_CHI2_SQ = 1,      /* Loss_logca_diff2 :318 / Loss_visamp_diff :342 */
+       DPI_CHI2_LOGSQ = 2,   /* Loss_logamp_diff :334 / Loss_logca_diff :310 */
+       DPI_CHI2_VIS = 3 };   /* Loss_vis_diff :326 (true [2,n], pred [B,2,n]) */
+/* loss[b] (fp64 for ANGLE, fp32 otherwise - matching the reference's promotion).
+ * If g_loss != NULL also writes g_pred = g_loss[b] * d loss[b] / d pred. */
+int dpi_chi2(int mode, int batch, int n, const float* y_true, const void* y_pred, const float* sigma,
+             void* loss, const void* g_loss, void* g_pred, dpi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MRI operator: DPI_MRI.py fft2c_torch :70-74 + MRI_helpers.py Loss_kspace_diff2 :23-26.
+ * ------------------------------------------------------------------------------------------ */
+/* kspace[b, ky, kx, 2] = ortho FFT2 of the real image */
+int dpi_fft2c_forward(int batch, int npix, const float* img, float* kspace, dpi_stream_t stream);
+/* g_img = adjoint applied to g_kspace (real part) */
+int dpi_fft2c_backward(int batch, int npix, const float* g_kspace, float* g_img, dpi_stream_t stream);
+/* Fused data term of DPI_MRI.py:181-182: loss[b] = mean((fft2c(img)*mask - kspace_true)^2)/sigma^2/mean_mask
+ * and, if g_img != NULL, g_img[b,:] = gw[b] * d loss[b]/d img. mask, kspace_true [npix,npix,2]. */
+int dpi_mri_data_loss(int batch, int npix, const float* img, const float* mask, const float* kspace_true,
+                      float sigma, float mean_mask, float* loss, const float* gw, float* g_img,
+                      dpi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: nn.utils.clip_grad_norm_ + optim.Adam (DPI_interferometry.py:172,233-235).
+ * ------------------------------------------------------------------------------------------ */
+size_t dpi_clip_adam_workspace_bytes(int64_t n);
+/* sq_out[0] (device fp64) = sum g^2, deterministic two-level reduction in one launch. */
+int dpi_grad_sqnorm(int64_t n, const float* g, double* sq_out, void* workspace, size_t workspace_bytes,
+                    dpi_stream_t stream);
+/* One fused pass: total norm = sqrt(sum sq_norms[0..n_sq)) * grad_scale,
+ * coef = min(1, clip / (norm + 1e-6)) (clip <= 0 disables), g' = coef * grad_scale * g, Adam update
+ * with the step number read from device memory (graph-replay safe).
+ * norm_out (may be NULL): [0] = norm before clipping, [1] = coef. */
+int dpi_clip_adam(int64_t n, float* p, const float* g, float* m, float* v, const double* sq_norms,
+                  int n_sq, float clip, float lr, float beta1, float beta2, float eps,
+                  const int64_t* step_dev, float grad_scale, float* norm_out, dpi_stream_t stream);
+int dpi_step_increment(int64_t* step_dev, dpi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPI_B200_H */
