@@ -51,6 +51,34 @@ struct dpi_flow_s {
 namespace dpi {
 namespace {
 
+// Flat parameter layout: nn.Module.parameters() order of the reference RealNVP, every tensor
+// start padded to 32 floats (128 B) so rows can be fetched with vector / bulk copies.
+void compute_layout(int ndim, int n_flow, int H, int has_bn, std::vector<long long>& act_off,
+                    std::vector<long long>& cpl_off, std::vector<long long>& bn_off, long long& n_params,
+                    long long& n_bn) {
+  const int Da = ndim - ndim / 2, Dout = 2 * (ndim / 2);
+  long long o = 0, ob = 0;
+  auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
+  act_off.assign((size_t)n_flow * 4, 0);
+  cpl_off.assign((size_t)n_flow * 2 * P_COUNT, -1);
+  bn_off.assign((size_t)n_flow * 2 * 4, -1);
+  for (int i = 0; i < n_flow; ++i) {
+    for (int k = 0; k < 4; ++k) act_off[(size_t)i * 4 + k] = take(1);
+    for (int c = 0; c < 2; ++c) {
+      long long* p = &cpl_off[((size_t)i * 2 + c) * P_COUNT];
+      p[P_W1] = take((long long)H * Da); p[P_B1] = take(H);
+      if (has_bn) { p[P_G1] = take(H); p[P_BE1] = take(H); }
+      p[P_W2] = take((long long)H * H); p[P_B2] = take(H);
+      if (has_bn) { p[P_G2] = take(H); p[P_BE2] = take(H); }
+      p[P_SCALE] = take(Dout); p[P_W3] = take((long long)Dout * H); p[P_B3] = take(Dout);
+      if (has_bn)
+        for (int k = 0; k < 4; ++k) { bn_off[((size_t)i * 2 + c) * 4 + k] = ob; ob += pad32(H); }
+    }
+  }
+  n_params = o;
+  n_bn = std::max(32LL, ob);
+}
+
 struct GemmPlan { int bn, tiles_n, splits, kchunk; };
 
 // Pick the column tile and split-K factor so a phase offers about `target` tiles.
@@ -302,27 +330,7 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   for (int i = 0; i < n_flow; ++i)
     for (int j = 0; j < ndim; ++j) DPI_REQUIRE(orders[(size_t)i * ndim + j] >= 0 && orders[(size_t)i * ndim + j] < ndim, "dpi_flow_create: orders[%d][%d] out of range", i, j);
 
-  // ---- flat parameter layout: nn.Module.parameters() order, tensor starts padded to 32 floats
-  long long o = 0, ob = 0;
-  auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
-  h->act_off.assign((size_t)n_flow * 4, 0);
-  h->cpl_off.assign((size_t)n_flow * 2 * P_COUNT, -1);
-  h->bn_off.assign((size_t)n_flow * 2 * 4, -1);
-  for (int i = 0; i < n_flow; ++i) {
-    for (int k = 0; k < 4; ++k) h->act_off[(size_t)i * 4 + k] = take(1);
-    for (int c = 0; c < 2; ++c) {
-      long long* p = &h->cpl_off[((size_t)i * 2 + c) * P_COUNT];
-      p[P_W1] = take((long long)H * Da); p[P_B1] = take(H);
-      if (h->has_bn) { p[P_G1] = take(H); p[P_BE1] = take(H); }
-      p[P_W2] = take((long long)H * H); p[P_B2] = take(H);
-      if (h->has_bn) { p[P_G2] = take(H); p[P_BE2] = take(H); }
-      p[P_SCALE] = take(Dout); p[P_W3] = take((long long)Dout * H); p[P_B3] = take(Dout);
-      if (h->has_bn)
-        for (int k = 0; k < 4; ++k) { h->bn_off[((size_t)i * 2 + c) * 4 + k] = ob; ob += pad32(H); }
-    }
-  }
-  h->n_params = o;
-  h->n_bn = std::max(32LL, ob);
+  compute_layout(D, n_flow, H, h->has_bn, h->act_off, h->cpl_off, h->bn_off, h->n_params, h->n_bn);
 
   // ---- stage table in reverse execution order
   h->stages.resize(h->S);
@@ -373,6 +381,24 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   return DPI_OK;
 }
 
+int dpi_flow_layout(int ndim, int n_flow, int hidden, int batch_norm, int64_t* param_offsets, int64_t* bn_offsets,
+                    int64_t* n_params, int64_t* n_bn) {
+  DPI_REQUIRE(ndim >= 2 && n_flow >= 1 && hidden >= 1, "dpi_flow_layout: bad dims");
+  std::vector<long long> act, cpl, bn;
+  long long np = 0, nb = 0;
+  compute_layout(ndim, n_flow, hidden, batch_norm ? 1 : 0, act, cpl, bn, np, nb);
+  if (param_offsets)
+    for (int i = 0; i < n_flow; ++i) {
+      for (int k = 0; k < 4; ++k) param_offsets[(size_t)i * (4 + 2 * P_COUNT) + k] = act[(size_t)i * 4 + k];
+      for (int k = 0; k < 2 * P_COUNT; ++k) param_offsets[(size_t)i * (4 + 2 * P_COUNT) + 4 + k] = cpl[(size_t)i * 2 * P_COUNT + k];
+    }
+  if (bn_offsets)
+    for (size_t i = 0; i < bn.size(); ++i) bn_offsets[i] = bn[i];
+  if (n_params) *n_params = np;
+  if (n_bn) *n_bn = nb;
+  return DPI_OK;
+}
+
 int dpi_flow_destroy(dpi_flow_t h) {
   if (!h) return DPI_OK;
   DeviceGuard g(h->device);
@@ -417,6 +443,24 @@ size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch) {
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
   return kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
+}
+
+int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
+  if (!h || batch < 1 || stage < 0 || stage >= h->S) return -1;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return -1;
+  long long o;
+  const long long B = batch;
+  switch (what) {
+    case 0: o = bp->oY + stage * B * h->D; break;
+    case 1: o = bp->oL1 + stage * B * h->H; break;
+    case 2: o = bp->oL2 + stage * B * h->H; break;
+    case 3: o = bp->oO + stage * B * h->Dout; break;
+    case 4: o = bp->oST + (long long)stage * 4 * h->H; break;
+    default: return -1;
+  }
+  return (int64_t)(kCtrlWords * sizeof(unsigned)) + o * (int64_t)sizeof(float);
 }
 
 int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {

@@ -148,6 +148,38 @@ __global__ void reduce_sum_kernel(int n, const float* __restrict__ in, float* __
   }
 }
 
+struct TermArgs {
+  const double* data64; const float* data32; const float* priors; const float* logdet_flow; const float* det;
+  float w64, w32, w_logdet; float wp[DPI_PRIOR_COUNT];
+};
+
+// Loss assembly of DPI_interferometry.py:224-229 / DPI_MRI.py:186-193 (means over the batch).
+// out: [0] loss, [1] mean data64 term, [2] mean data32 term, [3] mean weighted prior,
+//      [4] mean total logdet, [5..10] mean of each prior value
+__global__ void __launch_bounds__(256) step_terms_kernel(int B, TermArgs a, float* __restrict__ out) {
+  __shared__ double red[32];
+  double s64 = 0, s32 = 0, sld = 0, sp[DPI_PRIOR_COUNT] = {0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (a.data64) s64 += a.data64[b];
+    if (a.data32) s32 += (double)a.data32[b];
+    sld += (double)a.logdet_flow[b] + (double)a.det[b];
+    if (a.priors)
+      for (int t = 0; t < DPI_PRIOR_COUNT; ++t) sp[t] += (double)a.priors[(size_t)b * DPI_PRIOR_COUNT + t];
+  }
+  s64 = block_sum(s64, red); s32 = block_sum(s32, red); sld = block_sum(sld, red);
+  for (int t = 0; t < DPI_PRIOR_COUNT; ++t) sp[t] = block_sum(sp[t], red);
+  if (threadIdx.x == 0) {
+    const double inv = 1.0 / B;
+    double prior = 0;
+    for (int t = 0; t < DPI_PRIOR_COUNT; ++t) {
+      if (a.wp[t] != 0.f) prior += (double)a.wp[t] * sp[t] * inv;
+      out[5 + t] = (float)(sp[t] * inv);
+    }
+    out[1] = (float)(s64 * inv); out[2] = (float)(s32 * inv); out[3] = (float)prior; out[4] = (float)(sld * inv);
+    out[0] = (float)((double)a.w64 * s64 * inv + (double)a.w32 * s32 * inv + prior - (double)a.w_logdet * sld * inv);
+  }
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -201,6 +233,18 @@ int dpi_image_head(int batch, int npix, const float* x, const float* log_scale, 
   DPI_REQUIRE(!g_img || gw, "dpi_image_head: g_img requested without weights");
   return launch_priors(batch, npix, x, log_scale, img, det, prior_img, flux, center, values, gw, g_img,
                        (cudaStream_t)stream);
+}
+
+int dpi_step_terms(int batch, const double* data64, float w64, const float* data32, float w32, const float* priors,
+                   const float* prior_weights, const float* logdet_flow, const float* det, float w_logdet, float* out,
+                   dpi_stream_t stream) {
+  DPI_REQUIRE(batch >= 1 && logdet_flow && det && out, "dpi_step_terms: bad argument");
+  TermArgs a{data64, data32, priors, logdet_flow, det, w64, w32, w_logdet, {0, 0, 0, 0, 0, 0}};
+  if (prior_weights)
+    for (int t = 0; t < DPI_PRIOR_COUNT; ++t) a.wp[t] = prior_weights[t];
+  step_terms_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(batch, a, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
 }
 
 int dpi_reduce_sum(int n, const float* in, float* out, double* sq_out, dpi_stream_t stream) {

@@ -229,7 +229,7 @@ def mri_mask(npix=64, ratio=4, seed=0):
     pdf = np.exp(-3.0 * np.hypot(X, Y))
     pdf *= (npix * npix / ratio) / pdf.sum()
     mask = rng.rand(npix, npix) < np.clip(pdf, 0, 1)
-    c = npix // 2
-    mask[c - 8:c + 8, c - 8:c + 8] = 1
+    c, h = npix // 2, max(1, npix // 8)  # npix=64: rows/cols 24:40, as DPI_MRI.py:109
+    mask[c - h:c + h, c - h:c + h] = 1
     mask = np.fft.fftshift(mask)
     return np.stack((mask, mask), axis=-1).astype(np.float64)

@@ -1,0 +1,286 @@
+"""Fused DPI training steps: the benchmarked hot path.
+
+One `step(z)` = the loop body of DPI_interferometry.py:193-235 / DPI_MRI.py:162-207 (realnvp
+branch): flow reverse with log|det J| -> softplus positivity and learned scale -> measurement
+operator -> data + prior losses - entropy -> analytic backward through all of it -> global-norm
+clip -> Adam, as ~12 launches of libdpi_b200 kernels on the current stream (no autograd, no host
+synchronisation, no host reads). After warm-up the launch sequence is captured into a CUDA graph
+and replayed.
+
+Data parallel (one process per GPU): every rank runs the same step on its own z; the flat
+gradient buffer (flow parameters + log_scale) is averaged with one NCCL all-reduce between the
+backward pass and the clip (BatchNorm statistics stay per-replica = DDP semantics).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from dpi_b200 import _lib
+from dpi_b200.generative_model.realnvpfc_model import RealNVP
+
+_PRIOR_ORDER = ("l1", "tsv", "tv", "flux", "center", "mem")
+
+
+class _FusedTrainer:
+    def __init__(self, flow: RealNVP, log_scale_init: float, batch: int, npix: int, lr: float, clip: float,
+                 device, betas=(0.9, 0.999), eps=1e-8, process_group=None, use_graph=True):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dpi_b200 trainers need a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.flow = flow.to(self.device)
+        self.flow.train()
+        self.flow._init_reverse()
+        self.B, self.npix, self.D = int(batch), int(npix), int(npix) * int(npix)
+        assert self.D == flow.ndim
+        self.lr, self.clip, self.betas, self.eps = float(lr), float(clip), betas, float(eps)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev, f32 = self.device, torch.float32
+        P = self.flow.flat.numel()
+        self.P = P
+        # parameters: [flow flat | log_scale | pad]; gradients share the layout so ONE all-reduce covers both
+        self.params = self.flow.flat.data
+        self.log_scale = torch.full((32,), 0.0, dtype=f32, device=dev)
+        self.log_scale[0] = float(log_scale_init)
+        self.grads_all = torch.zeros(P + 32, dtype=f32, device=dev)
+        self.grads = self.grads_all[:P]
+        self.g_ls = self.grads_all[P:P + 1]
+        self.m = torch.zeros(P, dtype=f32, device=dev)
+        self.v = torch.zeros(P, dtype=f32, device=dev)
+        self.m_ls = torch.zeros(32, dtype=f32, device=dev)
+        self.v_ls = torch.zeros(32, dtype=f32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.sq = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.norm_out = torch.zeros(2, dtype=f32, device=dev)
+        self.terms = torch.zeros(16, dtype=f32, device=dev)
+        B, D = self.B, self.D
+        self.z = torch.zeros(B, D, dtype=f32, device=dev)
+        self.x = torch.empty(B, D, dtype=f32, device=dev)
+        self.logdet_flow = torch.empty(B, dtype=f32, device=dev)
+        self.img = torch.empty(B, D, dtype=f32, device=dev)
+        self.det = torch.empty(B, dtype=f32, device=dev)
+        self.prior_vals = torch.empty(B, 6, dtype=f32, device=dev)
+        self.g_img_prior = torch.empty(B, D, dtype=f32, device=dev)
+        self.g_img_data = torch.empty(B, D, dtype=f32, device=dev)
+        self.g_x = torch.empty(B, D, dtype=f32, device=dev)
+        self.g_ls_partial = torch.empty(B, dtype=f32, device=dev)
+        self.handle = self.flow._handle(dev)
+        nbytes = self.lib.dpi_flow_workspace_bytes(self.handle, B)
+        if nbytes == 0:
+            _lib.check(-1, "dpi_flow_workspace_bytes")
+        self.ws_flow = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.ws_opt = torch.zeros(self.lib.dpi_clip_adam_workspace_bytes(P), dtype=torch.uint8, device=dev)
+        self.use_graph = use_graph
+        self._graphs = None
+        self._warm = 0
+        self.launches_per_step = None
+
+    # -- subclass hooks -------------------------------------------------------------------------
+    def _data_forward_backward(self, st):
+        raise NotImplementedError
+
+    def _terms(self, st):
+        raise NotImplementedError
+
+    # -- the step, as two enqueue halves around the (optional) gradient all-reduce ------------------
+    def _enqueue_loss_grad(self):
+        lib, st, B = self.lib, _lib.stream_ptr(), self.B
+        fl = self.flow
+        _lib.check(lib.dpi_flow_run(self.handle, 0, 1, B, self.params.data_ptr(), fl.bn_running.data_ptr(),
+                                    self.z.data_ptr(), self.x.data_ptr(), self.logdet_flow.data_ptr(),
+                                    self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
+        _lib.check(lib.dpi_image_head(B, self.npix, self.x.data_ptr(), self.log_scale.data_ptr(), self.img.data_ptr(),
+                                      self.det.data_ptr(), _lib.ptr(self.prior_img), self.flux_target, self.center,
+                                      self.prior_vals.data_ptr(), self.gw_prior.data_ptr(),
+                                      self.g_img_prior.data_ptr(), st), "dpi_image_head")
+        self._data_forward_backward(st)
+        _lib.check(lib.dpi_positivity_backward(B, self.npix, self.x.data_ptr(), self.log_scale.data_ptr(),
+                                               self.img.data_ptr(), self.g_img_prior.data_ptr(),
+                                               self.g_img_data.data_ptr(), self.g_det.data_ptr(), self.g_x.data_ptr(),
+                                               self.g_ls_partial.data_ptr(), st), "dpi_positivity_backward")
+        _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(),
+                                         self.z.data_ptr(), self.g_x.data_ptr(), self.g_det.data_ptr(), None,
+                                         self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_backward")
+        _lib.check(lib.dpi_reduce_sum(B, self.g_ls_partial.data_ptr(), self.g_ls.data_ptr(), None, st),
+                   "dpi_reduce_sum")
+        self._terms(st)
+
+    def _enqueue_update(self):
+        lib, st = self.lib, _lib.stream_ptr()
+        gs = 1.0 / self.world
+        _lib.check(lib.dpi_grad_sqnorm(self.P + 1, self.grads_all.data_ptr(), self.sq.data_ptr(),
+                                       self.ws_opt.data_ptr(), self.ws_opt.numel(), st), "dpi_grad_sqnorm")
+        _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
+        b1, b2 = self.betas
+        _lib.check(lib.dpi_clip_adam(self.P, self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
+                                     self.v.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
+                                     self.step_dev.data_ptr(), gs, self.norm_out.data_ptr(), st), "dpi_clip_adam")
+        _lib.check(lib.dpi_clip_adam(1, self.log_scale.data_ptr(), self.g_ls.data_ptr(), self.m_ls.data_ptr(),
+                                     self.v_ls.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
+                                     self.step_dev.data_ptr(), gs, None, st), "dpi_clip_adam")
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads_all, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def loss_and_grad(self, z: Optional[torch.Tensor] = None):
+        """Forward + backward only (no update): fills self.grads / self.g_ls / self.terms."""
+        if z is not None:
+            self.z.copy_(z, non_blocking=True)
+        with torch.cuda.device(self.device):
+            self._enqueue_loss_grad()
+        self.flow._bump_bn()
+        return self.terms
+
+    def step(self, z: Optional[torch.Tensor] = None):
+        """One optimisation step. z [B, D] (host pinned or device) is copied into the static input
+        buffer; None re-uses whatever self.z holds (e.g. torch.randn written in place)."""
+        if z is not None:
+            self.z.copy_(z, non_blocking=True)
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
+                n0 = _lib.launch_count()
+                self._enqueue_loss_grad()
+                self._allreduce()
+                self._enqueue_update()
+                self.launches_per_step = _lib.launch_count() - n0
+            elif self._graphs is None:
+                n0 = _lib.launch_count()
+                self._enqueue_loss_grad()
+                self._allreduce()
+                self._enqueue_update()
+                self.launches_per_step = _lib.launch_count() - n0
+                self._warm += 1
+                if self._warm >= 2:
+                    self._capture()
+            else:
+                ga, gb = self._graphs
+                ga.replay()
+                self._allreduce()
+                gb.replay()
+        self.flow._bump_bn()
+        return self.terms
+
+    def _capture(self):
+        torch.cuda.synchronize(self.device)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # the captured launches must not change any state: save / restore what a step mutates
+        saved = [t.clone() for t in (self.params, self.log_scale, self.m, self.v, self.m_ls, self.v_ls, self.step_dev,
+                                     self.flow.bn_running)]
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(ga, stream=s):
+                self._enqueue_loss_grad()
+            with torch.cuda.graph(gb, stream=s):
+                self._enqueue_update()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        for t, sv in zip((self.params, self.log_scale, self.m, self.v, self.m_ls, self.v_ls, self.step_dev,
+                          self.flow.bn_running), saved):
+            t.copy_(sv)
+        self._graphs = (ga, gb)
+
+    # -- conveniences ---------------------------------------------------------------------------
+    def sample_z(self, generator=None):
+        """z ~ N(0, I) drawn on the device into the static input buffer."""
+        self.z.normal_(generator=generator)
+        return self.z
+
+    def log_scale_value(self) -> float:
+        return float(self.log_scale[0].item())
+
+    def algorithmic_bytes_per_step(self) -> int:
+        """40 P (weights fwd + bwd, grad write, Adam 4 reads + 3 writes) + saved activations
+        once written and once read + constants."""
+        C_ = 2 * self.flow.n_flow
+        return int(40 * self.flow.flat.numel() + 4 * self.B * self.D * (2 * C_ + 4) + self._const_bytes())
+
+    def _const_bytes(self):
+        return 0
+
+
+class InterferometryTrainer(_FusedTrainer):
+    """DPI_interferometry.py:191-235 (closure phase + log closure amplitude + 5 image priors)."""
+
+    def __init__(self, flow: RealNVP, wl: dict, batch: int, lr=1e-4, clip=1e-3, device="cuda", **kw):
+        super().__init__(flow, wl["log_scale_init"], batch, wl["npix"], lr, clip, device, **kw)
+        from dpi_b200.interferometry_helpers import _EhtOp
+        dev, f32, B = self.device, torch.float32, self.B
+        self.wl, w = wl, wl["w"]
+        self.op = _EhtOp(wl["npix"], wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"], dev)
+        self.cphase_true = wl["cphase_true"].to(dev, f32).contiguous()
+        self.logcamp_true = wl["logcamp_true"].to(dev, f32).contiguous()
+        self.sigma_cp = wl["sigma_cp"].to(dev, f32).contiguous()
+        self.sigma_ca = wl["sigma_ca"].to(dev, f32).contiguous()
+        self.prior_img = wl["prior"].to(dev, f32).contiguous()
+        self.flux_target, self.center = float(wl["flux"]), float(self.npix / 2 - 0.5)
+        self.w = w
+        wp = [w.get(k, 0.0) for k in _PRIOR_ORDER]
+        self.wp_host = (C.c_float * 6)(*wp)
+        self.gw_prior = (torch.tensor(wp, dtype=f32, device=dev) / B).repeat(B, 1).contiguous()
+        self.g_det = torch.full((B,), -w["logdet"] / B, dtype=f32, device=dev)
+        self.vis = torch.empty(B, 2, self.op.n_vis, dtype=f32, device=dev)
+        self.loss_cp = torch.empty(B, dtype=torch.float64, device=dev)
+        self.loss_ca = torch.empty(B, dtype=f32, device=dev)
+        self.ws_eht = self.op.workspace(B)
+
+    def _data_forward_backward(self, st):
+        lib, B, op = self.lib, self.B, self.op
+        _lib.check(lib.dpi_eht_forward(op.handle, B, self.img.data_ptr(), self.vis.data_ptr(), None, None, None,
+                                       self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_forward")
+        _lib.check(lib.dpi_eht_data_grad(op.handle, B, self.vis.data_ptr(), self.cphase_true.data_ptr(),
+                                         self.sigma_cp.data_ptr(), self.logcamp_true.data_ptr(),
+                                         self.sigma_ca.data_ptr(), self.w["cphase"] / B, self.w["camp"] / B,
+                                         self.loss_cp.data_ptr(), self.loss_ca.data_ptr(), self.g_img_data.data_ptr(),
+                                         self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_data_grad")
+
+    def _terms(self, st):
+        _lib.check(self.lib.dpi_step_terms(self.B, self.loss_cp.data_ptr(), self.w["cphase"], self.loss_ca.data_ptr(),
+                                           self.w["camp"], self.prior_vals.data_ptr(), self.wp_host,
+                                           self.logdet_flow.data_ptr(), self.det.data_ptr(), self.w["logdet"],
+                                           self.terms.data_ptr(), st), "dpi_step_terms")
+
+    def _const_bytes(self):
+        return 2 * 4 * self.op.P * 2 * self.op.n_vis  # F read forward and backward
+
+
+class MRITrainer(_FusedTrainer):
+    """DPI_MRI.py:160-207 (masked ortho FFT2 k-space chi^2 + TV/L1 priors)."""
+
+    def __init__(self, flow: RealNVP, wl: dict, batch: int, lr=1e-5, clip=1e-2, device="cuda", **kw):
+        super().__init__(flow, wl["log_scale_init"], batch, wl["npix"], lr, clip, device, **kw)
+        dev, f32, B = self.device, torch.float32, self.B
+        self.wl, w = wl, wl["w"]
+        self.w = w
+        self.mask = wl["mask"].to(dev, f32).contiguous()
+        self.kspace_true = wl["kspace_true"].to(dev, f32).contiguous()
+        self.sigma, self.mean_mask = float(wl["sigma"]), float(wl["mean_mask"])
+        self.prior_img = None
+        self.flux_target, self.center = 0.0, 0.0
+        wp = [w.get(k, 0.0) for k in _PRIOR_ORDER]
+        self.wp_host = (C.c_float * 6)(*wp)
+        self.gw_prior = (torch.tensor(wp, dtype=f32, device=dev) / B).repeat(B, 1).contiguous()
+        self.g_det = torch.full((B,), -w["logdet"] / B, dtype=f32, device=dev)
+        self.gw_data = torch.full((B,), w["kspace"] / B, dtype=f32, device=dev)
+        self.loss_k = torch.empty(B, dtype=f32, device=dev)
+
+    def _data_forward_backward(self, st):
+        _lib.check(self.lib.dpi_mri_data_loss(self.B, self.npix, self.img.data_ptr(), self.mask.data_ptr(),
+                                              self.kspace_true.data_ptr(), self.sigma, self.mean_mask,
+                                              self.loss_k.data_ptr(), self.gw_data.data_ptr(),
+                                              self.g_img_data.data_ptr(), st), "dpi_mri_data_loss")
+
+    def _terms(self, st):
+        _lib.check(self.lib.dpi_step_terms(self.B, None, 0.0, self.loss_k.data_ptr(), self.w["kspace"],
+                                           self.prior_vals.data_ptr(), self.wp_host, self.logdet_flow.data_ptr(),
+                                           self.det.data_ptr(), self.w["logdet"], self.terms.data_ptr(), st),
+                   "dpi_step_terms")

@@ -60,6 +60,10 @@ enum { DPI_R_MEAN1 = 0, DPI_R_VAR1 = 1, DPI_R_MEAN2 = 2, DPI_R_VAR2 = 3 };
 
 /* orders: host int32 [n_flow * ndim], orders[i] = the permutation applied after block i in
  * forward (RealNVP.__init__ :568-577). hidden = int(ndim / (2*seqfrac)). */
+/* Device-free layout query (same layout dpi_flow_create uses): param_offsets [n_flow][26] indexed by
+ * the tensor ids above (-1 where a tensor does not exist), bn_offsets [n_flow][2][4]. */
+int dpi_flow_layout(int ndim, int n_flow, int hidden, int batch_norm, int64_t* param_offsets,
+                    int64_t* bn_offsets, int64_t* n_params, int64_t* n_bn);
 int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidden, int batch_norm,
                     const int32_t* orders);
 int dpi_flow_destroy(dpi_flow_t h);
@@ -71,6 +75,10 @@ int64_t dpi_flow_bn_offset(dpi_flow_t h, int flow, int coupling /*0|1*/, int sta
 int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out);
 
 size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch);
+/* Byte offset inside the workspace of a saved activation of execution stage `stage`:
+ * what 0: stage output y [batch, ndim]; 1/2: LeakyReLU outputs [batch, hidden]; 3: ZeroFC output
+ * [batch, 2*(ndim/2)]; 4: batch statistics (mean1, rstd1, mean2, rstd2) [4, hidden]. */
+int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage);
 
 /* RealNVP.reverse (direction 0, :594-603) / RealNVP.forward (direction 1, :583-592).
  * in/out [batch, ndim], logdet [batch]. train!=0: BatchNorm batch statistics, running stats in
@@ -118,6 +126,14 @@ int dpi_image_priors(int batch, int npix, const float* img, const float* prior_i
 int dpi_image_head(int batch, int npix, const float* x, const float* log_scale, float* img, float* det,
                    const float* prior_img, float flux, float center, float* values, const float* gw,
                    float* g_img, dpi_stream_t stream);
+/* Loss assembly (DPI_interferometry.py:224-229, DPI_MRI.py:186-193), batch means on the device.
+ * data64 / data32: per-sample data terms (either may be NULL) with weights w64 / w32; priors [batch, 6]
+ * with host weights prior_weights[6] (both may be NULL); total logdet = logdet_flow + det.
+ * out[0] = loss, [1] = mean data64, [2] = mean data32, [3] = mean weighted prior, [4] = mean logdet,
+ * [5..10] = mean of each prior value. */
+int dpi_step_terms(int batch, const double* data64, float w64, const float* data32, float w32,
+                   const float* priors, const float* prior_weights /*host*/, const float* logdet_flow,
+                   const float* det, float w_logdet, float* out /*[16]*/, dpi_stream_t stream);
 /* out[0] = sum(in[0..n)); sq_out[0] = out[0]^2 (either may be NULL). Deterministic, one CTA. */
 int dpi_reduce_sum(int n, const float* in, float* out, double* sq_out, dpi_stream_t stream);
 

@@ -1,0 +1,233 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference modules (build container only).
+
+    python tests/golden/make_golden.py
+
+Every fixture is produced by importing /root/reference/DPItorch (see ref_shim.py) and running the
+reference classes / functions on seeded inputs; the loop bodies of the reference scripts
+(DPI_interferometry.py:201-235, DPI_MRI.py:170-207 - scripts that cannot be imported because they
+load ehtim data at module scope) are assembled here around those imported pieces, with
+torch.optim.Adam and nn.utils.clip_grad_norm_ as the scripts use them.
+The oracle (oracle/dpi_oracle.py) is NOT used here: these files pin the oracle, not vice versa.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_shim  # noqa: E402
+from dpi_b200 import synthetic as syn  # noqa: E402
+from oracle.dpi_oracle import init_state  # noqa: E402  (weight generator only: a seeded tensor factory)
+
+R = ref_shim.import_reference()
+RealNVP = R["realnvp"].RealNVP
+IH = R["interferometry"]
+MH = R["mri"]
+
+
+def sd_to_np(sd, prefix="sd."):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def flow_case(name, D, NF, B, seqfrac, seed, batch_norm=True):
+    torch.manual_seed(seed)
+    ref = RealNVP(D, NF, seqfrac=seqfrac, batch_norm=batch_norm)
+    sd = init_state(D, NF, seqfrac=seqfrac, seed=seed, randomize=True, batch_norm=batch_norm)
+    ref.load_state_dict(sd)
+    out = dict(D=D, NF=NF, B=B, seqfrac=seqfrac, batch_norm=int(batch_norm))
+    out.update(sd_to_np(sd))
+    z = torch.randn(B, D)
+    out["z"] = z.numpy()
+    # --- reverse, train mode, with gradients of a generic scalar objective
+    zz = z.clone().requires_grad_(True)
+    x, ld = ref.reverse(zz)
+    cx = torch.randn(B, D)
+    cl = torch.randn(B)
+    loss = (x * cx).sum() + (ld * cl).sum()
+    loss.backward()
+    out.update(x_rev=x.detach().numpy(), ld_rev=ld.detach().numpy(), cx=cx.numpy(), cl=cl.numpy(),
+               g_z=zz.grad.numpy())
+    for k, p in ref.named_parameters():
+        out["grad." + k] = p.grad.detach().numpy()
+    out.update(sd_to_np(ref.state_dict(), "sd_after_rev."))
+    # --- forward (density evaluation) from the produced x, still train mode
+    with torch.no_grad():
+        zf, ldf = ref.forward(x.detach())
+        out.update(z_fwd=zf.numpy(), ld_fwd=ldf.numpy())
+        # --- eval mode (running statistics)
+        ref.eval()
+        xe, lde = ref.reverse(z)
+        ze, ldze = ref.forward(xe)
+        out.update(x_rev_eval=xe.numpy(), ld_rev_eval=lde.numpy(), z_fwd_eval=ze.numpy(), ld_fwd_eval=ldze.numpy())
+    # --- data-dependent ActNorm init on a fresh model's first forward
+    torch.manual_seed(seed + 100)
+    ref2 = RealNVP(D, NF, seqfrac=seqfrac, batch_norm=batch_norm)
+    out.update(sd_to_np(ref2.state_dict(), "sd_fresh."))
+    with torch.no_grad():
+        x0 = torch.randn(B, D) * 1.7 + 0.3
+        z0, l0 = ref2.forward(x0)
+    out.update(x_fresh=x0.numpy(), z_fresh=z0.numpy(), ld_fresh=l0.numpy())
+    out.update(sd_to_np(ref2.state_dict(), "sd_fresh_after."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", sum(v.nbytes for v in out.values() if hasattr(v, "nbytes")) // 1024, "KiB")
+
+
+def obs_arrays(obs):
+    """Station names -> integer codes so the fixture is plain numeric."""
+    names = sorted(set(obs.data["t1"]) | set(obs.data["t2"]))
+    code = {n: i for i, n in enumerate(names)}
+    enc = lambda a: np.array([code[x] for x in a], dtype=np.int64)  # noqa: E731
+    return dict(time=obs.data["time"].copy(), t1=enc(obs.data["t1"]), t2=enc(obs.data["t2"]), u=obs.data["u"].copy(),
+                v=obs.data["v"].copy(),
+                cp_time=obs.cphase["time"].copy(), cp_t1=enc(obs.cphase["t1"]), cp_t2=enc(obs.cphase["t2"]),
+                cp_t3=enc(obs.cphase["t3"]),
+                ca_time=obs.camp["time"].copy(), ca_t1=enc(obs.camp["t1"]), ca_t2=enc(obs.camp["t2"]),
+                ca_t3=enc(obs.camp["t3"]), ca_t4=enc(obs.camp["t4"]))
+
+
+def closure_map_case(name, n_stations, n_scans, seed, npix, min_vis=2):
+    obs = syn.SyntheticObs(n_stations=n_stations, n_scans=n_scans, seed=seed, min_vis=min_vis, flip_frac=0.4)
+    sim = syn.SimImage(npix, 160.0)
+    dft, ktraj, pf, cpi, cps, cai = IH.Obs_params_torch(obs, sim, snrcut=0.0, ttype="direct")
+    out = obs_arrays(obs)
+    out.update(npix=npix, n_stations=n_stations, n_scans=n_scans, seed=seed, min_vis=min_vis,
+               dft_mat=dft.numpy() if npix <= 8 else dft.numpy()[:, :16], ktraj=ktraj.numpy(), pulsefac=pf.numpy(),
+               cp_ind=np.stack([t.numpy() for t in cpi]), cp_sign=np.stack([t.numpy() for t in cps]),
+               ca_ind=np.stack([t.numpy() for t in cai]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok n_vis", len(obs.data), "n_cp", len(obs.cphase), "n_ca", len(obs.camp))
+
+
+def interferometry_case(name, npix, NF, B, seed, n_stations=5, n_scans=8, steps=3):
+    """DPI_interferometry.py:201-235 assembled from the reference modules."""
+    from dpi_b200.workloads import interferometry_workload
+    wl = interferometry_workload(npix=npix, seed=seed, n_stations=n_stations, n_scans=n_scans)
+    # operator tables from the reference's own loops (checked equal to ours in test_host_logic)
+    obs = syn.SyntheticObs(n_stations=n_stations, n_scans=n_scans, seed=seed, min_vis=2)
+    dft, ktraj, pf, cpi, cps, cai = IH.Obs_params_torch(obs, syn.SimImage(npix, 160.0), ttype="direct")
+    dev = torch.device("cpu")
+    eht = IH.eht_observation_pytorch(npix, ref_shim.types.SimpleNamespace(to=lambda **k: None), dft, ktraj, pf, cpi, cps,
+                                     cai, dev, ttype="direct")
+    w = wl["w"]
+    torch.manual_seed(seed)
+    gen = RealNVP(npix * npix, NF)
+    sd = init_state(npix * npix, NF, seed=seed, randomize=True)
+    gen.load_state_dict(sd)
+    log_scale = torch.nn.Parameter(torch.tensor([wl["log_scale_init"]], dtype=torch.float32))
+    L_center = IH.Loss_center(dev, center=npix / 2 - 0.5, dim=npix)
+    L_flux = IH.Loss_flux(wl["flux"])
+    L_cp = IH.Loss_angle_diff(wl["sigma_cp"].numpy(), dev)
+    L_ca = IH.Loss_logca_diff2(wl["sigma_ca"].numpy(), dev)
+    params = list(gen.parameters()) + [log_scale]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    out = dict(npix=npix, NF=NF, B=B, seed=seed, n_stations=n_stations, n_scans=n_scans, steps=steps, lr=1e-4,
+               clip=1e-3)
+    out.update(sd_to_np(sd))
+    zs, hist = [], []
+    for k in range(steps):
+        z = torch.randn(B, npix * npix)
+        zs.append(z.numpy())
+        img_samp, logdet = gen.reverse(z)
+        img_samp = img_samp.reshape((-1, npix, npix))
+        scale_factor = torch.exp(log_scale)
+        img = torch.nn.Softplus()(img_samp) * scale_factor
+        det_softplus = torch.sum(img_samp - torch.nn.Softplus()(img_samp), (1, 2))
+        logdet = logdet + det_softplus + log_scale * npix * npix
+        vis, visamp, cphase, logcamp = eht(img)
+        l_center, l_l1, l_tsv = L_center(img), IH.Loss_l1(img), IH.Loss_TSV(img)
+        l_mem = IH.Loss_cross_entropy(wl["prior"], img)
+        l_flux = L_flux(img)
+        l_cp = L_cp(wl["cphase_true"], cphase)
+        l_ca = L_ca(wl["logcamp_true"], logcamp)
+        loss_data = w["camp"] * l_ca + w["cphase"] * l_cp
+        loss_prior = w["mem"] * l_mem + w["flux"] * l_flux + w["tsv"] * l_tsv + w["center"] * l_center + w["l1"] * l_l1
+        loss = torch.mean(loss_data) + torch.mean(loss_prior) - w["logdet"] * torch.mean(logdet)
+        opt.zero_grad()
+        loss.backward()
+        if k == 0:
+            out.update(img0=img.detach().numpy(), vis0=vis.detach().numpy(), visamp0=visamp.detach().numpy(),
+                       cphase0=cphase.detach().numpy(), logcamp0=logcamp.detach().numpy(),
+                       l_cp0=l_cp.detach().numpy(), l_ca0=l_ca.detach().numpy(), l_center0=l_center.detach().numpy(),
+                       l_l10=l_l1.detach().numpy(), l_tsv0=l_tsv.detach().numpy(), l_mem0=l_mem.detach().numpy(),
+                       l_flux0=l_flux.detach().numpy(), l_tv0=IH.Loss_TV(img).detach().numpy(),
+                       logdet0=logdet.detach().numpy(), g_log_scale0=log_scale.grad.numpy().copy())
+            for kk, p in gen.named_parameters():
+                out["grad0." + kk] = p.grad.detach().numpy().copy()
+        norm = torch.nn.utils.clip_grad_norm_(params, 1e-3)
+        opt.step()
+        hist.append([float(loss), float(l_cp.mean()), float(l_ca.mean()), float(loss_prior.mean()),
+                     float(logdet.mean()), float(norm), float(log_scale)])
+    out["z"] = np.stack(zs)
+    out["hist"] = np.array(hist, dtype=np.float64)
+    out.update(sd_to_np(gen.state_dict(), "sd_final."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", hist[-1])
+
+
+def mri_case(name, npix, NF, B, seed, steps=3):
+    """DPI_MRI.py:170-207 assembled from the reference modules (fft2c_torch restated with torch.fft.fft2,
+    the removed torch.fft(x, 2, normalized=True) it calls is the same transform as its numpy twin :63-67)."""
+    from dpi_b200.workloads import mri_workload
+    wl = mri_workload(npix=npix, seed=seed)
+    w = wl["w"]
+    torch.manual_seed(seed)
+    gen = RealNVP(npix * npix, NF)
+    sd = init_state(npix * npix, NF, seed=seed, randomize=True)
+    gen.load_state_dict(sd)
+    log_scale = torch.nn.Parameter(torch.tensor([wl["log_scale_init"]], dtype=torch.float32))
+    L_k = MH.Loss_kspace_diff2(wl["sigma"])
+    params = list(gen.parameters()) + [log_scale]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    out = dict(npix=npix, NF=NF, B=B, seed=seed, steps=steps, lr=1e-5, clip=1e-2)
+    out.update(sd_to_np(sd))
+    zs, hist = [], []
+    mask, ktrue = wl["mask"], wl["kspace_true"]
+    for k in range(steps):
+        z = torch.randn(B, npix * npix)
+        zs.append(z.numpy())
+        img_samp, logdet = gen.reverse(z)
+        img_samp = img_samp.reshape((-1, npix, npix))
+        img = torch.nn.Softplus()(img_samp) * torch.exp(log_scale)
+        det_softplus = torch.sum(img_samp - torch.nn.Softplus()(img_samp), (1, 2))
+        logdet = logdet + det_softplus + log_scale * npix * npix
+        kpred = torch.view_as_real(torch.fft.fft2(img, norm="ortho"))
+        loss_data = L_k(ktrue, kpred * mask) / float(mask.mean())
+        l_tv = MH.Loss_TV(img)
+        loss_prior = w["tv"] * l_tv
+        loss = torch.mean(loss_data) + torch.mean(loss_prior) - w["logdet"] * torch.mean(logdet)
+        opt.zero_grad()
+        loss.backward()
+        if k == 0:
+            out.update(img0=img.detach().numpy(), kpred0=kpred.detach().numpy(), l_data0=loss_data.detach().numpy(),
+                       l_tv0=l_tv.detach().numpy(), logdet0=logdet.detach().numpy(),
+                       g_log_scale0=log_scale.grad.numpy().copy())
+            for kk, p in gen.named_parameters():
+                out["grad0." + kk] = p.grad.detach().numpy().copy()
+        norm = torch.nn.utils.clip_grad_norm_(params, 1e-2)
+        opt.step()
+        hist.append([float(loss), float(loss_data.mean()), float(loss_prior.mean()), float(logdet.mean()),
+                     float(norm), float(log_scale)])
+    out["z"] = np.stack(zs)
+    out["hist"] = np.array(hist, dtype=np.float64)
+    out.update(sd_to_np(gen.state_dict(), "sd_final."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", hist[-1])
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    flow_case("flow_even", D=20, NF=2, B=6, seqfrac=1, seed=11)          # H=10, one row tile
+    flow_case("flow_odd", D=9, NF=2, B=5, seqfrac=0.25, seed=12)         # odd ndim: chunk gives 5 + 4, H=18
+    flow_case("flow_bigbatch", D=12, NF=2, B=80, seqfrac=0.5, seed=13)   # batch spans two 64-row tiles, H=12
+    flow_case("flow_nobn", D=16, NF=2, B=7, seqfrac=1, seed=14, batch_norm=False)
+    flow_case("flow_toy", D=2, NF=3, B=33, seqfrac=1 / 16, seed=15)      # DPI_2Dtoydist shape class (H=16)
+    closure_map_case("closure_small", n_stations=5, n_scans=8, seed=3, npix=8)
+    closure_map_case("closure_eht", n_stations=7, n_scans=100, seed=190, npix=32)
+    interferometry_case("interferometry_small", npix=8, NF=2, B=6, seed=3)
+    mri_case("mri_small", npix=8, NF=2, B=6, seed=5)

@@ -1,0 +1,137 @@
+"""GPU parity of the RealNVP flow (C-ABI path) against the golden fixtures from the reference and
+against the CPU oracle on the same seeded inputs. Tolerance: 1e-4 relative (north_star, fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL, load_golden, rel_err, split_sd
+from oracle import dpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+FLOW_CASES = ["flow_even", "flow_odd", "flow_bigbatch", "flow_nobn", "flow_toy"]
+
+
+def _model(g, sd, persistent):
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    m = RealNVP(int(g["D"]), int(g["NF"]), seqfrac=float(g["seqfrac"]), batch_norm=bool(g["batch_norm"]))
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.set_flow_mode(persistent)
+    return m
+
+
+def test_library_loaded_and_gather_maps_bit_exact():
+    from dpi_b200 import _lib
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    assert _lib.load().dpi_version() >= 100
+    D, NF = 1024, 3
+    m = RealNVP(D, NF).cuda()
+    flip = np.arange(D - 1, -1, -1)
+    for e in range(2 * NF):
+        i = NF - 1 - e // 2
+        want = m.inverse_orders[i][flip] if e % 2 == 0 else flip           # x[:, inv][:, flip]  (:599, :459)
+        assert np.array_equal(m.gather_map(0, e), want.astype(np.int32)), e
+        i = e // 2
+        if e % 2 == 1:
+            want = flip
+        elif i == 0:
+            want = np.arange(D)
+        else:
+            want = flip[m.orders[i - 1]]                                      # y[:, flip][:, order]  (:446, :590)
+        assert np.array_equal(m.gather_map(1, e), want.astype(np.int32)), e
+    assert np.array_equal(m.gather_map(2, 0), flip[m.orders[NF - 1]].astype(np.int32))
+
+
+@pytest.mark.parametrize("persistent", [False, True])
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_flow_matches_reference_fixture(name, persistent):
+    g = load_golden(name)
+    m = _model(g, split_sd(g), persistent)
+    z = torch.from_numpy(g["z"]).cuda().requires_grad_(True)
+    x, ld = m.reverse(z)
+    assert rel_err(x, g["x_rev"]) < RTOL, rel_err(x, g["x_rev"])
+    assert rel_err(ld, g["ld_rev"]) < RTOL
+    loss = (x * torch.from_numpy(g["cx"]).cuda()).sum() + (ld * torch.from_numpy(g["cl"]).cuda()).sum()
+    loss.backward()
+    assert rel_err(z.grad, g["g_z"]) < RTOL
+    bad = []
+    for k, gv in m.named_grad_views():
+        e = rel_err(gv, g["grad." + k])
+        if not e < 2 * RTOL:   # scalar ActNorm gradients are cancelling sums of B*D terms
+            bad.append((k, e))
+    assert not bad, bad
+    after = split_sd(g, "sd_after_rev.")
+    mine = m.state_dict()
+    for k, v in after.items():
+        assert rel_err(mine[k].float(), v.float()) < RTOL, k
+    with torch.no_grad():
+        zf, ldf = m.forward(x.detach())
+        assert rel_err(zf, g["z_fwd"]) < RTOL and rel_err(ldf, g["ld_fwd"]) < RTOL
+        m.eval()
+        xe, lde = m.reverse(z.detach())
+        ze, ldze = m.forward(xe)
+        assert rel_err(xe, g["x_rev_eval"]) < RTOL and rel_err(lde, g["ld_rev_eval"]) < RTOL
+        assert rel_err(ze, g["z_fwd_eval"]) < RTOL and rel_err(ldze, g["ld_fwd_eval"]) < RTOL
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_fresh_forward_data_dependent_actnorm_init(name):
+    g = load_golden(name)
+    m = _model(g, split_sd(g, "sd_fresh."), True)
+    with torch.no_grad():
+        z0, l0 = m.forward(torch.from_numpy(g["x_fresh"]).cuda())
+    assert rel_err(z0, g["z_fresh"]) < RTOL and rel_err(l0, g["ld_fresh"]) < RTOL
+    mine = m.state_dict()
+    for k, v in split_sd(g, "sd_fresh_after.").items():
+        assert rel_err(mine[k].float(), v.float()) < RTOL, k
+
+
+def test_fresh_reverse_is_a_permutation_with_zero_logdet():
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    m = RealNVP(64, 3).cuda()
+    z = torch.randn(16, 64, device="cuda")
+    x, ld = m.reverse(z)
+    assert torch.equal(torch.sort(x, 1).values, torch.sort(z, 1).values)   # ZeroFC zero-init (:133-135)
+    assert float(ld.abs().max()) == 0.0
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    xo, _ = O.realnvp_reverse(sd, z.cpu(), train=True)
+    assert torch.equal(x.cpu(), xo)                                          # index maps: bit exact
+
+
+@pytest.mark.parametrize("D,NF,B,seqfrac", [(1024, 16, 64, 4), (256, 4, 200, 4), (18, 4, 300, 1 / 16)])
+def test_flow_vs_oracle_at_config_sizes(D, NF, B, seqfrac):
+    """C1 flow shape (and a multi-tile batch, and the DPIx 18-parameter shape) against the CPU oracle."""
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    sd = O.init_state(D, NF, seqfrac=seqfrac, seed=7, randomize=True)
+    m = RealNVP(D, NF, seqfrac=seqfrac)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(3)
+    z = torch.randn(B, D)
+    cx, cl = torch.randn(B, D), torch.randn(B)
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    zo = z.clone().requires_grad_(True)
+    xo, ldo = O.realnvp_reverse(sd, zo, train=True)
+    ((xo * cx).sum() + (ldo * cl).sum()).backward()
+    zg = z.cuda().requires_grad_(True)
+    x, ld = m.reverse(zg)
+    ((x * cx.cuda()).sum() + (ld * cl.cuda()).sum()).backward()
+    assert rel_err(x, xo) < RTOL and rel_err(ld, ldo) < RTOL
+    assert rel_err(zg.grad, zo.grad) < RTOL
+    worst = max(((rel_err(gv, sd[k].grad), k) for k, gv in m.named_grad_views()))
+    assert worst[0] < 3 * RTOL, worst
+    # size-independent properties: invertibility and logdet antisymmetry
+    with torch.no_grad():
+        zb, ldb = m.forward(x.detach())
+    assert float((zb - zg.detach()).abs().max()) < 5e-4
+    assert float((ldb + ld.detach()).abs().max()) < 1e-3 * max(1.0, float(ld.abs().max()))
+
+
+def test_reverse_requires_two_samples_in_train_mode():
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    m = RealNVP(16, 1, seqfrac=1).cuda()
+    with pytest.raises(RuntimeError, match="more than 1 value"):
+        m.reverse(torch.randn(1, 16, device="cuda"))
+    m.eval()
+    m.reverse(torch.randn(1, 16, device="cuda"))

@@ -1,0 +1,232 @@
+"""GPU parity of the measurement operators, losses, priors and optimiser kernels (C-ABI path)
+against the CPU oracle / golden fixtures. 1e-4 relative unless a test states otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL, load_golden, rel_err, split_sd
+from oracle import dpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _wl(npix=8, seed=3, n_stations=5, n_scans=8):
+    from dpi_b200.workloads import interferometry_workload
+    return interferometry_workload(npix=npix, seed=seed, n_stations=n_stations, n_scans=n_scans)
+
+
+def _eht_func(wl):
+    from dpi_b200 import interferometry_helpers as ih
+    return ih.eht_observation_pytorch(wl["npix"], None, wl["dft_mat"], wl["ktraj"], wl["pulsefac"], wl["cphase_ind"],
+                                      wl["cphase_sign"], wl["camp_ind"], torch.device("cuda"), ttype="direct")
+
+
+def test_eht_forward_matches_reference_fixture():
+    g = load_golden("interferometry_small")
+    wl = _wl()
+    f = _eht_func(wl)
+    vis, amp, cph, lca = f(torch.from_numpy(g["img0"]).cuda())
+    assert cph.dtype == torch.float64 and vis.shape == g["vis0"].shape
+    assert rel_err(vis, g["vis0"]) < RTOL and rel_err(amp, g["visamp0"]) < RTOL
+    assert rel_err(cph, g["cphase0"]) < RTOL and rel_err(lca, g["logcamp0"]) < RTOL
+
+
+@pytest.mark.parametrize("npix,ns,nsc,B", [(8, 5, 8, 6), (32, 7, 100, 64), (16, 6, 20, 130)])
+def test_eht_forward_backward_vs_oracle(npix, ns, nsc, B):
+    wl = _wl(npix, 190 if npix == 32 else 3, ns, nsc)
+    f = _eht_func(wl)
+    torch.manual_seed(1)
+    img = (torch.rand(B, npix, npix) * 2.0 / (npix * npix) * 2).requires_grad_(True)
+    vo, ao, co, lo = O.eht_observe(img, wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"])
+    cv, ca, cc, cl = torch.randn_like(vo), torch.randn_like(ao), torch.randn_like(co), torch.randn_like(lo)
+    ((vo * cv).sum() + (ao * ca).sum() + (co * cc).sum() + (lo * cl).sum()).backward()
+    ig = img.detach().cuda().requires_grad_(True)
+    v, a, c, l = f(ig)
+    ((v * cv.cuda()).sum() + (a * ca.cuda()).sum() + (c * cc.cuda()).sum() + (l * cl.cuda()).sum()).backward()
+    assert rel_err(v, vo) < RTOL and rel_err(a, ao) < RTOL and rel_err(c, co) < RTOL and rel_err(l, lo) < RTOL
+    assert rel_err(ig.grad.reshape(img.shape), img.grad) < RTOL
+    # partial use of the outputs (unused ones arrive as None)
+    ig2 = img.detach().cuda().requires_grad_(True)
+    f(ig2)[3].sum().backward()
+    img2 = img.detach().clone().requires_grad_(True)
+    O.eht_observe(img2, wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"])[3].sum().backward()
+    assert rel_err(ig2.grad.reshape(img.shape), img2.grad) < RTOL
+
+
+def test_chi2_losses_vs_oracle():
+    from dpi_b200 import interferometry_helpers as ih
+    torch.manual_seed(0)
+    B, n = 7, 301
+    dev = torch.device("cuda")
+    sigma = np.random.RandomState(0).uniform(0.5, 3.0, n)
+    st = torch.tensor(sigma, dtype=torch.float32)
+    yt = torch.randn(n) * 40
+    yp = (torch.randn(B, n, dtype=torch.float64) * 40).requires_grad_(True)
+    gl = torch.randn(B, dtype=torch.float64)
+    (O.loss_angle_diff(st, yt, yp) * gl).sum().backward()
+    ypg = yp.detach().cuda().requires_grad_(True)
+    out = ih.Loss_angle_diff(sigma, dev)(yt.cuda(), ypg)
+    (out * gl.cuda()).sum().backward()
+    assert out.dtype == torch.float64
+    assert rel_err(out, O.loss_angle_diff(st, yt, yp)) < 1e-6 and rel_err(ypg.grad, yp.grad) < 1e-6
+    cases = [("Loss_logca_diff2", O.loss_logca_diff2, False), ("Loss_visamp_diff", O.loss_logca_diff2, False),
+             ("Loss_logamp_diff", O.loss_logamp_diff, True), ("Loss_logca_diff", O.loss_logamp_diff, True)]
+    for name, fo, positive in cases:
+        yt = torch.rand(n) + 0.5 if positive else torch.randn(n)
+        yp = ((torch.rand(B, n) + 0.5) if positive else torch.randn(B, n)).requires_grad_(True)
+        glf = torch.randn(B)
+        (fo(st, yt, yp) * glf).sum().backward()
+        ypg = yp.detach().cuda().requires_grad_(True)
+        out = getattr(ih, name)(sigma, dev)(yt.cuda(), ypg)
+        (out * glf.cuda()).sum().backward()
+        assert rel_err(out, fo(st, yt, yp)) < RTOL and rel_err(ypg.grad, yp.grad) < RTOL, name
+    yt = torch.randn(2, n)
+    yp = torch.randn(B, 2, n, requires_grad=True)
+    glf = torch.randn(B)
+    (O.loss_vis_diff(st, yt, yp) * glf).sum().backward()
+    ypg = yp.detach().cuda().requires_grad_(True)
+    out = ih.Loss_vis_diff(sigma, dev)(yt.cuda(), ypg)
+    (out * glf.cuda()).sum().backward()
+    assert rel_err(out, O.loss_vis_diff(st, yt, yp)) < RTOL and rel_err(ypg.grad, yp.grad) < RTOL
+
+
+@pytest.mark.parametrize("npix,B", [(8, 6), (32, 64), (64, 9), (5, 3)])
+def test_image_priors_vs_oracle(npix, B):
+    from dpi_b200 import interferometry_helpers as ih
+    from dpi_b200 import synthetic as syn
+    torch.manual_seed(2)
+    dev = torch.device("cuda")
+    flux = 2.0
+    img = (torch.rand(B, npix, npix) * 2 * flux / npix ** 2).requires_grad_(True)
+    prior = torch.tensor(syn.gaussian_prior_image(npix, 160.0, 50.0, flux), dtype=torch.float32)
+    c0 = npix / 2 - 0.5
+    funcs = [
+        (lambda x: O.loss_l1(x), lambda x: ih.Loss_l1(x)),
+        (lambda x: O.loss_tsv(x), lambda x: ih.Loss_TSV(x)),
+        (lambda x: O.loss_tv(x), lambda x: ih.Loss_TV(x)),
+        (lambda x: O.loss_flux(flux, x), lambda x: ih.Loss_flux(flux)(x)),
+        (lambda x: O.loss_center(x, c0, npix), lambda x: ih.Loss_center(dev, center=c0, dim=npix)(x)),
+        (lambda x: O.loss_cross_entropy(prior, x), lambda x: ih.Loss_cross_entropy(prior.cuda(), x)),
+    ]
+    gl = torch.randn(B)
+    for i, (fo, fg) in enumerate(funcs):
+        img.grad = None
+        lo = fo(img)
+        (lo * gl).sum().backward()
+        ig = img.detach().cuda().requires_grad_(True)
+        lg = fg(ig)
+        (lg * gl.cuda()).sum().backward()
+        assert lg.shape == lo.shape
+        assert rel_err(lg, lo) < RTOL, (i, rel_err(lg, lo))
+        assert rel_err(ig.grad, img.grad) < RTOL, (i, rel_err(ig.grad, img.grad))
+
+
+def test_prior_values_match_reference_fixture():
+    from dpi_b200 import interferometry_helpers as ih
+    g = load_golden("interferometry_small")
+    wl = _wl()
+    img = torch.from_numpy(g["img0"]).cuda()
+    npix = wl["npix"]
+    dev = torch.device("cuda")
+    assert rel_err(ih.Loss_l1(img), g["l_l10"]) < RTOL
+    assert rel_err(ih.Loss_TSV(img), g["l_tsv0"]) < RTOL
+    assert rel_err(ih.Loss_TV(img), g["l_tv0"]) < RTOL
+    assert rel_err(ih.Loss_flux(wl["flux"])(img), g["l_flux0"]) < RTOL
+    assert rel_err(ih.Loss_center(dev, center=npix / 2 - 0.5, dim=npix)(img), g["l_center0"]) < RTOL
+    assert rel_err(ih.Loss_cross_entropy(wl["prior"].cuda(), img), g["l_mem0"]) < RTOL
+    cph = torch.from_numpy(g["cphase0"]).cuda()
+    lca = torch.from_numpy(g["logcamp0"]).cuda()
+    assert rel_err(ih.Loss_angle_diff(wl["sigma_cp"].numpy(), dev)(wl["cphase_true"].cuda(), cph), g["l_cp0"]) < RTOL
+    assert rel_err(ih.Loss_logca_diff2(wl["sigma_ca"].numpy(), dev)(wl["logcamp_true"].cuda(), lca), g["l_ca0"]) < RTOL
+
+
+@pytest.mark.parametrize("npix,B", [(8, 6), (64, 5), (12, 3)])
+def test_fft2c_and_kspace_loss_vs_oracle(npix, B):
+    from dpi_b200 import MRI_helpers as mh
+    torch.manual_seed(4)
+    img = torch.rand(B, npix, npix, requires_grad=True)
+    ko = O.fft2c(img)
+    ck = torch.randn_like(ko)
+    (ko * ck).sum().backward()
+    ig = img.detach().cuda().requires_grad_(True)
+    k = mh.fft2c_torch(ig)
+    (k * ck.cuda()).sum().backward()
+    assert k.shape == ko.shape
+    assert rel_err(k, ko) < RTOL and rel_err(ig.grad, img.grad) < RTOL
+    sigma = 0.37
+    yt = torch.randn(npix, npix, 2)
+    for fo, fg in [(O.loss_kspace_diff2, mh.Loss_kspace_diff2), (O.loss_kspace_diff, mh.Loss_kspace_diff)]:
+        kp = ko.detach().clone().requires_grad_(True)
+        lo = fo(sigma, yt, kp)
+        lo.sum().backward()
+        kg = ko.detach().cuda().requires_grad_(True)
+        lg = fg(sigma)(yt.cuda(), kg)
+        lg.sum().backward()
+        assert rel_err(lg, lo) < RTOL and rel_err(kg.grad, kp.grad) < RTOL
+
+
+def test_mri_fixture_kspace():
+    from dpi_b200 import MRI_helpers as mh
+    g = load_golden("mri_small")
+    k = mh.fft2c_torch(torch.from_numpy(g["img0"]).cuda())
+    assert rel_err(k, g["kpred0"]) < RTOL
+
+
+def test_clip_adam_matches_torch_optimizer():
+    import ctypes as C
+    from dpi_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(5)
+    n = 100003
+    p0 = torch.randn(n)
+    p_ref = p0.clone().requires_grad_(True)
+    extra = torch.zeros(1, requires_grad=True)
+    opt = torch.optim.Adam([p_ref, extra], lr=1e-4)
+    dev = torch.device("cuda")
+    npad = (n + 31) // 32 * 32
+    p = torch.zeros(npad, device=dev); p[:n] = p0.cuda()
+    g = torch.zeros(npad, device=dev)
+    m, v = torch.zeros(npad, device=dev), torch.zeros(npad, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    sq = torch.zeros(1, dtype=torch.float64, device=dev)
+    norm_out = torch.zeros(2, device=dev)
+    ws = torch.zeros(lib.dpi_clip_adam_workspace_bytes(npad), dtype=torch.uint8, device=dev)
+    st = _lib.stream_ptr()
+    for it in range(4):
+        gr = torch.randn(n) * (10.0 if it < 3 else 1e-9)   # last step: norm below the clip threshold
+        p_ref.grad = gr.clone(); extra.grad = torch.zeros(1)
+        tn = torch.nn.utils.clip_grad_norm_([p_ref, extra], 1e-3)
+        opt.step()
+        g[:n] = gr.cuda()
+        _lib.check(lib.dpi_grad_sqnorm(npad, g.data_ptr(), sq.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        _lib.check(lib.dpi_step_increment(step.data_ptr(), st))
+        _lib.check(lib.dpi_clip_adam(npad, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), sq.data_ptr(), 1,
+                                     1e-3, 1e-4, 0.9, 0.999, 1e-8, step.data_ptr(), 1.0, norm_out.data_ptr(), st))
+        assert rel_err(norm_out[0], tn) < 1e-5
+        assert rel_err(p[:n], p_ref.detach()) < 1e-6, it
+        assert float((p[:n].cpu() - p_ref.detach()).abs().max()) < 1e-7
+    assert int(step) == 4
+
+
+def test_positivity_roundtrip():
+    import ctypes as C
+    from dpi_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(6)
+    B, npix = 5, 16
+    x = (torch.randn(B, npix * npix) * 3).requires_grad_(True)
+    ls = torch.tensor([-3.3], requires_grad=True)
+    img, det = O.positivity(x, ls, npix)
+    ci, cd = torch.randn_like(img), torch.randn(B)
+    ((img * ci).sum() + (det * cd).sum()).backward()
+    dev = torch.device("cuda")
+    xg, lsg = x.detach().cuda(), ls.detach().cuda()
+    im, de = torch.empty(B, npix * npix, device=dev), torch.empty(B, device=dev)
+    st = _lib.stream_ptr()
+    _lib.check(lib.dpi_positivity_forward(B, npix, xg.data_ptr(), lsg.data_ptr(), im.data_ptr(), de.data_ptr(), st))
+    assert rel_err(im.view_as(img), img) < RTOL and rel_err(de, det) < RTOL
+    gx, gp = torch.empty_like(xg), torch.empty(B, device=dev)
+    cig, cdg = ci.reshape(B, -1).cuda().contiguous(), cd.cuda()
+    _lib.check(lib.dpi_positivity_backward(B, npix, xg.data_ptr(), lsg.data_ptr(), im.data_ptr(), cig.data_ptr(), None,
+                                           cdg.data_ptr(), gx.data_ptr(), gp.data_ptr(), st))
+    assert rel_err(gx, x.grad) < RTOL and rel_err(gp.sum(), ls.grad.sum()) < RTOL

@@ -1,0 +1,136 @@
+"""GPU: the fused training step (the benchmarked hot path) against the reference-run fixtures and the
+CPU oracle trainer on the same z stream. 1e-4 relative on loss terms, logdet, gradients."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import RTOL, load_golden, rel_err, split_sd
+from oracle import dpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _flow(D, NF, sd):
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    m = RealNVP(D, NF)
+    m.load_state_dict(sd)
+    return m
+
+
+def _consts(wl):
+    if wl["kind"] == "mri":
+        return dict(npix=wl["npix"], mask=wl["mask"], kspace_true=wl["kspace_true"], sigma=wl["sigma"], w=wl["w"])
+    return dict(npix=wl["npix"], dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"], cphase_sign=wl["cphase_sign"],
+                camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"], logcamp_true=wl["logcamp_true"],
+                sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], prior=wl["prior"], flux=wl["flux"], w=wl["w"])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_interferometry_trainer_matches_reference_run(use_graph):
+    from dpi_b200.trainer import InterferometryTrainer
+    from dpi_b200.workloads import interferometry_workload
+    g = load_golden("interferometry_small")
+    wl = interferometry_workload(npix=int(g["npix"]), seed=int(g["seed"]), n_stations=int(g["n_stations"]),
+                                 n_scans=int(g["n_scans"]))
+    sd0 = split_sd(g)
+    steps = int(g["steps"])
+    z = torch.from_numpy(g["z"])
+    if use_graph:  # graph capture needs two warm-up steps: replay the 3-step run after rewinding the state
+        steps_run = list(range(steps))
+    tr = InterferometryTrainer(_flow(int(g["npix"]) ** 2, int(g["NF"]), sd0), wl, int(g["B"]), lr=float(g["lr"]),
+                               clip=float(g["clip"]), use_graph=False)
+    # gradients of the first step
+    tr.loss_and_grad(z[0].cuda())
+    torch.cuda.synchronize()
+    bad = [(k, rel_err(gv, g["grad0." + k])) for k, gv in tr.flow.named_grad_views(tr.grads)
+           if not rel_err(gv, g["grad0." + k]) < 3 * RTOL]
+    assert not bad, bad
+    assert rel_err(tr.g_ls, g["g_log_scale0"]) < RTOL
+    assert rel_err(tr.img.view(-1, wl["npix"], wl["npix"]), g["img0"]) < RTOL
+    assert rel_err(tr.loss_cp, g["l_cp0"]) < RTOL and rel_err(tr.loss_ca, g["l_ca0"]) < RTOL
+    assert rel_err(tr.logdet_flow + tr.det, g["logdet0"]) < RTOL
+    # full 3-step trajectory from a fresh trainer
+    tr = InterferometryTrainer(_flow(int(g["npix"]) ** 2, int(g["NF"]), sd0), wl, int(g["B"]), lr=float(g["lr"]),
+                               clip=float(g["clip"]), use_graph=use_graph)
+    if use_graph:
+        snap = [t.clone() for t in (tr.params, tr.log_scale, tr.m, tr.v, tr.m_ls, tr.v_ls, tr.step_dev, tr.flow.bn_running)]
+        tr.step(z[0].cuda()); tr.step(z[0].cuda())          # warm-up + capture
+        assert tr._graphs is not None
+        for t, s in zip((tr.params, tr.log_scale, tr.m, tr.v, tr.m_ls, tr.v_ls, tr.step_dev, tr.flow.bn_running), snap):
+            t.copy_(s)
+    for k in range(steps):
+        terms = tr.step(z[k].cuda()).cpu()
+        h = g["hist"][k]
+        got = [float(terms[0]), float(terms[1]), float(terms[2]), float(terms[3]), float(terms[4]),
+               float(tr.norm_out[0])]
+        assert np.allclose(got, h[:6], rtol=RTOL), (k, got, h[:6])
+    assert abs(tr.log_scale_value() - g["hist"][-1][6]) < 1e-6
+    mine = tr.flow.state_dict()
+    for k, v in split_sd(g, "sd_final.").items():
+        if "tracked" in k:
+            continue
+        assert rel_err(mine[k].float(), v.float()) < RTOL, k
+
+
+def test_mri_trainer_matches_reference_run():
+    from dpi_b200.trainer import MRITrainer
+    from dpi_b200.workloads import mri_workload
+    g = load_golden("mri_small")
+    wl = mri_workload(npix=int(g["npix"]), seed=int(g["seed"]))
+    sd0 = split_sd(g)
+    z = torch.from_numpy(g["z"])
+    tr = MRITrainer(_flow(int(g["npix"]) ** 2, int(g["NF"]), sd0), wl, int(g["B"]), lr=float(g["lr"]),
+                    clip=float(g["clip"]), use_graph=False)
+    tr.loss_and_grad(z[0].cuda())
+    torch.cuda.synchronize()
+    assert rel_err(tr.loss_k, g["l_data0"]) < RTOL
+    assert rel_err(tr.prior_vals[:, 2], g["l_tv0"]) < RTOL
+    bad = [(k, rel_err(gv, g["grad0." + k])) for k, gv in tr.flow.named_grad_views(tr.grads)
+           if not rel_err(gv, g["grad0." + k]) < 3 * RTOL]
+    assert not bad, bad
+    assert rel_err(tr.g_ls, g["g_log_scale0"]) < RTOL
+    tr = MRITrainer(_flow(int(g["npix"]) ** 2, int(g["NF"]), sd0), wl, int(g["B"]), lr=float(g["lr"]),
+                    clip=float(g["clip"]), use_graph=False)
+    for k in range(int(g["steps"])):
+        terms = tr.step(z[k].cuda()).cpu()
+        h = g["hist"][k]
+        got = [float(terms[0]), float(terms[2]), float(terms[3]), float(terms[4]), float(tr.norm_out[0])]
+        assert np.allclose(got, h[:5], rtol=RTOL), (k, got, h[:5])
+    mine = tr.flow.state_dict()
+    for k, v in split_sd(g, "sd_final.").items():
+        if "tracked" in k:
+            continue
+        assert rel_err(mine[k].float(), v.float()) < RTOL, k
+
+
+@pytest.mark.parametrize("kind", ["interferometry", "mri"])
+def test_full_size_step_vs_oracle(kind):
+    """BASELINE configs C1 (npix=32, n_flow=16, B=64) / C2 shape class (npix=64, B=64; n_flow reduced to 4 so
+    the CPU oracle finishes in seconds): two optimisation steps, non-trivial weights."""
+    from dpi_b200.trainer import InterferometryTrainer, MRITrainer
+    from dpi_b200.workloads import interferometry_workload, mri_workload
+    if kind == "interferometry":
+        wl, NF, B, lr, clip = interferometry_workload(npix=32), 16, 64, 1e-4, 1e-3
+        T, loss_fn = InterferometryTrainer, O.interferometry_loss
+    else:
+        wl, NF, B, lr, clip = mri_workload(npix=64), 4, 64, 1e-5, 1e-2
+        T, loss_fn = MRITrainer, O.mri_loss
+    D = wl["npix"] ** 2
+    sd = O.init_state(D, NF, seed=21, randomize=True)
+    tr = T(_flow(D, NF, {k: v.clone() for k, v in sd.items()}), wl, B, lr=lr, clip=clip, use_graph=False)
+    ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
+    ot = O.OracleTrainer(sd, ls, loss_fn, _consts(wl), lr=lr, clip=clip)
+    torch.manual_seed(9)
+    for k in range(2):
+        z = torch.randn(B, D)
+        lo, to = ot.step(z)
+        terms = tr.step(z.cuda()).cpu()
+        assert rel_err(terms[0], lo) < RTOL, (k, float(terms[0]), float(lo))
+        assert rel_err(terms[4], to["logdet"]) < RTOL
+        assert rel_err(tr.norm_out[0], to["grad_norm"]) < RTOL
+        if k == 0:
+            assert rel_err(tr.x, to["x"]) < RTOL and rel_err(tr.img.view_as(to["img"]), to["img"]) < RTOL
+    mine = tr.flow.state_dict()
+    for k in ot.keys:
+        assert rel_err(mine[k], sd[k].detach()) < RTOL, k
+    assert abs(tr.log_scale_value() - float(ls)) < 1e-6

@@ -1,0 +1,128 @@
+"""CPU: the oracle restatement vs the fixtures generated from the live reference (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_sd, rel_err
+from oracle import dpi_oracle as O
+
+FLOW_CASES = ["flow_even", "flow_odd", "flow_bigbatch", "flow_nobn", "flow_toy"]
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_flow_reverse_forward_grads(name):
+    g = load_golden(name)
+    sd = split_sd(g)
+    z = torch.from_numpy(g["z"]).requires_grad_(True)
+    keys = O.param_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    x, ld = O.realnvp_reverse(sd, z, train=True)
+    assert rel_err(x, g["x_rev"]) < 1e-6 and rel_err(ld, g["ld_rev"]) < 1e-6
+    loss = (x * torch.from_numpy(g["cx"])).sum() + (ld * torch.from_numpy(g["cl"])).sum()
+    loss.backward()
+    assert rel_err(z.grad, g["g_z"]) < 1e-5
+    for k in keys:
+        assert rel_err(sd[k].grad, g["grad." + k]) < 1e-4, k  # scalar ActNorm grads are cancelling sums
+    after = split_sd(g, "sd_after_rev.")
+    for k, v in after.items():
+        assert rel_err(sd[k].detach().float(), v.float()) < 1e-6, k
+    with torch.no_grad():
+        zf, ldf = O.realnvp_forward(sd, x.detach(), train=True)
+        assert rel_err(zf, g["z_fwd"]) < 1e-6 and rel_err(ldf, g["ld_fwd"]) < 1e-6
+        xe, lde = O.realnvp_reverse(sd, z.detach(), train=False)
+        ze, ldze = O.realnvp_forward(sd, xe, train=False)
+        assert rel_err(xe, g["x_rev_eval"]) < 1e-6 and rel_err(lde, g["ld_rev_eval"]) < 1e-6
+        assert rel_err(ze, g["z_fwd_eval"]) < 1e-6 and rel_err(ldze, g["ld_fwd_eval"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_flow_fresh_forward_actnorm_init(name):
+    g = load_golden(name)
+    sd = split_sd(g, "sd_fresh.")
+    with torch.no_grad():
+        z0, l0 = O.realnvp_forward(sd, torch.from_numpy(g["x_fresh"]), train=True)
+    assert rel_err(z0, g["z_fresh"]) < 1e-6 and rel_err(l0, g["ld_fresh"]) < 1e-6
+    for k, v in split_sd(g, "sd_fresh_after.").items():
+        assert rel_err(sd[k].float(), v.float()) < 1e-6, k
+
+
+def test_orders_are_the_seeded_permutations():
+    orders, inv = O.make_orders(1024, 4)
+    for i in range(4):
+        assert np.array_equal(orders[i], np.random.RandomState(seed=i).permutation(1024))
+        assert np.array_equal(orders[i][inv[i]], np.arange(1024))
+        assert np.array_equal(inv[i][orders[i]], np.arange(1024))
+
+
+def _interferometry_consts(g):
+    from dpi_b200.workloads import interferometry_workload
+    wl = interferometry_workload(npix=int(g["npix"]), seed=int(g["seed"]), n_stations=int(g["n_stations"]),
+                                 n_scans=int(g["n_scans"]))
+    c = dict(npix=wl["npix"], dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"], cphase_sign=wl["cphase_sign"],
+             camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"], logcamp_true=wl["logcamp_true"],
+             sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], prior=wl["prior"], flux=wl["flux"], w=wl["w"])
+    return wl, c
+
+
+def test_interferometry_step_matches_reference_run():
+    g = load_golden("interferometry_small")
+    wl, c = _interferometry_consts(g)
+    sd = split_sd(g)
+    ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
+    tr = O.OracleTrainer(sd, ls, O.interferometry_loss, c, lr=float(g["lr"]), clip=float(g["clip"]))
+    for k in range(int(g["steps"])):
+        z = torch.from_numpy(g["z"][k])
+        if k == 0:
+            loss, t = tr.loss_and_grads(z)
+            assert rel_err(t["img"], g["img0"]) < 1e-6
+            assert rel_err(t["vis"], g["vis0"]) < 1e-5
+            assert rel_err(t["cphase_pred"], g["cphase0"]) < 1e-6
+            assert rel_err(t["logcamp_pred"], g["logcamp0"]) < 1e-5
+            assert rel_err(t["logdet_vec"], g["logdet0"]) < 1e-6
+            for kk in tr.keys:
+                assert rel_err(sd[kk].grad, g["grad0." + kk]) < 1e-4, kk
+            assert rel_err(ls.grad, g["g_log_scale0"]) < 1e-5
+            # undo the BatchNorm running-stat side effect of the probe pass
+            sd0 = split_sd(g)
+            for kk in sd:
+                if "running" in kk or "tracked" in kk:
+                    sd[kk].copy_(sd0[kk])
+        loss, t = tr.step(z)
+        h = g["hist"][k]
+        got = [float(loss), float(t["cphase"]), float(t["logca"]), float(t["prior"]), float(t["logdet"]),
+               float(t["grad_norm"])]
+        assert np.allclose(got, h[:6], rtol=2e-5), (k, got, h)
+    for k, v in split_sd(g, "sd_final.").items():
+        assert rel_err(sd[k].detach().float(), v.float()) < 1e-5, k
+
+
+def test_mri_step_matches_reference_run():
+    from dpi_b200.workloads import mri_workload
+    g = load_golden("mri_small")
+    wl = mri_workload(npix=int(g["npix"]), seed=int(g["seed"]))
+    c = dict(npix=wl["npix"], mask=wl["mask"], kspace_true=wl["kspace_true"], sigma=wl["sigma"], w=wl["w"])
+    sd = split_sd(g)
+    ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
+    tr = O.OracleTrainer(sd, ls, O.mri_loss, c, lr=float(g["lr"]), clip=float(g["clip"]))
+    for k in range(int(g["steps"])):
+        loss, t = tr.step(torch.from_numpy(g["z"][k]))
+        h = g["hist"][k]
+        got = [float(loss), float(t["kspace"]), float(t["prior"]), float(t["logdet"]), float(t["grad_norm"])]
+        assert np.allclose(got, h[:5], rtol=2e-5), (k, got, h)
+    for k, v in split_sd(g, "sd_final.").items():
+        assert rel_err(sd[k].detach().float(), v.float()) < 1e-5, k
+
+
+def test_adam_restatement_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(1000)
+    p2 = p.clone().requires_grad_(True)
+    m, v = torch.zeros(1000), torch.zeros(1000)
+    opt = torch.optim.Adam([p2], lr=1e-3)
+    for step in range(1, 4):
+        g = torch.randn(1000) * 1e-6
+        p2.grad = g.clone()
+        opt.step()
+        O.adam_update(p, g, m, v, step, 1e-3)
+        assert rel_err(p, p2.detach()) < 1e-6
