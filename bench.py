@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py - DPI training-step throughput (samples/s) on N B200s, next to the CPU reference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c4] [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic batch: z ~ N(0,I) drawn on the device ->
+RealNVP reverse with log|det J| -> positivity -> measurement operator -> data/prior/entropy losses
+-> backward -> (gradient all-reduce) -> global-norm clip -> Adam. Default workload = BASELINE.json
+configs[1]: DPI_interferometry npix=32, n_flow=16, batch=64 per GPU, synthetic EHT uv-coverage.
+Prints ONE JSON line (rank 0). `--impl reference` times the CPU restatement of the reference step
+(oracle/ port; the reference itself is pure Python and cannot travel to the GPU box) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, npix, n_flow, per-GPU batch, lr, clip, description)
+    "c1": ("interferometry", 32, 16, 64, 1e-4, 1e-3,
+           "DPI_interferometry npix=32 n_flow=16 batch=64/GPU, synthetic EHT uv-coverage (938 vis, 582 cphase, "
+           "493 logcamp), closure phase + log closure amp + MEM/TSV/L1/flux/center"),
+    "c2": ("mri", 64, 16, 64, 1e-5, 1e-2,
+           "DPI_MRI npix=64 n_flow=16 ratio=4 batch=64/GPU, knee-shaped phantom + 4x mask, masked FFT + TV, "
+           "sigma=5e-7"),
+    "c4": ("interferometry", 64, 32, 1024, 1e-4, 1e-3,
+           "DPI_interferometry scale-up npix=64 n_flow=32 batch=1024/GPU (weak scaling), synthetic EHT uv-coverage"),
+}
+METRIC = "DPI train samples/sec (flow+logdet+fwd-model, fwd+bwd)"
+
+
+def build_workload(name):
+    from dpi_b200.workloads import interferometry_workload, mri_workload
+    kind, npix, nf, B, lr, clip, desc = WORKLOADS[name]
+    wl = interferometry_workload(npix=npix) if kind == "interferometry" else mri_workload(npix=npix)
+    return wl, kind, npix, nf, B, lr, clip, desc
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step (oracle/ is test infrastructure; this leg and the
+# tests are the only places allowed to run it)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(name, steps, warmup, max_seconds=25.0):
+    from oracle import dpi_oracle as O
+    wl, kind, npix, nf, B, lr, clip, desc = build_workload(name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    D = npix * npix
+    sd = O.init_state(D, nf, seed=0, randomize=False)
+    ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
+    if kind == "interferometry":
+        c = dict(npix=npix, dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"], cphase_sign=wl["cphase_sign"],
+                 camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"], logcamp_true=wl["logcamp_true"],
+                 sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], prior=wl["prior"], flux=wl["flux"], w=wl["w"])
+        tr = O.OracleTrainer(sd, ls, O.interferometry_loss, c, lr=lr, clip=clip)
+    else:
+        c = dict(npix=npix, mask=wl["mask"], kspace_true=wl["kspace_true"], sigma=wl["sigma"], w=wl["w"])
+        tr = O.OracleTrainer(sd, ls, O.mri_loss, c, lr=lr, clip=clip)
+    torch.manual_seed(1234)
+    for _ in range(warmup):
+        tr.step(torch.randn(B, D))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        tr.step(torch.randn(B, D))      # DPI_interferometry.py:193 draws z on the host every step
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=B * done / dt, ms_per_step=1e3 * dt / done, steps=done, cores=torch.get_num_threads(),
+                batch=B, desc=desc)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def gpu_run(args):
+    import torch.distributed as dist
+    from dpi_b200 import _lib
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    from dpi_b200.trainer import InterferometryTrainer, MRITrainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the dpi_b200 product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    wl, kind, npix, nf, B, lr, clip, desc = build_workload(args.workload)
+    D = npix * npix
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    flow = RealNVP(D, nf)
+    T = InterferometryTrainer if kind == "interferometry" else MRITrainer
+    tr = T(flow, wl, B, lr=lr, clip=clip, device=dev, use_graph=not args.no_graph)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)              # per-rank z stream
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        tr.sample_z(gen)
+        tr.step()
+    barrier()
+    # ---- timed region: K steps, each between its own CUDA events; L2 flushed between steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for s, e in evs:
+            if not args.no_flush:
+                l2_flush.fill_(1)
+            s.record()
+            tr.sample_z(gen)                  # z ~ N(0,I) drawn on the device, inside the timed step
+            tr.step()
+            e.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [s.elapsed_time(e) for s, e in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    launches = (tr.launches_per_step or 0) * args.steps
+
+    # ---- end-to-end through the public step API with host buffers: pinned z -> H2D, loss -> D2H
+    zs = [torch.randn(B, D).pin_memory() for _ in range(4)]
+    host_terms = torch.empty(16, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        tr.step(zs[k % 4])
+        host_terms.copy_(tr.terms, non_blocking=False)     # the step's loss read back every step
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s)
+
+    # ---- per-kernel timing of the dominant kernels (eager launches, CUDA events on the launch stream)
+    prof = tr.profile_kernels(steps=min(args.steps, 10), flush=None if args.no_flush else l2_flush)
+    barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    roof = dict(bound="hbm", kernel=dom, achieved=prof[dom]["bytes"] / (prof[dom]["ms"] * 1e-3) / 1e9, peak=hbm_peak,
+                peak_source=peak_src, unit="GB/s", traffic=None, algorithmic_bytes=prof[dom]["bytes"],
+                ms_per_launch=prof[dom]["ms"],
+                step=dict(algorithmic_bytes=tr.algorithmic_bytes_per_step(),
+                          achieved=tr.algorithmic_bytes_per_step() / (total_ms / args.steps * 1e-3) / 1e9),
+                kernels={k: dict(ms=round(v["ms"], 5), gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)) for k, v in prof.items()})
+    roof["frac"] = roof["achieved"] / hbm_peak
+    roof["step"]["frac"] = roof["step"]["achieved"] / hbm_peak
+    cpu = cpu_reference_run(args.workload, steps=args.cpu_steps, warmup=2)
+    out = {
+        "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "global_batch": world * B, "batch_per_gpu": B,
+                   "params": int(flow.flat.numel()), "cuda_graph": not args.no_graph,
+                   "l2": "flushed between timed steps (192 MiB fill)" if not args.no_flush else "not flushed",
+                   "bn": "per-replica batch statistics", "wall_s_timed_region": round(t_wall, 4)},
+        "clocks": clocks.summary(),
+        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": 64, "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu["value"], "unit": "samples/s", "cores": cpu["cores"], "kind": "port",
+                         "sample": f"{cpu['steps']} steps of the same workload (batch {cpu['batch']}) after 2 warm-up, "
+                                   f"{cpu['ms_per_step']:.1f} ms/step, torch {torch.__version__} CPU"},
+        "loss": float(host_terms[0]),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_run(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.workload, steps=args.steps, warmup=min(args.warmup, 3), max_seconds=120.0)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": world,
+           "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": r["desc"], "name": args.workload, "batch_per_gpu": r["batch"]},
+           "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                            "sample": f"{r['steps']} steps (batch {r['batch']}) of the oracle port of the reference step "
+                                      "on the host cores; the reference is pure Python and cannot travel to the GPU box"},
+           "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="dpi_b200", choices=["dpi_b200", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_run(args)
+    else:
+        gpu_run(args)
+
+
+if __name__ == "__main__":
+    main()

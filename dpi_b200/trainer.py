@@ -79,6 +79,7 @@ class _FusedTrainer:
         self.ws_flow = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.ws_opt = torch.zeros(self.lib.dpi_clip_adam_workspace_bytes(P), dtype=torch.uint8, device=dev)
         self.use_graph = use_graph
+        self._prof = None
         self._graphs = None
         self._warm = 0
         self.launches_per_step = None
@@ -91,27 +92,40 @@ class _FusedTrainer:
         raise NotImplementedError
 
     # -- the step, as two enqueue halves around the (optional) gradient all-reduce ------------------
+    def _mark(self, name):
+        if self._prof is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._prof.append((name, ev))
+
     def _enqueue_loss_grad(self):
         lib, st, B = self.lib, _lib.stream_ptr(), self.B
         fl = self.flow
+        self._mark("start")
         _lib.check(lib.dpi_flow_run(self.handle, 0, 1, B, self.params.data_ptr(), fl.bn_running.data_ptr(),
                                     self.z.data_ptr(), self.x.data_ptr(), self.logdet_flow.data_ptr(),
                                     self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
+        self._mark("flow_reverse_fwd")
         _lib.check(lib.dpi_image_head(B, self.npix, self.x.data_ptr(), self.log_scale.data_ptr(), self.img.data_ptr(),
                                       self.det.data_ptr(), _lib.ptr(self.prior_img), self.flux_target, self.center,
                                       self.prior_vals.data_ptr(), self.gw_prior.data_ptr(),
                                       self.g_img_prior.data_ptr(), st), "dpi_image_head")
+        self._mark("image_head")
         self._data_forward_backward(st)
+        self._mark("measurement_fwd_bwd")
         _lib.check(lib.dpi_positivity_backward(B, self.npix, self.x.data_ptr(), self.log_scale.data_ptr(),
                                                self.img.data_ptr(), self.g_img_prior.data_ptr(),
                                                self.g_img_data.data_ptr(), self.g_det.data_ptr(), self.g_x.data_ptr(),
                                                self.g_ls_partial.data_ptr(), st), "dpi_positivity_backward")
+        self._mark("positivity_bwd")
         _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(),
                                          self.z.data_ptr(), self.g_x.data_ptr(), self.g_det.data_ptr(), None,
                                          self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_backward")
+        self._mark("flow_reverse_bwd")
         _lib.check(lib.dpi_reduce_sum(B, self.g_ls_partial.data_ptr(), self.g_ls.data_ptr(), None, st),
                    "dpi_reduce_sum")
         self._terms(st)
+        self._mark("loss_terms")
 
     def _enqueue_update(self):
         lib, st = self.lib, _lib.stream_ptr()
@@ -126,8 +140,13 @@ class _FusedTrainer:
         _lib.check(lib.dpi_clip_adam(1, self.log_scale.data_ptr(), self.g_ls.data_ptr(), self.m_ls.data_ptr(),
                                      self.v_ls.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
                                      self.step_dev.data_ptr(), gs, None, st), "dpi_clip_adam")
+        self._mark("clip_adam")
 
     def _allreduce(self):
+        self._allreduce_impl()
+        self._mark("grad_allreduce")
+
+    def _allreduce_impl(self):
         if self.world > 1:
             torch.distributed.all_reduce(self.grads_all, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
@@ -198,6 +217,53 @@ class _FusedTrainer:
     def log_scale_value(self) -> float:
         return float(self.log_scale[0].item())
 
+    def kernel_bytes(self):
+        """Algorithmic bytes per launch group, used for per-kernel roofline lines."""
+        fl = self.flow
+        S, B, D, H = 2 * fl.n_flow, self.B, self.D, fl.hidden
+        P = fl.flat.numel()
+        act = B * (D + 2 * H + 2 * (D // 2))          # per stage: y, l1, l2, o
+        return {
+            "flow_reverse_fwd": 4 * (P + B * D + S * act + B * D),
+            "image_head": 4 * (3 * B * D + D),
+            "measurement_fwd_bwd": self._data_bytes(),
+            "positivity_bwd": 4 * 5 * B * D,
+            "flow_reverse_bwd": 4 * (2 * P + S * act + B * D),
+            "loss_terms": 4 * 10 * B,
+            "clip_adam": 4 * 8 * P,                      # norm pass (1 read) + Adam (4 reads, 3 writes)
+            "grad_allreduce": 4 * P,
+        }
+
+    def _data_bytes(self):
+        return 4 * 2 * self.B * self.D
+
+    def profile_kernels(self, steps=5, flush=None):
+        """Average CUDA-event duration of each launch group over `steps` eager (non-graph) steps."""
+        acc, kb = {}, self.kernel_bytes()
+        for _ in range(steps):
+            if flush is not None:
+                flush.fill_(1)
+            self.sample_z()
+            self._prof = []
+            with torch.cuda.device(self.device):
+                self._enqueue_loss_grad()
+                self._allreduce()
+                self._enqueue_update()
+            torch.cuda.synchronize(self.device)
+            prev = None
+            for name, ev in self._prof:
+                if prev is not None and name != "start":
+                    acc.setdefault(name, []).append(prev.elapsed_time(ev))
+                prev = ev
+            self._prof = None
+            self.flow._bump_bn()
+        out = {}
+        for name, v in acc.items():
+            if name == "grad_allreduce" and self.world == 1:
+                continue
+            out[name] = dict(ms=sum(v) / len(v), bytes=kb.get(name, 0))
+        return out
+
     def algorithmic_bytes_per_step(self) -> int:
         """40 P (weights fwd + bwd, grad write, Adam 4 reads + 3 writes) + saved activations
         once written and once read + constants."""
@@ -251,6 +317,10 @@ class InterferometryTrainer(_FusedTrainer):
 
     def _const_bytes(self):
         return 2 * 4 * self.op.P * 2 * self.op.n_vis  # F read forward and backward
+
+    def _data_bytes(self):
+        nv2 = 2 * self.op.n_vis
+        return 4 * (2 * self.op.P * nv2 + 2 * self.B * self.D + 4 * self.B * nv2)
 
 
 class MRITrainer(_FusedTrainer):

@@ -79,21 +79,26 @@ def init_state(ndim: int, n_flow: int, seqfrac: float = 4, seed: int = 0, random
             sd[p + "loc"] = rn(1, std=0.1) if randomize else torch.zeros(1, dtype=dtype)
             sd[p + "log_scale_inv"] = rn(1, std=0.1) if randomize else torch.zeros(1, dtype=dtype)
             sd[p + "initialized"] = torch.tensor(1 if randomize else 0, dtype=torch.uint8)
-        for cn in ("coupling", "coupling2"):
+        for cn in ("coupling", "coupling2"):  # key order = the reference module's state_dict order
             p = f"blocks.{i}.{cn}.net."
-            second = "3" if batch_norm else "2"
-            last = "6" if batch_norm else "4"
+
+            def bn_layer(idx):
+                sd[p + idx + ".weight"] = (1 + rn(H, std=0.1)) if randomize else torch.ones(H, dtype=dtype)
+                sd[p + idx + ".bias"] = rn(H, std=0.1) if randomize else torch.zeros(H, dtype=dtype)
+                sd[p + idx + ".running_mean"] = torch.zeros(H, dtype=dtype)
+                sd[p + idx + ".running_var"] = torch.ones(H, dtype=dtype)
+                sd[p + idx + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+
             sd[p + "0.weight"] = rn(H, Da, std=0.05)
             sd[p + "0.bias"] = rn(H, std=0.05) if randomize else torch.zeros(H, dtype=dtype)
+            if batch_norm:
+                bn_layer("2")
+            second = "3" if batch_norm else "2"
             sd[p + second + ".weight"] = rn(H, H, std=0.05)
             sd[p + second + ".bias"] = rn(H, std=0.05) if randomize else torch.zeros(H, dtype=dtype)
             if batch_norm:
-                for bn in ("2", "5"):
-                    sd[p + bn + ".weight"] = (1 + rn(H, std=0.1)) if randomize else torch.ones(H, dtype=dtype)
-                    sd[p + bn + ".bias"] = rn(H, std=0.1) if randomize else torch.zeros(H, dtype=dtype)
-                    sd[p + bn + ".running_mean"] = torch.zeros(H, dtype=dtype)
-                    sd[p + bn + ".running_var"] = torch.ones(H, dtype=dtype)
-                    sd[p + bn + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+                bn_layer("5")
+            last = "6" if batch_norm else "4"
             sd[p + last + ".scale"] = rn(Dout, std=0.05) if randomize else torch.zeros(Dout, dtype=dtype)
             sd[p + last + ".fc.weight"] = rn(Dout, H, std=0.02) if randomize else torch.zeros(Dout, H, dtype=dtype)
             sd[p + last + ".fc.bias"] = rn(Dout, std=0.02) if randomize else torch.zeros(Dout, dtype=dtype)

@@ -83,7 +83,10 @@ def test_fresh_forward_data_dependent_actnorm_init(name):
     assert rel_err(z0, g["z_fresh"]) < RTOL and rel_err(l0, g["ld_fresh"]) < RTOL
     mine = m.state_dict()
     for k, v in split_sd(g, "sd_fresh_after.").items():
-        assert rel_err(mine[k].float(), v.float()) < RTOL, k
+        if k.endswith(".loc") or k.endswith(".log_scale_inv"):  # -mean / log(std) of normalised activations are ~0
+            assert float((mine[k].float().cpu() - v.float()).abs().max()) < 1e-5, k
+        else:
+            assert rel_err(mine[k].float(), v.float()) < RTOL, k
 
 
 def test_fresh_reverse_is_a_permutation_with_zero_logdet():

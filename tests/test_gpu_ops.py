@@ -204,7 +204,7 @@ def test_clip_adam_matches_torch_optimizer():
                                      1e-3, 1e-4, 0.9, 0.999, 1e-8, step.data_ptr(), 1.0, norm_out.data_ptr(), st))
         assert rel_err(norm_out[0], tn) < 1e-5
         assert rel_err(p[:n], p_ref.detach()) < 1e-6, it
-        assert float((p[:n].cpu() - p_ref.detach()).abs().max()) < 1e-7
+        assert float((p[:n].cpu() - p_ref.detach()).abs().max()) < 3e-7   # <= 2 ulp at |p| ~ 2
     assert int(step) == 4
 
 
