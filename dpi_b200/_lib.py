@@ -34,6 +34,8 @@ PROTOTYPES = {
     "dpi_flow_ws_offset": (i64, [vp, i32, i32, i32]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "dpi_flow_debug_timing": (i32, [vp, i32]),
+    "dpi_flow_debug_read": (i32, [vp, vp, vp, i32]),
     "dpi_flow_set_mode": (i32, [vp, i32, i32]),
     "dpi_positivity_forward": (i32, [i32, i32, vp, vp, vp, vp, vp]),
     "dpi_positivity_backward": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

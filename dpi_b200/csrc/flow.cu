@@ -20,6 +20,7 @@ struct Program {
   int n_phases = 0;
   int max_tiles = 0;
   std::vector<int> phase_tiles;
+  std::vector<int> ops;
 };
 
 struct BatchPlan {
@@ -46,6 +47,9 @@ struct dpi_flow_s {
   int* d_gmaps = nullptr;
   std::mutex mu;
   std::map<int, std::unique_ptr<dpi::BatchPlan>> plans;
+  unsigned long long* d_tbuf = nullptr;       // debug timing stamps (2 per phase)
+  int tbuf_phases = 0;
+  std::vector<int> last_ops;                  // op codes of the last launched program (debug)
 };
 
 namespace dpi {
@@ -159,6 +163,7 @@ int upload(Builder& b, Program& prog) {
   for (auto& p : b.phases) {
     int t = p.sub[0].ntiles + (p.nsub > 1 ? p.sub[1].ntiles : 0);
     prog.phase_tiles.push_back(t);
+    prog.ops.push_back(p.sub[0].op * 100 + p.sub[0].which * 10 + (p.nsub > 1 ? 1 : 0));
     prog.max_tiles = std::max(prog.max_tiles, t);
     for (int i = 0; i < p.nsub; ++i)
       if (p.sub[i].splits > 1 && p.sub[i].ctr_off + p.sub[i].tiles_m * p.sub[i].tiles_n > kCtrlWords) {
@@ -200,7 +205,7 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
         o.kchunk = H; o.ntiles = tm * tiles_j;
         b.add(e, o);
       }
-      SubOp fin = strip_subop(OP_LOGDET_FINAL, 0, (B + kThreads - 1) / kThreads);
+      SubOp fin = strip_subop(OP_LOGDET_FINAL, 0, (B + 31) / 32);
       if (dir == 1) {
         long long n = ((long long)B * D + kThreads - 1) / kThreads;
         b.add(S - 1, fin, strip_subop(OP_GATHER_OUT, 0, (int)n));
@@ -280,6 +285,12 @@ void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
 
 int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t stream) {
   a.phases = prog.d_phases;
+  a.tbuf = nullptr;
+  if (h->d_tbuf && prog.n_phases <= 4096) {
+    a.tbuf = h->d_tbuf;
+    h->tbuf_phases = prog.n_phases;
+    h->last_ops = prog.ops;
+  }
   DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), stream));
   if (h->persistent) {
     int grid = std::min(prog.max_tiles, h->n_sm * std::min(h->ctas_per_sm, h->coop_max_per_sm));
@@ -409,6 +420,7 @@ int dpi_flow_destroy(dpi_flow_t h) {
   }
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
+  cudaFree(h->d_tbuf);
   delete h;
   return DPI_OK;
 }
@@ -461,6 +473,32 @@ int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
     default: return -1;
   }
   return (int64_t)(kCtrlWords * sizeof(unsigned)) + o * (int64_t)sizeof(float);
+}
+
+int dpi_flow_debug_timing(dpi_flow_t h, int enable) {
+  DPI_REQUIRE(h, "dpi_flow_debug_timing: null handle");
+  DeviceGuard g(h->device);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (enable && !h->d_tbuf) {
+    DPI_CUDA(cudaMalloc(&h->d_tbuf, sizeof(unsigned long long) * 2 * 4096));
+    DPI_CUDA(cudaMemset(h->d_tbuf, 0, sizeof(unsigned long long) * 2 * 4096));
+  } else if (!enable && h->d_tbuf) {
+    cudaDeviceSynchronize();
+    cudaFree(h->d_tbuf);
+    h->d_tbuf = nullptr;
+  }
+  return DPI_OK;
+}
+
+int dpi_flow_debug_read(dpi_flow_t h, uint64_t* stamps, int32_t* ops, int max_phases) {
+  DPI_REQUIRE(h && stamps && ops, "dpi_flow_debug_read: null argument");
+  DPI_REQUIRE(h->d_tbuf, "dpi_flow_debug_read: timing not enabled");
+  DeviceGuard g(h->device);
+  DPI_CUDA(cudaDeviceSynchronize());
+  const int n = std::min(h->tbuf_phases, max_phases);
+  DPI_CUDA(cudaMemcpy(stamps, h->d_tbuf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) ops[i] = h->last_ops[i];
+  return n;
 }
 
 int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {

@@ -21,6 +21,7 @@ struct StageTab {
   long long p[P_COUNT];  // float offsets into the flat parameter / gradient buffers
   long long loc, lsi;    // ActNorm.loc / .log_scale_inv
   long long r[4];        // running_mean1, running_var1, running_mean2, running_var2 (flat bn buffer)
+  long long pad_;        // keeps sizeof a multiple of 16 (staged into shared memory with int4 copies)
 };
 
 enum Op : int {
@@ -48,8 +49,11 @@ struct SubOp {
 struct Phase {
   int stage;                  // execution position e in [0, S)
   int nsub;
+  int pad_[2];
   SubOp sub[2];
 };
+
+static_assert(sizeof(Phase) % 16 == 0 && sizeof(StageTab) % 16 == 0, "tables are staged with 16-byte copies");
 
 struct KArgs {
   const StageTab* st;
@@ -64,6 +68,7 @@ struct KArgs {
   const float* in; float* out; float* logdet;
   const float* g_out; const float* g_ld; float* g_in;
   unsigned* ctrl;
+  unsigned long long* tbuf;   // debug: per-phase globaltimer stamps of CTA 0 (start, work done), or nullptr
   int phase_begin, phase_end, persistent;
 };
 

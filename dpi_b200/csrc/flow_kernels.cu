@@ -10,33 +10,30 @@
 namespace dpi {
 
 // ----------------------------------------------------------------------------- grid barrier
-// Sense-reversal barrier over all CTAs of a cooperative launch. ctrl[0]=arrivals, ctrl[1]=generation,
-// ctrl[2]=error flag. The spin is bounded (about 2 s) so a protocol bug cannot hang the GPU.
-__device__ __forceinline__ void grid_sync(unsigned* ctrl, unsigned nblocks) {
-  __threadfence();
+// Monotonic-counter barrier over all CTAs of a cooperative launch: ctrl[0] counts arrivals over the
+// whole launch (zeroed by the host before the launch), barrier number `idx` completes when it reaches
+// (idx + 1) * nblocks. Thread 0 publishes the CTA's writes with a release-add (cumulative over the
+// preceding bar.sync) and polls with acquire loads. The spin is bounded (about 2 s) so a protocol bug
+// cannot hang the GPU; ctrl[2] is the error flag.
+__device__ __forceinline__ void grid_sync(unsigned* ctrl, unsigned nblocks, unsigned idx) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned gen;
-    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(ctrl + 1) : "memory");
-    unsigned old = atomicAdd(ctrl, 1u);
-    if (old == nblocks - 1) {
-      ctrl[0] = 0;
-      __threadfence();
-      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(ctrl + 1), "r"(gen + 1) : "memory");
-    } else {
-      long long t0 = clock64();
-      unsigned cur;
+    const unsigned target = (idx + 1u) * nblocks;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctrl), "r"(1u) : "memory");
+    unsigned cur;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(ctrl) : "memory");
+    if (cur < target) {
+      const long long t0 = clock64();
       do {
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(ctrl + 1) : "memory");
-        if (cur == gen && clock64() - t0 > 4000000000LL) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(ctrl) : "memory");
+        if (cur < target && clock64() - t0 > 4000000000LL) {
           atomicExch(ctrl + 2, 1u);
           break;
         }
-      } while (cur == gen);
+      } while (cur < target);
     }
   }
   __syncthreads();
-  __threadfence();
 }
 
 // ----------------------------------------------------------------------------- loaders
@@ -375,20 +372,38 @@ __device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, 
   }
 }
 
-// logdet[m] = sum over stages/tiles of the coupling partials + sum_s (+-) D * log_scale_inv_s
-__device__ __noinline__ void op_logdet_final(const KArgs& a, int t) {
-  const int m = t * kThreads + threadIdx.x;
-  if (m >= a.B) return;
-  float s = 0.f;
-  for (int e = 0; e < a.S; ++e) {
-    const float* ldp = a.W + a.oLDP + (size_t)e * a.ldp_tiles * a.B;
-    float se = 0.f;
-    for (int j = 0; j < a.ldp_tiles; ++j) se += ldcg(ldp + (size_t)j * a.B + m);
-    const StageTab& st = a.st[a.dir ? a.S - 1 - e : e];
-    const float lsi = __ldg(a.P + st.lsi);
-    s += se + (a.dir == 0 ? (float)a.D * lsi : -(float)a.D * lsi);
+// logdet[m] = sum over stages/tiles of the coupling partials + sum_s (+-) D * log_scale_inv_s.
+// One CTA per 32 samples: lane = sample (coalesced), 8 warps each sum a fixed slice of the S*tiles
+// partials with independent loads in flight; slices are combined in a fixed order (deterministic).
+__device__ __noinline__ void op_logdet_final(const KArgs& a, int t, float* sRed) {
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int m = t * 32 + lane;
+  const int n = a.S * a.ldp_tiles;
+  const float* ldp = a.W + a.oLDP;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (m < a.B) {
+    const int per = (n + 7) / 8, lo = slice * per, hi = min(n, lo + per);
+    int i = lo;
+    for (; i + 4 <= hi; i += 4) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldcg(ldp + (size_t)(i + u) * a.B + m);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += v[u];
+    }
+    for (; i < hi; ++i) acc[0] += ldcg(ldp + (size_t)i * a.B + m);
   }
-  a.logdet[m] = s;
+  __syncthreads();
+  sRed[slice * 32 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (slice == 0 && m < a.B) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += sRed[r * 32 + lane];
+    float lsum = 0.f;
+    for (int e = 0; e < a.S; ++e) lsum += __ldg(a.P + a.st[e].lsi);
+    a.logdet[m] = s + (a.dir == 0 ? (float)a.D * lsum : -(float)a.D * lsum);
+  }
 }
 
 // RealNVP.forward ends with out[:, orders[-1]] after the last flip (:590 after :446)
@@ -759,13 +774,38 @@ __device__ __forceinline__ void run_gemm_op(const KArgs& a, int e, const SubOp& 
   }
 }
 
+constexpr int kSmemPhases = 136;   // programs up to this many phases are staged in shared memory
+constexpr int kSmemStages = 64;
+
 __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
   __shared__ float sA[kBM * (kBK + 1)];
   __shared__ float sB[64 * (kBK + 1)];
   __shared__ float sRed[1024 + 128];
   __shared__ int sFlag;
+  __shared__ __align__(16) Phase sPh[kSmemPhases];
+  __shared__ __align__(16) StageTab sSt[kSmemStages];
+  const int np = a.phase_end - a.phase_begin;
+  const bool ph_smem = np <= kSmemPhases;
+  if (ph_smem) {
+    const int4* src = reinterpret_cast<const int4*>(a.phases + a.phase_begin);
+    int4* dst = reinterpret_cast<int4*>(sPh);
+    for (int i = threadIdx.x; i < np * (int)(sizeof(Phase) / 16); i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (a.S <= kSmemStages) {
+    const int4* src = reinterpret_cast<const int4*>(a.st);
+    int4* dst = reinterpret_cast<int4*>(sSt);
+    for (int i = threadIdx.x; i < a.S * (int)(sizeof(StageTab) / 16); i += kThreads) dst[i] = __ldg(src + i);
+    a.st = sSt;
+  }
+  __syncthreads();
+  unsigned bar = 0;
   for (int p = a.phase_begin; p < a.phase_end; ++p) {
-    const Phase& ph = a.phases[p];
+    const Phase& ph = ph_smem ? sPh[p - a.phase_begin] : a.phases[p];
+    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.tbuf[2 * p] = t;
+    }
     const int n0 = ph.sub[0].ntiles;
     const int total = n0 + (ph.nsub > 1 ? ph.sub[1].ntiles : 0);
     for (int tt = blockIdx.x; tt < total; tt += gridDim.x) {
@@ -777,7 +817,7 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
           else op_fwd_out<32>(a, ph.stage, so, t, sA, sB);
           break;
         case OP_BN_STATS: op_bn_stats(a, ph.stage, so, t, sRed); break;
-        case OP_LOGDET_FINAL: op_logdet_final(a, t); break;
+        case OP_LOGDET_FINAL: op_logdet_final(a, t, sRed); break;
         case OP_GATHER_OUT: op_gather_out(a, t); break;
         case OP_B0: op_b0(a, ph.stage, so, t, sRed); break;
         case OP_BNBWD_STATS: op_bnbwd_stats(a, ph.stage, so, t, sRed); break;
@@ -791,7 +831,12 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
       }
       __syncthreads();
     }
-    if (a.persistent && p + 1 < a.phase_end) grid_sync(a.ctrl, gridDim.x);
+    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.tbuf[2 * p + 1] = t;
+    }
+    if (a.persistent && p + 1 < a.phase_end) grid_sync(a.ctrl, gridDim.x, bar++);
   }
 }
 

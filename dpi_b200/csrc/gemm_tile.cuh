@@ -22,11 +22,11 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[4][BN / 16], LA& la, LB& 
   constexpr int NB = BN * kBK / kThreads;
   constexpr int LD = kBK + 1;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float ra[NA], rb[NB];
+  float ra0[NA], rb0[NB], ra1[NA], rb1[NB];   // two k-tiles in flight while a third is computed
   la.init();
   lb.init();
 
-  auto fetch = [&](int k0) {
+  auto fetch = [&](int k0, float (&ra)[NA], float (&rb)[NB]) {
     la.ktile(k0);
     lb.ktile(k0);
 #pragma unroll
@@ -46,7 +46,7 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[4][BN / 16], LA& la, LB& 
       rb[i] = (k < kend) ? lb(nn, k) : 0.f;
     }
   };
-  auto stash = [&]() {
+  auto stash = [&](const float (&ra)[NA], const float (&rb)[NB]) {
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int e = tid + i * kThreads;
@@ -62,13 +62,7 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[4][BN / 16], LA& la, LB& 
       sB[nn * LD + kk] = rb[i];
     }
   };
-
-  if (kbeg < kend) fetch(kbeg);
-  for (int k0 = kbeg; k0 < kend; k0 += kBK) {
-    __syncthreads();  // previous tile's readers are done
-    stash();
-    __syncthreads();
-    if (k0 + kBK < kend) fetch(k0 + kBK);
+  auto compute = [&]() {
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
       float a[4], b[TN];
@@ -81,6 +75,22 @@ __device__ __forceinline__ void gemm_tile(float (&acc)[4][BN / 16], LA& la, LB& 
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+  };
+
+  if (kbeg < kend) fetch(kbeg, ra0, rb0);
+  if (kbeg + kBK < kend) fetch(kbeg + kBK, ra1, rb1);
+  for (int k0 = kbeg; k0 < kend; k0 += 2 * kBK) {
+    __syncthreads();  // previous tile's readers are done
+    stash(ra0, rb0);
+    __syncthreads();
+    if (k0 + 2 * kBK < kend) fetch(k0 + 2 * kBK, ra0, rb0);
+    compute();
+    if (k0 + kBK >= kend) break;
+    __syncthreads();
+    stash(ra1, rb1);
+    __syncthreads();
+    if (k0 + 3 * kBK < kend) fetch(k0 + 3 * kBK, ra1, rb1);
+    compute();
   }
   __syncthreads();
 }
@@ -113,12 +123,24 @@ __device__ __forceinline__ bool splitk_reduce(float (&acc)[4][BN / 16], float* p
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float* src = part + (size_t)s * (kBM * BN);
+  // four splits' partials in flight at a time; summation order stays s = 0, 1, 2, ...
+  for (int s0 = 0; s0 < splits; s0 += 4) {
+    float v[4][4][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int u = 0; u < 4; ++u) {
+      const float* src = part + (size_t)(s0 + u) * (kBM * BN);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] += ldcg(src + (ty * 4 + i) * BN + j * 16 + tx);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          v[u][i][j] = (s0 + u < splits) ? ldcg(src + (ty * 4 + i) * BN + j * 16 + tx) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += v[u][i][j];
   }
   return true;
 }

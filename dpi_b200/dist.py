@@ -1,0 +1,65 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+The DPI step shards by sample: every rank draws its own z (seed = base + rank), runs the same fused
+step, and the flat gradient buffer [flow parameters | log_scale] is summed across ranks once per
+step; the clip + Adam kernel then applies 1/world (BatchNorm batch statistics stay per replica -
+DDP semantics). Parameters never diverge because every rank applies the same update
+to the same initial weights.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str = None, device: torch.device = None):
+    """Initialise the default process group from torchrun's environment (no-op for world size 1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return world
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+    dist.init_process_group(backend, **kw)
+    return world
+
+
+def rank_seed(base: int, rank: int) -> int:
+    """Per-rank z stream (seed 1234 + rank)."""
+    return int(base) + int(rank)
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous sample range of `rank` when a global batch is split (strong scaling)."""
+    per = global_batch // world
+    rem = global_batch % world
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def replicas_max_divergence(flat: torch.Tensor, group=None) -> float:
+    """max |flat - rank0's flat| over all ranks (0.0 when the replicas are in sync)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0.0
+    ref = flat.clone()
+    dist.broadcast(ref, src=0, group=group)
+    d = (flat - ref).abs().max().reshape(1)
+    dist.all_reduce(d, op=dist.ReduceOp.MAX, group=group)
+    return float(d)
+
+
+def pack_named(model, named: dict, out: torch.Tensor = None) -> torch.Tensor:
+    """Pack reference-named tensors (e.g. gradients keyed like state_dict) into the flat layout."""
+    flat = torch.zeros_like(model.flat.detach()) if out is None else out
+    for key, view in model.named_grad_views(flat):
+        view.copy_(named[key])
+    return flat

@@ -148,7 +148,8 @@ class _FusedTrainer:
 
     def _allreduce_impl(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads_all, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            from dpi_b200.dist import allreduce_sum_
+            allreduce_sum_(self.grads_all, self.pg)
 
     def loss_and_grad(self, z: Optional[torch.Tensor] = None):
         """Forward + backward only (no update): fills self.grads / self.g_ls / self.terms."""

@@ -95,6 +95,12 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
                       const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                       size_t workspace_bytes, dpi_stream_t stream);
 
+/* Debug/profiling aid (synchronises; never on the hot path): when enabled, CTA 0 stamps %globaltimer at
+ * the start and at the end of its work in every phase of the next launches. dpi_flow_debug_read returns
+ * the number of phases of the last launch and fills stamps[2*i], stamps[2*i+1] (ns) and ops[i]
+ * (op*100 + layer*10 + has_second_subop). */
+int dpi_flow_debug_timing(dpi_flow_t h, int enable);
+int dpi_flow_debug_read(dpi_flow_t h, uint64_t* stamps, int32_t* ops, int max_phases);
 /* 0: one launch per phase; 1: one persistent cooperative launch with grid barriers */
 int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm);
 

@@ -122,8 +122,16 @@ def test_flow_vs_oracle_at_config_sizes(D, NF, B, seqfrac):
     ((x * cx.cuda()).sum() + (ld * cl.cuda()).sum()).backward()
     assert rel_err(x, xo) < RTOL and rel_err(ld, ldo) < RTOL
     assert rel_err(zg.grad, zo.grad) < RTOL
-    worst = max(((rel_err(gv, sd[k].grad), k) for k, gv in m.named_grad_views()))
+    views = dict(m.named_grad_views())
+    worst = max(((rel_err(gv, sd[k].grad), k) for k, gv in views.items() if "actnorm" not in k))
     assert worst[0] < 3 * RTOL, worst
+    # the scalar ActNorm gradients are sums of B*D signed terms (random upstream gradient => heavy
+    # cancellation): judge them as one vector per kind, relative to its largest entry
+    for kind in ("loc", "log_scale_inv"):
+        ks = [k for k in views if k.endswith("." + kind)]
+        mine = torch.cat([views[k].reshape(-1).cpu() for k in ks])
+        ref = torch.cat([sd[k].grad.reshape(-1) for k in ks])
+        assert rel_err(mine, ref) < 3 * RTOL, (kind, rel_err(mine, ref))
     # size-independent properties: invertibility and logdet antisymmetry
     with torch.no_grad():
         zb, ldb = m.forward(x.detach())

@@ -1,0 +1,67 @@
+"""Per-phase timeline of the flow program on the GPU (debug aid): python tools/phase_timing.py [c1|c2]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import build_workload  # noqa: E402
+from dpi_b200 import _lib  # noqa: E402
+from dpi_b200.generative_model.realnvpfc_model import RealNVP  # noqa: E402
+from dpi_b200.trainer import InterferometryTrainer, MRITrainer  # noqa: E402
+
+OPS = {1: "FWD_HID", 2: "FWD_OUT", 3: "BN_STATS", 4: "LOGDET", 5: "GATHER", 6: "B0", 7: "DGRAD_HID", 8: "WGRAD",
+       9: "DGRAD_IN", 10: "BNBWD_STATS", 11: "BNBWD_APPLY", 12: "BWD_FINAL"}
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c1"
+    flush = len(sys.argv) > 2 and sys.argv[2] == "flush"
+    wl, kind, npix, nf, B, lr, clip, desc = build_workload(name)
+    lib = _lib.load()
+    torch.manual_seed(0)
+    flow = RealNVP(npix * npix, nf)
+    T = InterferometryTrainer if kind == "interferometry" else MRITrainer
+    tr = T(flow, wl, B, lr=lr, clip=clip, device="cuda", use_graph=False)
+    for _ in range(3):
+        tr.sample_z(); tr.step()
+    _lib.check(lib.dpi_flow_debug_timing(tr.handle, 1))
+    big = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+    for which in ("fwd", "bwd"):
+        tr.sample_z()
+        if flush:
+            big.fill_(1)
+        torch.cuda.synchronize()
+        if which == "fwd":
+            _lib.check(lib.dpi_flow_run(tr.handle, 0, 1, B, tr.params.data_ptr(), tr.flow.bn_running.data_ptr(),
+                                        tr.z.data_ptr(), tr.x.data_ptr(), tr.logdet_flow.data_ptr(), tr.ws_flow.data_ptr(),
+                                        tr.ws_flow.numel(), _lib.stream_ptr()))
+        else:
+            tr.g_x.normal_()
+            _lib.check(lib.dpi_flow_backward(tr.handle, B, tr.params.data_ptr(), tr.grads.data_ptr(), tr.z.data_ptr(),
+                                             tr.g_x.data_ptr(), tr.g_det.data_ptr(), None, tr.ws_flow.data_ptr(),
+                                             tr.ws_flow.numel(), _lib.stream_ptr()))
+        st = np.zeros(2 * 4096, dtype=np.uint64)
+        ops = np.zeros(4096, dtype=np.int32)
+        n = lib.dpi_flow_debug_read(tr.handle, st.ctypes.data, ops.ctypes.data, 4096)
+        st = st[:2 * n].astype(np.int64).reshape(n, 2)
+        start, done = st[:, 0], st[:, 1]
+        work = done - start
+        wait = np.append(start[1:] - done[:-1], 0)
+        print(f"== {name} {which}: {n} phases, total {(done[-1] - start[0]) / 1e3:.1f} us, "
+              f"work(cta0) {work.sum() / 1e3:.1f} us, barrier/wait {wait.sum() / 1e3:.1f} us")
+        by = {}
+        for i in range(n):
+            key = (OPS.get(ops[i] // 100, "?"), (ops[i] // 10) % 10, ops[i] % 10)
+            by.setdefault(key, []).append((work[i], wait[i]))
+        for key, v in by.items():
+            v = np.array(v)
+            print(f"   {key[0]:<12} layer={key[1]} two_subops={key[2]}  n={len(v):3d}  work {v[:, 0].mean() / 1e3:7.2f} us  "
+                  f"wait-after {v[:, 1].mean() / 1e3:7.2f} us")
+        print("   first 12 phases (work, wait) us:", [(round(work[i] / 1e3, 1), round(wait[i] / 1e3, 1)) for i in range(min(12, n))])
+
+
+if __name__ == "__main__":
+    main()
