@@ -25,10 +25,10 @@ struct Program {
 
 struct BatchPlan {
   int B = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
-  long long oY, oL1, oL2, oO, oST, oLDP, oGY, oGPRE, oGN, oGP1, oGP2, oPART, oRED, total_floats;
+  long long oZT, oYT, oL1T, oL2T, oN1T, oN2T, oOT, oST, oLDP, oGYT, oGPRET, oGNT, oGP1T, oGP2T, oPART, oRED, total_floats;
   // [dir][train] forward programs, and the backward program
   Program fwd[2][2];
-  Program bwd;
+  Program bwd[2];   // [1]: also produces the gradient wrt the flow input
 };
 
 }  // namespace
@@ -183,77 +183,72 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.tiles_m = (B + kBM - 1) / kBM;
   const int tm = bp.tiles_m;
   const bool sep_stats = tm > 1;
+  const int tr_tiles = ((B + 31) / 32) * ((D + 31) / 32);
 
   // output layer: BJ = 32 (BN 64) when that still fills the grid, else BJ = 16
   int bj = 32;
   if ((long long)tm * ((Db + 31) / 32) < target) bj = 16;
   const int tiles_j = (Db + bj - 1) / bj;
   bp.ldp_tiles = tiles_j;
-  bp.red_tiles = (Db + 31) / 32;
+  bp.red_tiles = (Db + 7) / 8;
 
   long long max_part = 0;
   for (int dir = 0; dir < 2; ++dir)
     for (int train = 0; train < 2; ++train) {
       Builder b;
+      b.add(0, strip_subop(OP_TRANSPOSE, 0, tr_tiles));
       for (int e = 0; e < S; ++e) {
         b.add(e, gemm_subop(OP_FWD_HID, 1, tm, plan_gemm(tm, H, Da, target, true)));
-        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 1, (H + 31) / 32));
+        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 1, (H + 7) / 8));
         b.add(e, gemm_subop(OP_FWD_HID, 2, tm, plan_gemm(tm, H, H, target, true)));
-        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 2, (H + 31) / 32));
+        if (h->has_bn && train && sep_stats) b.add(e, strip_subop(OP_BN_STATS, 2, (H + 7) / 8));
         SubOp o{};
         o.op = OP_FWD_OUT; o.which = 3; o.tiles_m = tm; o.tiles_n = tiles_j; o.splits = 1; o.bn = 2 * bj;
         o.kchunk = H; o.ntiles = tm * tiles_j;
         b.add(e, o);
       }
-      SubOp fin = strip_subop(OP_LOGDET_FINAL, 0, (B + 31) / 32);
-      if (dir == 1) {
-        long long n = ((long long)B * D + kThreads - 1) / kThreads;
-        b.add(S - 1, fin, strip_subop(OP_GATHER_OUT, 0, (int)n));
-      } else {
-        b.add(S - 1, fin);
-      }
+      b.add(S - 1, strip_subop(OP_LOGDET_FINAL, 0, (B + 31) / 32), strip_subop(OP_TRANSPOSE, dir == 0 ? 2 : 3, tr_tiles));
       max_part = std::max(max_part, b.max_part);
       int rc = upload(b, bp.fwd[dir][train]);
       if (rc) return rc;
     }
-  {
+  for (int want_gin = 0; want_gin < 2; ++want_gin) {
     Builder b;
+    b.add(S - 1, strip_subop(OP_TRANSPOSE, 1, tr_tiles));
     for (int e = S - 1; e >= 0; --e) {
       b.add(e, strip_subop(OP_B0, 0, bp.red_tiles));
       b.add(e, gemm_subop(OP_DGRAD_HID, 2, tm, plan_gemm(tm, H, Dout, target, true)),
-            gemm_subop(OP_WGRAD, 3, (Dout + kBM - 1) / kBM, plan_gemm((Dout + kBM - 1) / kBM, H, B, target, false)));
-      if (sep_stats) {
-        if (h->has_bn) b.add(e, strip_subop(OP_BNBWD_STATS, 2, (H + 31) / 32));
-        b.add(e, strip_subop(OP_BNBWD_APPLY, 2, (H + 31) / 32));
-      }
+            gemm_subop(OP_WGRAD, 3, (H + kBM - 1) / kBM, plan_gemm((H + kBM - 1) / kBM, Dout, B, target, false)));
+      if (sep_stats) b.add(e, strip_subop(OP_BNBWD, 2, (H + 7) / 8));
       b.add(e, gemm_subop(OP_DGRAD_HID, 1, tm, plan_gemm(tm, H, H, target, true)),
             gemm_subop(OP_WGRAD, 2, (H + kBM - 1) / kBM, plan_gemm((H + kBM - 1) / kBM, H, B, target, false)));
-      if (sep_stats) {
-        if (h->has_bn) b.add(e, strip_subop(OP_BNBWD_STATS, 1, (H + 31) / 32));
-        b.add(e, strip_subop(OP_BNBWD_APPLY, 1, (H + 31) / 32));
-      }
+      if (sep_stats) b.add(e, strip_subop(OP_BNBWD, 1, (H + 7) / 8));
       b.add(e, gemm_subop(OP_DGRAD_IN, 1, tm, plan_gemm(tm, Da, H, target, false)),
-            gemm_subop(OP_WGRAD, 1, (H + kBM - 1) / kBM, plan_gemm((H + kBM - 1) / kBM, Da, B, target, false)));
+            gemm_subop(OP_WGRAD, 1, (Da + kBM - 1) / kBM, plan_gemm((Da + kBM - 1) / kBM, H, B, target, false)));
     }
-    b.add(0, strip_subop(OP_BWD_FINAL, 0, 1));
+    if (want_gin) b.add(0, strip_subop(OP_BWD_FINAL, 0, 1), strip_subop(OP_TRANSPOSE, 4, tr_tiles));
+    else b.add(0, strip_subop(OP_BWD_FINAL, 0, 1));
     max_part = std::max(max_part, b.max_part);
-    int rc = upload(b, bp.bwd);
+    int rc = upload(b, bp.bwd[want_gin]);
     if (rc) return rc;
   }
 
   long long o = 0;
   auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
-  bp.oY = take((long long)S * B * D);
-  bp.oL1 = take((long long)S * B * H);
-  bp.oL2 = take((long long)S * B * H);
-  bp.oO = take((long long)S * B * Dout);
+  bp.oZT = take((long long)D * B);
+  bp.oYT = take((long long)S * D * B);
+  bp.oL1T = take((long long)S * H * B);
+  bp.oL2T = take((long long)S * H * B);
+  bp.oN1T = take((long long)S * H * B);
+  bp.oN2T = take((long long)S * H * B);
+  bp.oOT = take((long long)S * Dout * B);
   bp.oST = take((long long)S * 4 * H);
   bp.oLDP = take((long long)S * bp.ldp_tiles * B);
-  bp.oGY = take(2LL * B * D);
-  bp.oGPRE = take((long long)B * Dout);
-  bp.oGN = take((long long)B * H);
-  bp.oGP1 = take((long long)B * H);
-  bp.oGP2 = take((long long)B * H);
+  bp.oGYT = take(2LL * D * B);
+  bp.oGPRET = take((long long)Dout * B);
+  bp.oGNT = take((long long)H * B);
+  bp.oGP1T = take((long long)H * B);
+  bp.oGP2T = take((long long)H * B);
   bp.oPART = take(std::max(32LL, max_part));
   bp.oRED = take((long long)S * bp.red_tiles * 2);
   bp.total_floats = o;
@@ -277,8 +272,9 @@ void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
   a.st = h->d_stages; a.gmaps = h->d_gmaps;
   a.D = h->D; a.Da = h->Da; a.Db = h->Db; a.Dout = h->Dout; a.H = h->H; a.S = h->S; a.has_bn = h->has_bn;
   a.B = bp.B; a.tiles_m = bp.tiles_m; a.ldp_tiles = bp.ldp_tiles; a.red_tiles = bp.red_tiles;
-  a.oY = bp.oY; a.oL1 = bp.oL1; a.oL2 = bp.oL2; a.oO = bp.oO; a.oST = bp.oST; a.oLDP = bp.oLDP; a.oGY = bp.oGY;
-  a.oGPRE = bp.oGPRE; a.oGN = bp.oGN; a.oGP1 = bp.oGP1; a.oGP2 = bp.oGP2; a.oPART = bp.oPART; a.oRED = bp.oRED;
+  a.oZT = bp.oZT; a.oYT = bp.oYT; a.oL1T = bp.oL1T; a.oL2T = bp.oL2T; a.oN1T = bp.oN1T; a.oN2T = bp.oN2T;
+  a.oOT = bp.oOT; a.oST = bp.oST; a.oLDP = bp.oLDP; a.oGYT = bp.oGYT; a.oGPRET = bp.oGPRET; a.oGNT = bp.oGNT;
+  a.oGP1T = bp.oGP1T; a.oGP2T = bp.oGP2T; a.oPART = bp.oPART; a.oRED = bp.oRED;
   a.ctrl = (unsigned*)workspace;
   a.W = (float*)((char*)workspace + kCtrlWords * sizeof(unsigned));
 }
@@ -297,14 +293,14 @@ int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t st
     grid = std::max(grid, 1);
     a.phase_begin = 0; a.phase_end = prog.n_phases; a.persistent = 1;
     void* params[] = {&a};
-    DPI_CUDA(cudaLaunchCooperativeKernel(flow_kernel_ptr(), dim3(grid), dim3(kThreads), params, 0, stream));
+    DPI_CUDA(cudaLaunchCooperativeKernel(flow_kernel_ptr(), dim3(grid), dim3(kThreads), params, kTileSmemBytes, stream));
     count_launch();
   } else {
     a.persistent = 0;
     void* params[] = {&a};
     for (int p = 0; p < prog.n_phases; ++p) {
       a.phase_begin = p; a.phase_end = p + 1;
-      DPI_CUDA(cudaLaunchKernel(flow_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, 0, stream));
+      DPI_CUDA(cudaLaunchKernel(flow_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, kTileSmemBytes, stream));
       count_launch();
     }
   }
@@ -330,7 +326,8 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   h->n_sm = sm_count(device);
   DPI_REQUIRE(h->n_sm > 0, "dpi_flow_create: no CUDA device %d", device);
   int nb = 0;
-  DPI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)flow_kernel_ptr(), kThreads, 0));
+  DPI_CUDA(cudaFuncSetAttribute((const void*)flow_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  DPI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)flow_kernel_ptr(), kThreads, kTileSmemBytes));
   h->coop_max_per_sm = std::max(1, nb);
   const char* mode = getenv("DPI_B200_FLOW_MODE");
   h->persistent = (mode && mode[0] == 's') ? 0 : 1;
@@ -416,7 +413,8 @@ int dpi_flow_destroy(dpi_flow_t h) {
   for (auto& kv : h->plans) {
     for (int d = 0; d < 2; ++d)
       for (int t = 0; t < 2; ++t) cudaFree(kv.second->fwd[d][t].d_phases);
-    cudaFree(kv.second->bwd.d_phases);
+    cudaFree(kv.second->bwd[0].d_phases);
+    cudaFree(kv.second->bwd[1].d_phases);
   }
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
@@ -465,10 +463,10 @@ int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
   long long o;
   const long long B = batch;
   switch (what) {
-    case 0: o = bp->oY + stage * B * h->D; break;
-    case 1: o = bp->oL1 + stage * B * h->H; break;
-    case 2: o = bp->oL2 + stage * B * h->H; break;
-    case 3: o = bp->oO + stage * B * h->Dout; break;
+    case 0: o = bp->oYT + stage * B * h->D; break;
+    case 1: o = bp->oL1T + stage * B * h->H; break;
+    case 2: o = bp->oL2T + stage * B * h->H; break;
+    case 3: o = bp->oOT + stage * B * h->Dout; break;
     case 4: o = bp->oST + (long long)stage * 4 * h->H; break;
     default: return -1;
   }
@@ -513,7 +511,8 @@ int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {
     for (auto& kv : h->plans) {
       for (int d = 0; d < 2; ++d)
         for (int t = 0; t < 2; ++t) cudaFree(kv.second->fwd[d][t].d_phases);
-      cudaFree(kv.second->bwd.d_phases);
+      cudaFree(kv.second->bwd[0].d_phases);
+      cudaFree(kv.second->bwd[1].d_phases);
     }
     h->plans.clear();
   }
@@ -564,7 +563,7 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   a.dir = 0; a.train = 1;
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
-  return launch_program(h, bp->bwd, a, (cudaStream_t)stream);
+  return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -6,10 +6,13 @@
 // cooperative kernel (grid barrier between phases) or as one launch per phase.
 #pragma once
 #include "common.cuh"
-#include "gemm_tile.cuh"
+#include "tile_cp.cuh"
 
 namespace dpi {
 
+constexpr int kThreads = kNT;
+constexpr int kBM = kTM;
+constexpr int kBK = kTK;
 constexpr int kCtrlWords = 4096;  // barrier + error flag + split-K tile counters (uint32)
 
 // indices into StageTab::p - order == registration order of one AffineCoupling
@@ -27,15 +30,14 @@ struct StageTab {
 enum Op : int {
   OP_FWD_HID = 1,    // Linear + LeakyReLU (+ BatchNorm batch statistics)  net.0-2 / net.3-5
   OP_FWD_OUT,        // ZeroFC + tanh/exp affine coupling + ActNorm + logdet partials
-  OP_BN_STATS,       // batch statistics when the batch spans several row tiles
+  OP_BN_STATS,       // batch statistics + normalisation when the batch spans several row tiles
   OP_LOGDET_FINAL,   // deterministic reduction of logdet partials
-  OP_GATHER_OUT,     // trailing permutation of RealNVP.forward
+  OP_TRANSPOSE,      // sample-major <-> feature-major at the flow's boundary (+ trailing permutation)
   OP_B0,             // backward of ActNorm + coupling elementwise part
   OP_DGRAD_HID,      // dgrad through W3 / W2 (+ fused BatchNorm/LeakyReLU backward)
   OP_WGRAD,          // weight gradients
-  OP_DGRAD_IN,       // dgrad through W1 + scatter through the fused permutation
-  OP_BNBWD_STATS,    // BatchNorm backward column sums (large batch)
-  OP_BNBWD_APPLY,    // BatchNorm/LeakyReLU backward elementwise (large batch)
+  OP_DGRAD_IN,       // dgrad through W1, written through the fused permutation
+  OP_BNBWD,          // BatchNorm/LeakyReLU backward for large batches
   OP_BWD_FINAL       // ActNorm gradients from per-tile partials
 };
 
@@ -62,7 +64,7 @@ struct KArgs {
   int D, Da, Db, Dout, H, S, has_bn, B, tiles_m, dir, train;
   int ldp_tiles, red_tiles;
   // workspace layout (float offsets from W)
-  long long oY, oL1, oL2, oO, oST, oLDP, oGY, oGPRE, oGN, oGP1, oGP2, oPART, oRED;
+  long long oZT, oYT, oL1T, oL2T, oN1T, oN2T, oOT, oST, oLDP, oGYT, oGPRET, oGNT, oGP1T, oGP2T, oPART, oRED;
   // bases
   const float* P; float* G; float* R; float* W;
   const float* in; float* out; float* logdet;

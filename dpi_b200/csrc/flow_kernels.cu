@@ -1,10 +1,15 @@
-// flow_kernels.cu - device code of the RealNVP phase program (fp32 SIMT path).
+// flow_kernels.cu - device code of the RealNVP phase program (fp32 SIMT path, feature-major layout).
 //
 // Math follows generative_model/realnvpfc_model.py:
 //   AffineCoupling.reverse :240-249, .forward :222-231, net :171-187, ZeroFC :137-141,
 //   ActNorm.reverse :49-66, .forward :30-47, Flow.reverse :457-474, RealNVP.reverse :594-603.
-// The fixed permutations (:443,446,459,462,590,599) never run as separate gathers: each stage
-// reads its input through a fused index map and writes a contiguous output.
+//
+// Data layout in HBM: every activation / gradient of the flow is stored FEATURE-MAJOR,
+// X^T[feature][sample]. The fixed permutations of the flow (:443,446,459,462,590,599) then never
+// move data: a stage reads the previous stage's output ROWS through a fused index map (coalesced
+// 256-byte row reads instead of 4-byte gathers) and writes its own rows contiguously. BatchNorm
+// statistics are reductions along a row. Only the flow's input and output are sample-major
+// ([batch, ndim], the reference's layout); two transposes per pass convert.
 #include "flow.cuh"
 
 namespace dpi {
@@ -36,129 +41,49 @@ __device__ __forceinline__ void grid_sync(unsigned* ctrl, unsigned nblocks, unsi
   __syncthreads();
 }
 
-// ----------------------------------------------------------------------------- loaders
-// A operand of the forward hidden/output layers: rows = samples, k = input feature.
-//   value = src[m*ld + col(k)] * a_k + c_k
-// layer 1: col = fused permutation map, (a, c) = ActNorm pre-affine (forward direction) or (1, 0)
-// layer 2/3: col = k, (a_k, c_k) = BatchNorm affine from batch (train) or running (eval) statistics
-struct LdActRow {
-  static constexpr bool kContig = true;
-  const float* src; int ld; const int* idx; int m0, M, K;
-  int mode;  // 0: scalar affine, 1: per-k BatchNorm affine, 2: identity
-  float a, c;
-  const float *gamma, *beta, *mean, *rstd;  // mode 1 (rstd_is_var: eval mode passes running_var)
-  int rstd_is_var;
-  int col;
-  __device__ __forceinline__ void init() {}
-  __device__ __forceinline__ void ktile(int k0) {
-    const int k = k0 + (threadIdx.x % kBK);
-    if (k < K) {
-      col = idx ? __ldg(idx + k) : k;
-      if (mode == 1) {
-        float rs = rstd_is_var ? 1.f / sqrtf(ldcg(rstd + k) + kBnEps) : ldcg(rstd + k);
-        a = __ldg(gamma + k) * rs;
-        c = __ldg(beta + k) - ldcg(mean + k) * a;
-      }
-    } else {
-      col = 0;
-    }
-  }
-  __device__ __forceinline__ float operator()(int mm, int k) const {
-    const int m = m0 + mm;
-    if (m >= M || k >= K) return 0.f;
-    const float v = ldcg(src + (size_t)m * ld + col);
-    return mode == 2 ? v : fmaf(v, a, c);
-  }
-};
-
-// A operand of wgrad: rows = output features i, k = sample: value = g[k*ld + i]
-struct LdGradCol {
-  static constexpr bool kContig = false;
-  const float* g; int ld; int i0, I, K;
-  __device__ __forceinline__ void init() {}
-  __device__ __forceinline__ void ktile(int) {}
-  __device__ __forceinline__ float operator()(int mm, int k) const {
-    const int i = i0 + mm;
-    return (i < I && k < K) ? ldcg(g + (size_t)k * ld + i) : 0.f;
-  }
-};
-
-// B operand of wgrad: columns = input features j, k = sample:
-//   value = act[k*ld + col(j)] * a_j + c_j  (BatchNorm affine recomputed, or the permuted flow input)
-template <int BN>
-struct LdActCol {
-  static constexpr bool kContig = false;
-  const float* src; int ld; const int* idx; int j0, J, K;
-  int mode;  // 1: BatchNorm affine (batch statistics), 2: identity
-  const float *gamma, *beta, *mean, *rstd;
-  float a, c; int col; bool ok;
-  __device__ __forceinline__ void init() {
-    const int j = j0 + (threadIdx.x % BN);
-    ok = j < J;
-    a = 1.f; c = 0.f; col = 0;
-    if (ok) {
-      col = idx ? __ldg(idx + j) : j;
-      if (mode == 1) {
-        a = __ldg(gamma + j) * ldcg(rstd + j);
-        c = __ldg(beta + j) - ldcg(mean + j) * a;
-      }
-    }
-  }
-  __device__ __forceinline__ void ktile(int) {}
-  __device__ __forceinline__ float operator()(int, int k) const {
-    if (!ok || k >= K) return 0.f;
-    const float v = ldcg(src + (size_t)k * ld + col);
-    return mode == 2 ? v : fmaf(v, a, c);
-  }
-};
-
 // ----------------------------------------------------------------------------- addressing helpers
 struct Ctx {
   const KArgs& a;
   int e;                 // execution position
   const StageTab& st;
-  const int* gmap;       // fused gather map of this stage's input
+  const int* gmap;       // fused row map of this stage's input
+  bool vec;              // 16-byte accesses along the sample axis are legal
   __device__ Ctx(const KArgs& a_, int e_)
-      : a(a_), e(e_), st(a_.st[a_.dir ? a_.S - 1 - e_ : e_]), gmap(a_.gmaps + ((size_t)a_.dir * a_.S + e_) * a_.D) {}
-  __device__ __forceinline__ const float* yprev() const { return e == 0 ? a.in : a.W + a.oY + (size_t)(e - 1) * a.B * a.D; }
-  __device__ __forceinline__ float* y() const { return a.W + a.oY + (size_t)e * a.B * a.D; }
-  __device__ __forceinline__ float* L(int which) const {
-    return a.W + (which == 1 ? a.oL1 : a.oL2) + (size_t)e * a.B * a.H;
+      : a(a_), e(e_), st(a_.st[a_.dir ? a_.S - 1 - e_ : e_]),
+        gmap(a_.gmaps + ((size_t)a_.dir * a_.S + e_) * a_.D), vec((a_.B & 3) == 0) {}
+  __device__ __forceinline__ const float* yprev() const {
+    return e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * a.D * a.B;
   }
-  __device__ __forceinline__ float* O() const { return a.W + a.oO + (size_t)e * a.B * a.Dout; }
+  __device__ __forceinline__ float* y() const { return a.W + a.oYT + (size_t)e * a.D * a.B; }
+  __device__ __forceinline__ float* L(int which) const {
+    return a.W + (which == 1 ? a.oL1T : a.oL2T) + (size_t)e * a.H * a.B;
+  }
+  __device__ __forceinline__ float* Nrm(int which) const {
+    return a.W + (which == 1 ? a.oN1T : a.oN2T) + (size_t)e * a.H * a.B;
+  }
+  __device__ __forceinline__ float* O() const { return a.W + a.oOT + (size_t)e * a.Dout * a.B; }
   __device__ __forceinline__ float* stats(int which, int what) const {  // what: 0 mean, 1 rstd
     return a.W + a.oST + ((size_t)e * 4 + (which - 1) * 2 + what) * a.H;
   }
   __device__ __forceinline__ const float* P(int id) const { return a.P + st.p[id]; }
   __device__ __forceinline__ float* G(int id) const { return a.G + st.p[id]; }
-  // gradient wrt this stage's output / the buffer receiving the gradient wrt its input
-  __device__ __forceinline__ const float* gy() const {
-    return e == a.S - 1 ? a.g_out : a.W + a.oGY + (size_t)(e & 1) * a.B * a.D;
-  }
-  __device__ __forceinline__ float* gyprev() const {
-    return e == 0 ? a.g_in : a.W + a.oGY + (size_t)((e - 1) & 1) * a.B * a.D;
-  }
-  // ActNorm as pre-affine (forward direction) / post-affine (reverse direction)
-  __device__ __forceinline__ void affines(float& pre_a, float& pre_c, float& post_a, float& post_c) const {
-    const float lsi = __ldg(a.P + st.lsi), loc = __ldg(a.P + st.loc);
-    if (a.dir == 0) {  // reverse: y = w * exp(lsi) - loc               (:66)
-      pre_a = 1.f; pre_c = 0.f; post_a = expf(lsi); post_c = -loc;
-    } else {           // forward: v = (u + loc) / exp(lsi)             (:45)
-      const float inv = 1.0f / expf(lsi);
-      pre_a = inv; pre_c = loc * inv; post_a = 1.f; post_c = 0.f;
-    }
-  }
-  __device__ __forceinline__ void bn_loader(LdActRow& l, int which) const {
-    // A rows of layer which+1 = BatchNorm_which(LeakyReLU output)
-    l.src = L(which); l.ld = a.H; l.idx = nullptr; l.K = a.H;
-    if (!a.has_bn) { l.mode = 2; return; }
-    l.mode = 1;
-    l.gamma = P(which == 1 ? P_G1 : P_G2);
-    l.beta = P(which == 1 ? P_BE1 : P_BE2);
-    if (a.train) {
-      l.mean = stats(which, 0); l.rstd = stats(which, 1); l.rstd_is_var = 0;
+  __device__ __forceinline__ const float* gy() const { return a.W + a.oGYT + (size_t)(e & 1) * a.D * a.B; }
+  __device__ __forceinline__ float* gyprev() const { return a.W + a.oGYT + (size_t)((e - 1) & 1) * a.D * a.B; }
+  // Affine applied to this stage's coupling output before it is stored:
+  //   reverse: this stage's ActNorm.reverse, y = w * exp(lsi) - loc                              (:66)
+  //   forward: the NEXT stage's ActNorm.forward, v = (w + loc') / exp(lsi')                      (:45)
+  //            (scalar and elementwise, so it commutes with the permutation in between)
+  __device__ __forceinline__ void post_affine(float& qa, float& qc) const {
+    if (a.dir == 0) {
+      qa = expf(__ldg(a.P + st.lsi));
+      qc = -__ldg(a.P + st.loc);
+    } else if (e + 1 < a.S) {
+      const StageTab& nx = a.st[a.S - 2 - e];
+      const float inv = 1.0f / expf(__ldg(a.P + nx.lsi));
+      qa = inv;
+      qc = __ldg(a.P + nx.loc) * inv;
     } else {
-      l.mean = a.R + st.r[(which - 1) * 2]; l.rstd = a.R + st.r[(which - 1) * 2 + 1]; l.rstd_is_var = 1;
+      qa = 1.f; qc = 0.f;
     }
   }
 };
@@ -170,124 +95,165 @@ __device__ __forceinline__ void decode_tile(const SubOp& so, int t, int& tm, int
   tm = mn / so.tiles_n;
 }
 
+template <int TN>
+__device__ __forceinline__ void zero_acc(float (&acc)[4][TN]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+}
+
+// ----------------------------------------------------------------------------- transposes
+// 32 x 32 tiles through shared memory. mode (so.which):
+//   0 forward pass input : in [B][D]           -> ZT [D][B]   (forward direction: stage-0 ActNorm applied)
+//   1 backward pass input: g_out [B][D]        -> GYT[(S-1)&1] [D][B]
+//   2 reverse output     : YT[S-1] [D][B]      -> out [B][D]
+//   3 forward output     : YT[S-1][gf[j]][m]   -> out [B][D]  (trailing permutation :590 after :446)
+//   4 backward output    : GYT[1] [D][B]       -> g_in [B][D]
+__device__ __noinline__ void op_transpose(const KArgs& a, const SubOp& so, int t, float* sT) {
+  const int mode = so.which;
+  const bool to_fm = mode <= 1;            // sample-major -> feature-major
+  const int R = to_fm ? a.B : a.D;         // source rows
+  const int C = to_fm ? a.D : a.B;         // source cols
+  const float* src; float* dst; const int* map = nullptr;
+  float fa = 1.f, fc = 0.f;
+  if (mode == 0) {
+    src = a.in; dst = a.W + a.oZT;
+    if (a.dir == 1) {  // first ActNorm.forward of RealNVP.forward
+      const StageTab& s0 = a.st[a.S - 1];
+      const float inv = 1.0f / expf(__ldg(a.P + s0.lsi));
+      fa = inv; fc = __ldg(a.P + s0.loc) * inv;
+    }
+  } else if (mode == 1) {
+    src = a.g_out; dst = a.W + a.oGYT + (size_t)((a.S - 1) & 1) * a.D * a.B;
+  } else if (mode == 2 || mode == 3) {
+    src = a.W + a.oYT + (size_t)(a.S - 1) * a.D * a.B; dst = a.out;
+    if (mode == 3) map = a.gmaps + (size_t)2 * a.S * a.D;
+  } else {
+    src = a.W + a.oGYT + (size_t)1 * a.D * a.B; dst = a.g_in;
+  }
+  const int tiles_c = (C + 31) / 32;
+  const int tr = t / tiles_c, tc = t % tiles_c;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr * 32 + ly + 8 * i, c = tc * 32 + lx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      const int rr = map ? __ldg(map + r) : r;
+      v = __ldcg(src + (size_t)rr * C + c);
+    }
+    sT[(ly + 8 * i) * 33 + lx] = fmaf(v, fa, fc);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tc * 32 + ly + 8 * i, r = tr * 32 + lx;   // dst is [C][R]
+    if (r < R && c < C) __stcg(dst + (size_t)c * R + r, sT[lx * 33 + ly + 8 * i]);
+  }
+}
+
 // ----------------------------------------------------------------------------- forward ops
-// net.0/net.3 Linear + LeakyReLU(0.01) (+ BatchNorm1d batch statistics, eps 1e-2) :171-187
+// net.0 / net.3: Linear + LeakyReLU(0.01) (+ BatchNorm1d batch statistics, eps 1e-2) :171-187.
+// Output rows (features) n, columns (samples) m: L^T (saved for backward) and the normalised N^T.
 template <int BN>
-__device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB, float* sRed, int* sFlag) {
+__device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   int tm, tn, ks;
   decode_tile(so, t, tm, tn, ks);
   const int which = so.which;
   const int K = which == 1 ? a.Da : a.H;
-  LdActRow la;
-  la.m0 = tm * kBM; la.M = a.B;
-  if (which == 1) {
-    float pa, pc, qa, qc;
-    c.affines(pa, pc, qa, qc);
-    la.src = c.yprev(); la.ld = a.D; la.idx = c.gmap; la.K = K;
-    la.mode = (a.dir == 0) ? 2 : 0; la.a = pa; la.c = pc;
-  } else {
-    c.bn_loader(la, 1);
-  }
-  LdWeightK lb{c.P(which == 1 ? P_W1 : P_W2), K, tn * BN, a.H, 0, 0};
+  OperandA A{which == 1 ? c.yprev() : c.Nrm(1), a.B, which == 1 ? c.gmap : nullptr, tm * kTM, a.B, K, c.vec};
+  OperandB B{c.P(which == 1 ? P_W1 : P_W2), K, nullptr, tn * BN, a.H, K, (K & 3) == 0, 0, 0};
   float acc[4][TN];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  zero_acc<TN>(acc);
   const int kbeg = ks * so.kchunk, kend = min(K, kbeg + so.kchunk);
-  gemm_tile<BN>(acc, la, lb, kbeg, kend, sA, sB);
-  float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kBM * BN);
-  if (!splitk_reduce<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
+  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, kbeg, kend, smem);
+  float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
+  if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m = tm * kTM + tx * 4;
+  const int nvalid = a.B - m;  // rows of this thread that exist (may be <= 0)
   const float* bias = c.P(which == 1 ? P_B1 : P_B2);
-  float* Lout = c.L(which);
-  float psum[TN];
+  const bool fused = a.has_bn && a.train && a.tiles_m == 1;
+  const float invB = 1.0f / (float)a.B;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = tn * BN + j * 16 + tx;
-    const float bj = n < a.H ? __ldg(bias + n) : 0.f;
-    psum[j] = 0.f;
+    const int n = tn * BN + ty + 16 * j;
+    const bool okn = n < a.H;
+    const float bj = okn ? __ldg(bias + n) : 0.f;
+    float v[4], s = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      const float v = lrelu_f(acc[i][j] + bj);
-      acc[i][j] = v;
-      if (m < a.B && n < a.H) {
-        __stcg(Lout + (size_t)m * a.H + n, v);
-        psum[j] += v;
-      }
+      v[i] = lrelu_f(acc[i][j] + bj);
+      if (i < nvalid) s += v[i];
     }
-  }
-  if (!(a.has_bn && a.train && a.tiles_m == 1)) return;
-  // fused batch statistics: this CTA owns complete columns
-  float tot[TN], mean[TN], pvar[TN];
-  col_total<TN>(psum, tot, sRed, BN);
+    if (okn && nvalid > 0) store4(c.L(which) + (size_t)n * a.B + m, v, nvalid, c.vec);
+    float nv[4];
+    if (!a.has_bn) {
 #pragma unroll
-  for (int j = 0; j < TN; ++j) {
-    mean[j] = tot[j] / (float)a.B;
-    pvar[j] = 0.f;
-    const int n = tn * BN + j * 16 + tx;
+      for (int i = 0; i < 4; ++i) nv[i] = v[i];
+    } else if (fused) {
+      const float mean = col_sum16(s) * invB;
+      float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      if (m < a.B && n < a.H) {
-        const float d = acc[i][j] - mean[j];
-        pvar[j] = fmaf(d, d, pvar[j]);
-      }
-    }
-  }
-  col_total<TN>(pvar, tot, sRed, BN);
-  if (ty == 0) {
+      for (int i = 0; i < 4; ++i)
+        if (i < nvalid) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+      const float var = col_sum16(q) * invB;
+      const float rstd = 1.0f / sqrtf(var + kBnEps);
+      const float ga = okn ? __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) * rstd : 0.f;
+      const float be = okn ? __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n) : 0.f;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = tn * BN + j * 16 + tx;
-      if (n < a.H) {
-        const float var = tot[j] / (float)a.B;
-        __stcg(c.stats(which, 0) + n, mean[j]);
-        __stcg(c.stats(which, 1) + n, 1.0f / sqrtf(var + kBnEps));
+      for (int i = 0; i < 4; ++i) nv[i] = fmaf(v[i] - mean, ga, be);
+      if (tx == 0 && okn) {
+        __stcg(c.stats(which, 0) + n, mean);
+        __stcg(c.stats(which, 1) + n, rstd);
         float* rm = a.R + c.st.r[(which - 1) * 2] + n;
         float* rv = a.R + c.st.r[(which - 1) * 2 + 1] + n;
-        *rm = (1.f - kBnMomentum) * *rm + kBnMomentum * mean[j];
+        *rm = (1.f - kBnMomentum) * *rm + kBnMomentum * mean;
         *rv = (1.f - kBnMomentum) * *rv + kBnMomentum * (var * (float)a.B / (float)(a.B - 1));
       }
+    } else if (!a.train) {  // eval: running statistics
+      float ga = 0.f, be = 0.f;
+      if (okn) {
+        const float rs = 1.0f / sqrtf(a.R[c.st.r[(which - 1) * 2 + 1] + n] + kBnEps);
+        ga = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) * rs;
+        be = __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n) - a.R[c.st.r[(which - 1) * 2] + n] * ga;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nv[i] = fmaf(v[i], ga, be);
+    } else {
+      continue;  // large batch: statistics + normalisation in OP_BN_STATS
     }
+    if (okn && nvalid > 0) store4(c.Nrm(which) + (size_t)n * a.B + m, nv, nvalid, c.vec);
   }
 }
 
-// Batch statistics for batches spanning several row tiles: strip of 32 features, two passes.
-__device__ __noinline__ void op_bn_stats(const KArgs& a, int e, const SubOp& so, int t, float* sRed) {
+// Batch statistics + normalisation when the batch spans several row tiles: one warp per feature row.
+__device__ __noinline__ void op_bn_stats(const KArgs& a, int e, const SubOp& so, int t) {
   Ctx c(a, e);
   const int which = so.which;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = t * 32 + tx;
-  const float* Lp = c.L(which);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = t * 8 + w;
+  if (n >= a.H) return;
+  const float* row = c.L(which) + (size_t)n * a.B;
   float s = 0.f;
-  if (n < a.H)
-    for (int m = ty; m < a.B; m += 8) s += ldcg(Lp + (size_t)m * a.H + n);
-  __syncthreads();
-  sRed[ty * 32 + tx] = s;
-  __syncthreads();
-  float tot = 0.f;
-  for (int r = 0; r < 8; ++r) tot += sRed[r * 32 + tx];
-  const float mean = tot / (float)a.B;
+  for (int m = lane; m < a.B; m += 32) s += __ldcg(row + m);
+  const float mean = warp_sum(s) / (float)a.B;
   float q = 0.f;
-  if (n < a.H)
-    for (int m = ty; m < a.B; m += 8) {
-      const float d = ldcg(Lp + (size_t)m * a.H + n) - mean;
-      q = fmaf(d, d, q);
-    }
-  __syncthreads();
-  sRed[ty * 32 + tx] = q;
-  __syncthreads();
-  if (ty == 0 && n < a.H) {
-    float tq = 0.f;
-    for (int r = 0; r < 8; ++r) tq += sRed[r * 32 + tx];
-    const float var = tq / (float)a.B;
+  for (int m = lane; m < a.B; m += 32) { const float d = __ldcg(row + m) - mean; q = fmaf(d, d, q); }
+  const float var = warp_sum(q) / (float)a.B;
+  const float rstd = 1.0f / sqrtf(var + kBnEps);
+  const float ga = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) * rstd;
+  const float be = __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n);
+  float* out = c.Nrm(which) + (size_t)n * a.B;
+  for (int m = lane; m < a.B; m += 32) __stcg(out + m, fmaf(__ldcg(row + m) - mean, ga, be));
+  if (lane == 0) {
     __stcg(c.stats(which, 0) + n, mean);
-    __stcg(c.stats(which, 1) + n, 1.0f / sqrtf(var + kBnEps));
+    __stcg(c.stats(which, 1) + n, rstd);
     float* rm = a.R + c.st.r[(which - 1) * 2] + n;
     float* rv = a.R + c.st.r[(which - 1) * 2 + 1] + n;
     *rm = (1.f - kBnMomentum) * *rm + kBnMomentum * mean;
@@ -299,76 +265,70 @@ __device__ __noinline__ void op_bn_stats(const KArgs& a, int e, const SubOp& so,
 // The tile covers BJ = BN/2 coupling columns j and computes both log_s (row j of fc.weight) and
 // t (row Db + j) so the coupling is applied in registers.
 template <int BN>
-__device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB) {
+__device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, int t, float* smem, float* sRed) {
   constexpr int TN = BN / 16, BJ = BN / 2, TJ = TN / 2;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
-  LdActRow la;
-  la.m0 = tm * kBM; la.M = a.B;
-  c.bn_loader(la, 2);
-  LdWeightK lb{c.P(P_W3), a.H, tn * BJ, a.Dout, BJ, a.Db};
+  OperandA A{c.Nrm(2), a.B, nullptr, tm * kTM, a.B, a.H, c.vec};
+  OperandB B{c.P(P_W3), a.H, nullptr, tn * BJ, a.Dout, a.H, (a.H & 3) == 0, BJ, a.Db};
   float acc[4][TN];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  gemm_tile<BN>(acc, la, lb, 0, a.H, sA, sB);
+  zero_acc<TN>(acc);
+  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem);
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float pa, pc, qa, qc;
-  c.affines(pa, pc, qa, qc);
+  const int m = tm * kTM + tx * 4;
+  const int nvalid = a.B - m;
+  float qa, qc;
+  c.post_affine(qa, qc);
   const float* yp = c.yprev();
-  float* y = c.y();
-  float* O = c.O();
-  const bool last = (e == a.S - 1) && a.dir == 0;  // reverse: last stage output is the flow output
   float ld[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int jp = 0; jp < TJ; ++jp) {
-    const int col = tn * BJ + jp * 16 + tx;
-    if (col >= a.Db) continue;
+    const int col = tn * BJ + ty + 16 * jp;
+    if (col >= a.Db || nvalid <= 0) continue;
     const float e_ls = expf(3.f * __ldg(c.P(P_SCALE) + col));
     const float e_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
     const float b_ls = __ldg(c.P(P_B3) + col), b_t = __ldg(c.P(P_B3) + a.Db + col);
     const int gb = __ldg(c.gmap + a.Da + col), ga = __ldg(c.gmap + col);
+    float bv[4], av[4], ols[4], ot[4], yb[4], ya[4];
+    load4(yp + (size_t)gb * a.B + m, bv, nvalid, c.vec);
+    load4(yp + (size_t)ga * a.B + m, av, nvalid, c.vec);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      if (m >= a.B) continue;
-      const float o_ls = (acc[i][jp] + b_ls) * e_ls;
-      const float o_t = (acc[i][jp + TJ] + b_t) * e_t;
-      __stcg(O + (size_t)m * a.Dout + col, o_ls);
-      __stcg(O + (size_t)m * a.Dout + a.Db + col, o_t);
-      const float ls = tanhf(o_ls);
-      const float bv = fmaf(ldcg(yp + (size_t)m * a.D + gb), pa, pc);
-      const float av = fmaf(ldcg(yp + (size_t)m * a.D + ga), pa, pc);
+      ols[i] = (acc[i][jp] + b_ls) * e_ls;
+      ot[i] = (acc[i][jp + TJ] + b_t) * e_t;
+      const float ls = tanhf(ols[i]);
       float bp;
-      if (a.dir == 0) { bp = bv / expf(ls) - o_t; ld[i] -= ls; }
-      else            { bp = (bv + o_t) * expf(ls); ld[i] += ls; }
-      const float yb = fmaf(bp, qa, qc), ya = fmaf(av, qa, qc);
-      __stcg(y + (size_t)m * a.D + a.Da + col, yb);
-      __stcg(y + (size_t)m * a.D + col, ya);
-      if (last) { a.out[(size_t)m * a.D + a.Da + col] = yb; a.out[(size_t)m * a.D + col] = ya; }
+      if (a.dir == 0) { bp = bv[i] / expf(ls) - ot[i]; if (i < nvalid) ld[i] -= ls; }
+      else            { bp = (bv[i] + ot[i]) * expf(ls); if (i < nvalid) ld[i] += ls; }
+      yb[i] = fmaf(bp, qa, qc);
+      ya[i] = fmaf(av[i], qa, qc);
     }
+    store4(c.O() + (size_t)col * a.B + m, ols, nvalid, c.vec);
+    store4(c.O() + (size_t)(a.Db + col) * a.B + m, ot, nvalid, c.vec);
+    store4(c.y() + (size_t)(a.Da + col) * a.B + m, yb, nvalid, c.vec);
+    store4(c.y() + (size_t)col * a.B + m, ya, nvalid, c.vec);
   }
-  // odd D: the a-half has one more column than the b-half (chunk(2,1) semantics, :241)
-  if (a.Da > a.Db && tn == 0 && tx == 0) {
+  // odd D: the a-half has one more row than the b-half (chunk(2,1) semantics, :241)
+  if (a.Da > a.Db && tn == 0 && ty == 0 && nvalid > 0) {
     const int col = a.Da - 1;
-    const int ga = __ldg(c.gmap + col);
+    float av[4], ya[4];
+    load4(yp + (size_t)__ldg(c.gmap + col) * a.B + m, av, nvalid, c.vec);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      if (m >= a.B) continue;
-      const float ya = fmaf(fmaf(ldcg(yp + (size_t)m * a.D + ga), pa, pc), qa, qc);
-      __stcg(y + (size_t)m * a.D + col, ya);
-      if (last) a.out[(size_t)m * a.D + col] = ya;
-    }
+    for (int i = 0; i < 4; ++i) ya[i] = fmaf(av[i], qa, qc);
+    store4(c.y() + (size_t)col * a.B + m, ya, nvalid, c.vec);
   }
-  float* ldp = a.W + a.oLDP + ((size_t)e * a.ldp_tiles + tn) * a.B;
+  // per-sample logdet partial of this column tile: sum over the 16 column groups in fixed order
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float s = half_warp_sum(ld[i]);
-    const int m = tm * kBM + ty * 4 + i;
-    if (tx == 0 && m < a.B) __stcg(ldp + m, s);
+  for (int i = 0; i < 4; ++i) sRed[ty * 64 + tx * 4 + i] = ld[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s += sRed[r * 64 + threadIdx.x];
+    const int mm = tm * kTM + threadIdx.x;
+    if (mm < a.B) __stcg(a.W + a.oLDP + ((size_t)e * a.ldp_tiles + tn) * a.B + mm, s);
   }
 }
 
@@ -406,92 +366,72 @@ __device__ __noinline__ void op_logdet_final(const KArgs& a, int t, float* sRed)
   }
 }
 
-// RealNVP.forward ends with out[:, orders[-1]] after the last flip (:590 after :446)
-__device__ __noinline__ void op_gather_out(const KArgs& a, int t) {
-  const size_t i = (size_t)t * kThreads + threadIdx.x;
-  if (i >= (size_t)a.B * a.D) return;
-  const int m = (int)(i / a.D), j = (int)(i % a.D);
-  const int* gf = a.gmaps + (size_t)2 * a.S * a.D;  // trailing map is appended after both tables
-  const float* ylast = a.W + a.oY + (size_t)(a.S - 1) * a.B * a.D;
-  a.out[i] = ldcg(ylast + (size_t)m * a.D + __ldg(gf + j));
-}
-
 // ----------------------------------------------------------------------------- backward ops
-// Elementwise backward of ActNorm.reverse and the coupling tail for a strip of 32 coupling
-// columns. Produces g_pre (gradient wrt ZeroFC's linear output), the
-// gradients of net.6.scale / net.6.fc.bias, the b-half of the gradient wrt the stage input, and
-// per-strip partials of the ActNorm gradients.
+// Elementwise backward of ActNorm.reverse and the coupling tail, one warp per coupling column
+// (SURVEY Appendix A). Produces g_pre^T (gradient wrt ZeroFC's linear output), the gradients of
+// net.6.scale / net.6.fc.bias, the b-half rows of the gradient wrt the stage input, and per-tile
+// partials of the ActNorm gradients.
 __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t, float* sRed) {
   Ctx c(a, e);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = t * 32 + tx;
-  const bool ok = col < a.Db;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = t * 8 + w;
   const float lsi = __ldg(a.P + c.st.lsi), loc = __ldg(a.P + c.st.loc);
   const float e_lsi = expf(lsi);
-  const float* gy = c.gy();
-  const float* y = c.y();
-  const float* O = c.O();
-  const float* yp = c.yprev();
-  float* gpre = a.W + a.oGPRE;
-  float* dst = c.gyprev();
-  float E_ls = 0.f, E_t = 0.f;
-  int gcol = 0;
-  if (ok) {
-    E_ls = expf(3.f * __ldg(c.P(P_SCALE) + col));
-    E_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
-    gcol = __ldg(c.gmap + a.Da + col);
-  }
-  float sc_ls = 0.f, sc_t = 0.f, b3_ls = 0.f, b3_t = 0.f, S1 = 0.f, S2 = 0.f;
-  if (ok) {
-    for (int m = ty; m < a.B; m += 8) {
-      const size_t r = (size_t)m * a.D;
-      const float gya = ldcg(gy + r + col), gyb = ldcg(gy + r + a.Da + col);
-      const float ya = ldcg(y + r + col), yb = ldcg(y + r + a.Da + col);
-      S1 += gya + gyb;
-      S2 += gya * (ya + loc) + gyb * (yb + loc);
-      const float gbp = gyb * e_lsi;
-      const float o_ls = ldcg(O + (size_t)m * a.Dout + col), o_t = ldcg(O + (size_t)m * a.Dout + a.Db + col);
+  const size_t B = a.B;
+  float S1 = 0.f, S2 = 0.f;
+  if (col < a.Db) {
+    const float E_ls = expf(3.f * __ldg(c.P(P_SCALE) + col));
+    const float E_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
+    const int gcol = __ldg(c.gmap + a.Da + col);
+    const float* gya = c.gy() + (size_t)col * B;
+    const float* gyb = c.gy() + (size_t)(a.Da + col) * B;
+    const float* ya = c.y() + (size_t)col * B;
+    const float* yb = c.y() + (size_t)(a.Da + col) * B;
+    const float* ols = c.O() + (size_t)col * B;
+    const float* ot = c.O() + (size_t)(a.Db + col) * B;
+    const float* bp = c.yprev() + (size_t)gcol * B;
+    float* gp_ls = a.W + a.oGPRET + (size_t)col * B;
+    float* gp_t = a.W + a.oGPRET + (size_t)(a.Db + col) * B;
+    float* dst = c.gyprev() + (size_t)gcol * B;
+    float sc_ls = 0.f, sc_t = 0.f, b3_ls = 0.f, b3_t = 0.f;
+    for (int m = lane; m < a.B; m += 32) {
+      const float ga_ = __ldcg(gya + m), gb_ = __ldcg(gyb + m);
+      S1 += ga_ + gb_;
+      S2 += ga_ * (__ldcg(ya + m) + loc) + gb_ * (__ldcg(yb + m) + loc);
+      const float gbp = gb_ * e_lsi;
+      const float o_ls = __ldcg(ols + m), o_t = __ldcg(ot + m);
       const float ls = tanhf(o_ls);
       const float ei = 1.0f / expf(ls);
-      const float b = ldcg(yp + r + gcol);
-      const float g_b = gbp * ei;
+      const float b = __ldcg(bp + m);
       const float g_t = -gbp;
-      const float g_ls = -gbp * b * ei - ldcg(a.g_ld + m);
+      const float g_ls = -gbp * b * ei - __ldcg(a.g_ld + m);
       const float g_ols = g_ls * (1.f - ls * ls);
-      const float gp_ls = g_ols * E_ls, gp_t = g_t * E_t;
-      __stcg(gpre + (size_t)m * a.Dout + col, gp_ls);
-      __stcg(gpre + (size_t)m * a.Dout + a.Db + col, gp_t);
+      const float v_ls = g_ols * E_ls, v_t = g_t * E_t;
+      __stcg(gp_ls + m, v_ls);
+      __stcg(gp_t + m, v_t);
       sc_ls += 3.f * g_ols * o_ls;
       sc_t += 3.f * g_t * o_t;
-      b3_ls += gp_ls;
-      b3_t += gp_t;
-      if (dst) __stcg(dst + r + gcol, g_b);
+      b3_ls += v_ls;
+      b3_t += v_t;
+      __stcg(dst + m, gbp * ei);
+    }
+    sc_ls = warp_sum(sc_ls); sc_t = warp_sum(sc_t); b3_ls = warp_sum(b3_ls); b3_t = warp_sum(b3_t);
+    if (lane == 0) {
+      c.G(P_SCALE)[col] = sc_ls; c.G(P_SCALE)[a.Db + col] = sc_t;
+      c.G(P_B3)[col] = b3_ls;    c.G(P_B3)[a.Db + col] = b3_t;
     }
   }
-  if (a.Da > a.Db && t == 0) {  // odd D: last a-column contributes to the ActNorm sums
-    const int ca = a.Da - 1;
+  if (a.Da > a.Db && t == 0) {  // odd D: last a-row contributes to the ActNorm sums
+    const float* g = c.gy() + (size_t)(a.Da - 1) * B;
+    const float* yv = c.y() + (size_t)(a.Da - 1) * B;
     for (int m = threadIdx.x; m < a.B; m += kThreads) {
-      const float g = ldcg(gy + (size_t)m * a.D + ca);
-      S1 += g;
-      S2 += g * (ldcg(y + (size_t)m * a.D + ca) + loc);
+      const float gv = __ldcg(g + m);
+      S1 += gv;
+      S2 += gv * (__ldcg(yv + m) + loc);
     }
   }
-  // column sums over the 8 row lanes
-  float vals[4] = {sc_ls, sc_t, b3_ls, b3_t};
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) sRed[(q * 8 + ty) * 32 + tx] = vals[q];
-  __syncthreads();
-  if (ty < 4 && ok) {
-    float s = 0.f;
-    for (int r = 0; r < 8; ++r) s += sRed[(ty * 8 + r) * 32 + tx];
-    if (ty == 0) c.G(P_SCALE)[col] = s;
-    else if (ty == 1) c.G(P_SCALE)[a.Db + col] = s;
-    else if (ty == 2) c.G(P_B3)[col] = s;
-    else c.G(P_B3)[a.Db + col] = s;
-  }
-  const float t1 = block_sum(S1, sRed + 1024);
-  const float t2 = block_sum(S2, sRed + 1024 + 64);
+  const float t1 = block_sum(S1, sRed);
+  const float t2 = block_sum(S2, sRed + 64);
   if (threadIdx.x == 0) {
     float* red = a.W + a.oRED + ((size_t)e * a.red_tiles + t) * 2;
     __stcg(red, t1);
@@ -499,250 +439,188 @@ __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t
   }
 }
 
-// BatchNorm1d + LeakyReLU backward applied to a column-complete tile held in registers.
-// gn = dL/d(BN output); returns g_p = dL/d(pre-activation) in acc and writes the BN and bias grads.
+// dgrad through fc.weight (which=2: K = Dout, source g_pre^T) or net.3.weight (which=1: K = H, source
+// g_p2^T); result = gradient wrt the BatchNorm output of hidden layer `which`, with the BatchNorm +
+// LeakyReLU backward fused when this CTA owns complete feature rows (batch <= 64).
 template <int BN>
-__device__ __forceinline__ void bn_lrelu_bwd_tile(const KArgs& a, const Ctx& c, int which, int tm, int tn,
-                                                  float (&acc)[4][BN / 16], float* sRed) {
-  constexpr int TN = BN / 16;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const float* Lp = c.L(which);
-  float l[4][TN], xh[4][TN];
-  float mean[TN], rstd[TN], gam[TN];
-  float p1[TN], p2[TN];
-#pragma unroll
-  for (int j = 0; j < TN; ++j) {
-    const int n = tn * BN + j * 16 + tx;
-    const bool okn = n < a.H;
-    mean[j] = (okn && a.has_bn) ? ldcg(c.stats(which, 0) + n) : 0.f;
-    rstd[j] = (okn && a.has_bn) ? ldcg(c.stats(which, 1) + n) : 1.f;
-    gam[j] = (okn && a.has_bn) ? __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) : 1.f;
-    p1[j] = 0.f; p2[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      const bool ok = okn && m < a.B;
-      l[i][j] = ok ? ldcg(Lp + (size_t)m * a.H + n) : 0.f;
-      xh[i][j] = (l[i][j] - mean[j]) * rstd[j];
-      if (!ok) acc[i][j] = 0.f;
-      p1[j] += acc[i][j];
-      p2[j] = fmaf(acc[i][j], xh[i][j], p2[j]);
-    }
-  }
-  float gbeta[TN], ggamma[TN], p3[TN], gbias[TN];
-  if (a.has_bn) {
-    col_total<TN>(p1, gbeta, sRed, BN);
-    col_total<TN>(p2, ggamma, sRed, BN);
-  }
-  const float invB = 1.0f / (float)a.B;
-#pragma unroll
-  for (int j = 0; j < TN; ++j) {
-    p3[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      const int n = tn * BN + j * 16 + tx;
-      float gl = acc[i][j];
-      if (a.has_bn) gl = gam[j] * rstd[j] * (acc[i][j] - gbeta[j] * invB - xh[i][j] * ggamma[j] * invB);
-      const float gp = (m < a.B && n < a.H) ? gl * (l[i][j] > 0.f ? 1.f : kLreluSlope) : 0.f;
-      acc[i][j] = gp;
-      p3[j] += gp;
-    }
-  }
-  col_total<TN>(p3, gbias, sRed, BN);
-  if (ty == 0) {
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = tn * BN + j * 16 + tx;
-      if (n < a.H) {
-        if (a.has_bn) {
-          c.G(which == 1 ? P_G1 : P_G2)[n] = ggamma[j];
-          c.G(which == 1 ? P_BE1 : P_BE2)[n] = gbeta[j];
-        }
-        c.G(which == 1 ? P_B1 : P_B2)[n] = gbias[j];
-      }
-    }
-  }
-}
-
-// dgrad through fc.weight (which=2: K = Dout, source g_pre) or net.3.weight (which=1: K = H, source
-// g_p2); result = gradient wrt the BatchNorm output of hidden layer `which`.
-template <int BN>
-__device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB, float* sRed, int* sFlag) {
+__device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   int tm, tn, ks;
   decode_tile(so, t, tm, tn, ks);
   const int which = so.which;
   const int K = which == 2 ? a.Dout : a.H;
-  LdGradRow la{which == 2 ? a.W + a.oGPRE : a.W + a.oGP2, K, tm * kBM, a.B, K};
-  LdWeightN lb{c.P(which == 2 ? P_W3 : P_W2), a.H, tn * BN, a.H, K};
+  OperandA A{a.W + (which == 2 ? a.oGPRET : a.oGP2T), a.B, nullptr, tm * kTM, a.B, K, c.vec};
+  OperandB B{c.P(which == 2 ? P_W3 : P_W2), a.H, nullptr, tn * BN, a.H, K, (a.H & 3) == 0, 0, 0};
   float acc[4][TN];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  zero_acc<TN>(acc);
   const int kbeg = ks * so.kchunk, kend = min(K, kbeg + so.kchunk);
-  gemm_tile<BN>(acc, la, lb, kbeg, kend, sA, sB);
-  float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kBM * BN);
-  if (!splitk_reduce<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
+  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, kbeg, kend, smem);
+  float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
+  if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
+
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float* dst;
-  if (a.tiles_m == 1) {
-    bn_lrelu_bwd_tile<BN>(a, c, which, tm, tn, acc, sRed);
-    dst = a.W + (which == 2 ? a.oGP2 : a.oGP1);
-  } else {
-    dst = a.W + a.oGN;
-  }
+  const int m = tm * kTM + tx * 4;
+  const int nvalid = a.B - m;
+  const float invB = 1.0f / (float)a.B;
+  const bool fused = a.tiles_m == 1;
+  float* dstbuf = a.W + (fused ? (which == 2 ? a.oGP2T : a.oGP1T) : a.oGNT);
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = tn * BN + j * 16 + tx;
+    const int n = tn * BN + ty + 16 * j;
+    const bool okn = n < a.H;
+    float g[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      if (m < a.B && n < a.H) __stcg(dst + (size_t)m * a.H + n, acc[i][j]);
+    for (int i = 0; i < 4; ++i) g[i] = (i < nvalid && okn) ? acc[i][j] : 0.f;
+    if (fused) {
+      float l[4] = {0.f, 0.f, 0.f, 0.f};
+      if (okn && nvalid > 0) load4(c.L(which) + (size_t)n * a.B + m, l, nvalid, c.vec);
+      float gam = 1.f, rstd = 1.f, mean = 0.f, gbeta = 0.f, ggamma = 0.f;
+      float xh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.has_bn) {
+        if (okn) {
+          mean = __ldcg(c.stats(which, 0) + n); rstd = __ldcg(c.stats(which, 1) + n);
+          gam = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n);
+        }
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[i] = (l[i] - mean) * rstd;
+          p1 += g[i];
+          p2 = fmaf(g[i], xh[i], p2);
+        }
+        gbeta = col_sum16(p1);
+        ggamma = col_sum16(p2);
+      }
+      float p3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float gl = g[i];
+        if (a.has_bn) gl = gam * rstd * (g[i] - gbeta * invB - xh[i] * ggamma * invB);
+        g[i] = (i < nvalid && okn) ? gl * (l[i] > 0.f ? 1.f : kLreluSlope) : 0.f;
+        p3 += g[i];
+      }
+      const float gbias = col_sum16(p3);
+      if (tx == 0 && okn) {
+        if (a.has_bn) {
+          c.G(which == 1 ? P_G1 : P_G2)[n] = ggamma;
+          c.G(which == 1 ? P_BE1 : P_BE2)[n] = gbeta;
+        }
+        c.G(which == 1 ? P_B1 : P_B2)[n] = gbias;
+      }
     }
+    if (okn && nvalid > 0) store4(dstbuf + (size_t)n * a.B + m, g, nvalid, c.vec);
   }
 }
 
-// Large-batch BatchNorm backward, step 1: g_beta = sum_m g_n, g_gamma = sum_m g_n * xhat (strip of 32)
-__device__ __noinline__ void op_bnbwd_stats(const KArgs& a, int e, const SubOp& so, int t, float* sRed) {
+// Large-batch BatchNorm + LeakyReLU backward: one warp per feature row (stats pass, then apply pass).
+__device__ __noinline__ void op_bnbwd(const KArgs& a, int e, const SubOp& so, int t) {
   Ctx c(a, e);
   const int which = so.which;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = t * 32 + tx;
-  const float* gn = a.W + a.oGN;
-  const float* Lp = c.L(which);
-  float s1 = 0.f, s2 = 0.f;
-  if (n < a.H) {
-    const float mean = ldcg(c.stats(which, 0) + n), rstd = ldcg(c.stats(which, 1) + n);
-    for (int m = ty; m < a.B; m += 8) {
-      const float g = ldcg(gn + (size_t)m * a.H + n);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = t * 8 + w;
+  if (n >= a.H) return;
+  const float* gn = a.W + a.oGNT + (size_t)n * a.B;
+  const float* lr = c.L(which) + (size_t)n * a.B;
+  float* gp = a.W + (which == 2 ? a.oGP2T : a.oGP1T) + (size_t)n * a.B;
+  float mean = 0.f, rstd = 1.f, gam = 1.f, gbeta = 0.f, ggamma = 0.f;
+  if (a.has_bn) {
+    mean = __ldcg(c.stats(which, 0) + n); rstd = __ldcg(c.stats(which, 1) + n);
+    gam = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n);
+    float s1 = 0.f, s2 = 0.f;
+    for (int m = lane; m < a.B; m += 32) {
+      const float g = __ldcg(gn + m);
       s1 += g;
-      s2 = fmaf(g, (ldcg(Lp + (size_t)m * a.H + n) - mean) * rstd, s2);
+      s2 = fmaf(g, (__ldcg(lr + m) - mean) * rstd, s2);
     }
+    gbeta = warp_sum(s1);
+    ggamma = warp_sum(s2);
   }
-  __syncthreads();
-  sRed[ty * 32 + tx] = s1;
-  sRed[256 + ty * 32 + tx] = s2;
-  __syncthreads();
-  if (ty < 2 && n < a.H) {
-    float s = 0.f;
-    for (int r = 0; r < 8; ++r) s += sRed[ty * 256 + r * 32 + tx];
-    if (ty == 0) c.G(which == 1 ? P_BE1 : P_BE2)[n] = s;
-    else c.G(which == 1 ? P_G1 : P_G2)[n] = s;
+  const float invB = 1.0f / (float)a.B;
+  float s3 = 0.f;
+  for (int m = lane; m < a.B; m += 32) {
+    const float g = __ldcg(gn + m), l = __ldcg(lr + m);
+    float gl = g;
+    if (a.has_bn) gl = gam * rstd * (g - gbeta * invB - (l - mean) * rstd * ggamma * invB);
+    const float v = gl * (l > 0.f ? 1.f : kLreluSlope);
+    __stcg(gp + m, v);
+    s3 += v;
   }
-}
-
-// Large-batch step 2: g_p = BN/LeakyReLU backward elementwise, bias gradient = column sum
-__device__ __noinline__ void op_bnbwd_apply(const KArgs& a, int e, const SubOp& so, int t, float* sRed) {
-  Ctx c(a, e);
-  const int which = so.which;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = t * 32 + tx;
-  const float* gn = a.W + a.oGN;
-  const float* Lp = c.L(which);
-  float* gp = a.W + (which == 2 ? a.oGP2 : a.oGP1);
-  float s = 0.f;
-  if (n < a.H) {
-    float mean = 0.f, rstd = 1.f, gam = 1.f, gbeta = 0.f, ggamma = 0.f;
+  s3 = warp_sum(s3);
+  if (lane == 0) {
     if (a.has_bn) {
-      mean = ldcg(c.stats(which, 0) + n); rstd = ldcg(c.stats(which, 1) + n);
-      gam = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n);
-      gbeta = ldcg(c.G(which == 1 ? P_BE1 : P_BE2) + n);
-      ggamma = ldcg(c.G(which == 1 ? P_G1 : P_G2) + n);
+      c.G(which == 1 ? P_G1 : P_G2)[n] = ggamma;
+      c.G(which == 1 ? P_BE1 : P_BE2)[n] = gbeta;
     }
-    const float invB = 1.0f / (float)a.B;
-    for (int m = ty; m < a.B; m += 8) {
-      const float g = ldcg(gn + (size_t)m * a.H + n);
-      const float l = ldcg(Lp + (size_t)m * a.H + n);
-      float gl = g;
-      if (a.has_bn) gl = gam * rstd * (g - gbeta * invB - (l - mean) * rstd * ggamma * invB);
-      const float v = gl * (l > 0.f ? 1.f : kLreluSlope);
-      __stcg(gp + (size_t)m * a.H + n, v);
-      s += v;
-    }
-  }
-  __syncthreads();
-  sRed[ty * 32 + tx] = s;
-  __syncthreads();
-  if (ty == 0 && n < a.H) {
-    float tsum = 0.f;
-    for (int r = 0; r < 8; ++r) tsum += sRed[r * 32 + tx];
-    c.G(which == 1 ? P_B1 : P_B2)[n] = tsum;
+    c.G(which == 1 ? P_B1 : P_B2)[n] = s3;
   }
 }
 
-// Weight gradients: gW[i, j] = sum_m g[m, i] * act[m, j]  (which = 3: fc.weight, 2: net.3, 1: net.0)
+// Weight gradients gW[i][j] = sum_m g^T[i][m] * act^T[j][m]  (which = 3: fc.weight, 2: net.3, 1: net.0).
+// GEMM rows = j (the contiguous axis of gW -> float4 stores), GEMM columns = i, GEMM k = sample.
 template <int BN>
-__device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB) {
+__device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, int t, float* smem) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
   const int which = so.which;
   const int I = which == 3 ? a.Dout : a.H;
   const int J = which == 1 ? a.Da : a.H;
-  const float* gsrc = a.W + (which == 3 ? a.oGPRE : which == 2 ? a.oGP2 : a.oGP1);
-  LdGradCol la{gsrc, which == 3 ? a.Dout : a.H, tm * kBM, I, a.B};
-  LdActCol<BN> lb;
-  lb.j0 = tn * BN; lb.J = J; lb.K = a.B;
-  if (which == 1) {
-    lb.src = c.yprev(); lb.ld = a.D; lb.idx = c.gmap; lb.mode = 2;
-  } else {
-    const int hl = which - 1;  // BatchNorm layer feeding this Linear
-    lb.src = c.L(hl); lb.ld = a.H; lb.idx = nullptr; lb.mode = a.has_bn ? 1 : 2;
-    lb.gamma = c.P(hl == 1 ? P_G1 : P_G2); lb.beta = c.P(hl == 1 ? P_BE1 : P_BE2);
-    lb.mean = c.stats(hl, 0); lb.rstd = c.stats(hl, 1);
-  }
+  const float* act = which == 1 ? c.yprev() : c.Nrm(which - 1);
+  const float* gsrc = a.W + (which == 3 ? a.oGPRET : which == 2 ? a.oGP2T : a.oGP1T);
+  OperandA A{act, a.B, which == 1 ? c.gmap : nullptr, tm * kTM, J, a.B, false};
+  OperandB B{gsrc, a.B, nullptr, tn * BN, I, a.B, c.vec, 0, 0};
   float acc[4][TN];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  gemm_tile<BN>(acc, la, lb, 0, a.B, sA, sB);
+  zero_acc<TN>(acc);
+  tile_gemm<BN, A_KCONTIG, B_KCONTIG>(acc, A, B, 0, a.B, smem);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j0 = tm * kTM + tx * 4;
+  const int nvalid = J - j0;
+  if (nvalid <= 0) return;
   float* gw = c.G(which == 3 ? P_W3 : which == 2 ? P_W2 : P_W1);
+  const bool vecw = (J & 3) == 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = tm * kBM + ty * 4 + i;
+  for (int j = 0; j < TN; ++j) {
+    const int i = tn * BN + ty + 16 * j;
+    if (i >= I) continue;
+    const float v[4] = {acc[0][j], acc[1][j], acc[2][j], acc[3][j]};
+    float* p = gw + (size_t)i * J + j0;
+    if (vecw && nvalid >= 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int col = tn * BN + j * 16 + tx;
-      if (r < I && col < J) gw[(size_t)r * J + col] = acc[i][j];
+      for (int u = 0; u < 4; ++u)
+        if (u < nvalid) p[u] = v[u];
     }
   }
 }
 
-// dgrad through net.0.weight, plus the direct path through the a-half and ActNorm, scattered
-// through the fused permutation into the gradient wrt the previous stage's output.
+// dgrad through net.0.weight, plus the direct path through the a-half and ActNorm, written through
+// the fused permutation into the rows of the gradient wrt the previous stage's output.
 template <int BN>
-__device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB) {
+__device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so, int t, float* smem) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
-  LdGradRow la{a.W + a.oGP1, a.H, tm * kBM, a.B, a.H};
-  LdWeightN lb{c.P(P_W1), a.Da, tn * BN, a.Da, a.H};
+  OperandA A{a.W + a.oGP1T, a.B, nullptr, tm * kTM, a.B, a.H, c.vec};
+  OperandB B{c.P(P_W1), a.Da, nullptr, tn * BN, a.Da, a.H, (a.Da & 3) == 0, 0, 0};
   float acc[4][TN];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  gemm_tile<BN>(acc, la, lb, 0, a.H, sA, sB);
-  float* dst = c.gyprev();
-  if (!dst) return;
+  zero_acc<TN>(acc);
+  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m = tm * kTM + tx * 4;
+  const int nvalid = a.B - m;
+  if (nvalid <= 0) return;
   const float e_lsi = expf(__ldg(a.P + c.st.lsi));
-  const float* gy = c.gy();
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = tn * BN + j * 16 + tx;
+    const int n = tn * BN + ty + 16 * j;
     if (n >= a.Da) continue;
-    const int g = __ldg(c.gmap + n);
+    float gy[4], gu[4];
+    load4(c.gy() + (size_t)n * a.B + m, gy, nvalid, c.vec);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = tm * kBM + ty * 4 + i;
-      if (m < a.B) __stcg(dst + (size_t)m * a.D + g, fmaf(ldcg(gy + (size_t)m * a.D + n), e_lsi, acc[i][j]));
-    }
+    for (int i = 0; i < 4; ++i) gu[i] = fmaf(gy[i], e_lsi, acc[i][j]);
+    store4(c.gyprev() + (size_t)__ldg(c.gmap + n) * a.B + m, gu, nvalid, c.vec);
   }
 }
 
@@ -763,13 +641,12 @@ __device__ __noinline__ void op_bwd_final(const KArgs& a, float* sRed) {
 
 // ----------------------------------------------------------------------------- dispatcher
 template <int BN>
-__device__ __forceinline__ void run_gemm_op(const KArgs& a, int e, const SubOp& so, int t, float* sA, float* sB,
-                                            float* sRed, int* sFlag) {
+__device__ __forceinline__ void run_gemm_op(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
   switch (so.op) {
-    case OP_FWD_HID: op_fwd_hid<BN>(a, e, so, t, sA, sB, sRed, sFlag); break;
-    case OP_DGRAD_HID: op_dgrad_hid<BN>(a, e, so, t, sA, sB, sRed, sFlag); break;
-    case OP_WGRAD: op_wgrad<BN>(a, e, so, t, sA, sB); break;
-    case OP_DGRAD_IN: op_dgrad_in<BN>(a, e, so, t, sA, sB); break;
+    case OP_FWD_HID: op_fwd_hid<BN>(a, e, so, t, smem, sFlag); break;
+    case OP_DGRAD_HID: op_dgrad_hid<BN>(a, e, so, t, smem, sFlag); break;
+    case OP_WGRAD: op_wgrad<BN>(a, e, so, t, smem); break;
+    case OP_DGRAD_IN: op_dgrad_in<BN>(a, e, so, t, smem); break;
     default: break;
   }
 }
@@ -778,8 +655,7 @@ constexpr int kSmemPhases = 136;   // programs up to this many phases are staged
 constexpr int kSmemStages = 64;
 
 __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
-  __shared__ float sA[kBM * (kBK + 1)];
-  __shared__ float sB[64 * (kBK + 1)];
+  extern __shared__ __align__(16) float smem[];   // kTileSmemBytes: cp.async ring (also transpose scratch)
   __shared__ float sRed[1024 + 128];
   __shared__ int sFlag;
   __shared__ __align__(16) Phase sPh[kSmemPhases];
@@ -813,20 +689,19 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
       const int t = tt < n0 ? tt : tt - n0;
       switch (so.op) {
         case OP_FWD_OUT:
-          if (so.bn == 64) op_fwd_out<64>(a, ph.stage, so, t, sA, sB);
-          else op_fwd_out<32>(a, ph.stage, so, t, sA, sB);
+          if (so.bn == 64) op_fwd_out<64>(a, ph.stage, so, t, smem, sRed);
+          else op_fwd_out<32>(a, ph.stage, so, t, smem, sRed);
           break;
-        case OP_BN_STATS: op_bn_stats(a, ph.stage, so, t, sRed); break;
+        case OP_TRANSPOSE: op_transpose(a, so, t, smem); break;
+        case OP_BN_STATS: op_bn_stats(a, ph.stage, so, t); break;
         case OP_LOGDET_FINAL: op_logdet_final(a, t, sRed); break;
-        case OP_GATHER_OUT: op_gather_out(a, t); break;
         case OP_B0: op_b0(a, ph.stage, so, t, sRed); break;
-        case OP_BNBWD_STATS: op_bnbwd_stats(a, ph.stage, so, t, sRed); break;
-        case OP_BNBWD_APPLY: op_bnbwd_apply(a, ph.stage, so, t, sRed); break;
+        case OP_BNBWD: op_bnbwd(a, ph.stage, so, t); break;
         case OP_BWD_FINAL: op_bwd_final(a, sRed); break;
         default:
-          if (so.bn == 64) run_gemm_op<64>(a, ph.stage, so, t, sA, sB, sRed, &sFlag);
-          else if (so.bn == 32) run_gemm_op<32>(a, ph.stage, so, t, sA, sB, sRed, &sFlag);
-          else run_gemm_op<16>(a, ph.stage, so, t, sA, sB, sRed, &sFlag);
+          if (so.bn == 64) run_gemm_op<64>(a, ph.stage, so, t, smem, &sFlag);
+          else if (so.bn == 32) run_gemm_op<32>(a, ph.stage, so, t, smem, &sFlag);
+          else run_gemm_op<16>(a, ph.stage, so, t, smem, &sFlag);
           break;
       }
       __syncthreads();

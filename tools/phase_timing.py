@@ -12,8 +12,8 @@ from dpi_b200 import _lib  # noqa: E402
 from dpi_b200.generative_model.realnvpfc_model import RealNVP  # noqa: E402
 from dpi_b200.trainer import InterferometryTrainer, MRITrainer  # noqa: E402
 
-OPS = {1: "FWD_HID", 2: "FWD_OUT", 3: "BN_STATS", 4: "LOGDET", 5: "GATHER", 6: "B0", 7: "DGRAD_HID", 8: "WGRAD",
-       9: "DGRAD_IN", 10: "BNBWD_STATS", 11: "BNBWD_APPLY", 12: "BWD_FINAL"}
+OPS = {1: "FWD_HID", 2: "FWD_OUT", 3: "BN_STATS", 4: "LOGDET", 5: "TRANSPOSE", 6: "B0", 7: "DGRAD_HID", 8: "WGRAD",
+       9: "DGRAD_IN", 10: "BNBWD", 11: "BWD_FINAL"}
 
 
 def main():
