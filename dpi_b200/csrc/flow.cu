@@ -102,7 +102,8 @@ GemmPlan plan_gemm(int tiles_m, int N, int K, int target, bool allow_split, int 
   if (allow_split) {
     const int mn = tiles_m * g.tiles_n;
     int want = std::max(1, target / std::max(1, mn));
-    const int max_splits = std::max(1, K / (2 * kBK));  // at least two k-tiles per split
+    static const int min_kt = []() { const char* e = getenv("DPI_B200_MIN_KTILES"); return e ? std::max(1, atoi(e)) : 4; }();
+    const int max_splits = std::max(1, K / (min_kt * kBK));  // at least min_kt k-tiles per split
     want = std::min(std::min(want, max_splits), 32);
     if (want > 1) {
       int chunk = (K + want - 1) / want;

@@ -170,21 +170,33 @@ __device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, 
   float acc[4][TN];
   zero_acc<TN>(acc);
   const int kbeg = ks * so.kchunk, kend = min(K, kbeg + so.kchunk);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // the epilogue's per-column parameters do not depend on the GEMM: issue their loads first so the
+  // latency is hidden behind the pipeline instead of being paid after it
+  float pb[TN], pg[TN], pbe[TN], prm[TN], prv[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = tn * BN + ty + 16 * j;
+    const bool okn = n < a.H;
+    pb[j] = okn ? __ldg(c.P(which == 1 ? P_B1 : P_B2) + n) : 0.f;
+    pg[j] = (okn && a.has_bn) ? __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) : 0.f;
+    pbe[j] = (okn && a.has_bn) ? __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n) : 0.f;
+    prm[j] = (okn && a.has_bn) ? a.R[c.st.r[(which - 1) * 2] + n] : 0.f;
+    prv[j] = (okn && a.has_bn) ? a.R[c.st.r[(which - 1) * 2 + 1] + n] : 1.f;
+  }
   tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, kbeg, kend, smem);
   float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
   if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
 
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m = tm * kTM + tx * 4;
   const int nvalid = a.B - m;  // rows of this thread that exist (may be <= 0)
-  const float* bias = c.P(which == 1 ? P_B1 : P_B2);
   const bool fused = a.has_bn && a.train && a.tiles_m == 1;
   const float invB = 1.0f / (float)a.B;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     const int n = tn * BN + ty + 16 * j;
     const bool okn = n < a.H;
-    const float bj = okn ? __ldg(bias + n) : 0.f;
+    const float bj = pb[j];
     float v[4], s = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -204,25 +216,21 @@ __device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, 
         if (i < nvalid) { const float d = v[i] - mean; q = fmaf(d, d, q); }
       const float var = col_sum16(q) * invB;
       const float rstd = 1.0f / sqrtf(var + kBnEps);
-      const float ga = okn ? __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) * rstd : 0.f;
-      const float be = okn ? __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n) : 0.f;
+      const float ga = pg[j] * rstd;
+      const float be = pbe[j];
 #pragma unroll
       for (int i = 0; i < 4; ++i) nv[i] = fmaf(v[i] - mean, ga, be);
       if (tx == 0 && okn) {
         __stcg(c.stats(which, 0) + n, mean);
         __stcg(c.stats(which, 1) + n, rstd);
-        float* rm = a.R + c.st.r[(which - 1) * 2] + n;
-        float* rv = a.R + c.st.r[(which - 1) * 2 + 1] + n;
-        *rm = (1.f - kBnMomentum) * *rm + kBnMomentum * mean;
-        *rv = (1.f - kBnMomentum) * *rv + kBnMomentum * (var * (float)a.B / (float)(a.B - 1));
+        a.R[c.st.r[(which - 1) * 2] + n] = (1.f - kBnMomentum) * prm[j] + kBnMomentum * mean;
+        a.R[c.st.r[(which - 1) * 2 + 1] + n] =
+            (1.f - kBnMomentum) * prv[j] + kBnMomentum * (var * (float)a.B / (float)(a.B - 1));
       }
     } else if (!a.train) {  // eval: running statistics
-      float ga = 0.f, be = 0.f;
-      if (okn) {
-        const float rs = 1.0f / sqrtf(a.R[c.st.r[(which - 1) * 2 + 1] + n] + kBnEps);
-        ga = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n) * rs;
-        be = __ldg(c.P(which == 1 ? P_BE1 : P_BE2) + n) - a.R[c.st.r[(which - 1) * 2] + n] * ga;
-      }
+      const float rs = 1.0f / sqrtf(prv[j] + kBnEps);
+      const float ga = pg[j] * rs;
+      const float be = pbe[j] - prm[j] * ga;
 #pragma unroll
       for (int i = 0; i < 4; ++i) nv[i] = fmaf(v[i], ga, be);
     } else {
@@ -273,26 +281,39 @@ __device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, 
   OperandB B{c.P(P_W3), a.H, nullptr, tn * BJ, a.Dout, a.H, (a.H & 3) == 0, BJ, a.Db};
   float acc[4][TN];
   zero_acc<TN>(acc);
-  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem);
-
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m = tm * kTM + tx * 4;
   const int nvalid = a.B - m;
+  const float* yp = c.yprev();
+  // everything the epilogue needs besides the GEMM result is independent of it: load it first
   float qa, qc;
   c.post_affine(qa, qc);
-  const float* yp = c.yprev();
+  float p_els[TJ], p_et[TJ], p_bls[TJ], p_bt[TJ], p_bv[TJ][4], p_av[TJ][4];
+#pragma unroll
+  for (int jp = 0; jp < TJ; ++jp) {
+    const int col = tn * BJ + ty + 16 * jp;
+    const bool ok = col < a.Db && nvalid > 0;
+    p_els[jp] = ok ? __ldg(c.P(P_SCALE) + col) : 0.f;
+    p_et[jp] = ok ? __ldg(c.P(P_SCALE) + a.Db + col) : 0.f;
+    p_bls[jp] = ok ? __ldg(c.P(P_B3) + col) : 0.f;
+    p_bt[jp] = ok ? __ldg(c.P(P_B3) + a.Db + col) : 0.f;
+    const int gb = ok ? __ldg(c.gmap + a.Da + col) : 0, ga = ok ? __ldg(c.gmap + col) : 0;
+    load4(yp + (size_t)gb * a.B + m, p_bv[jp], ok ? nvalid : 0, c.vec);
+    load4(yp + (size_t)ga * a.B + m, p_av[jp], ok ? nvalid : 0, c.vec);
+  }
+  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem);
+
   float ld[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int jp = 0; jp < TJ; ++jp) {
     const int col = tn * BJ + ty + 16 * jp;
     if (col >= a.Db || nvalid <= 0) continue;
-    const float e_ls = expf(3.f * __ldg(c.P(P_SCALE) + col));
-    const float e_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
-    const float b_ls = __ldg(c.P(P_B3) + col), b_t = __ldg(c.P(P_B3) + a.Db + col);
-    const int gb = __ldg(c.gmap + a.Da + col), ga = __ldg(c.gmap + col);
-    float bv[4], av[4], ols[4], ot[4], yb[4], ya[4];
-    load4(yp + (size_t)gb * a.B + m, bv, nvalid, c.vec);
-    load4(yp + (size_t)ga * a.B + m, av, nvalid, c.vec);
+    const float e_ls = expf(3.f * p_els[jp]);
+    const float e_t = expf(3.f * p_et[jp]);
+    const float b_ls = p_bls[jp], b_t = p_bt[jp];
+    const float (&bv)[4] = p_bv[jp];
+    const float (&av)[4] = p_av[jp];
+    float ols[4], ot[4], yb[4], ya[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       ols[i] = (acc[i][jp] + b_ls) * e_ls;
@@ -344,12 +365,12 @@ __device__ __noinline__ void op_logdet_final(const KArgs& a, int t, float* sRed)
   if (m < a.B) {
     const int per = (n + 7) / 8, lo = slice * per, hi = min(n, lo + per);
     int i = lo;
-    for (; i + 4 <= hi; i += 4) {
-      float v[4];
+    for (; i + 16 <= hi; i += 16) {   // 16 independent loads in flight, fixed summation order
+      float v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldcg(ldp + (size_t)(i + u) * a.B + m);
+      for (int u = 0; u < 16; ++u) v[u] = ldcg(ldp + (size_t)(i + u) * a.B + m);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += v[u];
+      for (int u = 0; u < 16; ++u) acc[u & 3] += v[u];
     }
     for (; i < hi; ++i) acc[0] += ldcg(ldp + (size_t)i * a.B + m);
   }
@@ -455,15 +476,32 @@ __device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so
   float acc[4][TN];
   zero_acc<TN>(acc);
   const int kbeg = ks * so.kchunk, kend = min(K, kbeg + so.kchunk);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m = tm * kTM + tx * 4;
+  const int nvalid = a.B - m;
+  const bool fused = a.tiles_m == 1;
+  // epilogue operands that do not depend on the GEMM: load before it
+  float p_l[TN][4], p_mean[TN], p_rstd[TN], p_gam[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = tn * BN + ty + 16 * j;
+    const bool okn = n < a.H;
+    p_mean[j] = 0.f; p_rstd[j] = 1.f; p_gam[j] = 1.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p_l[j][i] = 0.f;
+    if (fused) {
+      if (okn && nvalid > 0) load4(c.L(which) + (size_t)n * a.B + m, p_l[j], nvalid, c.vec);
+      if (okn && a.has_bn) {
+        p_mean[j] = __ldcg(c.stats(which, 0) + n); p_rstd[j] = __ldcg(c.stats(which, 1) + n);
+        p_gam[j] = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n);
+      }
+    }
+  }
   tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, kbeg, kend, smem);
   float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
   if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
 
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m = tm * kTM + tx * 4;
-  const int nvalid = a.B - m;
   const float invB = 1.0f / (float)a.B;
-  const bool fused = a.tiles_m == 1;
   float* dstbuf = a.W + (fused ? (which == 2 ? a.oGP2T : a.oGP1T) : a.oGNT);
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -473,15 +511,11 @@ __device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so
 #pragma unroll
     for (int i = 0; i < 4; ++i) g[i] = (i < nvalid && okn) ? acc[i][j] : 0.f;
     if (fused) {
-      float l[4] = {0.f, 0.f, 0.f, 0.f};
-      if (okn && nvalid > 0) load4(c.L(which) + (size_t)n * a.B + m, l, nvalid, c.vec);
-      float gam = 1.f, rstd = 1.f, mean = 0.f, gbeta = 0.f, ggamma = 0.f;
+      const float (&l)[4] = p_l[j];
+      const float gam = p_gam[j], rstd = p_rstd[j], mean = p_mean[j];
+      float gbeta = 0.f, ggamma = 0.f;
       float xh[4] = {0.f, 0.f, 0.f, 0.f};
       if (a.has_bn) {
-        if (okn) {
-          mean = __ldcg(c.stats(which, 0) + n); rstd = __ldcg(c.stats(which, 1) + n);
-          gam = __ldg(c.P(which == 1 ? P_G1 : P_G2) + n);
-        }
         float p1 = 0.f, p2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -568,7 +602,7 @@ __device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, in
   const int J = which == 1 ? a.Da : a.H;
   const float* act = which == 1 ? c.yprev() : c.Nrm(which - 1);
   const float* gsrc = a.W + (which == 3 ? a.oGPRET : which == 2 ? a.oGP2T : a.oGP1T);
-  OperandA A{act, a.B, which == 1 ? c.gmap : nullptr, tm * kTM, J, a.B, false};
+  OperandA A{act, a.B, which == 1 ? c.gmap : nullptr, tm * kTM, J, a.B, c.vec};
   OperandB B{gsrc, a.B, nullptr, tn * BN, I, a.B, c.vec, 0, 0};
   float acc[4][TN];
   zero_acc<TN>(acc);
@@ -606,36 +640,50 @@ __device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so,
   OperandB B{c.P(P_W1), a.Da, nullptr, tn * BN, a.Da, a.H, (a.Da & 3) == 0, 0, 0};
   float acc[4][TN];
   zero_acc<TN>(acc);
-  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m = tm * kTM + tx * 4;
   const int nvalid = a.B - m;
-  if (nvalid <= 0) return;
   const float e_lsi = expf(__ldg(a.P + c.st.lsi));
+  float p_gy[TN][4];
+  int p_row[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {   // independent of the GEMM: in flight while it runs
+    const int n = tn * BN + ty + 16 * j;
+    const bool ok = n < a.Da && nvalid > 0;
+    p_row[j] = ok ? __ldg(c.gmap + n) : 0;
+    load4(c.gy() + (size_t)(ok ? n : 0) * a.B + m, p_gy[j], ok ? nvalid : 0, c.vec);
+  }
+  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem);
+  if (nvalid <= 0) return;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     const int n = tn * BN + ty + 16 * j;
     if (n >= a.Da) continue;
-    float gy[4], gu[4];
-    load4(c.gy() + (size_t)n * a.B + m, gy, nvalid, c.vec);
+    float gu[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gu[i] = fmaf(gy[i], e_lsi, acc[i][j]);
-    store4(c.gyprev() + (size_t)__ldg(c.gmap + n) * a.B + m, gu, nvalid, c.vec);
+    for (int i = 0; i < 4; ++i) gu[i] = fmaf(p_gy[j][i], e_lsi, acc[i][j]);
+    store4(c.gyprev() + (size_t)p_row[j] * a.B + m, gu, nvalid, c.vec);
   }
 }
 
-// ActNorm.reverse gradients: g_loc = -sum g_y, g_lsi = sum g_y * (y + loc) + D * sum_m g_ld[m]
+// ActNorm.reverse gradients: g_loc = -sum g_y, g_lsi = sum g_y * (y + loc) + D * sum_m g_ld[m].
+// One warp per stage sums that stage's per-tile partials (lane-strided, then a fixed shuffle tree).
 __device__ __noinline__ void op_bwd_final(const KArgs& a, float* sRed) {
   float s = 0.f;
   for (int m = threadIdx.x; m < a.B; m += kThreads) s += ldcg(a.g_ld + m);
   const float gld = block_sum(s, sRed);
-  for (int e = threadIdx.x; e < a.S; e += kThreads) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int e = w; e < a.S; e += kThreads / 32) {
     const float* red = a.W + a.oRED + (size_t)e * a.red_tiles * 2;
     float s1 = 0.f, s2 = 0.f;
-    for (int t = 0; t < a.red_tiles; ++t) { s1 += ldcg(red + 2 * t); s2 += ldcg(red + 2 * t + 1); }
-    const StageTab& st = a.st[e];
-    a.G[st.loc] = -s1;
-    a.G[st.lsi] = s2 + (float)a.D * gld;
+    for (int t = lane; t < a.red_tiles; t += 32) { s1 += ldcg(red + 2 * t); s2 += ldcg(red + 2 * t + 1); }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      const StageTab& st = a.st[e];
+      a.G[st.loc] = -s1;
+      a.G[st.lsi] = s2 + (float)a.D * gld;
+    }
   }
 }
 

@@ -1,10 +1,15 @@
 // tile_cp.cuh - fp32 SIMT tile GEMM core for FEATURE-MAJOR activations ([features][batch]) with a
 // cp.async multi-stage shared-memory pipeline.
 //
-// 256 threads form a 16 x 16 grid: thread (tx, ty) owns rows m = tx*4 + i (i < 4, contiguous -> float4)
-// and columns n = ty + 16*j (j < BN/16). In the flow the GEMM-M axis is the batch (or, for weight
-// gradients, the contiguous axis of the weight matrix), so every global access of an activation or a
-// gradient is a run of consecutive floats and the fixed permutations of the flow are ROW gathers.
+// The k-loop runs on the legacy tensor path: mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in fp32), which keeps fp32-level accuracy
+// (the 1e-4 parity bar) while cutting the shared-memory operand traffic of an FFMA micro-tile by ~4x -
+// these 64 x {16,32,64} tiles were LDS-bound, not FMA-bound (tools/bench_tile.cu). 8 warps = 4 (rows of
+// 16) x 2 (column halves). The accumulator fragments are then re-laid through shared memory so that the
+// epilogues see: thread (tx, ty) owns rows m = tx*4 + i (i < 4, contiguous -> float4) and columns
+// n = ty + 16*j (j < BN/16). In the flow the GEMM-M axis is the batch (or, for weight gradients, the
+// contiguous axis of the weight matrix), so every global access of an activation or a gradient is a run
+// of consecutive floats and the fixed permutations of the flow are ROW gathers.
 //
 // Operand sources (all plain copies -> cp.async, no register staging):
 //   A_MCONTIG : A(m, k) = base + row(k)*ld + m      (feature-major activation rows; row(k) optional map)
@@ -19,7 +24,10 @@ namespace dpi {
 constexpr int kTM = 64;        // tile rows
 constexpr int kTK = 32;        // k-tile
 constexpr int kNT = 256;       // threads
-constexpr int kStages = 4;     // cp.async ring depth
+#ifndef DPI_KSTAGES
+#define DPI_KSTAGES 4
+#endif
+constexpr int kStages = DPI_KSTAGES;     // cp.async ring depth
 constexpr int kStageFloatsA = 64 * 36;
 constexpr int kStageFloatsB = 64 * 36;
 constexpr int kStageFloats = kStageFloatsA + kStageFloatsB;
@@ -67,26 +75,29 @@ __device__ __forceinline__ void fetch_rows(const OperandA& a, int k0, int kend, 
     rows[i] = (k < kend) ? (a.map ? __ldg(a.map + k) : k) : -1;
   }
 }
-// Row indices for an A_KCONTIG operand: fixed for the whole tile (8 GEMM rows per thread).
-__device__ __forceinline__ void fetch_rows_k(const OperandA& a, int (&rows)[8]) {
+// Row indices for an A_KCONTIG operand: fixed for the whole tile (2 GEMM rows per thread).
+__device__ __forceinline__ void fetch_rows_k(const OperandA& a, int (&rows)[2]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = a.m0 + ((threadIdx.x + i * kNT) >> 5);
+  for (int i = 0; i < 2; ++i) {
+    const int m = a.m0 + ((threadIdx.x + i * kNT) >> 3);
     rows[i] = (m < a.M) ? (a.map ? __ldg(a.map + m) : m) : -1;
   }
 }
 
+constexpr int kLdaM = 72;   // A_MCONTIG smem row stride (floats): [kk][72], bank-conflict-free fragment reads
+constexpr int kLdK = 36;    // K-contiguous smem row stride (floats): [row][36]
+
 template <int AK>
 __device__ __forceinline__ void issue_A(float* sA, const OperandA& a, int k0, int kend, const int (&rows)[2],
-                                        const int (&rowsk)[8]) {
+                                        const int (&rowsk)[2]) {
   const int tid = threadIdx.x;
-  if (AK == A_MCONTIG) {  // smem [kk][64]
+  if (AK == A_MCONTIG) {  // smem [kk][72]
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = tid + i * kNT;          // 32 rows x 16 chunks of 4 floats
       const int kk = c >> 4, m4 = (c & 15) * 4;
       const int m = a.m0 + m4;
-      float* dst = sA + kk * 64 + m4;
+      float* dst = sA + kk * kLdaM + m4;
       const bool krow = rows[i] >= 0;
       const float* src = a.base + (size_t)(krow ? rows[i] : 0) * a.ld + m;
       if (a.vec) {
@@ -100,14 +111,25 @@ __device__ __forceinline__ void issue_A(float* sA, const OperandA& a, int k0, in
         }
       }
     }
-  } else {  // A_KCONTIG: smem [mm][33], element copies
+  } else {  // A_KCONTIG: smem [mm][36], 64 rows x 8 chunks of 4 k
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int e = tid + i * kNT;
-      const int kk = e & 31, mm = e >> 5;
-      const int k = k0 + kk;
-      const bool ok = (k < kend) && rowsk[i] >= 0;
-      cp_async4(sA + mm * 33 + kk, ok ? a.base + (size_t)rowsk[i] * a.ld + k : a.base, ok);
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + i * kNT;
+      const int mm = c >> 3, k4 = (c & 7) * 4;
+      const int k = k0 + k4;
+      float* dst = sA + mm * kLdK + k4;
+      const bool okm = rowsk[i] >= 0;
+      const float* src = a.base + (size_t)(okm ? rowsk[i] : 0) * a.ld + k;
+      if (a.vec) {
+        const int left = okm ? (kend - k) : 0;
+        cp_async16(dst, left > 0 ? src : a.base, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = okm && (k + u < kend);
+          cp_async4(dst + u, ok ? src + u : a.base, ok);
+        }
+      }
     }
   }
 }
@@ -147,8 +169,8 @@ __device__ __forceinline__ void issue_B(float* sB, const OperandB& b, int k0, in
         }
       }
     }
-  } else {  // B_NCONTIG: smem [kk][BN + 4]
-    constexpr int LDN = BN + 4, CPR = BN / 4, CH = 32 * CPR;
+  } else {  // B_NCONTIG: smem [kk][BN + 8]
+    constexpr int LDN = BN + 8, CPR = BN / 4, CH = 32 * CPR;
 #pragma unroll
     for (int i = 0; i < (CH + kNT - 1) / kNT; ++i) {
       const int c = tid + i * kNT;
@@ -173,14 +195,31 @@ __device__ __forceinline__ void issue_B(float* sB, const OperandB& b, int k0, in
   }
 }
 
-// acc[i][j] += sum_{k in [kbeg, kend)} A(m0 + tx*4 + i, k) * B(n0 + ty + 16 j, k)
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// acc[i][j] = sum_{k in [kbeg, kend)} A(m0 + tx*4 + i, k) * B(n0 + ty + 16 j, k)   (acc is overwritten)
 template <int BN, int AK, int BK_>
 __device__ __forceinline__ void tile_gemm(float (&acc)[4][BN / 16], const OperandA& a, const OperandB& b, int kbeg,
                                           int kend, float* smem) {
   constexpr int TN = BN / 16;
+  constexpr int NB = BN / 16;            // 8-column blocks per warp (warp owns BN/2 columns)
+  constexpr int LDN = BN + 8;
+  constexpr int LDC = 68;                // accumulator staging [n][68]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * (BN / 2);
   const int nkt = (kend - kbeg + kTK - 1) / kTK;
-  int rowsk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int rowsk[2] = {0, 0};
   int rows[kStages][2];
   if (AK == A_KCONTIG) {
     fetch_rows_k(a, rowsk);
@@ -190,6 +229,11 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[4][BN / 16], const Operan
 #pragma unroll
     for (int s = 0; s < kStages; ++s) fetch_rows(a, kbeg + s * kTK, kend, rows[s]);  // all in flight together
   }
+  float c[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[nb][q] = 0.f;
   __syncthreads();  // the ring may still be read by the previous tile
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
@@ -217,25 +261,60 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[4][BN / 16], const Operan
     const float* sA = smem + (t % kStages) * kStageFloats;
     const float* sB = sA + kStageFloatsA;
 #pragma unroll
-    for (int kk = 0; kk < kTK; ++kk) {
-      float av[4], bv[TN];
+    for (int ks = 0; ks < kTK / 8; ++ks) {
+      float af[4];
       if (AK == A_MCONTIG) {
-        const float4 v = *reinterpret_cast<const float4*>(sA + kk * 64 + tx * 4);
-        av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+        af[0] = sA[(ks * 8 + t4) * kLdaM + wm + g];
+        af[1] = sA[(ks * 8 + t4) * kLdaM + wm + g + 8];
+        af[2] = sA[(ks * 8 + t4 + 4) * kLdaM + wm + g];
+        af[3] = sA[(ks * 8 + t4 + 4) * kLdaM + wm + g + 8];
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = sA[(tx * 4 + i) * 33 + kk];
+        af[0] = sA[(wm + g) * kLdK + ks * 8 + t4];
+        af[1] = sA[(wm + g + 8) * kLdK + ks * 8 + t4];
+        af[2] = sA[(wm + g) * kLdK + ks * 8 + t4 + 4];
+        af[3] = sA[(wm + g + 8) * kLdK + ks * 8 + t4 + 4];
       }
+      unsigned ah[4], al[4];
 #pragma unroll
-      for (int j = 0; j < TN; ++j)
-        bv[j] = (BK_ == B_KCONTIG) ? sB[(ty + 16 * j) * 36 + kk] : sB[kk * (BN + 4) + ty + 16 * j];
+      for (int q = 0; q < 4; ++q) split_tf32(af[q], ah[q], al[q]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = wn + nb * 8 + g;
+        float bf[2];
+        if (BK_ == B_KCONTIG) {
+          bf[0] = sB[n * kLdK + ks * 8 + t4];
+          bf[1] = sB[n * kLdK + ks * 8 + t4 + 4];
+        } else {
+          bf[0] = sB[(ks * 8 + t4) * LDN + n];
+          bf[1] = sB[(ks * 8 + t4 + 4) * LDN + n];
+        }
+        unsigned bh[2], bl[2];
+        split_tf32(bf[0], bh[0], bl[0]);
+        split_tf32(bf[1], bh[1], bl[1]);
+        mma_tf32(c[nb], al, bh);   // small terms first
+        mma_tf32(c[nb], ah, bl);
+        mma_tf32(c[nb], ah, bh);
+      }
     }
   }
   cp_async_wait<0>();
+  __syncthreads();
+  // fragments -> [n][68] staging -> the epilogue's (4 consecutive rows) x (columns ty + 16 j) ownership
+  float* sC = smem;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const int n = wn + nb * 8 + 2 * t4;
+    sC[n * LDC + wm + g] = c[nb][0];
+    sC[(n + 1) * LDC + wm + g] = c[nb][1];
+    sC[n * LDC + wm + g + 8] = c[nb][2];
+    sC[(n + 1) * LDC + wm + g + 8] = c[nb][3];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(sC + (ty + 16 * j) * LDC + tx * 4);
+    acc[0][j] = v.x; acc[1][j] = v.y; acc[2][j] = v.z; acc[3][j] = v.w;
+  }
   __syncthreads();
 }
 
