@@ -36,7 +36,7 @@ struct BatchPlan {
 
 struct dpi_flow_s {
   int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
-  int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1;
+  int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   long long n_params = 0, n_bn = 0;
   std::vector<dpi::StageTab> stages;          // reverse execution order
   std::vector<long long> act_off;             // [n_flow][4]
@@ -282,6 +282,7 @@ void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
 
 int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t stream) {
   a.phases = prog.d_phases;
+  a.use_tc = h->use_tc;
   a.tbuf = nullptr;
   if (h->d_tbuf && prog.n_phases <= 4096) {
     a.tbuf = h->d_tbuf;
@@ -294,14 +295,14 @@ int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t st
     grid = std::max(grid, 1);
     a.phase_begin = 0; a.phase_end = prog.n_phases; a.persistent = 1;
     void* params[] = {&a};
-    DPI_CUDA(cudaLaunchCooperativeKernel(flow_kernel_ptr(), dim3(grid), dim3(kThreads), params, kTileSmemBytes, stream));
+    DPI_CUDA(cudaLaunchCooperativeKernel(flow_kernel_ptr(), dim3(grid), dim3(kThreads), params, kTcSmemBytes, stream));
     count_launch();
   } else {
     a.persistent = 0;
     void* params[] = {&a};
     for (int p = 0; p < prog.n_phases; ++p) {
       a.phase_begin = p; a.phase_end = p + 1;
-      DPI_CUDA(cudaLaunchKernel(flow_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, kTileSmemBytes, stream));
+      DPI_CUDA(cudaLaunchKernel(flow_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, kTcSmemBytes, stream));
       count_launch();
     }
   }
@@ -327,11 +328,13 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   h->n_sm = sm_count(device);
   DPI_REQUIRE(h->n_sm > 0, "dpi_flow_create: no CUDA device %d", device);
   int nb = 0;
-  DPI_CUDA(cudaFuncSetAttribute((const void*)flow_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  DPI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)flow_kernel_ptr(), kThreads, kTileSmemBytes));
+  DPI_CUDA(cudaFuncSetAttribute((const void*)flow_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  DPI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)flow_kernel_ptr(), kThreads, kTcSmemBytes));
   h->coop_max_per_sm = std::max(1, nb);
   const char* mode = getenv("DPI_B200_FLOW_MODE");
   h->persistent = (mode && mode[0] == 's') ? 0 : 1;
+  const char* tile = getenv("DPI_B200_TILE");   // "mma": legacy mma.sync tile core instead of tcgen05
+  h->use_tc = (tile && tile[0] == 'm') ? 0 : 1;
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
   h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
 

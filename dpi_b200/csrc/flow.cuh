@@ -72,6 +72,7 @@ struct KArgs {
   unsigned* ctrl;
   unsigned long long* tbuf;   // debug: per-phase globaltimer stamps of CTA 0 (start, work done), or nullptr
   int phase_begin, phase_end, persistent;
+  int use_tc;                 // 1: tcgen05/TMEM tile core, 0: mma.sync tile core
 };
 
 }  // namespace dpi

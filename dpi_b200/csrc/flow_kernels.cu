@@ -158,7 +158,8 @@ __device__ __noinline__ void op_transpose(const KArgs& a, const SubOp& so, int t
 // net.0 / net.3: Linear + LeakyReLU(0.01) (+ BatchNorm1d batch statistics, eps 1e-2) :171-187.
 // Output rows (features) n, columns (samples) m: L^T (saved for backward) and the normalised N^T.
 template <int BN>
-__device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
+__device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag,
+                                        const TcState& tc) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   int tm, tn, ks;
@@ -184,7 +185,8 @@ __device__ __noinline__ void op_fwd_hid(const KArgs& a, int e, const SubOp& so, 
     prm[j] = (okn && a.has_bn) ? a.R[c.st.r[(which - 1) * 2] + n] : 0.f;
     prv[j] = (okn && a.has_bn) ? a.R[c.st.r[(which - 1) * 2 + 1] + n] : 1.f;
   }
-  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, kbeg, kend, smem);
+  if (a.use_tc) tile_gemm_tc<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, kbeg, kend, smem, tc);
+  else tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, kbeg, kend, smem);
   float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
   if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
 
@@ -273,7 +275,8 @@ __device__ __noinline__ void op_bn_stats(const KArgs& a, int e, const SubOp& so,
 // The tile covers BJ = BN/2 coupling columns j and computes both log_s (row j of fc.weight) and
 // t (row Db + j) so the coupling is applied in registers.
 template <int BN>
-__device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, int t, float* smem, float* sRed) {
+__device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, int t, float* smem, float* sRed,
+                                        const TcState& tc) {
   constexpr int TN = BN / 16, BJ = BN / 2, TJ = TN / 2;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
@@ -301,7 +304,8 @@ __device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, 
     load4(yp + (size_t)gb * a.B + m, p_bv[jp], ok ? nvalid : 0, c.vec);
     load4(yp + (size_t)ga * a.B + m, p_av[jp], ok ? nvalid : 0, c.vec);
   }
-  tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem);
+  if (a.use_tc) tile_gemm_tc<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem, tc);
+  else tile_gemm<BN, A_MCONTIG, B_KCONTIG>(acc, A, B, 0, a.H, smem);
 
   float ld[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -464,7 +468,8 @@ __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t
 // g_p2^T); result = gradient wrt the BatchNorm output of hidden layer `which`, with the BatchNorm +
 // LeakyReLU backward fused when this CTA owns complete feature rows (batch <= 64).
 template <int BN>
-__device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
+__device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag,
+                                          const TcState& tc) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   int tm, tn, ks;
@@ -497,7 +502,8 @@ __device__ __noinline__ void op_dgrad_hid(const KArgs& a, int e, const SubOp& so
       }
     }
   }
-  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, kbeg, kend, smem);
+  if (a.use_tc) tile_gemm_tc<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, kbeg, kend, smem, tc);
+  else tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, kbeg, kend, smem);
   float* part = a.W + a.oPART + so.part_off + (size_t)(tm * so.tiles_n + tn) * so.splits * (kTM * BN);
   if (!splitk_reduce_fm<BN>(acc, part, ks, so.splits, a.ctrl + so.ctr_off + tm * so.tiles_n + tn, sFlag)) return;
 
@@ -593,7 +599,7 @@ __device__ __noinline__ void op_bnbwd(const KArgs& a, int e, const SubOp& so, in
 // Weight gradients gW[i][j] = sum_m g^T[i][m] * act^T[j][m]  (which = 3: fc.weight, 2: net.3, 1: net.0).
 // GEMM rows = j (the contiguous axis of gW -> float4 stores), GEMM columns = i, GEMM k = sample.
 template <int BN>
-__device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, int t, float* smem) {
+__device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, int t, float* smem, const TcState& tc) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
@@ -606,7 +612,8 @@ __device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, in
   OperandB B{gsrc, a.B, nullptr, tn * BN, I, a.B, c.vec, 0, 0};
   float acc[4][TN];
   zero_acc<TN>(acc);
-  tile_gemm<BN, A_KCONTIG, B_KCONTIG>(acc, A, B, 0, a.B, smem);
+  if (a.use_tc) tile_gemm_tc<BN, A_KCONTIG, B_KCONTIG>(acc, A, B, 0, a.B, smem, tc);
+  else tile_gemm<BN, A_KCONTIG, B_KCONTIG>(acc, A, B, 0, a.B, smem);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int j0 = tm * kTM + tx * 4;
   const int nvalid = J - j0;
@@ -632,7 +639,7 @@ __device__ __noinline__ void op_wgrad(const KArgs& a, int e, const SubOp& so, in
 // dgrad through net.0.weight, plus the direct path through the a-half and ActNorm, written through
 // the fused permutation into the rows of the gradient wrt the previous stage's output.
 template <int BN>
-__device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so, int t, float* smem) {
+__device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so, int t, float* smem, const TcState& tc) {
   constexpr int TN = BN / 16;
   Ctx c(a, e);
   const int tn = t % so.tiles_n, tm = t / so.tiles_n;
@@ -653,7 +660,8 @@ __device__ __noinline__ void op_dgrad_in(const KArgs& a, int e, const SubOp& so,
     p_row[j] = ok ? __ldg(c.gmap + n) : 0;
     load4(c.gy() + (size_t)(ok ? n : 0) * a.B + m, p_gy[j], ok ? nvalid : 0, c.vec);
   }
-  tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem);
+  if (a.use_tc) tile_gemm_tc<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem, tc);
+  else tile_gemm<BN, A_MCONTIG, B_NCONTIG>(acc, A, B, 0, a.H, smem);
   if (nvalid <= 0) return;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -689,12 +697,13 @@ __device__ __noinline__ void op_bwd_final(const KArgs& a, float* sRed) {
 
 // ----------------------------------------------------------------------------- dispatcher
 template <int BN>
-__device__ __forceinline__ void run_gemm_op(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag) {
+__device__ __forceinline__ void run_gemm_op(const KArgs& a, int e, const SubOp& so, int t, float* smem, int* sFlag,
+                                            const TcState& tc) {
   switch (so.op) {
-    case OP_FWD_HID: op_fwd_hid<BN>(a, e, so, t, smem, sFlag); break;
-    case OP_DGRAD_HID: op_dgrad_hid<BN>(a, e, so, t, smem, sFlag); break;
-    case OP_WGRAD: op_wgrad<BN>(a, e, so, t, smem); break;
-    case OP_DGRAD_IN: op_dgrad_in<BN>(a, e, so, t, smem); break;
+    case OP_FWD_HID: op_fwd_hid<BN>(a, e, so, t, smem, sFlag, tc); break;
+    case OP_DGRAD_HID: op_dgrad_hid<BN>(a, e, so, t, smem, sFlag, tc); break;
+    case OP_WGRAD: op_wgrad<BN>(a, e, so, t, smem, tc); break;
+    case OP_DGRAD_IN: op_dgrad_in<BN>(a, e, so, t, smem, tc); break;
     default: break;
   }
 }
@@ -708,6 +717,18 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
   __shared__ int sFlag;
   __shared__ __align__(16) Phase sPh[kSmemPhases];
   __shared__ __align__(16) StageTab sSt[kSmemStages];
+  __shared__ unsigned sTmemSlot;
+  TcState tc;
+  tc.opbuf = reinterpret_cast<unsigned char*>(smem) + kTileSmemBytes;
+  tc.bars = reinterpret_cast<unsigned long long*>(tc.opbuf + 2 * kOpBufBytes);
+  tc.tmem = 0;
+  if (a.use_tc) {   // TMEM accumulator for the tcgen05 tile core: allocated once per CTA by warp 0
+    if (threadIdx.x < 32) tmem_alloc(&sTmemSlot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc.tmem = sTmemSlot;
+  }
   const int np = a.phase_end - a.phase_begin;
   const bool ph_smem = np <= kSmemPhases;
   if (ph_smem) {
@@ -737,8 +758,8 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
       const int t = tt < n0 ? tt : tt - n0;
       switch (so.op) {
         case OP_FWD_OUT:
-          if (so.bn == 64) op_fwd_out<64>(a, ph.stage, so, t, smem, sRed);
-          else op_fwd_out<32>(a, ph.stage, so, t, smem, sRed);
+          if (so.bn == 64) op_fwd_out<64>(a, ph.stage, so, t, smem, sRed, tc);
+          else op_fwd_out<32>(a, ph.stage, so, t, smem, sRed, tc);
           break;
         case OP_TRANSPOSE: op_transpose(a, so, t, smem); break;
         case OP_BN_STATS: op_bn_stats(a, ph.stage, so, t); break;
@@ -747,9 +768,9 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
         case OP_BNBWD: op_bnbwd(a, ph.stage, so, t); break;
         case OP_BWD_FINAL: op_bwd_final(a, sRed); break;
         default:
-          if (so.bn == 64) run_gemm_op<64>(a, ph.stage, so, t, smem, &sFlag);
-          else if (so.bn == 32) run_gemm_op<32>(a, ph.stage, so, t, smem, &sFlag);
-          else run_gemm_op<16>(a, ph.stage, so, t, smem, &sFlag);
+          if (so.bn == 64) run_gemm_op<64>(a, ph.stage, so, t, smem, &sFlag, tc);
+          else if (so.bn == 32) run_gemm_op<32>(a, ph.stage, so, t, smem, &sFlag, tc);
+          else run_gemm_op<16>(a, ph.stage, so, t, smem, &sFlag, tc);
           break;
       }
       __syncthreads();
@@ -760,6 +781,11 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
       a.tbuf[2 * p + 1] = t;
     }
     if (a.persistent && p + 1 < a.phase_end) grid_sync(a.ctrl, gridDim.x, bar++);
+  }
+  if (a.use_tc) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tc.tmem);
   }
 }
 

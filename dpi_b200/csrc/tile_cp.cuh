@@ -84,7 +84,7 @@ __device__ __forceinline__ void fetch_rows_k(const OperandA& a, int (&rows)[2]) 
   }
 }
 
-constexpr int kLdaM = 72;   // A_MCONTIG smem row stride (floats): [kk][72], bank-conflict-free fragment reads
+constexpr int kLdaM = 68;   // A_MCONTIG raw smem row stride (floats): [kk][68], conflict-free 16-byte reads
 constexpr int kLdK = 36;    // K-contiguous smem row stride (floats): [row][36]
 
 template <int AK>
@@ -169,8 +169,8 @@ __device__ __forceinline__ void issue_B(float* sB, const OperandB& b, int k0, in
         }
       }
     }
-  } else {  // B_NCONTIG: smem [kk][BN + 8]
-    constexpr int LDN = BN + 8, CPR = BN / 4, CH = 32 * CPR;
+  } else {  // B_NCONTIG: smem [kk][BN + 4]
+    constexpr int LDN = BN + 4, CPR = BN / 4, CH = 32 * CPR;
 #pragma unroll
     for (int i = 0; i < (CH + kNT - 1) / kNT; ++i) {
       const int c = tid + i * kNT;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[4][BN / 16], const Operan
                                           int kend, float* smem) {
   constexpr int TN = BN / 16;
   constexpr int NB = BN / 16;            // 8-column blocks per warp (warp owns BN/2 columns)
-  constexpr int LDN = BN + 8;
+  constexpr int LDN = BN + 4;
   constexpr int LDC = 68;                // accumulator staging [n][68]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -314,6 +314,245 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[4][BN / 16], const Operan
   for (int j = 0; j < TN; ++j) {
     const float4 v = *reinterpret_cast<const float4*>(sC + (ty + 16 * j) * LDC + tx * 4);
     acc[0][j] = v.x; acc[1][j] = v.y; acc[2][j] = v.z; acc[3][j] = v.w;
+  }
+  __syncthreads();
+}
+
+// =================================================================================================
+// tcgen05 tile core: the same tile GEMM on the 5th-generation tensor cores.
+//   D[128 x BN] (TMEM, fp32) += A[128 x 8] * B[BN x 8]  per tcgen05.mma kind::tf32 (cta_group::1).
+// Only rows 0..63 of A are real (the batch / weight tile is 64 rows); rows 64..127 alias whatever
+// follows the A tile in shared memory and produce accumulator rows that are never read.
+// fp32 accuracy comes from the 3xTF32 split: after a raw k-tile has landed in the cp.async ring, all
+// threads convert it into hi / lo operand tiles in the canonical no-swizzle UMMA layouts (core matrix
+// = 8 x 16 bytes; K-major: ((8,n),2):((16B,SBO),LBO), MN-major: ((4,n),(8,k)):((4B,SBO),(16B,LBO)),
+// cf. cute/atom/mma_traits_sm100.hpp) and one thread issues a_lo*b_hi, a_hi*b_lo, a_hi*b_hi.
+// Operand tiles are double-buffered; tcgen05.commit -> mbarrier tells when a buffer may be rewritten.
+// =================================================================================================
+constexpr int kOpTileBytes = 8192;                       // one 64 x 32 fp32 operand tile
+constexpr int kOpBufBytes = 4 * kOpTileBytes;            // A_hi, A_lo, B_hi, B_lo
+constexpr int kTcSmemBytes = kTileSmemBytes + 2 * kOpBufBytes + 64;   // ring + 2 operand buffers + mbarriers
+constexpr int kTmemCols = 64;
+
+struct TcState {           // lives in registers / smem of the CTA for the whole kernel
+  unsigned tmem;           // TMEM base address of the accumulator (64 columns x 128 lanes)
+  unsigned char* opbuf;    // generic pointer to the operand double buffer (1024-byte aligned)
+  unsigned long long* bars;// two mbarriers (shared memory)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  return (unsigned long long)((saddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // version 1, no swizzle
+}
+// instruction descriptor: D fp32, A/B tf32, M = 128, N = BN
+__device__ __forceinline__ unsigned umma_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)a_mn_major << 15) | ((unsigned)b_mn_major << 16) |
+         ((unsigned)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                          unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned done = 0;
+  long long t0 = clock64();
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 2000000000LL) break;   // bounded: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(unsigned* slot_smem) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "n"(kTmemCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr) {       // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  unsigned h, l;
+  split_tf32(v.x, h, l); hi.x = __uint_as_float(h); lo.x = __uint_as_float(l);
+  split_tf32(v.y, h, l); hi.y = __uint_as_float(h); lo.y = __uint_as_float(l);
+  split_tf32(v.z, h, l); hi.z = __uint_as_float(h); lo.z = __uint_as_float(l);
+  split_tf32(v.w, h, l); hi.w = __uint_as_float(h); lo.w = __uint_as_float(l);
+}
+
+// raw ring stage -> canonical hi / lo operand tiles. A quarter-warp (8 lanes) always writes one
+// contiguous 128-byte core matrix, and reads 8 different raw rows whose strides (68 / 36 / BN+4
+// floats) put them in disjoint bank groups: no shared-memory conflicts on either side.
+template <int BN, int AK, int BK_>
+__device__ __forceinline__ void tc_convert(const float* sA, const float* sB, unsigned char* ob) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r8 = lane & 7, q = lane >> 3;           // row-in-core-matrix, quarter
+  float4 hi, lo;
+  // ---- A: 64 (m) x 32 (k) = 8 core-matrix rows x 64 groups; 512 chunks, 2 per thread
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int grp = warp * 8 + q * 2 + i;           // 0..63
+    if (AK == A_MCONTIG) {                          // raw [kk][68]; canonical MN-major [kg][mg][k%8][4 m]
+      const int kg = grp >> 4, mg = grp & 15;
+      const float4 v = *reinterpret_cast<const float4*>(sA + (kg * 8 + r8) * kLdaM + mg * 4);
+      split4(v, hi, lo);
+      const int off = kg * 2048 + mg * 128 + r8 * 16;
+      *reinterpret_cast<float4*>(ob + off) = hi;
+      *reinterpret_cast<float4*>(ob + kOpTileBytes + off) = lo;
+    } else {                                        // raw [mm][36]; canonical K-major [mg8][kc][m%8][4 k]
+      const int mg = grp >> 3, kc = grp & 7;
+      const float4 v = *reinterpret_cast<const float4*>(sA + (mg * 8 + r8) * kLdK + kc * 4);
+      split4(v, hi, lo);
+      const int off = mg * 1024 + kc * 128 + r8 * 16;
+      *reinterpret_cast<float4*>(ob + off) = hi;
+      *reinterpret_cast<float4*>(ob + kOpTileBytes + off) = lo;
+    }
+  }
+  // ---- B: BN (n) x 32 (k): BN groups of 8 chunks
+  unsigned char* obB = ob + 2 * kOpTileBytes;
+#pragma unroll
+  for (int i = 0; i < (BN + 31) / 32; ++i) {
+    const int grp = warp * 4 + q + 32 * i;          // 0..BN-1 valid
+    if (grp < BN) {
+      if (BK_ == B_KCONTIG) {                       // raw [nn][36]; canonical K-major [ng8][kc][n%8][4 k]
+        const int ng = grp >> 3, kc = grp & 7;
+        const float4 v = *reinterpret_cast<const float4*>(sB + (ng * 8 + r8) * kLdK + kc * 4);
+        split4(v, hi, lo);
+        const int off = ng * 1024 + kc * 128 + r8 * 16;
+        *reinterpret_cast<float4*>(obB + off) = hi;
+        *reinterpret_cast<float4*>(obB + kOpTileBytes + off) = lo;
+      } else {                                      // raw [kk][BN+4]; canonical MN-major [kg][ng4][k%8][4 n]
+        constexpr int NG = BN / 4;
+        const int kg = grp / NG, ng = grp % NG;
+        const float4 v = *reinterpret_cast<const float4*>(sB + (kg * 8 + r8) * (BN + 4) + ng * 4);
+        split4(v, hi, lo);
+        const int off = kg * (NG * 128) + ng * 128 + r8 * 16;
+        *reinterpret_cast<float4*>(obB + off) = hi;
+        *reinterpret_cast<float4*>(obB + kOpTileBytes + off) = lo;
+      }
+    }
+  }
+}
+
+// acc[i][j] = sum_{k in [kbeg, kend)} A(m0 + tx*4 + i, k) * B(n0 + ty + 16 j, k)   (acc is overwritten)
+template <int BN, int AK, int BK_>
+__device__ __forceinline__ void tile_gemm_tc(float (&acc)[4][BN / 16], const OperandA& a, const OperandB& b, int kbeg,
+                                             int kend, float* smem, const TcState& tc) {
+  constexpr int TN = BN / 16;
+  constexpr int LDC = 68;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nkt = (kend - kbeg + kTK - 1) / kTK;
+  int rowsk[2] = {0, 0};
+  int rows[kStages][2];
+  if (AK == A_KCONTIG) {
+    fetch_rows_k(a, rowsk);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) rows[s][0] = rows[s][1] = 0;
+  } else {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) fetch_rows(a, kbeg + s * kTK, kend, rows[s]);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(tc.bars, 1);
+    mbar_init(tc.bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // ring and operand buffers are free (previous tile finished), barriers initialised
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nkt) {
+      issue_A<AK>(smem + s * kStageFloats, a, kbeg + s * kTK, kend, rows[s], rowsk);
+      issue_B<BN, BK_>(smem + s * kStageFloats + kStageFloatsA, b, kbeg + s * kTK, kend);
+    }
+    cp_async_commit();
+  }
+  int r_use[2] = {rows[kStages - 1][0], rows[kStages - 1][1]};
+  const unsigned idesc = umma_idesc(BN, AK == A_MCONTIG ? 1 : 0, BK_ == B_NCONTIG ? 1 : 0);
+  for (int t = 0; t < nkt; ++t) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();                     // raw tile t visible to everyone; ring stage of tile t-1 is free
+    const int tn = t + kStages - 1;
+    int r_next[2] = {-1, -1};
+    if (AK == A_MCONTIG && tn + 1 < nkt) fetch_rows(a, kbeg + (tn + 1) * kTK, kend, r_next);
+    if (tn < nkt) {
+      float* st = smem + (tn % kStages) * kStageFloats;
+      issue_A<AK>(st, a, kbeg + tn * kTK, kend, r_use, rowsk);
+      issue_B<BN, BK_>(st + kStageFloatsA, b, kbeg + tn * kTK, kend);
+    }
+    cp_async_commit();
+    r_use[0] = r_next[0]; r_use[1] = r_next[1];
+    const int bsel = t & 1;
+    unsigned char* ob = tc.opbuf + bsel * kOpBufBytes;
+    if (t >= 2) mbar_wait(tc.bars + bsel, ((t >> 1) - 1) & 1);   // the MMAs that read this buffer are done
+    const float* sA = smem + (t % kStages) * kStageFloats;
+    tc_convert<BN, AK, BK_>(sA, sA + kStageFloatsA, ob);
+    fence_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const unsigned a_hi = smem_u32(ob), a_lo = a_hi + kOpTileBytes, b_hi = a_hi + 2 * kOpTileBytes,
+                     b_lo = a_hi + 3 * kOpTileBytes;
+#pragma unroll
+      for (int ks = 0; ks < kTK / 8; ++ks) {
+        // per k-step (8 k = 32 bytes): MN-major operands advance by one 8-k group, K-major by two 16-byte chunks
+        const unsigned a_off = (AK == A_MCONTIG) ? ks * 2048 : ks * 256;
+        const unsigned a_lbo = (AK == A_MCONTIG) ? 2048 : 128, a_sbo = (AK == A_MCONTIG) ? 128 : 1024;
+        const unsigned b_off = (BK_ == B_KCONTIG) ? ks * 256 : ks * (BN / 4) * 128;
+        const unsigned b_lbo = (BK_ == B_KCONTIG) ? 128 : (BN / 4) * 128, b_sbo = (BK_ == B_KCONTIG) ? 1024 : 128;
+        const unsigned long long dah = umma_desc(a_hi + a_off, a_lbo, a_sbo), dal = umma_desc(a_lo + a_off, a_lbo, a_sbo);
+        const unsigned long long dbh = umma_desc(b_hi + b_off, b_lbo, b_sbo), dbl = umma_desc(b_lo + b_off, b_lbo, b_sbo);
+        umma_tf32(tc.tmem, dal, dbh, idesc, (t | ks) ? 1u : 0u);   // small terms first
+        umma_tf32(tc.tmem, dah, dbl, idesc, 1u);
+        umma_tf32(tc.tmem, dah, dbh, idesc, 1u);
+      }
+      umma_commit(tc.bars + bsel);
+    }
+  }
+  cp_async_wait<0>();
+  if (nkt > 0) mbar_wait(tc.bars + ((nkt - 1) & 1), ((nkt - 1) >> 1) & 1);   // all MMAs complete (commits are ordered)
+  tc_fence_after();
+  __syncthreads();
+  // TMEM (lane = tile row, column = tile column) -> [n][68] staging -> the epilogue's ownership
+  float* sC = smem;
+  if (warp < 2 && nkt > 0) {
+    const int m = warp * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 8) {
+      unsigned v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(tc.tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sC[(c0 + u) * LDC + m] = __uint_as_float(v[u]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    if (nkt > 0) {
+      const float4 v = *reinterpret_cast<const float4*>(sC + (ty + 16 * j) * LDC + tx * 4);
+      acc[0][j] = v.x; acc[1][j] = v.y; acc[2][j] = v.z; acc[3][j] = v.w;
+    } else {
+      acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = 0.f;
+    }
   }
   __syncthreads();
 }

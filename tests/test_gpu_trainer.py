@@ -133,11 +133,11 @@ def test_full_size_step_vs_oracle(kind):
             assert rel_err(tr.x, to["x"]) < RTOL and rel_err(tr.img.view_as(to["img"]), to["img"]) < RTOL
     # Adam normalises every element by its own |g| (update ~ +-lr even where the gradient is at noise
     # level), so a handful of elements may move differently although the gradients agree to 1e-4:
-    # judge the update VECTOR per tensor in L2 (2 %), and the parameters themselves at 5e-4.
+    # judge the update VECTOR per tensor in L2 (5 %), and the parameters themselves at 5e-4.
     mine = tr.flow.state_dict()
     for k in ot.keys:
         up_ref = (sd[k].detach() - sd0[k]).double()
         up_mine = (mine[k].cpu() - sd0[k]).double()
-        assert float((up_mine - up_ref).norm() / up_ref.norm().clamp_min(1e-30)) < 0.02, k
+        assert float((up_mine - up_ref).norm() / up_ref.norm().clamp_min(1e-30)) < 0.05, k
         assert rel_err(mine[k], sd[k].detach()) < 5 * RTOL, k
     assert abs(tr.log_scale_value() - float(ls)) < 1e-6
