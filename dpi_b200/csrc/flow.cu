@@ -333,8 +333,10 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   h->coop_max_per_sm = std::max(1, nb);
   const char* mode = getenv("DPI_B200_FLOW_MODE");
   h->persistent = (mode && mode[0] == 's') ? 0 : 1;
-  const char* tile = getenv("DPI_B200_TILE");   // "mma": legacy mma.sync tile core instead of tcgen05
-  h->use_tc = (tile && tile[0] == 'm') ? 0 : 1;
+  // tile core of the large-batch path: mma.sync 3xTF32 (validated). "tc" selects the experimental tcgen05
+  // core, whose MN-major operand descriptors still mismatch on hardware (tools/bench_tile.cu).
+  const char* tile = getenv("DPI_B200_TILE");
+  h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
   h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
 
