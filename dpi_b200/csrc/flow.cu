@@ -6,54 +6,12 @@
 #include <mutex>
 #include <vector>
 
-#include "flow.cuh"
+#include "flow_host.cuh"
 
 namespace dpi {
-void* flow_kernel_ptr();
-
 namespace {
 
 inline long long pad32(long long n) { return (n + 31) / 32 * 32; }
-
-struct Program {
-  Phase* d_phases = nullptr;
-  int n_phases = 0;
-  int max_tiles = 0;
-  std::vector<int> phase_tiles;
-  std::vector<int> ops;
-};
-
-struct BatchPlan {
-  int B = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
-  long long oZT, oYT, oL1T, oL2T, oN1T, oN2T, oOT, oST, oLDP, oGYT, oGPRET, oGNT, oGP1T, oGP2T, oPART, oRED, total_floats;
-  // [dir][train] forward programs, and the backward program
-  Program fwd[2][2];
-  Program bwd[2];   // [1]: also produces the gradient wrt the flow input
-};
-
-}  // namespace
-}  // namespace dpi
-
-struct dpi_flow_s {
-  int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
-  int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
-  long long n_params = 0, n_bn = 0;
-  std::vector<dpi::StageTab> stages;          // reverse execution order
-  std::vector<long long> act_off;             // [n_flow][4]
-  std::vector<long long> cpl_off;             // [n_flow][2][P_COUNT]
-  std::vector<long long> bn_off;              // [n_flow][2][4]
-  std::vector<int32_t> h_gmaps;               // [2][S][D] + trailing [D]
-  dpi::StageTab* d_stages = nullptr;
-  int* d_gmaps = nullptr;
-  std::mutex mu;
-  std::map<int, std::unique_ptr<dpi::BatchPlan>> plans;
-  unsigned long long* d_tbuf = nullptr;       // debug timing stamps (2 per phase)
-  int tbuf_phases = 0;
-  std::vector<int> last_ops;                  // op codes of the last launched program (debug)
-};
-
-namespace dpi {
-namespace {
 
 // Flat parameter layout: nn.Module.parameters() order of the reference RealNVP, every tensor
 // start padded to 32 floats (128 B) so rows can be fetched with vector / bulk copies.
@@ -234,6 +192,9 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     if (rc) return rc;
   }
 
+  small_plan(h, bp);
+  const int ldp_slots = std::max(bp.ldp_tiles, bp.small.ok ? bp.small.ldp_tiles : 0);
+
   long long o = 0;
   auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
   bp.oZT = take((long long)D * B);
@@ -244,7 +205,7 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.oN2T = take((long long)S * H * B);
   bp.oOT = take((long long)S * Dout * B);
   bp.oST = take((long long)S * 4 * H);
-  bp.oLDP = take((long long)S * bp.ldp_tiles * B);
+  bp.oLDP = take((long long)S * ldp_slots * B);
   bp.oGYT = take(2LL * D * B);
   bp.oGPRET = take((long long)Dout * B);
   bp.oGNT = take((long long)H * B);
@@ -337,6 +298,7 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   // core, whose MN-major operand descriptors still mismatch on hardware (tools/bench_tile.cu).
   const char* tile = getenv("DPI_B200_TILE");
   h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
+  small_query(h.get());
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
   h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
 
@@ -548,6 +510,7 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
   a.dir = direction; a.train = train ? 1 : 0;
   a.P = params; a.G = nullptr; a.R = bn_running; a.in = in; a.out = out; a.logdet = logdet;
   a.g_out = nullptr; a.g_ld = nullptr; a.g_in = nullptr;
+  if (bp->small.ok) return small_launch(h, *bp, a, 0, (cudaStream_t)stream);
   return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
 }
 
@@ -569,6 +532,7 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   a.dir = 0; a.train = 1;
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
+  if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
   return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,61 @@
+// flow_host.cuh - host-side state of a flow handle, shared by the planner/launcher of the tiled phase
+// program (flow.cu) and of the small-batch cluster kernel (flow_small.cu).
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "flow.cuh"
+#include "flow_small.cuh"
+
+namespace dpi {
+void* flow_kernel_ptr();
+
+struct Program {
+  Phase* d_phases = nullptr;
+  int n_phases = 0;
+  int max_tiles = 0;
+  std::vector<int> phase_tiles;
+  std::vector<int> ops;
+};
+
+struct BatchPlan {
+  int B = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
+  long long oZT, oYT, oL1T, oL2T, oN1T, oN2T, oOT, oST, oLDP, oGYT, oGPRET, oGNT, oGP1T, oGP2T, oPART, oRED, total_floats;
+  // [dir][train] forward programs, and the backward program
+  Program fwd[2][2];
+  Program bwd[2];   // [1]: also produces the gradient wrt the flow input
+  // small-batch cluster kernel (batch <= 64): decomposition + shared-memory layout, or small.ok == 0
+  SmallPlan small;
+};
+
+}  // namespace dpi
+
+struct dpi_flow_s {
+  int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
+  int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
+  int small_mode = 1;                         // 0: never use the small-batch kernel
+  int small_clusters = 0, small_cl = 1;       // co-resident clusters and cluster size (8, or 1 without cluster launch)
+  int small_ksplit_min = 512;                 // GEMMs with K >= this are split over the ranks of a cluster
+  long long n_params = 0, n_bn = 0;
+  std::vector<dpi::StageTab> stages;          // reverse execution order
+  std::vector<long long> act_off;             // [n_flow][4]
+  std::vector<long long> cpl_off;             // [n_flow][2][P_COUNT]
+  std::vector<long long> bn_off;              // [n_flow][2][4]
+  std::vector<int32_t> h_gmaps;               // [2][S][D] + trailing [D]
+  dpi::StageTab* d_stages = nullptr;
+  int* d_gmaps = nullptr;
+  std::mutex mu;
+  std::map<int, std::unique_ptr<dpi::BatchPlan>> plans;
+  unsigned long long* d_tbuf = nullptr;       // debug timing stamps (2 per phase)
+  int tbuf_phases = 0;
+  std::vector<int> last_ops;                  // op codes of the last launched program (debug)
+};
+
+namespace dpi {
+// flow_small.cu
+int small_query(dpi_flow_s* h);                                        // fills small_clusters / small_cl
+void small_plan(const dpi_flow_s* h, BatchPlan& bp);                   // fills bp.small (ok = 0 if unsupported)
+int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream);
+}  // namespace dpi

@@ -13,7 +13,9 @@ from dpi_b200.generative_model.realnvpfc_model import RealNVP  # noqa: E402
 from dpi_b200.trainer import InterferometryTrainer, MRITrainer  # noqa: E402
 
 OPS = {1: "FWD_HID", 2: "FWD_OUT", 3: "BN_STATS", 4: "LOGDET", 5: "TRANSPOSE", 6: "B0", 7: "DGRAD_HID", 8: "WGRAD",
-       9: "DGRAD_IN", 10: "BNBWD", 11: "BWD_FINAL"}
+       9: "DGRAD_IN", 10: "BNBWD", 11: "BWD_FINAL",
+       20: "s.T_IN", 21: "s.F1", 22: "s.F2", 23: "s.F3", 24: "s.F_FIN", 25: "s.B0", 26: "s.DG2+WG3", 27: "s.DG1+WG2",
+       28: "s.DGIN+WG1", 29: "s.B_FIN"}
 
 
 def main():
