@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpi_b200.so")
+LIB_PATH = os.environ.get("DPI_B200_LIB") or os.path.join(_HERE, "libdpi_b200.so")   # override: A/B builds
 
 _lib = None
 _lock = threading.Lock()

@@ -195,22 +195,24 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   small_plan(h, bp);
   const int ldp_slots = std::max(bp.ldp_tiles, bp.small.ok ? bp.small.ldp_tiles : 0);
 
+  const long long LB = bp.small.ok ? (B + 3) / 4 * 4 : B;   // workspace row stride
+  bp.ldb = (int)LB;
   long long o = 0;
   auto take = [&](long long n) { long long r = o; o += pad32(n); return r; };
-  bp.oZT = take((long long)D * B);
-  bp.oYT = take((long long)S * D * B);
-  bp.oL1T = take((long long)S * H * B);
-  bp.oL2T = take((long long)S * H * B);
-  bp.oN1T = take((long long)S * H * B);
-  bp.oN2T = take((long long)S * H * B);
-  bp.oOT = take((long long)S * Dout * B);
+  bp.oZT = take((long long)D * LB);
+  bp.oYT = take((long long)S * D * LB);
+  bp.oL1T = take((long long)S * H * LB);
+  bp.oL2T = take((long long)S * H * LB);
+  bp.oN1T = take((long long)S * H * LB);
+  bp.oN2T = take((long long)S * H * LB);
+  bp.oOT = take((long long)S * Dout * LB);
   bp.oST = take((long long)S * 4 * H);
-  bp.oLDP = take((long long)S * ldp_slots * B);
-  bp.oGYT = take(2LL * D * B);
-  bp.oGPRET = take((long long)Dout * B);
-  bp.oGNT = take((long long)H * B);
-  bp.oGP1T = take((long long)H * B);
-  bp.oGP2T = take((long long)H * B);
+  bp.oLDP = take((long long)S * ldp_slots * LB);
+  bp.oGYT = take(2LL * D * LB);
+  bp.oGPRET = take((long long)Dout * LB);
+  bp.oGNT = take((long long)H * LB);
+  bp.oGP1T = take((long long)H * LB);
+  bp.oGP2T = take((long long)H * LB);
   bp.oPART = take(std::max(32LL, max_part));
   bp.oRED = take((long long)S * bp.red_tiles * 2);
   bp.total_floats = o;
@@ -233,7 +235,7 @@ int get_plan(dpi_flow_s* h, int B, BatchPlan** out) {
 void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
   a.st = h->d_stages; a.gmaps = h->d_gmaps;
   a.D = h->D; a.Da = h->Da; a.Db = h->Db; a.Dout = h->Dout; a.H = h->H; a.S = h->S; a.has_bn = h->has_bn;
-  a.B = bp.B; a.tiles_m = bp.tiles_m; a.ldp_tiles = bp.ldp_tiles; a.red_tiles = bp.red_tiles;
+  a.B = bp.B; a.ldb = bp.ldb; a.tiles_m = bp.tiles_m; a.ldp_tiles = bp.ldp_tiles; a.red_tiles = bp.red_tiles;
   a.oZT = bp.oZT; a.oYT = bp.oYT; a.oL1T = bp.oL1T; a.oL2T = bp.oL2T; a.oN1T = bp.oN1T; a.oN2T = bp.oN2T;
   a.oOT = bp.oOT; a.oST = bp.oST; a.oLDP = bp.oLDP; a.oGYT = bp.oGYT; a.oGPRET = bp.oGPRET; a.oGNT = bp.oGNT;
   a.oGP1T = bp.oGP1T; a.oGP2T = bp.oGP2T; a.oPART = bp.oPART; a.oRED = bp.oRED;
@@ -429,7 +431,8 @@ int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return -1;
   long long o;
-  const long long B = batch;
+  const long long B = bp->ldb;   // row stride of the saved matrices
+  if (what == 5) return bp->ldb;
   switch (what) {
     case 0: o = bp->oYT + stage * B * h->D; break;
     case 1: o = bp->oL1T + stage * B * h->H; break;
@@ -462,7 +465,9 @@ int dpi_flow_debug_read(dpi_flow_t h, uint64_t* stamps, int32_t* ops, int max_ph
   DeviceGuard g(h->device);
   DPI_CUDA(cudaDeviceSynchronize());
   const int n = std::min(h->tbuf_phases, max_phases);
-  DPI_CUDA(cudaMemcpy(stamps, h->d_tbuf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost));
+  // a caller that offers the whole buffer also gets the fine-grained stamps stored behind the phase stamps
+  DPI_CUDA(cudaMemcpy(stamps, h->d_tbuf, sizeof(unsigned long long) * 2 * (max_phases >= 4096 ? 4096 : n),
+                      cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; ++i) ops[i] = h->last_ops[i];
   return n;
 }

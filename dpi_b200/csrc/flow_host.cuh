@@ -21,7 +21,7 @@ struct Program {
 };
 
 struct BatchPlan {
-  int B = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
+  int B = 0, ldb = 0, tiles_m = 0, ldp_tiles = 0, red_tiles = 0;
   long long oZT, oYT, oL1T, oL2T, oN1T, oN2T, oOT, oST, oLDP, oGYT, oGPRET, oGNT, oGP1T, oGP2T, oPART, oRED, total_floats;
   // [dir][train] forward programs, and the backward program
   Program fwd[2][2];

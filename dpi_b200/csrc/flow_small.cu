@@ -42,6 +42,7 @@ struct Sm {
   int *idx, *idx2;
   float* red;             // 8 * 64 + 128 floats (static)
   const StageTab* st;     // stage table (staged into shared memory when it fits)
+  int phase;              // current phase (debug stamps)
 };
 
 // ------------------------------------------------------------------------------- synchronisation
@@ -91,6 +92,10 @@ __device__ __forceinline__ void grid_wait(unsigned* ctrl, unsigned target) {
   __syncthreads();
 }
 
+// Accurate expf / tanhf exist once in the binary (instruction-cache footprint, see the loaders' note).
+__device__ __noinline__ float exp_nf(float x) { return expf(x); }
+__device__ __noinline__ float tanh_nf(float x) { return tanhf(x); }
+
 // ------------------------------------------------------------------------------- addressing (as flow_kernels.cu Ctx)
 struct Cx {
   const KArgs& a;
@@ -98,29 +103,28 @@ struct Cx {
   const StageTab* stb;
   const StageTab& st;
   const int* gmap;
-  bool vec;
   __device__ Cx(const KArgs& a_, const StageTab* stb_, int e_)
       : a(a_), e(e_), stb(stb_), st(stb_[a_.dir ? a_.S - 1 - e_ : e_]),
-        gmap(a_.gmaps + ((size_t)a_.dir * a_.S + e_) * a_.D), vec((a_.B & 3) == 0) {}
-  __device__ __forceinline__ const float* yprev() const { return e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * a.D * a.B; }
-  __device__ __forceinline__ float* y() const { return a.W + a.oYT + (size_t)e * a.D * a.B; }
-  __device__ __forceinline__ float* L(int which) const { return a.W + (which == 1 ? a.oL1T : a.oL2T) + (size_t)e * a.H * a.B; }
-  __device__ __forceinline__ float* Nrm(int which) const { return a.W + (which == 1 ? a.oN1T : a.oN2T) + (size_t)e * a.H * a.B; }
-  __device__ __forceinline__ float* O() const { return a.W + a.oOT + (size_t)e * a.Dout * a.B; }
+        gmap(a_.gmaps + ((size_t)a_.dir * a_.S + e_) * a_.D) {}
+  __device__ __forceinline__ const float* yprev() const { return e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * a.D * a.ldb; }
+  __device__ __forceinline__ float* y() const { return a.W + a.oYT + (size_t)e * a.D * a.ldb; }
+  __device__ __forceinline__ float* L(int which) const { return a.W + (which == 1 ? a.oL1T : a.oL2T) + (size_t)e * a.H * a.ldb; }
+  __device__ __forceinline__ float* Nrm(int which) const { return a.W + (which == 1 ? a.oN1T : a.oN2T) + (size_t)e * a.H * a.ldb; }
+  __device__ __forceinline__ float* O() const { return a.W + a.oOT + (size_t)e * a.Dout * a.ldb; }
   __device__ __forceinline__ float* stats(int which, int what) const { return a.W + a.oST + ((size_t)e * 4 + (which - 1) * 2 + what) * a.H; }
   __device__ __forceinline__ const float* P(int id) const { return a.P + st.p[id]; }
   __device__ __forceinline__ float* G(int id) const { return a.G + st.p[id]; }
-  __device__ __forceinline__ const float* gy() const { return a.W + a.oGYT + (size_t)(e & 1) * a.D * a.B; }
-  __device__ __forceinline__ float* gyprev() const { return a.W + a.oGYT + (size_t)((e - 1) & 1) * a.D * a.B; }
+  __device__ __forceinline__ const float* gy() const { return a.W + a.oGYT + (size_t)(e & 1) * a.D * a.ldb; }
+  __device__ __forceinline__ float* gyprev() const { return a.W + a.oGYT + (size_t)((e - 1) & 1) * a.D * a.ldb; }
   // affine applied to the coupling output before it is stored (reverse: this stage's ActNorm.reverse :66;
   // forward: the NEXT stage's ActNorm.forward :45 - scalar, so it commutes with the permutation in between)
   __device__ __forceinline__ void post_affine(float& qa, float& qc) const {
     if (a.dir == 0) {
-      qa = expf(__ldg(a.P + st.lsi));
+      qa = exp_nf(__ldg(a.P + st.lsi));
       qc = -__ldg(a.P + st.loc);
     } else if (e + 1 < a.S) {
       const StageTab& nx = stb[a.S - 2 - e];
-      const float inv = 1.0f / expf(__ldg(a.P + nx.lsi));
+      const float inv = 1.0f / exp_nf(__ldg(a.P + nx.lsi));
       qa = inv;
       qc = __ldg(a.P + nx.loc) * inv;
     } else {
@@ -130,84 +134,72 @@ struct Cx {
 };
 
 // ------------------------------------------------------------------------------- asynchronous loaders
-// dst[r * ld + 0..63] <- row rowfn(r) of a feature-major matrix (B valid samples, zero-filled to 64);
-// rowfn(r) < 0 gives a zero row.
-template <typename RowFn>
-__device__ __forceinline__ void load_rows(float* dst, int ld, const float* base, int B, bool vec, int nrows, RowFn rowfn) {
-  for (int c = threadIdx.x; c < nrows * 16; c += kT) {
-    const int r = c >> 4, m4 = (c & 15) * 4;
-    const long long row = rowfn(r);
-    float* d = dst + r * ld + m4;
-    const float* s = base + (size_t)(row < 0 ? 0 : row) * B + m4;
-    const int left = row < 0 ? 0 : B - m4;
-    if (vec) {
-      cp_async16(d, left > 0 ? s : base, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
+// The kernel is instruction-fetch sensitive (a phase runs once, then ~100 other phases run before it runs
+// again): every helper below exists ONCE in the binary and all GEMM phases share them, so that the hot loop of
+// a pass stays resident in the instruction cache. Loops are deliberately not unrolled and avoid integer
+// division (tile extents are powers of two).
+// All rows of the workspace have a stride of LB = round_up4(B) floats and every weight row a length that
+// is a multiple of 4 (the planner guarantees it), so every copy is a 16-byte cp.async.
+//
+// dst[r * ld + 0..63] <- row (B valid samples, zero-filled to 64), r < nrows.
+//   mode 0: row = r0 + r; mode 1: row = idx[r]; mode 2: pair: half = r >> np_log, j = r & (np - 1), row = idx[half * 64 + j]
+//   valid while r0 + r (mode 2: r0 + j) < limit; invalid rows are zero-filled.
+__device__ __forceinline__ void load_rows(float* dst, int ld, const float* base, const int* idx, int mode, int r0, int limit,
+                                          int np_log, int LB, int B, int nrows) {
+  const int m4 = (threadIdx.x & 15) * 4;
+  const int left = B - m4;
+  const int bytes = left >= 4 ? 16 : (left > 0 ? left * 4 : 0);
+#pragma unroll 1
+  for (int r = threadIdx.x >> 4; r < nrows; r += 16) {
+    bool ok;
+    int row;
+    if (mode == 2) {
+      const int half = r >> np_log, j = r & ((1 << np_log) - 1);
+      ok = r0 + j < limit;
+      row = ok ? idx[half * 64 + j] : 0;
     } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = u < left;
-        cp_async4(d + u, ok ? s + u : base, ok);
-      }
+      ok = r0 + r < limit;
+      row = ok ? (mode == 1 ? idx[r] : r0 + r) : 0;
     }
+    const bool v = ok && bytes > 0;
+    cp_async16(dst + r * ld + m4, v ? base + (size_t)row * LB + m4 : base, v ? bytes : 0);
   }
 }
-// K-contiguous weight rows: W_s[r * ldw + kk] <- Wg[rowfn(r) * K + kb + kk], kk < knp, zero beyond klimit
-template <typename RowFn>
+// K-contiguous weight rows (one warp per row): W_s[r * ldw + kk] <- Wg[row(r) * K + kb + kk], kk < knp, zero beyond
+// klimit. row(r) = n0 + r (< N), or with np_log >= 0 the output-layer pairing (r >> np_log) * N + n0 + (r & (np-1)).
 __device__ __forceinline__ void load_w_k(float* W_s, int ldw, const float* Wg, int K, int nrows, int kb, int knp, int klimit,
-                                         RowFn rowfn) {
-  const int cpr = knp >> 2;
-  const bool vec = (K & 3) == 0;
-  for (int c = threadIdx.x; c < nrows * cpr; c += kT) {
-    const int r = c / cpr, k4 = (c - r * cpr) * 4;
-    const long long row = rowfn(r);
-    const int k = kb + k4;
-    const int left = row < 0 ? 0 : klimit - k;
-    float* d = W_s + r * ldw + k4;
-    const float* s = Wg + (size_t)(row < 0 ? 0 : row) * K + k;
-    if (vec) {
-      cp_async16(d, left > 0 ? s : Wg, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
+                                         int n0, int N, int np_log) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int r = threadIdx.x >> 5; r < nrows; r += 8) {
+    int row;
+    bool ok;
+    if (np_log >= 0) {
+      const int half = r >> np_log, j = n0 + (r & ((1 << np_log) - 1));
+      ok = j < N;
+      row = half * N + j;
     } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = u < left;
-        cp_async4(d + u, ok ? s + u : Wg, ok);
-      }
+      ok = n0 + r < N;
+      row = n0 + r;
+    }
+    const float* src = Wg + (size_t)(ok ? row : 0) * K + kb;
+#pragma unroll 1
+    for (int k4 = lane * 4; k4 < knp; k4 += 128) {
+      const int left = ok ? klimit - (kb + k4) : 0;
+      cp_async16(W_s + r * ldw + k4, left > 0 ? src + k4 : Wg, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
     }
   }
 }
-// N-contiguous weights: W_s[kk * ldw + nn] <- Wg[(kb + kk) * ldg + n0 + nn], nn < NT, zero beyond N / klimit
+// N-contiguous weights: W_s[kk * ldw + nn] <- Wg[(kb + kk) * ldg + n0 + nn], nn < NT = 4 << cpr_log
 __device__ __forceinline__ void load_w_n(float* W_s, int ldw, const float* Wg, int ldg, int kb, int knp, int klimit, int n0,
-                                         int NT, int N) {
-  const int cpr = NT >> 2;
-  const bool vec = (ldg & 3) == 0;
-  for (int c = threadIdx.x; c < knp * cpr; c += kT) {
-    const int kk = c / cpr, n4 = (c - kk * cpr) * 4;
+                                         int cpr_log, int N) {
+#pragma unroll 1
+  for (int c = threadIdx.x; c < (knp << cpr_log); c += kT) {
+    const int kk = c >> cpr_log, n4 = (c & ((1 << cpr_log) - 1)) * 4;
     const int k = kb + kk;
     const int left = k < klimit ? N - (n0 + n4) : 0;
-    float* d = W_s + kk * ldw + n4;
-    const float* s = Wg + (size_t)(k < klimit ? k : 0) * ldg + n0 + n4;
-    if (vec) {
-      cp_async16(d, left > 0 ? s : Wg, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = u < left;
-        cp_async4(d + u, ok ? s + u : Wg, ok);
-      }
-    }
-  }
-}
-// dst[t] <- src[n0 + t] for t < cnt (zero where n0 + t >= N)
-__device__ __forceinline__ void load_vec(float* dst, const float* src, int n0, int cnt, int N) {
-  for (int t = threadIdx.x; t < cnt; t += kT) {
-    const bool ok = n0 + t < N;
-    cp_async4(dst + t, ok ? src + n0 + t : src, ok);
-  }
-}
-__device__ __forceinline__ void load_ivec(int* dst, const int* src, int n0, int cnt, int N) {
-  for (int t = threadIdx.x; t < cnt; t += kT) {
-    const bool ok = n0 + t < N;
-    cp_async4(reinterpret_cast<float*>(dst + t), reinterpret_cast<const float*>(ok ? src + n0 + t : src), ok);
+    const float* src = left > 0 ? Wg + (size_t)k * ldg + n0 + n4 : Wg;
+    cp_async16(W_s + kk * ldw + n4, src, left >= 4 ? 16 : (left > 0 ? left * 4 : 0));
   }
 }
 
@@ -219,6 +211,7 @@ template <bool WK>
 __device__ __forceinline__ void act_mac(float (&acc)[4][4], const float* X_s, const float* W_s, int ldw, int knp, int sq,
                                         int fq, int kp, int KP) {
   if (WK) {
+#pragma unroll 1
     for (int k4 = 4 * kp; k4 < knp; k4 += 4 * KP) {
       float4 x[4], w[4];
 #pragma unroll
@@ -238,6 +231,7 @@ __device__ __forceinline__ void act_mac(float (&acc)[4][4], const float* X_s, co
       }
     }
   } else {
+#pragma unroll 2
     for (int k = kp; k < knp; k += KP) {
       const float4 x = *reinterpret_cast<const float4*>(X_s + k * kMB + 4 * sq);
       const float4 w = *reinterpret_cast<const float4*>(W_s + k * ldw + 4 * fq);
@@ -253,112 +247,162 @@ __device__ __forceinline__ void act_mac(float (&acc)[4][4], const float* X_s, co
   }
 }
 
-// One activation GEMM of a phase.
-struct ActDesc {
-  const ActPlan* pl;
-  const float* Xbase;   // feature-major activation matrix the k rows come from
-  const int* xmap;      // optional row map (k -> row), nullptr = identity
-  const float* Wg;      // weight matrix
-  int wk;               // 1: rows n are K-contiguous (row length = K); 0: rows k are N-contiguous (row length w_ld)
-  int w_ld;
-  int pair_np, pair_db; // F3: local row r -> (r / np) * db + j0 + r % np, valid while j0 + r % np < db
+// ------------------------------------------------------------------------------- phase descriptors
+// Every GEMM phase (F1, F2, F3, DG2, DG1, DGIN) is the same code driven by one of these.
+struct PD {
+  int kind, e, which;
+  // decomposition (copied from the plan)
+  int N, K, NT, nt_log, n_tiles, KC, KS, nq_log, kpn;
+  bool split, wk;
+  // operands
+  const float* Xbase; const int* xmap;      // activation rows (k axis) + optional row map
+  const float* Wg; int w_ld;                // weights; w_ld: row length when N-contiguous
+  int np_log, pair_db;                      // F3 row pairing (np_log < 0: none)
+  // per-tile parameter vectors -> s.Pm[64 * i + t] = pm[i][n0 + t], t < vcnt  (nullptr: unused)
+  const float* pm[5]; int pm_lim, vcnt;
+  // per-tile index vectors -> s.idx2[64 * i + t] = i2[i][n0 + t]
+  const int* i2[2]; int i2_lim;
+  // extra activation rows -> s.E: emode 0 none, 1 rows n0 + r of Ebase, 2 pair rows through idx2, 3 this rank's
+  // finalised features n0 + rank + nr * i of Ebase
+  const float* Ebase; int emode, elim;
+  // epilogue destinations (meaning per kind, see make_desc) and per-phase scalars
+  float* o[6];
+  float qa, qc, e_lsi;
 };
 
-__device__ __forceinline__ void issue_weights(const KArgs& a, const Sm& s, const ActDesc& d, int tile, int kb, int knp, int k_hi) {
-  const ActPlan& pl = *d.pl;
+__device__ __forceinline__ void plan_into(PD& d, const ActPlan& pl) {
+  d.N = pl.N; d.K = pl.K; d.NT = pl.NT; d.nt_log = pl.nt_log; d.n_tiles = pl.n_tiles; d.KC = pl.KC; d.KS = pl.KS;
+  d.nq_log = pl.nq_log; d.kpn = pl.kp; d.split = pl.ksplit != 0;
+}
+
+__device__ __noinline__ PD make_desc(const SArgs& A, const StageTab* stb, int kind, int e) {
+  const KArgs& a = A.k;
+  PD d;
+  d.kind = kind; d.e = e; d.which = 0;
+  d.xmap = nullptr; d.w_ld = 0; d.np_log = -1; d.pair_db = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) d.pm[i] = nullptr;
+  d.i2[0] = d.i2[1] = nullptr;
+  d.pm_lim = a.H; d.i2_lim = 0; d.Ebase = nullptr; d.emode = 0; d.elim = 0;
+  d.N = d.K = d.NT = d.nt_log = d.n_tiles = d.KC = d.KS = d.nq_log = d.kpn = 0; d.split = false; d.wk = true;
+  d.Xbase = nullptr; d.Wg = nullptr; d.vcnt = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d.o[i] = nullptr;
+  d.qa = 1.f; d.qc = 0.f; d.e_lsi = 1.f;
+  if (kind < K_F1 || kind == K_FFIN || kind == K_B0 || kind == K_BFIN) return d;
+  Cx c(a, stb, e);
+  switch (kind) {
+    case K_F1:
+    case K_F2: {
+      const int which = kind == K_F1 ? 1 : 2;
+      d.which = which;
+      plan_into(d, which == 1 ? A.sp.f1 : A.sp.f2);
+      d.wk = true;
+      d.Xbase = which == 1 ? c.yprev() : c.Nrm(1);
+      d.xmap = which == 1 ? c.gmap : nullptr;
+      d.Wg = c.P(which == 1 ? P_W1 : P_W2);
+      d.vcnt = d.NT;
+      d.pm[0] = c.P(which == 1 ? P_B1 : P_B2);
+      if (a.has_bn) {
+        d.pm[1] = c.P(which == 1 ? P_G1 : P_G2);
+        d.pm[2] = c.P(which == 1 ? P_BE1 : P_BE2);
+        d.pm[3] = a.R + c.st.r[(which - 1) * 2];
+        d.pm[4] = a.R + c.st.r[(which - 1) * 2 + 1];
+        d.o[2] = c.stats(which, 0); d.o[3] = c.stats(which, 1);
+        d.o[4] = a.R + c.st.r[(which - 1) * 2]; d.o[5] = a.R + c.st.r[(which - 1) * 2 + 1];
+      }
+      d.o[0] = c.L(which); d.o[1] = c.Nrm(which);     // saved LeakyReLU output / normalised activation rows
+      break;
+    }
+    case K_F3: {
+      plan_into(d, A.sp.f3);
+      d.wk = true;
+      d.Xbase = c.Nrm(2);
+      d.Wg = c.P(P_W3);
+      d.np_log = d.nt_log - 1; d.pair_db = a.Db;
+      d.vcnt = d.NT >> 1;
+      d.pm[0] = c.P(P_SCALE); d.pm[1] = c.P(P_SCALE) + a.Db; d.pm[2] = c.P(P_B3); d.pm[3] = c.P(P_B3) + a.Db;
+      d.pm_lim = a.Db;
+      d.i2[0] = c.gmap; d.i2[1] = c.gmap + a.Da; d.i2_lim = a.Db;
+      d.Ebase = c.yprev(); d.emode = 2; d.elim = a.Db;
+      d.o[0] = c.O(); d.o[1] = c.y(); d.o[2] = a.W + a.oLDP + (size_t)e * A.sp.ldp_tiles * a.ldb;
+      c.post_affine(d.qa, d.qc);
+      break;
+    }
+    case K_DG2:
+    case K_DG1: {
+      const int which = kind == K_DG2 ? 2 : 1;
+      d.which = which;
+      plan_into(d, which == 2 ? A.sp.dg2 : A.sp.dg1);
+      d.wk = false;
+      d.Xbase = a.W + (which == 2 ? a.oGPRET : a.oGP2T);
+      d.Wg = c.P(which == 2 ? P_W3 : P_W2); d.w_ld = a.H;
+      d.vcnt = d.NT;
+      if (a.has_bn) {
+        d.pm[0] = c.stats(which, 0); d.pm[1] = c.stats(which, 1); d.pm[2] = c.P(which == 1 ? P_G1 : P_G2);
+      }
+      d.Ebase = c.L(which); d.emode = 3; d.elim = a.H;
+      d.o[0] = a.W + (which == 2 ? a.oGP2T : a.oGP1T);
+      if (a.has_bn) { d.o[1] = c.G(which == 1 ? P_G1 : P_G2); d.o[2] = c.G(which == 1 ? P_BE1 : P_BE2); }
+      d.o[3] = c.G(which == 1 ? P_B1 : P_B2);
+      break;
+    }
+    default: {   // K_DGIN
+      plan_into(d, A.sp.dgin);
+      d.wk = false;
+      d.Xbase = a.W + a.oGP1T;
+      d.Wg = c.P(P_W1); d.w_ld = a.Da;
+      d.vcnt = d.NT;
+      d.i2[0] = c.gmap; d.i2_lim = a.Da;
+      d.Ebase = c.gy(); d.emode = 1; d.elim = a.Da;
+      d.o[0] = c.gyprev();
+      d.e_lsi = exp_nf(__ldg(a.P + c.st.lsi));
+      break;
+    }
+  }
+  return d;
+}
+
+// weights + row indices of one k-chunk of `tile`
+__device__ __forceinline__ void issue_weights(const Sm& s, const PD& d, int tile, int kb, int knp, int k_hi) {
   if (d.wk) {
-    const int ldw = pl.KS + 4;
-    if (d.pair_np) {
-      const int np = d.pair_np, db = d.pair_db, j0 = tile * np;
-      load_w_k(s.W, ldw, d.Wg, pl.K, pl.NT, kb, knp, k_hi, [=](int r) -> long long {
-        const int half = r / np, j = j0 + (r - half * np);
-        return j < db ? (long long)half * db + j : -1;
-      });
-    } else {
-      const int n0 = tile * pl.NT, N = pl.N;
-      load_w_k(s.W, ldw, d.Wg, pl.K, pl.NT, kb, knp, k_hi, [=](int r) -> long long { return n0 + r < N ? n0 + r : -1; });
-    }
+    if (d.np_log >= 0) load_w_k(s.W, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.np_log, d.pair_db, d.np_log);
+    else load_w_k(s.W, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.nt_log, d.N, -1);
   } else {
-    load_w_n(s.W, pl.NT + 4, d.Wg, d.w_ld, kb, knp, k_hi, tile * pl.NT, pl.NT, pl.N);
+    load_w_n(s.W, d.NT + 4, d.Wg, d.w_ld, kb, knp, k_hi, tile << d.nt_log, d.nt_log - 2, d.N);
   }
-  if (d.xmap) load_ivec(s.idx, d.xmap, kb, knp, k_hi);
+  if (d.xmap)
+    for (int t = threadIdx.x; t < knp; t += kT) {
+      const bool ok = kb + t < k_hi;
+      cp_async4(reinterpret_cast<float*>(s.idx + t), reinterpret_cast<const float*>(ok ? d.xmap + kb + t : d.xmap), ok);
+    }
+}
+// per-tile parameter / index vectors
+__device__ __forceinline__ void issue_params(const Sm& s, const PD& d, int tile) {
+  const int t = threadIdx.x & 63, which = threadIdx.x >> 6;      // 4 vectors per pass of the CTA
+  const int n0 = tile * d.vcnt;
+  if (t < d.vcnt) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      if ((i & 3) == which && d.pm[i]) {
+        const bool ok = n0 + t < d.pm_lim;
+        cp_async4(s.Pm + 64 * i + t, ok ? d.pm[i] + n0 + t : d.pm[i], ok);
+      }
+    }
+    if (which >= 2 && d.i2[which - 2]) {
+      const int* src = d.i2[which - 2];
+      const bool ok = n0 + t < d.i2_lim;
+      cp_async4(reinterpret_cast<float*>(s.idx2 + 64 * (which - 2) + t), reinterpret_cast<const float*>(ok ? src + n0 + t : src), ok);
+    }
+  }
 }
 
-// Issues (does not wait for) the first chunk of weights and row indices of `tile` for this rank.
-__device__ __forceinline__ void prefetch_act(const KArgs& a, const Sm& s, const ActDesc& d, int tile, int rank) {
-  const ActPlan& pl = *d.pl;
-  const int k_lo = rank * pl.KC, k_hi = min(pl.K, k_lo + pl.KC);
-  const int kn = max(0, min(pl.KS, k_hi - k_lo)), knp = (kn + 3) & ~3;
-  issue_weights(a, s, d, tile, k_lo, knp, k_hi);
-}
-
-// Computes the tile into s.R ([NT][64], this rank's partial when split). On return s.R is visible to
-// the CTA (and, when split, to the whole cluster). `extra` issues further activation loads that ride
-// in the same cp.async batch as the first chunk.
-template <typename Extra>
-__device__ __forceinline__ void act_tile(const KArgs& a, const Sm& s, const ActDesc& d, int tile, int rank, bool split,
-                                         bool prefetched, bool& cl_pending, Extra extra) {
-  const ActPlan& pl = *d.pl;
-  const int NT = pl.NT;
-  const int k_lo = rank * pl.KC, k_hi = min(pl.K, k_lo + pl.KC);
-  const int sq = threadIdx.x & 15, g = threadIdx.x >> 4, fq = g % pl.nq, kp = g / pl.nq;
-  const int ldw = d.wk ? pl.KS + 4 : NT + 4;
-  const bool vec = (a.B & 3) == 0;
-  float acc[4][4];
-#pragma unroll
-  for (int f = 0; f < 4; ++f)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[f][i] = 0.f;
-  bool first = true;
-  for (int kb = k_lo; first || kb < k_hi; kb += pl.KS) {
-    const int kn = max(0, min(pl.KS, k_hi - kb)), knp = (kn + 3) & ~3;
-    if (!(prefetched && first)) {
-      __syncthreads();   // earlier readers of W / idx / X are done
-      issue_weights(a, s, d, tile, kb, knp, k_hi);
-      cp_async_commit();
-    }
-    cp_async_wait<0>();
-    __syncthreads();     // weights + indices landed (and X of the previous chunk is free)
-    const int* idx = s.idx;
-    const bool mapped = d.xmap != nullptr;
-    load_rows(s.X, kMB, d.Xbase, a.B, vec, knp, [=](int r) -> long long {
-      const int k = kb + r;
-      return k < k_hi ? (mapped ? idx[r] : k) : -1;
-    });
-    if (first) extra();
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    if (d.wk) act_mac<true>(acc, s.X, s.W, ldw, knp, sq, fq, kp, pl.kp);
-    else act_mac<false>(acc, s.X, s.W, ldw, knp, sq, fq, kp, pl.kp);
-    first = false;
-  }
-  // k-part partials -> P_s[kp][n][m]
-#pragma unroll
-  for (int f = 0; f < 4; ++f)
-    *reinterpret_cast<float4*>(s.P + ((size_t)(kp * NT + 4 * fq + f)) * kMB + 4 * sq) =
-        make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
-  if (cl_pending) {      // the peers have finished reading the previous contents of R_s
-    cluster_wait();
-    cl_pending = false;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NT * 16; i += kT) {
-    const int n = i >> 4, m4 = (i & 15) * 4;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < pl.kp; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(s.P + ((size_t)(q * NT + n)) * kMB + m4);
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-    }
-    *reinterpret_cast<float4*>(s.R + n * kMB + m4) = t;
-  }
-  if (split) {
-    cluster_arrive();
-    cluster_wait();
-  } else {
-    __syncthreads();
-  }
-}
+#define STAMP(i)                                                                        \
+  do {                                                                                  \
+    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      a.tbuf[1024 + 8 * s.phase + (i)] = (unsigned long long)clock64();                 \
+    }                                                                                   \
+  } while (0)
 
 // sum over the ranks of the cluster (fixed order) of R_s[nl][lane], R_s[nl][lane + 32]
 __device__ __forceinline__ void combine(const Sm& s, int nl, int lane, int nr, float& s0, float& s1) {
@@ -375,228 +419,276 @@ __device__ __forceinline__ void combine(const Sm& s, int nl, int lane, int nr, f
   }
 }
 
-// ------------------------------------------------------------------------------- phases: forward pass
-struct Who {            // which unit of a phase this CTA is
-  int unit, units, rank, nr;
-  bool split;
-};
-__device__ __forceinline__ Who who(const SArgs& A, const ActPlan& pl) {
-  Who w;
-  w.split = pl.ksplit != 0;
-  if (w.split) {
-    w.unit = blockIdx.x / A.sp.cl; w.units = A.sp.G; w.rank = (int)cluster_rank(); w.nr = A.sp.cl;
-  } else {
-    w.unit = blockIdx.x; w.units = A.sp.NC; w.rank = 0; w.nr = 1;
+// ------------------------------------------------------------------------------- the generic GEMM phase
+// prefetch: everything of the phase's first tile that does not depend on the previous phase
+__device__ __forceinline__ void prefetch_gemm(const SArgs& A, const Sm& s, const PD& d) {
+  if (d.kind >= K_F1 && d.kind != K_FFIN && d.kind != K_B0 && d.kind != K_BFIN) {
+    const int unit = d.split ? blockIdx.x / A.sp.cl : blockIdx.x;
+    const int rank = d.split ? (int)cluster_rank() : 0;
+    if (unit < d.n_tiles) {
+      const int k_lo = rank * d.KC, k_hi = min(d.K, k_lo + d.KC);
+      const int kn = max(0, min(d.KS, k_hi - k_lo)), knp = (kn + 3) & ~3;
+      issue_weights(s, d, unit, k_lo, knp, k_hi);
+      issue_params(s, d, unit);
+    }
   }
-  return w;
+  cp_async_commit();
 }
 
-__device__ __forceinline__ ActDesc desc_hid_fwd(const SArgs& A, const Cx& c, int which) {
-  ActDesc d;
-  d.pl = which == 1 ? &A.sp.f1 : &A.sp.f2;
-  d.Xbase = which == 1 ? c.yprev() : c.Nrm(1);
-  d.xmap = which == 1 ? c.gmap : nullptr;
-  d.Wg = c.P(which == 1 ? P_W1 : P_W2);
-  d.wk = 1; d.w_ld = 0; d.pair_np = 0; d.pair_db = 0;
-  return d;
-}
-// per-feature parameters of a hidden-layer tile: Pm[0] bias, [1] gamma, [2] beta, [3] running_mean, [4] running_var
-__device__ __forceinline__ void issue_pm_hid_fwd(const KArgs& a, const Sm& s, const Cx& c, int which, int n0, int NT) {
-  load_vec(s.Pm, c.P(which == 1 ? P_B1 : P_B2), n0, NT, a.H);
-  if (a.has_bn) {
-    load_vec(s.Pm + 64, c.P(which == 1 ? P_G1 : P_G2), n0, NT, a.H);
-    load_vec(s.Pm + 128, c.P(which == 1 ? P_BE1 : P_BE2), n0, NT, a.H);
-    load_vec(s.Pm + 192, a.R + c.st.r[(which - 1) * 2], n0, NT, a.H);
-    load_vec(s.Pm + 256, a.R + c.st.r[(which - 1) * 2 + 1], n0, NT, a.H);
-  }
-}
-
-// net.0-2 / net.3-5: Linear + LeakyReLU(0.01) + BatchNorm1d(eps 1e-2)  (:171-187)
-__device__ void run_hid_fwd(const SArgs& A, const Sm& s, int e, int which, bool prefetched, bool& cl_pending) {
+__device__ __forceinline__ void run_gemm(const SArgs& A, const Sm& s, const PD& d, bool& cl_pending) {
   const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_hid_fwd(A, c, which);
-  const ActPlan& pl = *d.pl;
-  const Who w = who(A, pl);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int LB = a.ldb, NT = d.NT;
   const float invB = 1.0f / (float)a.B;
-  bool pf = prefetched;
-  for (int tile = w.unit; tile < pl.n_tiles; tile += w.units) {
-    const int n0 = tile * pl.NT;
+  const int unit = d.split ? blockIdx.x / A.sp.cl : blockIdx.x;
+  const int units = d.split ? A.sp.G : A.sp.NC;
+  const int rank = d.split ? (int)cluster_rank() : 0;
+  const int nr = d.split ? A.sp.cl : 1;
+  const int sq = threadIdx.x & 15, g = threadIdx.x >> 4, fq = g & ((1 << d.nq_log) - 1), kp = g >> d.nq_log;
+  const int ldw = d.wk ? d.KS + 4 : NT + 4;
+  const int k_lo = rank * d.KC, k_hi = min(d.K, k_lo + d.KC);
+  const float qa = d.qa, qc = d.qc, e_lsi = d.e_lsi;   // per-phase scalars of the epilogues
+  bool pf = true;
+#pragma unroll 1
+  for (int tile = unit; tile < d.n_tiles; tile += units) {
+    const int n0 = tile * d.vcnt;          // first feature (F3: first coupling column) of the tile
     if (!pf) {
       __syncthreads();
-      issue_pm_hid_fwd(a, s, c, which, n0, pl.NT);   // joins the weight batch committed inside act_tile
+      issue_params(s, d, tile);            // joins the weight batch committed below
     }
-    act_tile(a, s, d, tile, w.rank, w.split, pf, cl_pending, [] {});
-    pf = false;
-    for (int i = warp;; i += 8) {
-      const int nl = w.rank + w.nr * i;
-      if (nl >= pl.NT) break;
-      float s0, s1;
-      combine(s, nl, lane, w.nr, s0, s1);
-      const int n = n0 + nl;
-      if (n >= a.H) continue;
-      const bool ok0 = lane < a.B, ok1 = lane + 32 < a.B;
-      const float bj = s.Pm[nl];
-      const float v0 = lrelu_f(s0 + bj), v1 = lrelu_f(s1 + bj);
-      float* Lr = c.L(which) + (size_t)n * a.B;
-      if (ok0) __stcg(Lr + lane, v0);
-      if (ok1) __stcg(Lr + lane + 32, v1);
-      float n0v = v0, n1v = v1;
-      if (a.has_bn) {
-        const float gam = s.Pm[64 + nl], bet = s.Pm[128 + nl], rm = s.Pm[192 + nl], rv = s.Pm[256 + nl];
-        if (a.train) {
-          const float mean = warp_sum((ok0 ? v0 : 0.f) + (ok1 ? v1 : 0.f)) * invB;
-          const float d0 = v0 - mean, d1 = v1 - mean;
-          const float var = warp_sum((ok0 ? d0 * d0 : 0.f) + (ok1 ? d1 * d1 : 0.f)) * invB;
-          const float rstd = 1.0f / sqrtf(var + kBnEps);
-          const float ga = gam * rstd;
-          n0v = fmaf(d0, ga, bet);
-          n1v = fmaf(d1, ga, bet);
-          if (lane == 0) {
-            __stcg(c.stats(which, 0) + n, mean);
-            __stcg(c.stats(which, 1) + n, rstd);
-            a.R[c.st.r[(which - 1) * 2] + n] = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
-            a.R[c.st.r[(which - 1) * 2 + 1] + n] =
-                (1.f - kBnMomentum) * rv + kBnMomentum * (var * (float)a.B / (float)(a.B - 1));
+    // ---- operands -> shared memory, micro-GEMM over this rank's K range (in chunks of KS rows)
+    float acc[4][4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[f][i] = 0.f;
+    bool first = true;
+#pragma unroll 1
+    for (int kb = k_lo; first || kb < k_hi; kb += d.KS) {
+      const int kn = max(0, min(d.KS, k_hi - kb)), knp = (kn + 3) & ~3;
+      if (!(pf && first)) {
+        __syncthreads();   // earlier readers of W / idx / X are done
+        issue_weights(s, d, tile, kb, knp, k_hi);
+        cp_async_commit();
+      }
+      cp_async_wait<0>();
+      __syncthreads();     // weights + indices + parameters landed (and X of the previous chunk is free)
+      if (first) STAMP(1);
+      load_rows(s.X, kMB, d.Xbase, s.idx, d.xmap ? 1 : 0, kb, k_hi, 0, LB, a.B, knp);
+      if (first && d.emode) {
+        if (d.emode == 3) {      // saved LeakyReLU outputs of the features this rank finalises
+          const int nslots = max(0, (NT - rank + nr - 1) / nr);
+          const int r = threadIdx.x >> 4;
+          const int m4 = (threadIdx.x & 15) * 4, left = a.B - m4;
+          const int bytes = left >= 4 ? 16 : (left > 0 ? left * 4 : 0);
+#pragma unroll 1
+          for (int i = r; i < nslots; i += 16) {
+            const int n = n0 + rank + nr * i;
+            const bool v = n < d.elim && bytes > 0;
+            cp_async16(s.E + i * kMB + m4, v ? d.Ebase + (size_t)n * LB + m4 : d.Ebase, v ? bytes : 0);
           }
-        } else {   // eval: running statistics
-          const float rs = 1.0f / sqrtf(rv + kBnEps);
-          const float ga = gam * rs;
-          const float be = bet - rm * ga;
-          n0v = fmaf(v0, ga, be);
-          n1v = fmaf(v1, ga, be);
+        } else {
+          load_rows(s.E, kMB, d.Ebase, s.idx2, d.emode == 2 ? 2 : 0, n0, d.elim, d.np_log, LB, a.B,
+                    d.emode == 2 ? NT : NT);
         }
       }
-      float* Nr = c.Nrm(which) + (size_t)n * a.B;
-      if (ok0) __stcg(Nr + lane, n0v);
-      if (ok1) __stcg(Nr + lane + 32, n1v);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      if (first) STAMP(2);
+      if (d.wk) act_mac<true>(acc, s.X, s.W, ldw, knp, sq, fq, kp, d.kpn);
+      else act_mac<false>(acc, s.X, s.W, ldw, knp, sq, fq, kp, d.kpn);
+      first = false;
     }
-    if (w.split) {
+    pf = false;
+    // ---- k-part partials -> P_s[kp][n][m] -> R_s[n][m]
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      *reinterpret_cast<float4*>(s.P + ((size_t)(kp * NT + 4 * fq + f)) * kMB + 4 * sq) =
+          make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
+    if (cl_pending) {      // the peers have finished reading the previous contents of R_s
+      cluster_wait();
+      cl_pending = false;
+    }
+    __syncthreads();
+    STAMP(3);
+#pragma unroll 1
+    for (int i = threadIdx.x; i < NT * 16; i += kT) {
+      const int n = i >> 4, m4 = (i & 15) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int q = 0; q < d.kpn; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(s.P + ((size_t)(q * NT + n)) * kMB + m4);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(s.R + n * kMB + m4) = t;
+    }
+    if (d.split) {
+      cluster_arrive();
+      cluster_wait();
+    } else {
+      __syncthreads();
+    }
+    STAMP(4);
+    // ---- fused epilogue
+    const bool ok0 = lane < a.B, ok1 = lane + 32 < a.B;
+    if (d.kind == K_F1 || d.kind == K_F2) {
+      // net.0-2 / net.3-5: bias + LeakyReLU(0.01) + BatchNorm1d(eps 1e-2)  (:171-187); one warp per feature
+      const int which = d.which;
+#pragma unroll 1
+      for (int i = warp;; i += 8) {
+        const int nl = rank + nr * i;
+        if (nl >= NT) break;
+        float s0, s1;
+        combine(s, nl, lane, nr, s0, s1);
+        const int n = n0 + nl;
+        if (n >= a.H) continue;
+        const float bj = s.Pm[nl];
+        const float v0 = lrelu_f(s0 + bj), v1 = lrelu_f(s1 + bj);
+        float* Lr = d.o[0] + (size_t)n * LB;
+        if (ok0) __stcg(Lr + lane, v0);
+        if (ok1) __stcg(Lr + lane + 32, v1);
+        float n0v = v0, n1v = v1;
+        if (a.has_bn) {
+          const float gam = s.Pm[64 + nl], bet = s.Pm[128 + nl], rm = s.Pm[192 + nl], rv = s.Pm[256 + nl];
+          if (a.train) {
+            const float mean = warp_sum((ok0 ? v0 : 0.f) + (ok1 ? v1 : 0.f)) * invB;
+            const float d0 = v0 - mean, d1 = v1 - mean;
+            const float var = warp_sum((ok0 ? d0 * d0 : 0.f) + (ok1 ? d1 * d1 : 0.f)) * invB;
+            const float rstd = 1.0f / sqrtf(var + kBnEps);
+            const float ga = gam * rstd;
+            n0v = fmaf(d0, ga, bet);
+            n1v = fmaf(d1, ga, bet);
+            if (lane == 0) {
+              __stcg(d.o[2] + n, mean);
+              __stcg(d.o[3] + n, rstd);
+              d.o[4][n] = (1.f - kBnMomentum) * rm + kBnMomentum * mean;
+              d.o[5][n] = (1.f - kBnMomentum) * rv + kBnMomentum * (var * (float)a.B / (float)(a.B - 1));
+            }
+          } else {   // eval: running statistics
+            const float rs = 1.0f / sqrtf(rv + kBnEps);
+            const float ga = gam * rs;
+            const float be = bet - rm * ga;
+            n0v = fmaf(v0, ga, be);
+            n1v = fmaf(v1, ga, be);
+          }
+        }
+        float* Nr = d.o[1] + (size_t)n * LB;
+        if (ok0) __stcg(Nr + lane, n0v);
+        if (ok1) __stcg(Nr + lane + 32, n1v);
+      }
+    } else if (d.kind == K_F3) {
+      // ZeroFC (:137-141) + affine coupling (:244-249 / :226-231) + ActNorm (:66 / :45) + logdet partial
+      const int NP = NT >> 1;
+      float ld0 = 0.f, ld1 = 0.f;
+#pragma unroll 1
+      for (int p = warp; p < NP; p += 8) {
+        const int col = n0 + p;
+        if (col >= a.Db) continue;
+        const float e_ls = exp_nf(3.f * s.Pm[p]), e_t = exp_nf(3.f * s.Pm[64 + p]);
+        const float b_ls = s.Pm[128 + p], b_t = s.Pm[192 + p];
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int m = lane + 32 * hh;
+          const float ols = (s.R[p * kMB + m] + b_ls) * e_ls;
+          const float ot = (s.R[(NP + p) * kMB + m] + b_t) * e_t;
+          const float av = s.E[p * kMB + m], bv = s.E[(NP + p) * kMB + m];
+          const float ls = tanh_nf(ols);
+          float bp, dl;
+          if (a.dir == 0) { bp = __fdividef(bv, exp_nf(ls)) - ot; dl = -ls; }
+          else            { bp = (bv + ot) * exp_nf(ls); dl = ls; }
+          if (m < a.B) {
+            __stcg(d.o[0] + (size_t)col * LB + m, ols);
+            __stcg(d.o[0] + (size_t)(a.Db + col) * LB + m, ot);
+            __stcg(d.o[1] + (size_t)(a.Da + col) * LB + m, fmaf(bp, qa, qc));
+            __stcg(d.o[1] + (size_t)col * LB + m, fmaf(av, qa, qc));
+            if (hh == 0) ld0 += dl; else ld1 += dl;
+          }
+        }
+      }
+      // odd D: the a-half has one more row than the b-half (chunk(2,1) semantics, :241)
+      if (a.Da > a.Db && tile == 0 && warp == 0) {
+        const int col = a.Da - 1;
+        const float* src = d.Ebase + (size_t)__ldg(d.i2[0] + col) * LB;
+        for (int m = lane; m < a.B; m += 32) __stcg(d.o[1] + (size_t)col * LB + m, fmaf(__ldcg(src + m), qa, qc));
+      }
+      // per-sample logdet partial of this tile: the 8 warps' sums in fixed order
+      s.red[warp * 64 + lane] = ld0;
+      s.red[warp * 64 + lane + 32] = ld1;
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += s.red[r * 64 + threadIdx.x];
+        if ((int)threadIdx.x < a.B) __stcg(d.o[2] + (size_t)tile * LB + threadIdx.x, t);
+      }
+      __syncthreads();
+    } else if (d.kind == K_DG2 || d.kind == K_DG1) {
+      // dgrad through net.6.fc.weight / net.3.weight + BatchNorm and LeakyReLU backward of hidden layer `which`
+      float* dstbuf = d.o[0];
+#pragma unroll 1
+      for (int i = warp;; i += 8) {
+        const int nl = rank + nr * i;
+        if (nl >= NT) break;
+        float g0, g1;
+        combine(s, nl, lane, nr, g0, g1);
+        const int n = n0 + nl;
+        if (n >= a.H) continue;
+        if (!ok0) g0 = 0.f;
+        if (!ok1) g1 = 0.f;
+        const float l0 = s.E[i * kMB + lane], l1 = s.E[i * kMB + lane + 32];
+        float gl0 = g0, gl1 = g1, gbeta = 0.f, ggamma = 0.f;
+        if (a.has_bn) {
+          const float mean = s.Pm[nl], rstd = s.Pm[64 + nl], gam = s.Pm[128 + nl];
+          const float xh0 = (l0 - mean) * rstd, xh1 = (l1 - mean) * rstd;
+          gbeta = warp_sum(g0 + g1);
+          ggamma = warp_sum(fmaf(g0, xh0, g1 * xh1));
+          gl0 = gam * rstd * (g0 - gbeta * invB - xh0 * ggamma * invB);
+          gl1 = gam * rstd * (g1 - gbeta * invB - xh1 * ggamma * invB);
+        }
+        const float p0 = ok0 ? gl0 * (l0 > 0.f ? 1.f : kLreluSlope) : 0.f;
+        const float p1 = ok1 ? gl1 * (l1 > 0.f ? 1.f : kLreluSlope) : 0.f;
+        const float gbias = warp_sum(p0 + p1);
+        float* dr = dstbuf + (size_t)n * LB;
+        if (ok0) __stcg(dr + lane, p0);
+        if (ok1) __stcg(dr + lane + 32, p1);
+        if (lane == 0) {
+          if (a.has_bn) {
+            d.o[1][n] = ggamma;
+            d.o[2][n] = gbeta;
+          }
+          d.o[3][n] = gbias;
+        }
+      }
+    } else {
+      // K_DGIN: dgrad through net.0.weight + the direct path through the a-half and ActNorm, written through the
+      // fused permutation into the rows of the gradient wrt the previous stage's output
+#pragma unroll 1
+      for (int nl = warp; nl < NT; nl += 8) {
+        const int n = n0 + nl;
+        if (n >= a.Da) continue;
+        float* dr = d.o[0] + (size_t)s.idx2[nl] * LB;
+        if (ok0) __stcg(dr + lane, fmaf(s.E[nl * kMB + lane], e_lsi, s.R[nl * kMB + lane]));
+        if (ok1) __stcg(dr + lane + 32, fmaf(s.E[nl * kMB + lane + 32], e_lsi, s.R[nl * kMB + lane + 32]));
+      }
+    }
+    if (d.split) {
       cluster_arrive();
       cl_pending = true;
     }
   }
 }
-__device__ void prefetch_hid_fwd(const SArgs& A, const Sm& s, int e, int which) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_hid_fwd(A, c, which);
-  const Who w = who(A, *d.pl);
-  if (w.unit >= d.pl->n_tiles) return;
-  prefetch_act(a, s, d, w.unit, w.rank);
-  issue_pm_hid_fwd(a, s, c, which, w.unit * d.pl->NT, d.pl->NT);
-}
 
-// ZeroFC (:137-141) + affine coupling (:244-249 / :226-231) + ActNorm (:66 / :45) + logdet partial.
-// A tile = NP coupling columns j: rows j (log_s) and Db + j (t) of net.6.fc.weight.
-__device__ __forceinline__ ActDesc desc_out(const SArgs& A, const Cx& c) {
-  ActDesc d;
-  d.pl = &A.sp.f3;
-  d.Xbase = c.Nrm(2); d.xmap = nullptr;
-  d.Wg = c.P(P_W3); d.wk = 1; d.w_ld = 0;
-  d.pair_np = A.sp.f3.NT / 2; d.pair_db = A.k.Db;
-  return d;
-}
-__device__ __forceinline__ void issue_pm_out(const KArgs& a, const Sm& s, const Cx& c, int j0, int NP) {
-  load_vec(s.Pm, c.P(P_SCALE), j0, NP, a.Db);
-  load_vec(s.Pm + 64, c.P(P_SCALE) + a.Db, j0, NP, a.Db);
-  load_vec(s.Pm + 128, c.P(P_B3), j0, NP, a.Db);
-  load_vec(s.Pm + 192, c.P(P_B3) + a.Db, j0, NP, a.Db);
-  load_ivec(s.idx2, c.gmap, j0, NP, a.Db);                 // a-half source rows
-  load_ivec(s.idx2 + 64, c.gmap + a.Da, j0, NP, a.Db);     // b-half source rows
-}
-__device__ void run_out(const SArgs& A, const Sm& s, int e, bool prefetched, bool& cl_pending) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_out(A, c);
-  const ActPlan& pl = *d.pl;
-  const int NP = pl.NT / 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* yp = c.yprev();
-  float qa, qc;
-  c.post_affine(qa, qc);
-  bool pf = prefetched;
-  for (int tile = blockIdx.x; tile < pl.n_tiles; tile += A.sp.NC) {
-    const int j0 = tile * NP;
-    if (!pf) {
-      __syncthreads();
-      issue_pm_out(a, s, c, j0, NP);
-    }
-    const int* idx2 = s.idx2;
-    float* E = s.E;
-    const int B = a.B, Db = a.Db;
-    const bool vec = c.vec;
-    act_tile(a, s, d, tile, 0, false, pf, cl_pending, [=] {
-      load_rows(E, kMB, yp, B, vec, 2 * NP, [=](int r) -> long long {
-        const int half = r / NP, j = j0 + (r - half * NP);
-        return j < Db ? idx2[half * 64 + (r - half * NP)] : -1;
-      });
-    });
-    pf = false;
-    float ld0 = 0.f, ld1 = 0.f;
-    for (int p = warp; p < NP; p += 8) {
-      const int col = j0 + p;
-      if (col >= a.Db) continue;
-      const float e_ls = expf(3.f * s.Pm[p]), e_t = expf(3.f * s.Pm[64 + p]);
-      const float b_ls = s.Pm[128 + p], b_t = s.Pm[192 + p];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int m = lane + 32 * hh;
-        const float ols = (s.R[p * kMB + m] + b_ls) * e_ls;
-        const float ot = (s.R[(NP + p) * kMB + m] + b_t) * e_t;
-        const float av = s.E[p * kMB + m], bv = s.E[(NP + p) * kMB + m];
-        const float ls = tanhf(ols);
-        float bp, dl;
-        if (a.dir == 0) { bp = bv / expf(ls) - ot; dl = -ls; }
-        else            { bp = (bv + ot) * expf(ls); dl = ls; }
-        if (m < a.B) {
-          __stcg(c.O() + (size_t)col * a.B + m, ols);
-          __stcg(c.O() + (size_t)(a.Db + col) * a.B + m, ot);
-          __stcg(c.y() + (size_t)(a.Da + col) * a.B + m, fmaf(bp, qa, qc));
-          __stcg(c.y() + (size_t)col * a.B + m, fmaf(av, qa, qc));
-          if (hh == 0) ld0 += dl; else ld1 += dl;
-        }
-      }
-    }
-    // odd D: the a-half has one more row than the b-half (chunk(2,1) semantics, :241)
-    if (a.Da > a.Db && tile == 0 && warp == 0) {
-      const int col = a.Da - 1;
-      const float* src = yp + (size_t)__ldg(c.gmap + col) * a.B;
-      for (int m = lane; m < a.B; m += 32) __stcg(c.y() + (size_t)col * a.B + m, fmaf(__ldcg(src + m), qa, qc));
-    }
-    // per-sample logdet partial of this tile: the 8 warps' sums in fixed order
-    s.red[warp * 64 + lane] = ld0;
-    s.red[warp * 64 + lane + 32] = ld1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      float t = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) t += s.red[r * 64 + threadIdx.x];
-      if ((int)threadIdx.x < a.B) __stcg(a.W + a.oLDP + ((size_t)e * A.sp.ldp_tiles + tile) * a.B + threadIdx.x, t);
-    }
-    __syncthreads();
-  }
-}
-__device__ void prefetch_out(const SArgs& A, const Sm& s, int e) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_out(A, c);
-  if ((int)blockIdx.x >= d.pl->n_tiles) return;
-  prefetch_act(a, s, d, blockIdx.x, 0);
-  issue_pm_out(a, s, c, blockIdx.x * (d.pl->NT / 2), d.pl->NT / 2);
-}
-
-// ------------------------------------------------------------------------------- transposes / finals
+// ------------------------------------------------------------------------------- transposes / finals (cold)
 // 32 x 32 tiles through shared memory. mode:
-//   0 pass input : in [B][D] -> ZT [D][B] (forward direction: stage-0 ActNorm applied)
-//   1 backward input: g_out [B][D] -> GYT[(S-1)&1] [D][B]
-//   2 reverse output: YT[S-1] [D][B] -> out [B][D]
+//   0 pass input : in [B][D] -> ZT [D][LB] (forward direction: stage-0 ActNorm applied)
+//   1 backward input: g_out [B][D] -> GYT[(S-1)&1] [D][LB]
+//   2 reverse output: YT[S-1] [D][LB] -> out [B][D]
 //   3 forward output: YT[S-1][gf[j]][m] -> out [B][D] (trailing permutation :590 after :446)
-//   4 backward output: GYT[1] [D][B] -> g_in [B][D]
-__device__ void run_transpose(const KArgs& a, const StageTab* stb, int mode, float* sT, int NC) {
-  const bool to_fm = mode <= 1;
-  const int R = to_fm ? a.B : a.D, C = to_fm ? a.D : a.B;
+//   4 backward output: GYT[1] [D][LB] -> g_in [B][D]
+__device__ __noinline__ void run_transpose(const KArgs& a, const StageTab* stb, int mode, float* sT, int NC) {
+  const bool to_fm = mode <= 1;      // sample-major [B][D] -> feature-major [D][LB]
+  const int LB = a.ldb;
   const float* src; float* dst; const int* map = nullptr;
   float fa = 1.f, fc = 0.f;
   if (mode == 0) {
@@ -607,13 +699,15 @@ __device__ void run_transpose(const KArgs& a, const StageTab* stb, int mode, flo
       fa = inv; fc = __ldg(a.P + s0.loc) * inv;
     }
   } else if (mode == 1) {
-    src = a.g_out; dst = a.W + a.oGYT + (size_t)((a.S - 1) & 1) * a.D * a.B;
+    src = a.g_out; dst = a.W + a.oGYT + (size_t)((a.S - 1) & 1) * a.D * LB;
   } else if (mode == 2 || mode == 3) {
-    src = a.W + a.oYT + (size_t)(a.S - 1) * a.D * a.B; dst = a.out;
+    src = a.W + a.oYT + (size_t)(a.S - 1) * a.D * LB; dst = a.out;
     if (mode == 3) map = a.gmaps + (size_t)2 * a.S * a.D;
   } else {
-    src = a.W + a.oGYT + (size_t)1 * a.D * a.B; dst = a.g_in;
+    src = a.W + a.oGYT + (size_t)1 * a.D * LB; dst = a.g_in;
   }
+  const int R = to_fm ? a.B : a.D, C = to_fm ? a.D : a.B;
+  const int lds = to_fm ? a.D : LB, ldd = to_fm ? LB : a.D;
   const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += NC) {
@@ -625,7 +719,7 @@ __device__ void run_transpose(const KArgs& a, const StageTab* stb, int mode, flo
       float v = 0.f;
       if (r < R && cc < C) {
         const int rr = map ? __ldg(map + r) : r;
-        v = __ldcg(src + (size_t)rr * C + cc);
+        v = __ldcg(src + (size_t)rr * lds + cc);
       }
       sT[(ly + 8 * i) * 33 + lx] = fmaf(v, fa, fc);
     }
@@ -633,16 +727,17 @@ __device__ void run_transpose(const KArgs& a, const StageTab* stb, int mode, flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int cc = tc * 32 + ly + 8 * i, r = tr * 32 + lx;
-      if (r < R && cc < C) __stcg(dst + (size_t)cc * R + r, sT[lx * 33 + ly + 8 * i]);
+      if (r < R && cc < C) __stcg(dst + (size_t)cc * ldd + r, sT[lx * 33 + ly + 8 * i]);
     }
   }
 }
 
 // logdet[m] = sum over stages / tiles of the coupling partials + sum_s (+-) D * log_scale_inv_s  (CTA 0)
-__device__ void run_logdet_final(const SArgs& A, const Sm& s) {
+__device__ __noinline__ void run_logdet_final(const SArgs& A, const Sm& s) {
   const KArgs& a = A.k;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int n = a.S * A.sp.ldp_tiles;
+  const int LB = a.ldb;
   const float* ldp = a.W + a.oLDP;
   float lsum = 0.f;
   for (int e = 0; e < a.S; ++e) lsum += __ldg(a.P + s.st[e].lsi);
@@ -655,11 +750,11 @@ __device__ void run_logdet_final(const SArgs& A, const Sm& s) {
       for (; i + 8 <= hi; i += 8) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ldcg(ldp + (size_t)(i + u) * a.B + m);
+        for (int u = 0; u < 8; ++u) v[u] = ldcg(ldp + (size_t)(i + u) * LB + m);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u & 3] += v[u];
       }
-      for (; i < hi; ++i) acc[0] += ldcg(ldp + (size_t)i * a.B + m);
+      for (; i < hi; ++i) acc[0] += ldcg(ldp + (size_t)i * LB + m);
     }
     __syncthreads();
     s.red[slice * 32 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
@@ -673,34 +768,35 @@ __device__ void run_logdet_final(const SArgs& A, const Sm& s) {
   }
 }
 
-// ------------------------------------------------------------------------------- phases: backward pass
+// ------------------------------------------------------------------------------- backward-only phases
 // Elementwise backward of ActNorm.reverse and the coupling tail, one warp per coupling column, a lane
 // owns samples lane and lane + 32. Produces g_pre^T, the gradients of net.6.scale /
 // net.6.fc.bias, the b-half rows of the gradient wrt the stage input and ActNorm partial sums.
-__device__ void run_b0(const SArgs& A, const Sm& s, int e) {
+__device__ __forceinline__ void run_b0(const SArgs& A, const Sm& s, int e) {
   const KArgs& a = A.k;
   Cx c(a, s.st, e);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float lsi = __ldg(a.P + c.st.lsi), loc = __ldg(a.P + c.st.loc);
-  const float e_lsi = expf(lsi);
-  const size_t B = a.B;
+  const float e_lsi = exp_nf(lsi);
+  const size_t LB = a.ldb;
+#pragma unroll 1
   for (int t = blockIdx.x; t < A.sp.red_tiles; t += A.sp.NC) {
     const int col = t * 8 + w;
     float S1 = 0.f, S2 = 0.f;
     if (col < a.Db) {
-      const float E_ls = expf(3.f * __ldg(c.P(P_SCALE) + col));
-      const float E_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
+      const float E_ls = exp_nf(3.f * __ldg(c.P(P_SCALE) + col));
+      const float E_t = exp_nf(3.f * __ldg(c.P(P_SCALE) + a.Db + col));
       const int gcol = __ldg(c.gmap + a.Da + col);
-      const float* gya = c.gy() + (size_t)col * B;
-      const float* gyb = c.gy() + (size_t)(a.Da + col) * B;
-      const float* ya = c.y() + (size_t)col * B;
-      const float* yb = c.y() + (size_t)(a.Da + col) * B;
-      const float* ols = c.O() + (size_t)col * B;
-      const float* ot = c.O() + (size_t)(a.Db + col) * B;
-      const float* bp = c.yprev() + (size_t)gcol * B;
-      float* gp_ls = a.W + a.oGPRET + (size_t)col * B;
-      float* gp_t = a.W + a.oGPRET + (size_t)(a.Db + col) * B;
-      float* dst = c.gyprev() + (size_t)gcol * B;
+      const float* gya = c.gy() + (size_t)col * LB;
+      const float* gyb = c.gy() + (size_t)(a.Da + col) * LB;
+      const float* ya = c.y() + (size_t)col * LB;
+      const float* yb = c.y() + (size_t)(a.Da + col) * LB;
+      const float* ols = c.O() + (size_t)col * LB;
+      const float* ot = c.O() + (size_t)(a.Db + col) * LB;
+      const float* bp = c.yprev() + (size_t)gcol * LB;
+      float* gp_ls = a.W + a.oGPRET + (size_t)col * LB;
+      float* gp_t = a.W + a.oGPRET + (size_t)(a.Db + col) * LB;
+      float* dst = c.gyprev() + (size_t)gcol * LB;
       float v_ga[2], v_gb[2], v_ya[2], v_yb[2], v_ols[2], v_ot[2], v_b[2], v_gld[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {          // all loads of both samples in flight together
@@ -712,7 +808,7 @@ __device__ void run_b0(const SArgs& A, const Sm& s, int e) {
         v_b[hh] = ok ? __ldcg(bp + m) : 0.f;   v_gld[hh] = ok ? __ldcg(a.g_ld + m) : 0.f;
       }
       float sc_ls = 0.f, sc_t = 0.f, b3_ls = 0.f, b3_t = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         const int m = lane + 32 * hh;
         if (m < a.B) {
@@ -721,8 +817,8 @@ __device__ void run_b0(const SArgs& A, const Sm& s, int e) {
           S2 += ga_ * (v_ya[hh] + loc) + gb_ * (v_yb[hh] + loc);
           const float gbp = gb_ * e_lsi;
           const float o_ls = v_ols[hh], o_t = v_ot[hh];
-          const float ls = tanhf(o_ls);
-          const float ei = 1.0f / expf(ls);
+          const float ls = tanh_nf(o_ls);
+          const float ei = exp_nf(-ls);
           const float g_t = -gbp;
           const float g_ls = -gbp * v_b[hh] * ei - v_gld[hh];
           const float g_ols = g_ls * (1.f - ls * ls);
@@ -743,8 +839,8 @@ __device__ void run_b0(const SArgs& A, const Sm& s, int e) {
       }
     }
     if (a.Da > a.Db && t == 0) {   // odd D: the last a-row contributes to the ActNorm sums
-      const float* gq = c.gy() + (size_t)(a.Da - 1) * B;
-      const float* yv = c.y() + (size_t)(a.Da - 1) * B;
+      const float* gq = c.gy() + (size_t)(a.Da - 1) * LB;
+      const float* yv = c.y() + (size_t)(a.Da - 1) * LB;
       for (int m = threadIdx.x; m < a.B; m += kT) {
         const float gv = __ldcg(gq + m);
         S1 += gv;
@@ -762,158 +858,10 @@ __device__ void run_b0(const SArgs& A, const Sm& s, int e) {
   }
 }
 
-// dgrad through net.6.fc.weight (which = 2: k = output row o, source g_pre^T) or net.3.weight (which = 1:
-// k = h', source g_p2^T), with the BatchNorm + LeakyReLU backward of hidden layer `which` fused.
-__device__ __forceinline__ ActDesc desc_dg_hid(const SArgs& A, const Cx& c, int which) {
-  ActDesc d;
-  d.pl = which == 2 ? &A.sp.dg2 : &A.sp.dg1;
-  d.Xbase = A.k.W + (which == 2 ? A.k.oGPRET : A.k.oGP2T); d.xmap = nullptr;
-  d.Wg = c.P(which == 2 ? P_W3 : P_W2); d.wk = 0; d.w_ld = A.k.H;
-  d.pair_np = 0; d.pair_db = 0;
-  return d;
-}
-__device__ __forceinline__ void issue_pm_dg_hid(const KArgs& a, const Sm& s, const Cx& c, int which, int n0, int NT) {
-  if (a.has_bn) {
-    load_vec(s.Pm, c.stats(which, 0), n0, NT, a.H);
-    load_vec(s.Pm + 64, c.stats(which, 1), n0, NT, a.H);
-    load_vec(s.Pm + 128, c.P(which == 1 ? P_G1 : P_G2), n0, NT, a.H);
-  }
-}
-__device__ void run_dg_hid(const SArgs& A, const Sm& s, int e, int which, bool prefetched, bool& cl_pending) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_dg_hid(A, c, which);
-  const ActPlan& pl = *d.pl;
-  const Who w = who(A, pl);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float invB = 1.0f / (float)a.B;
-  float* dstbuf = a.W + (which == 2 ? a.oGP2T : a.oGP1T);
-  bool pf = prefetched;
-  for (int tile = w.unit; tile < pl.n_tiles; tile += w.units) {
-    const int n0 = tile * pl.NT;
-    if (!pf) {
-      __syncthreads();
-      issue_pm_dg_hid(a, s, c, which, n0, pl.NT);
-    }
-    float* E = s.E;
-    const float* Lb = c.L(which);
-    const int B = a.B, H = a.H, NT = pl.NT, rank = w.rank, nr = w.nr;
-    const bool vec = c.vec;
-    const int nslots = (NT - rank + nr - 1) / nr;     // features this rank finalises: n0 + rank + nr * i
-    act_tile(a, s, d, tile, w.rank, w.split, pf, cl_pending, [=] {
-      load_rows(E, kMB, Lb, B, vec, nslots > 0 ? nslots : 0, [=](int i) -> long long {
-        const int n = n0 + rank + nr * i;
-        return n < H ? n : -1;
-      });
-    });
-    pf = false;
-    for (int i = warp;; i += 8) {
-      const int nl = w.rank + w.nr * i;
-      if (nl >= pl.NT) break;
-      float g0, g1;
-      combine(s, nl, lane, w.nr, g0, g1);
-      const int n = n0 + nl;
-      if (n >= a.H) continue;
-      const bool ok0 = lane < a.B, ok1 = lane + 32 < a.B;
-      if (!ok0) g0 = 0.f;
-      if (!ok1) g1 = 0.f;
-      const float l0 = s.E[i * kMB + lane], l1 = s.E[i * kMB + lane + 32];
-      float gl0 = g0, gl1 = g1, gbeta = 0.f, ggamma = 0.f;
-      if (a.has_bn) {
-        const float mean = s.Pm[nl], rstd = s.Pm[64 + nl], gam = s.Pm[128 + nl];
-        const float xh0 = (l0 - mean) * rstd, xh1 = (l1 - mean) * rstd;
-        gbeta = warp_sum(g0 + g1);
-        ggamma = warp_sum(fmaf(g0, xh0, g1 * xh1));
-        gl0 = gam * rstd * (g0 - gbeta * invB - xh0 * ggamma * invB);
-        gl1 = gam * rstd * (g1 - gbeta * invB - xh1 * ggamma * invB);
-      }
-      const float p0 = ok0 ? gl0 * (l0 > 0.f ? 1.f : kLreluSlope) : 0.f;
-      const float p1 = ok1 ? gl1 * (l1 > 0.f ? 1.f : kLreluSlope) : 0.f;
-      const float gbias = warp_sum(p0 + p1);
-      float* dr = dstbuf + (size_t)n * a.B;
-      if (ok0) __stcg(dr + lane, p0);
-      if (ok1) __stcg(dr + lane + 32, p1);
-      if (lane == 0) {
-        if (a.has_bn) {
-          c.G(which == 1 ? P_G1 : P_G2)[n] = ggamma;
-          c.G(which == 1 ? P_BE1 : P_BE2)[n] = gbeta;
-        }
-        c.G(which == 1 ? P_B1 : P_B2)[n] = gbias;
-      }
-    }
-    if (w.split) {
-      cluster_arrive();
-      cl_pending = true;
-    }
-  }
-}
-__device__ void prefetch_dg_hid(const SArgs& A, const Sm& s, int e, int which) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_dg_hid(A, c, which);
-  const Who w = who(A, *d.pl);
-  if (w.unit >= d.pl->n_tiles) return;
-  prefetch_act(a, s, d, w.unit, w.rank);
-  issue_pm_dg_hid(a, s, c, which, w.unit * d.pl->NT, d.pl->NT);
-}
-
-// dgrad through net.0.weight plus the direct path through the a-half and ActNorm, written through the
-// fused permutation into the rows of the gradient wrt the previous stage's output.
-__device__ __forceinline__ ActDesc desc_dg_in(const SArgs& A, const Cx& c) {
-  ActDesc d;
-  d.pl = &A.sp.dgin;
-  d.Xbase = A.k.W + A.k.oGP1T; d.xmap = nullptr;
-  d.Wg = c.P(P_W1); d.wk = 0; d.w_ld = A.k.Da;
-  d.pair_np = 0; d.pair_db = 0;
-  return d;
-}
-__device__ void run_dg_in(const SArgs& A, const Sm& s, int e, bool prefetched, bool& cl_pending) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_dg_in(A, c);
-  const ActPlan& pl = *d.pl;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float e_lsi = expf(__ldg(a.P + c.st.lsi));
-  bool pf = prefetched;
-  for (int tile = blockIdx.x; tile < pl.n_tiles; tile += A.sp.NC) {
-    const int n0 = tile * pl.NT;
-    if (!pf) {
-      __syncthreads();
-      load_ivec(s.idx2, c.gmap, n0, pl.NT, a.Da);
-    }
-    float* E = s.E;
-    const float* gyb = c.gy();
-    const int B = a.B, Da = a.Da, NT = pl.NT;
-    const bool vec = c.vec;
-    act_tile(a, s, d, tile, 0, false, pf, cl_pending, [=] {
-      load_rows(E, kMB, gyb, B, vec, NT, [=](int r) -> long long { return n0 + r < Da ? n0 + r : -1; });
-    });
-    pf = false;
-    for (int nl = warp; nl < pl.NT; nl += 8) {
-      const int n = n0 + nl;
-      if (n >= a.Da) continue;
-      float* dr = c.gyprev() + (size_t)s.idx2[nl] * a.B;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int m = lane + 32 * hh;
-        if (m < a.B) __stcg(dr + m, fmaf(s.E[nl * kMB + m], e_lsi, s.R[nl * kMB + m]));
-      }
-    }
-  }
-}
-__device__ void prefetch_dg_in(const SArgs& A, const Sm& s, int e) {
-  const KArgs& a = A.k;
-  Cx c(a, s.st, e);
-  const ActDesc d = desc_dg_in(A, c);
-  if ((int)blockIdx.x >= d.pl->n_tiles) return;
-  prefetch_act(a, s, d, blockIdx.x, 0);
-  load_ivec(s.idx2, c.gmap, blockIdx.x * d.pl->NT, d.pl->NT, a.Da);
-}
-
 // Weight gradients gW[i][j] = sum_m g^T[i][m] * act^T[j][m]  (which = 3: fc.weight, 2: net.3, 1: net.0), computed
 // in the shadow of the grid barrier. Tile TI x TJ, thread tile 4 x 4 (rows 4 iq + a, columns jq + (TJ/4) b).
 template <int TI, int TJ, int MS>
-__device__ __forceinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int which) {
+__device__ __noinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int which) {
   const KArgs& a = A.k;
   Cx c(a, s.st, e);
   const int I = which == 3 ? a.Dout : a.H;
@@ -927,20 +875,22 @@ __device__ __forceinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, 
   float* G_s = s.X;
   float* A_s = s.X + TI * kLdG;
   float* red = s.X + (TI + TJ) * kLdG;      // MS == 4: [4][16][64] floats
+  int* jidx = reinterpret_cast<int*>(red);  // which == 1: gathered row indices (dead before `red` is written)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int jq, iq, mp;
   if (MS == 4) { jq = lane & 15; iq = (lane >> 4) + 2 * (warp & 1); mp = warp >> 1; }
   else { jq = lane; iq = warp; mp = 0; }
-  const bool vec = c.vec;
+#pragma unroll 1
   for (int t = blockIdx.x; t < tiles_i * tiles_j; t += A.sp.NC) {
     const int ti = t / tiles_j, tj = t - ti * tiles_j;
     const int i0 = ti * TI, j0 = tj * TJ;
     __syncthreads();   // previous users of the X region are done
-    load_rows(G_s, kLdG, gsrc, a.B, vec, TI, [=](int r) -> long long { return i0 + r < I ? i0 + r : -1; });
-    load_rows(A_s, kLdG, act, a.B, vec, TJ, [=](int r) -> long long {
-      const int j = j0 + r;
-      return j < J ? (amap ? __ldg(amap + j) : j) : -1;
-    });
+    if (amap) {
+      for (int r = threadIdx.x; r < TJ; r += kT) jidx[r] = j0 + r < J ? __ldg(amap + j0 + r) : 0;
+      __syncthreads();
+    }
+    load_rows(G_s, kLdG, gsrc, nullptr, 0, i0, I, 0, a.ldb, a.B, TI);
+    load_rows(A_s, kLdG, act, jidx, amap ? 1 : 0, j0, J, 0, a.ldb, a.B, TJ);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -950,7 +900,7 @@ __device__ __forceinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, 
 #pragma unroll
       for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
     constexpr int MW = kMB / MS;
-#pragma unroll 2
+#pragma unroll 1
     for (int m = mp * MW; m < (mp + 1) * MW; m += 4) {
       float4 g[4], v[4];
 #pragma unroll
@@ -974,6 +924,7 @@ __device__ __forceinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, 
 #pragma unroll
         for (int y = 0; y < 4; ++y) red[((mp * 16) + x * 4 + y) * 64 + ij] = acc[x][y];
       __syncthreads();
+#pragma unroll 1
       for (int o = threadIdx.x; o < 1024; o += kT) {
         const int xy = o >> 6, ij2 = o & 63;
         const float t4 = ((red[(0 * 16 + xy) * 64 + ij2] + red[(1 * 16 + xy) * 64 + ij2]) +
@@ -992,13 +943,9 @@ __device__ __forceinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, 
     }
   }
 }
-__device__ void run_wgrad(const SArgs& A, const Sm& s, int e, int which) {
-  if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, e, which);
-  else wgrad_tiles<32, 128, 1>(A, s, e, which);
-}
 
 // ActNorm.reverse gradients: g_loc = -sum g_y, g_lsi = sum g_y * (y + loc) + D * sum_m g_ld[m]  (CTA 0)
-__device__ void run_bwd_final(const SArgs& A, const Sm& s) {
+__device__ __noinline__ void run_bwd_final(const SArgs& A, const Sm& s) {
   const KArgs& a = A.k;
   float sacc = 0.f;
   for (int m = threadIdx.x; m < a.B; m += kT) sacc += ldcg(a.g_ld + m);
@@ -1027,22 +974,9 @@ __device__ __forceinline__ void decode(const SArgs& A, int p, int& kind, int& e)
     else { kind = K_FFIN; e = S - 1; }
   } else {
     if (p == 0) { kind = K_TIN; e = S - 1; }
-    else if (p <= 4 * S) { e = S - 1 - (p - 1) / 4; kind = K_B0 + (p - 1) % 4; }
+    else if (p <= 4 * S) { e = S - 1 - ((p - 1) >> 2); kind = K_B0 + ((p - 1) & 3); }
     else { kind = K_BFIN; e = 0; }
   }
-}
-
-__device__ __forceinline__ void prefetch_phase(const SArgs& A, const Sm& s, int kind, int e) {
-  switch (kind) {
-    case K_F1: prefetch_hid_fwd(A, s, e, 1); break;
-    case K_F2: prefetch_hid_fwd(A, s, e, 2); break;
-    case K_F3: prefetch_out(A, s, e); break;
-    case K_DG2: prefetch_dg_hid(A, s, e, 2); break;
-    case K_DG1: prefetch_dg_hid(A, s, e, 1); break;
-    case K_DGIN: prefetch_dg_in(A, s, e); break;
-    default: break;
-  }
-  cp_async_commit();
 }
 
 }  // namespace
@@ -1062,6 +996,7 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
   s.idx2 = reinterpret_cast<int*>(smem_raw + A.sp.oIdx2);
   s.red = sRed;
   s.st = A.k.st;
+  s.phase = A.k.phase_begin;
   if (A.k.S <= 64) {
     const int4* src = reinterpret_cast<const int4*>(A.k.st);
     int4* dst = reinterpret_cast<int4*>(sSt);
@@ -1073,52 +1008,70 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
   bool cl_pending = false;
   unsigned bar = 0;
   const bool persistent = a.persistent != 0;
-  int kind, e;
-  decode(A, a.phase_begin, kind, e);
-  prefetch_phase(A, s, kind, e);
-  for (int p = a.phase_begin; p < a.phase_end; ++p) {
-    decode(A, p, kind, e);
-    if (persistent && p > a.phase_begin) grid_wait(a.ctrl, (++bar) * gridDim.x);
-    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      a.tbuf[2 * p] = t;
-    }
-    switch (kind) {
-      case K_TIN: run_transpose(a, s.st, A.bwd ? 1 : 0, s.X, A.sp.NC); break;
-      case K_F1: run_hid_fwd(A, s, e, 1, true, cl_pending); break;
-      case K_F2: run_hid_fwd(A, s, e, 2, true, cl_pending); break;
-      case K_F3: run_out(A, s, e, true, cl_pending); break;
-      case K_FFIN:
+  int kind = K_TIN, e = 0;
+  // Phase descriptors depend only on (kind, stage): all of them are built once, in parallel, into shared memory
+  // so that the per-phase critical path only reads them.
+  PD* pd = reinterpret_cast<PD*>(smem_raw + A.sp.oPD);
+  for (int p = a.phase_begin + (int)threadIdx.x; p < a.phase_end; p += kT) {
+    int k2, e2;
+    decode(A, p, k2, e2);
+    pd[p - a.phase_begin] = make_desc(A, s.st, k2, e2);
+  }
+  __syncthreads();
+  // iteration p = phase_begin - 1 is a virtual phase that only prefetches for the first one, so that
+  // prefetch_gemm has a single call site (instruction-cache footprint)
+#pragma unroll 1
+  for (int p = a.phase_begin - 1; p < a.phase_end; ++p) {
+    const bool real = p >= a.phase_begin;
+    if (real) {
+      const PD& d = pd[p - a.phase_begin];
+      s.phase = p;
+      if (persistent && p > a.phase_begin) grid_wait(a.ctrl, (++bar) * gridDim.x);
+      STAMP(0);
+      if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.tbuf[2 * p] = t;
+      }
+      kind = d.kind; e = d.e;
+      if (kind == K_B0) {
+        run_b0(A, s, e);
+      } else if (kind == K_TIN) {
+        run_transpose(a, s.st, A.bwd ? 1 : 0, s.X, A.sp.NC);
+      } else if (kind == K_FFIN) {
         if (blockIdx.x == 0) run_logdet_final(A, s);
         __syncthreads();
         run_transpose(a, s.st, a.dir == 0 ? 2 : 3, s.X, A.sp.NC);
-        break;
-      case K_B0: run_b0(A, s, e); break;
-      case K_DG2: run_dg_hid(A, s, e, 2, true, cl_pending); break;
-      case K_DG1: run_dg_hid(A, s, e, 1, true, cl_pending); break;
-      case K_DGIN: run_dg_in(A, s, e, true, cl_pending); break;
-      case K_BFIN:
+      } else if (kind == K_BFIN) {
         if (blockIdx.x == 0) run_bwd_final(A, s);
         __syncthreads();
         if (a.g_in) run_transpose(a, s.st, 4, s.X, A.sp.NC);
-        break;
-    }
-    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      a.tbuf[2 * p + 1] = t;
+      } else {
+        run_gemm(A, s, d, cl_pending);
+      }
+      STAMP(5);
+      if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.tbuf[2 * p + 1] = t;
+      }
     }
     if (p + 1 < a.phase_end) {
-      if (persistent) grid_arrive(a.ctrl); else __syncthreads();
-      int k2, e2;
-      decode(A, p + 1, k2, e2);
-      prefetch_phase(A, s, k2, e2);        // next hop's weights / indices / parameters -> shared memory
+      if (real) {
+        if (persistent) grid_arrive(a.ctrl); else __syncthreads();
+      }
+      prefetch_gemm(A, s, pd[p + 1 - a.phase_begin]);   // next hop's weights / indices / parameters -> shared memory
     }
-    // shadow of the barrier: weight gradients of this stage (inputs complete since the previous barrier)
-    if (kind == K_DG2) run_wgrad(A, s, e, 3);
-    else if (kind == K_DG1) run_wgrad(A, s, e, 2);
-    else if (kind == K_DGIN) run_wgrad(A, s, e, 1);
+    if (real) {
+      STAMP(6);
+      // shadow of the barrier: weight gradients of this stage (inputs complete since the previous barrier)
+      if (kind == K_DG2 || kind == K_DG1 || kind == K_DGIN) {
+        const int which = kind == K_DG2 ? 3 : (kind == K_DG1 ? 2 : 1);
+        if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, e, which);
+        else wgrad_tiles<32, 128, 1>(A, s, e, which);
+      }
+      STAMP(7);
+    }
   }
   cp_async_wait<0>();
   if (cl_pending) cluster_wait();
@@ -1153,6 +1106,9 @@ ActPlan plan_act(int N, int K, bool split, int G, int NC, int cl, bool wk, int m
   while (p.KS > 4 && wbytes(p.KS) > wmax) p.KS = up4(p.KS / 2);
   p.nq = nt / 4;
   p.kp = 16 / p.nq;
+  p.nt_log = 0;
+  while ((1 << p.nt_log) < nt) ++p.nt_log;
+  p.nq_log = p.nt_log - 2;
   return p;
 }
 
@@ -1195,7 +1151,7 @@ int small_query(dpi_flow_s* h) {
 void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
   SmallPlan& sp = bp.small;
   sp = SmallPlan{};
-  if (!h->small_mode || bp.B > kMB || h->H > 512 || h->S < 1) return;
+  if (!h->small_mode || bp.B > kMB || h->H > 512 || (h->H & 3) || (h->Da & 3)) return;
   const int cl = h->small_cl, G = h->small_clusters, NC = cl == 8 ? 8 * G : G;
   sp.NC = NC; sp.G = cl == 8 ? G : NC; sp.cl = cl;
   const int H = h->H, Da = h->Da, Db = h->Db, Dout = h->Dout;
@@ -1207,6 +1163,9 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
     while (np < 32 && (Db + np - 1) / np > NC) np *= 2;
     ActPlan p = plan_act(2 * np, H, false, sp.G, NC, cl, true, 0);
     p.NT = 2 * np; p.nq = p.NT / 4; p.kp = 16 / p.nq;
+    p.nt_log = 0;
+    while ((1 << p.nt_log) < p.NT) ++p.nt_log;
+    p.nq_log = p.nt_log - 2;
     p.N = Db; p.n_tiles = (Db + np - 1) / np;
     p.KS = std::min(p.KC, 512);
     while (p.KS > 4 && p.NT * (p.KS + 4) * 4 > 36 * 1024) p.KS = up4(p.KS / 2);
@@ -1228,7 +1187,7 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
     wb = std::max(wb, wk ? p.NT * (p.KS + 4) * 4 : p.KS * (p.NT + 4) * 4);
     ib = std::max(ib, p.KS * 4);
   }
-  const int wg_bytes = sp.wgv == 0 ? (16 + 64) * kLdG * 4 + 16 * 1024 : (32 + 128) * kLdG * 4;
+  const int wg_bytes = sp.wgv == 0 ? (16 + 64) * kLdG * 4 + 16 * 1024 : (32 + 128) * kLdG * 4 + 1024;
   xb = std::max(xb, std::max(wg_bytes, 33 * 32 * 4));
   auto al = [](int x) { return (x + 127) & ~127; };
   int o = 0;
@@ -1240,6 +1199,8 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
   sp.oPm = o; o += 5 * 64 * 4;
   sp.oIdx = o; o += al(ib);
   sp.oIdx2 = o; o += 128 * 4;
+  const int n_ph = 4 * h->S + 2;                       // backward pass has the most phases
+  sp.oPD = o; o += al(n_ph * (int)sizeof(PD));
   sp.smem_bytes = o;
   sp.ok = o <= 200 * 1024 ? 1 : 0;
 }

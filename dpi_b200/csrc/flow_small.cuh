@@ -20,6 +20,7 @@ struct ActPlan {
   int KC;          // K extent of one rank (multiple of 4)
   int KS;          // rows per shared-memory chunk (multiple of 4, <= KC)
   int nq, kp;      // feature quads per tile, k-parts per CTA (nq * kp == 16)
+  int nt_log, nq_log;  // log2(NT), log2(nq)
 };
 
 struct SmallPlan {
@@ -29,7 +30,7 @@ struct SmallPlan {
   int wgv;                     // weight-gradient tile variant: 0 = 16 x 64 (4-way sample split), 1 = 32 x 128
   int ldp_tiles, red_tiles;    // logdet partial slots per stage, ActNorm partial slots per stage
   // dynamic shared memory layout (byte offsets)
-  int oX, oW, oE, oP, oR, oPm, oIdx, oIdx2, smem_bytes;
+  int oX, oW, oE, oP, oR, oPm, oIdx, oIdx2, oPD, smem_bytes;
 };
 
 }  // namespace dpi

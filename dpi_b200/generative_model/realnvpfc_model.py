@@ -377,7 +377,8 @@ class RealNVP(nn.Module):
                     self.bn_running.copy_(saved_bn)
                     self._nbt = saved_nbt
                     off = lib.dpi_flow_ws_offset(h, B, 0, e - 1)
-                    src = self._last_ws[off:off + 4 * B * self.ndim].view(torch.float32).view(B, self.ndim)
+                    ld = lib.dpi_flow_ws_offset(h, B, 5, 0)       # row stride of the saved [ndim][ld] matrices
+                    src = self._last_ws[off:off + 4 * ld * self.ndim].view(torch.float32).view(self.ndim, ld)[:, :B]
                 self._view(f"blocks.{i}.{an}.loc").copy_(-src.mean().reshape(1))
                 self._view(f"blocks.{i}.{an}.log_scale_inv").copy_(torch.log(src.std().reshape(1) + 1e-6))
             self._initialized[i, a] = 1

@@ -75,9 +75,11 @@ int64_t dpi_flow_bn_offset(dpi_flow_t h, int flow, int coupling /*0|1*/, int sta
 int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out);
 
 size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch);
-/* Byte offset inside the workspace of a saved activation of execution stage `stage`:
- * what 0: stage output y [batch, ndim]; 1/2: LeakyReLU outputs [batch, hidden]; 3: ZeroFC output
- * [batch, 2*(ndim/2)]; 4: batch statistics (mean1, rstd1, mean2, rstd2) [4, hidden]. */
+/* Byte offset inside the workspace of a saved activation of execution stage `stage`. The saved matrices
+ * are feature-major [features][ld] with ld >= batch samples per row:
+ * what 0: stage output y [ndim][ld]; 1/2: LeakyReLU outputs [hidden][ld]; 3: ZeroFC output
+ * [2*(ndim/2)][ld]; 4: batch statistics (mean1, rstd1, mean2, rstd2) [4, hidden];
+ * what 5 returns the row stride ld (floats) instead of an offset. */
 int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage);
 
 /* RealNVP.reverse (direction 0, :594-603) / RealNVP.forward (direction 1, :583-592).

@@ -48,6 +48,7 @@ def main():
         st = np.zeros(2 * 4096, dtype=np.uint64)
         ops = np.zeros(4096, dtype=np.int32)
         n = lib.dpi_flow_debug_read(tr.handle, st.ctypes.data, ops.ctypes.data, 4096)
+        fine = st[1024:1024 + 8 * n].astype(np.int64).reshape(n, 8)
         st = st[:2 * n].astype(np.int64).reshape(n, 2)
         start, done = st[:, 0], st[:, 1]
         work = done - start
@@ -62,6 +63,29 @@ def main():
             v = np.array(v)
             print(f"   {key[0]:<12} layer={key[1]} two_subops={key[2]}  n={len(v):3d}  work {v[:, 0].mean() / 1e3:7.2f} us  "
                   f"wait-after {v[:, 1].mean() / 1e3:7.2f} us")
+        if fine.any():
+            ok = fine[:, 0] != 0
+            if ok.sum() > 2:
+                i0, i1 = np.flatnonzero(ok)[0], np.flatnonzero(ok)[-1]
+                mhz = (fine[i1, 0] - fine[i0, 0]) / max(1, (start[i1] - start[i0])) * 1e3
+                print(f"   SM clock during the pass (clock64 / globaltimer): {mhz:.0f} MHz")
+            # small-batch kernel: stamps 0 phase start, 1 prefetched weights landed, 2 activation rows landed,
+            # 3 micro-GEMM done, 4 k-part (+cluster) reduction done, 5 epilogue done, 6 arrive + next prefetch issued,
+            # 7 shadow (weight gradients) done; the next phase's stamp 0 closes the barrier wait
+            names = ["pf-wait", "act-load", "gemm", "reduce", "epilogue", "arrive+pf", "shadow", "barrier"]
+            byk = {}
+            for i in range(n - 1):
+                f = fine[i]
+                if f[0] == 0:
+                    continue
+                d = [f[1] - f[0], f[2] - f[1], f[3] - f[2], f[4] - f[3], f[5] - f[4], f[6] - f[5], f[7] - f[6],
+                     fine[i + 1][0] - f[7]]
+                if f[1] == 0 or f[4] == 0:      # phases without a GEMM tile on CTA 0
+                    d = [0, 0, 0, 0, f[5] - f[0], f[6] - f[5], f[7] - f[6], fine[i + 1][0] - f[7]]
+                byk.setdefault(OPS.get(ops[i] // 100, "?"), []).append(d)
+            for k, v in byk.items():
+                v = np.array(v[2:] if len(v) > 4 else v, dtype=np.float64) / 1.965e3   # SM cycles at 1965 MHz -> us
+                print(f"   {k:<12} " + "  ".join(f"{nm} {x:5.2f}" for nm, x in zip(names, v.mean(0))) + f"  | total {v.mean(0).sum():5.2f} us")
         print("   first 12 phases (work, wait) us:", [(round(work[i] / 1e3, 1), round(wait[i] / 1e3, 1)) for i in range(min(12, n))])
 
 
