@@ -50,6 +50,11 @@ PROTOTYPES = {
     "dpi_eht_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_eht_data_grad": (i32, [vp, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, sz, vp]),
     "dpi_chi2": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "dpi_crescent_forward": (i32, [i32, i32, i32, f32, vp, vp, vp]),
+    "dpi_crescent_backward": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+    "dpi_sigmoid_forward": (i32, [i32, i32, vp, vp, vp, vp]),
+    "dpi_sigmoid_backward": (i32, [i32, i32, vp, vp, vp, vp, vp]),
+    "dpi_alpha_objective": (i32, [i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "dpi_fft2c_forward": (i32, [i32, i32, vp, vp, vp]),
     "dpi_fft2c_backward": (i32, [i32, i32, vp, vp, vp]),
     "dpi_mri_data_loss": (i32, [i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp]),

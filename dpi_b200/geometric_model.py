@@ -1,0 +1,77 @@
+"""Drop-in for the reference's `geometric_model.SimpleCrescentNuisanceFloor_Param2Img`
+(DPItorch/geometric_model.py:237-389): crescent (asymmetric ring + erf disk floor) + n elliptical nuisance
+Gaussians rendered from parameters in (0, 1), unit total flux. Forward and backward run as hand-written CUDA
+(dpi_b200/csrc/crescent.cu, one CTA per image) through a torch.autograd.Function; there is no CPU fallback.
+
+Only the configuration DPIx_interferometry.py uses for data_product 'cphase_logcamp' is implemented:
+flux_flag=False and the constructor's default parameter ranges (r_range [10, 40] as the script passes).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from dpi_b200 import _lib
+
+
+class _CrescentFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, npix, n_gaussian, fov):
+        if not params.is_cuda:
+            raise RuntimeError("dpi_b200.geometric_model runs on CUDA only (no CPU fallback); got a CPU tensor")
+        lib = _lib.load()
+        p = params.contiguous().float()
+        B = p.shape[0]
+        img = torch.empty(B, npix, npix, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.dpi_crescent_forward(B, npix, n_gaussian, float(fov), p.data_ptr(), img.data_ptr(),
+                                                _lib.stream_ptr()), "dpi_crescent_forward")
+        ctx.save_for_backward(p)
+        ctx.cfg = (npix, n_gaussian, float(fov))
+        return img
+
+    @staticmethod
+    def backward(ctx, g_img):
+        (p,) = ctx.saved_tensors
+        npix, n_gaussian, fov = ctx.cfg
+        lib = _lib.load()
+        g = g_img.contiguous().float()
+        gp = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.dpi_crescent_backward(p.shape[0], npix, n_gaussian, fov, p.data_ptr(), g.data_ptr(), None,
+                                                 gp.data_ptr(), _lib.stream_ptr()), "dpi_crescent_backward")
+        return gp, None, None, None
+
+
+class SimpleCrescentNuisanceFloor_Param2Img(nn.Module):
+    """Same constructor signature and `forward(params) -> img [B, npix, npix]` as the reference class."""
+
+    def __init__(self, npix, n_gaussian=1, fov=160, r_range=[10.0, 40.0], asym_range=[1e-3, 0.99],
+                 width_range=[1.0, 40.0], floor_range=[0.0, 1.0], flux_range=[0.8, 1.2], crescent_flux_range=[1e-3, 2.0],
+                 shift_range=[-200.0, 200.0], sigma_range=[1.0, 100.0], gaussian_scale_range=[1e-3, 2.0], flux_flag=False):
+        super().__init__()
+        defaults = dict(r_range=[10.0, 40.0], asym_range=[1e-3, 0.99], width_range=[1.0, 40.0], floor_range=[0.0, 1.0],
+                        crescent_flux_range=[1e-3, 2.0], shift_range=[-200.0, 200.0], sigma_range=[1.0, 100.0],
+                        gaussian_scale_range=[1e-3, 2.0])
+        given = dict(r_range=r_range, asym_range=asym_range, width_range=width_range, floor_range=floor_range,
+                     crescent_flux_range=crescent_flux_range, shift_range=shift_range, sigma_range=sigma_range,
+                     gaussian_scale_range=gaussian_scale_range)
+        for k, v in defaults.items():
+            if [float(x) for x in given[k]] != v:
+                raise NotImplementedError(f"dpi_b200: only the default {k}={v} is compiled into the CUDA renderer")
+        if flux_flag:
+            raise NotImplementedError("dpi_b200: flux_flag=True (7 + 6 g parameters) is not implemented")
+        if not 0 <= n_gaussian <= 4:
+            raise NotImplementedError("dpi_b200: 0..4 nuisance Gaussians")
+        self.npix, self.n_gaussian, self.fov, self.flux_flag = int(npix), int(n_gaussian), float(fov), False
+        self.nparams = 4 + 6 * n_gaussian + 2          # geometric_model.py:258
+        self.eps = 1e-4
+
+    def compute_features(self, params):
+        raise NotImplementedError("dpi_b200: features are computed inside the CUDA kernel")
+
+    def forward(self, params):
+        return _CrescentFunction.apply(params, self.npix, self.n_gaussian, self.fov)
+
+    def to(self, device=None, **kw):      # the reference overrides .to() to move its grids by hand (:384-389)
+        return self

@@ -355,3 +355,144 @@ class MRITrainer(_FusedTrainer):
                                            self.prior_vals.data_ptr(), self.wp_host, self.logdet_flow.data_ptr(),
                                            self.det.data_ptr(), self.w["logdet"], self.terms.data_ptr(), st),
                    "dpi_step_terms")
+
+
+class DPIxTrainer:
+    """alpha-DPI step, DPIx_interferometry.py:329-386 (geometric_model 'simple_crescent_floor_nuisance',
+    data_product 'cphase_logcamp'): flow over the model parameters -> sigmoid -> crescent renderer -> closure
+    operator -> per-sample objective -> self-normalised importance weights over the whole batch -> backward ->
+    clip -> Adam. All device work is libdpi_b200 kernels; under data parallel the softmax statistics (max, sum)
+    and the flat gradient are all-reduced."""
+
+    def __init__(self, flow: RealNVP, wl: dict, batch: int, lr=1e-4, clip=1e-4, device="cuda", start_order=4,
+                 decay_rate=2000, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        from dpi_b200.interferometry_helpers import _EhtOp
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dpi_b200 trainers need a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        dev, f32 = self.device, torch.float32
+        self.flow = flow.to(dev)
+        self.flow.train()
+        self.flow._init_reverse()
+        self.B, self.npix, self.np_, self.ng = int(batch), int(wl["npix"]), int(wl["nparams"]), int(wl["n_gaussian"])
+        assert self.np_ == flow.ndim
+        self.fov, self.alpha, self.w = float(wl["fov"]), float(wl["alpha"]), wl["w"]
+        self.lr, self.clip, self.betas, self.eps = float(lr), float(clip), betas, float(eps)
+        self.start_order, self.decay_rate, self.k = start_order, decay_rate, 0
+        self.pg, self.world = process_group, 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.op = _EhtOp(self.npix, wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"], dev)
+        self.cphase_true = wl["cphase_true"].to(dev, f32).contiguous()
+        self.logcamp_true = wl["logcamp_true"].to(dev, f32).contiguous()
+        self.sigma_cp = wl["sigma_cp"].to(dev, f32).contiguous()
+        self.sigma_ca = wl["sigma_ca"].to(dev, f32).contiguous()
+        B, D, P = self.B, self.npix * self.npix, self.flow.flat.numel()
+        self.P = P
+        self.params = self.flow.flat.data
+        self.grads = torch.zeros(P, dtype=f32, device=dev)
+        self.m, self.v = torch.zeros(P, dtype=f32, device=dev), torch.zeros(P, dtype=f32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.sq = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.norm_out = torch.zeros(2, dtype=f32, device=dev)
+        self.terms = torch.zeros(8, dtype=f32, device=dev)
+        self.stats = torch.zeros(2, dtype=f32, device=dev)
+        self.z = torch.zeros(B, self.np_, dtype=f32, device=dev)
+        self.ps = torch.empty(B, self.np_, dtype=f32, device=dev)
+        self.prm = torch.empty(B, self.np_, dtype=f32, device=dev)
+        self.logdet_flow, self.det = torch.empty(B, dtype=f32, device=dev), torch.empty(B, dtype=f32, device=dev)
+        self.img = torch.empty(B, D, dtype=f32, device=dev)
+        self.vis = torch.empty(B, 2, self.op.n_vis, dtype=f32, device=dev)
+        self.loss_cp = torch.empty(B, dtype=torch.float64, device=dev)
+        self.loss_ca = torch.empty(B, dtype=f32, device=dev)
+        self.loss_i = torch.empty(B, dtype=f32, device=dev)
+        self.g_img = torch.empty(B, D, dtype=f32, device=dev)
+        self.gscale, self.g_logdet = torch.empty(B, dtype=f32, device=dev), torch.empty(B, dtype=f32, device=dev)
+        self.g_prm = torch.empty(B, self.np_, dtype=f32, device=dev)
+        self.g_ps = torch.empty(B, self.np_, dtype=f32, device=dev)
+        self.handle = self.flow._handle(dev)
+        nbytes = self.lib.dpi_flow_workspace_bytes(self.handle, B)
+        if nbytes == 0:
+            _lib.check(-1, "dpi_flow_workspace_bytes")
+        self.ws_flow = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.ws_eht = self.op.workspace(B)
+        self.ws_opt = torch.zeros(self.lib.dpi_clip_adam_workspace_bytes(P), dtype=torch.uint8, device=dev)
+        self.launches_per_step = None
+
+    def data_weight(self):
+        return min(10.0 ** (-self.start_order + self.k / self.decay_rate), 1.0)      # DPIx_interferometry.py:331
+
+    def sample_z(self, generator=None):
+        self.z.normal_(generator=generator)
+        return self.z
+
+    def _objective(self, mode, dw, st):
+        _lib.check(self.lib.dpi_alpha_objective(self.B, self.np_, self.z.data_ptr(), self.loss_cp.data_ptr(),
+                                                self.loss_ca.data_ptr(), self.logdet_flow.data_ptr(), self.det.data_ptr(),
+                                                self.w["cphase"], self.w["camp"], self.w["scale_factor"], dw, self.alpha,
+                                                mode, self.B * self.world, self.loss_i.data_ptr(), self.gscale.data_ptr(),
+                                                self.g_logdet.data_ptr(), self.terms.data_ptr(), self.stats.data_ptr(), st),
+                   "dpi_alpha_objective")
+
+    def loss_and_grad(self, z=None, data_weight=None):
+        if z is not None:
+            self.z.copy_(z, non_blocking=True)
+        lib, B, st, fl = self.lib, self.B, _lib.stream_ptr(), self.flow
+        dw = self.data_weight() if data_weight is None else float(data_weight)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.dpi_flow_run(self.handle, 0, 1, B, self.params.data_ptr(), fl.bn_running.data_ptr(),
+                                        self.z.data_ptr(), self.ps.data_ptr(), self.logdet_flow.data_ptr(),
+                                        self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
+            _lib.check(lib.dpi_sigmoid_forward(B, self.np_, self.ps.data_ptr(), self.prm.data_ptr(), self.det.data_ptr(), st),
+                       "dpi_sigmoid_forward")
+            _lib.check(lib.dpi_crescent_forward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.img.data_ptr(), st),
+                       "dpi_crescent_forward")
+            _lib.check(lib.dpi_eht_forward(self.op.handle, B, self.img.data_ptr(), self.vis.data_ptr(), None, None, None,
+                                           self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_forward")
+            # unit-weight data gradient d(w_ca l_ca + w_cp l_cp)/d img; the per-sample importance weight enters as gscale
+            _lib.check(lib.dpi_eht_data_grad(self.op.handle, B, self.vis.data_ptr(), self.cphase_true.data_ptr(),
+                                             self.sigma_cp.data_ptr(), self.logcamp_true.data_ptr(), self.sigma_ca.data_ptr(),
+                                             self.w["cphase"], self.w["camp"], self.loss_cp.data_ptr(), self.loss_ca.data_ptr(),
+                                             self.g_img.data_ptr(), self.ws_eht.data_ptr(), self.ws_eht.numel(), st),
+                       "dpi_eht_data_grad")
+            if self.world > 1 and self.alpha != 1.0:
+                import torch.distributed as dist
+                self._objective(1, dw, st)
+                dist.all_reduce(self.stats[0:1], op=dist.ReduceOp.MAX, group=self.pg)
+                self._objective(2, dw, st)
+                dist.all_reduce(self.stats[1:2], op=dist.ReduceOp.SUM, group=self.pg)
+                self._objective(3, dw, st)
+            else:
+                self._objective(0, dw, st)
+            _lib.check(lib.dpi_crescent_backward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.g_img.data_ptr(),
+                                                 self.gscale.data_ptr(), self.g_prm.data_ptr(), st), "dpi_crescent_backward")
+            _lib.check(lib.dpi_sigmoid_backward(B, self.np_, self.ps.data_ptr(), self.g_prm.data_ptr(), self.g_logdet.data_ptr(),
+                                                self.g_ps.data_ptr(), st), "dpi_sigmoid_backward")
+            _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(), self.z.data_ptr(),
+                                             self.g_ps.data_ptr(), self.g_logdet.data_ptr(), None, self.ws_flow.data_ptr(),
+                                             self.ws_flow.numel(), st), "dpi_flow_backward")
+        self.flow._bump_bn()
+        return self.terms
+
+    def step(self, z=None, data_weight=None):
+        n0 = _lib.launch_count()
+        self.loss_and_grad(z, data_weight)
+        lib, st = self.lib, _lib.stream_ptr()
+        if self.world > 1:
+            from dpi_b200.dist import allreduce_sum_
+            allreduce_sum_(self.grads, self.pg)
+        b1, b2 = self.betas
+        with torch.cuda.device(self.device):
+            _lib.check(lib.dpi_grad_sqnorm(self.P, self.grads.data_ptr(), self.sq.data_ptr(), self.ws_opt.data_ptr(),
+                                           self.ws_opt.numel(), st), "dpi_grad_sqnorm")
+            _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
+            # under data parallel every rank's weights already sum to 1 over the GLOBAL batch: plain sum of gradients
+            _lib.check(lib.dpi_clip_adam(self.P, self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
+                                         self.v.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
+                                         self.step_dev.data_ptr(), 1.0, self.norm_out.data_ptr(), st), "dpi_clip_adam")
+        self.k += 1
+        self.launches_per_step = _lib.launch_count() - n0
+        return self.terms

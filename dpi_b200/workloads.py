@@ -52,6 +52,70 @@ def interferometry_workload(npix=32, fov_uas=160.0, prior_fwhm_uas=50.0, seed=19
                 gt=torch.tensor(gt, dtype=f32))
 
 
+def dpix_workload(npix=64, fov_uas=160.0, seed=77, n_stations=7, n_scans=25, n_gaussian=2, alpha=0.95, logdet=1.0):
+    """C3: DPIx_interferometry.py with geometric_model='simple_crescent_floor_nuisance', data_product
+    'cphase_logcamp' (flux_flag False -> 6 + 6 g = 18 parameters), M87-like coverage (7 stations, 25 scans),
+    alpha-divergence 0.95 (DPIx_interferometry.py:205-326). Targets: a crescent + two Gaussians rendered by
+    the same parametric model at fixed parameters, through the same operator, plus closure noise."""
+    obs = syn.SyntheticObs(n_stations=n_stations, n_scans=n_scans, seed=seed, min_vis=2)
+    simim = syn.SimImage(npix, fov_uas)
+    dft_mat, ktraj, pulsefac, cp_ind, cp_sign, ca_ind = Obs_params_torch(obs, simim, ttype='direct')
+    n_vis, n_cp, n_ca = dft_mat.shape[1], len(cp_ind[0]), len(ca_ind[0])
+    rng = np.random.RandomState(seed + 1)
+    gt_params = np.array([[0.45, 0.12, 0.5, 0.3, 0.6, 0.42, 0.2, 0.15, 0.2, 0.3, 0.35, 0.62, 0.15, 0.2, 0.12, 0.7,
+                           0.1, 0.5][:6 + 6 * n_gaussian]])
+    gt = _render_gt(gt_params, npix, fov_uas, n_gaussian)
+    Fc = dft_mat[:, :, 0].double().numpy() + 1j * dft_mat[:, :, 1].double().numpy()
+    vis = gt.reshape(-1) @ Fc
+    ang, amp = np.angle(vis), np.abs(vis)
+    cphase = sum(cp_sign[q].numpy() * ang[cp_ind[q].numpy()] for q in range(3)) * 180 / np.pi
+    logcamp = np.log(amp[ca_ind[0].numpy()]) + np.log(amp[ca_ind[1].numpy()]) \
+        - np.log(amp[ca_ind[2].numpy()]) - np.log(amp[ca_ind[3].numpy()])
+    sigma_cp = rng.uniform(2.0, 20.0, n_cp)
+    sigma_ca = rng.uniform(0.05, 0.5, n_ca)
+    f32 = torch.float32
+    w = dict(camp=1.0, cphase=n_cp / n_ca, logdet=2.0 * logdet / n_ca, scale_factor=1.0 / n_ca)
+    return dict(kind="dpix", npix=npix, fov=float(fov_uas), n_gaussian=n_gaussian, nparams=6 + 6 * n_gaussian,
+                n_vis=n_vis, n_cp=n_cp, n_ca=n_ca, alpha=float(alpha), dft_mat=dft_mat, cphase_ind=cp_ind,
+                cphase_sign=cp_sign, camp_ind=ca_ind,
+                cphase_true=torch.tensor(cphase + rng.normal(size=n_cp) * sigma_cp, dtype=f32),
+                logcamp_true=torch.tensor(logcamp + rng.normal(size=n_ca) * sigma_ca, dtype=f32),
+                sigma_cp=torch.tensor(sigma_cp, dtype=f32), sigma_ca=torch.tensor(sigma_ca, dtype=f32), w=w,
+                gt=torch.tensor(gt, dtype=f32))
+
+
+def _render_gt(params, npix, fov, n_gaussian):
+    """Host float64 evaluation of the parametric image (geometric_model.py:333-381) for the synthetic target."""
+    from scipy.special import erf
+    hf = 0.5 * fov
+    gap = 1.0 / npix
+    xs = np.arange(-1 + gap, 1, 2 * gap)
+    gy, gx = np.meshgrid(-xs, xs, indexing="ij")
+    gr, gth = np.sqrt(gx ** 2 + gy ** 2), np.arctan2(gy, gx)
+    p = params[0]
+    r = 10.0 / hf + p[0] * 30.0 / hf
+    sg = 1.0 / hf + p[1] * 39.0 / hf
+    s = 1e-3 + p[2] * (0.99 - 1e-3)
+    eta = 181 / 180 * np.pi * (2 * p[3] - 1)
+    floor = p[4 + 6 * n_gaussian]
+    cflux = 1e-3 + (2.0 - 1e-3) * p[5 + 6 * n_gaussian]
+    ring = np.exp(-0.5 * (gr - r) ** 2 / sg ** 2) * (1 + s * np.cos(gth - eta))
+    disk = 0.5 * (1 + erf((r - gr) / (np.sqrt(2) * sg)))
+    img = cflux * ((1 - floor) * ring / (ring.sum() + 1e-4) + floor * disk / (disk.sum() + 1e-4))
+    for k in range(n_gaussian):
+        x0 = -200.0 / hf + p[4 + 6 * k] * 400.0 / hf
+        y0 = -200.0 / hf + p[5 + 6 * k] * 400.0 / hf
+        a = 1e-3 + p[6 + 6 * k] * (2.0 - 1e-3)
+        sx = 1.0 / hf + p[7 + 6 * k] * 99.0 / hf
+        sy = 1.0 / hf + p[8 + 6 * k] * 99.0 / hf
+        th = 181 / 180 * 0.5 * np.pi * p[9 + 6 * k]
+        xc, yc = gx - x0, gy - y0
+        xr, yr = xc * np.cos(th) + yc * np.sin(th), -xc * np.sin(th) + yc * np.cos(th)
+        n = np.exp(-0.5 * (xr ** 2 / sx ** 2 + yr ** 2 / sy ** 2)) / (2 * np.pi * sx * sy)
+        img = img + a * n / (n.sum() + 1e-4)
+    return img / (img.sum() + 1e-4)
+
+
 def mri_workload(npix=64, ratio=4, sigma=5e-7, seed=0, tv=1e3, l1=0.0, logdet=1.0):
     img = syn.knee_phantom(npix)
     flux = float(img.sum())

@@ -184,6 +184,37 @@ int dpi_chi2(int mode, int batch, int n, const float* y_true, const void* y_pred
              void* loss, const void* g_loss, void* g_pred, dpi_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * alpha-DPI (DPIx_interferometry.py): geometric crescent renderer geometric_model.py
+ * SimpleCrescentNuisanceFloor_Param2Img :237-389 (flux_flag=False: 6 + 6 g parameters), sigmoid squashing
+ * :339,344 and the alpha-divergence objective :350-380.
+ * ------------------------------------------------------------------------------------------ */
+/* params [batch, 6 + 6*n_gaussian] in (0, 1) -> img [batch, npix, npix] (unit flux); forward() :333-381 */
+int dpi_crescent_forward(int batch, int npix, int n_gaussian, float fov, const float* params, float* img,
+                         dpi_stream_t stream);
+/* g_params[b, :] = gscale[b] * sum_p g_img[b, p] * d img[b, p] / d params[b, :]  (gscale may be NULL = 1) */
+int dpi_crescent_backward(int batch, int npix, int n_gaussian, float fov, const float* params,
+                          const float* g_img, const float* gscale, float* g_params, dpi_stream_t stream);
+/* params = sigmoid(ps); det[b] = sum_j(-ps - 2 softplus(-ps))   (DPIx_interferometry.py:339,344) */
+int dpi_sigmoid_forward(int batch, int n, const float* ps, float* params, float* det, dpi_stream_t stream);
+/* g_ps = g_params * s (1 - s) + g_det[b] * (1 - 2 s); g_params / g_det may be NULL */
+int dpi_sigmoid_backward(int batch, int n, const float* ps, const float* g_params, const float* g_det,
+                         float* g_ps, dpi_stream_t stream);
+/* The objective of DPIx_interferometry.py:350-380 over the whole batch (data_product 'cphase_logcamp'):
+ *   loss_i = data_weight * 0.5 (w_ca loss_ca[i] + w_cp loss_cp[i]) / scale_factor - (logdet_flow[i] + det[i]) - 0.5 |z_i|^2
+ *   weights w_i = 1 / global_batch (alpha == 1: KL) or softmax_i(-(1 - alpha) loss_i), detached
+ * outputs: terms[0] = sum_i w_i scale_factor loss_i, [1] = loss_orig, [2] = mean loss_cp, [3] = mean loss_ca,
+ * [4] = mean logdet, [5] = mean loss_i; gscale[i] = 0.5 data_weight w_i (the factor of
+ * d(w_ca loss_ca + w_cp loss_cp)/d img); g_logdet[i] = -w_i scale_factor; loss_i (may be NULL).
+ * mode 0: softmax over this batch. Data parallel, softmax over the global batch: mode 1 writes stats[0] = max_i
+ * t_i (t = -(1 - alpha) loss); mode 2 reads the all-reduced max and writes stats[1] = sum_i exp(t_i - max);
+ * mode 3 reads the all-reduced (max, sum) and finishes. */
+int dpi_alpha_objective(int batch, int nparams, const float* z, const double* loss_cp, const float* loss_ca,
+                        const float* logdet_flow, const float* det, float w_cp, float w_ca, float scale_factor,
+                        float data_weight, float alpha, int mode, int global_batch, float* loss_i,
+                        float* gscale, float* g_logdet, float* terms /*[8]*/, float* stats /*[2]*/,
+                        dpi_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * MRI operator: DPI_MRI.py fft2c_torch :70-74 + MRI_helpers.py Loss_kspace_diff2 :23-26.
  * ------------------------------------------------------------------------------------------ */
 /* kspace[b, ky, kx, 2] = ortho FFT2 of the real image */

@@ -347,6 +347,94 @@ def interferometry_loss(sd: State, log_scale: Tensor, z: Tensor, c: dict, train:
 
 
 # ----------------------------------------------------------------------------------------------
+# alpha-DPI: geometric crescent renderer + alpha-divergence objective
+# (DPItorch/geometric_model.py:237-389, DPItorch/DPIx_interferometry.py:329-380)
+# ----------------------------------------------------------------------------------------------
+CRESCENT_RANGES = dict(r_range=(10.0, 40.0), asym_range=(1e-3, 0.99), width_range=(1.0, 40.0),
+                       floor_range=(0.0, 1.0), crescent_flux_range=(1e-3, 2.0), shift_range=(-200.0, 200.0),
+                       sigma_range=(1.0, 100.0), gaussian_scale_range=(1e-3, 2.0))   # geometric_model.py:238-240
+
+
+def crescent_grids(npix: int, dtype=torch.float32):
+    """geometric_model.py:265-272: xs = arange(-1 + 1/npix, 1, 2/npix); grid_y, grid_x = meshgrid(-xs, xs)."""
+    gap = 1.0 / npix
+    xs = torch.arange(-1 + gap, 1, 2 * gap, dtype=dtype)
+    grid_y, grid_x = torch.meshgrid(-xs, xs, indexing="ij")
+    return grid_x, grid_y, torch.sqrt(grid_x ** 2 + grid_y ** 2), torch.atan2(grid_y, grid_x)
+
+
+def crescent_render(params: Tensor, npix: int, fov: float = 160.0, n_gaussian: int = 2, eps: float = 1e-4) -> Tensor:
+    """SimpleCrescentNuisanceFloor_Param2Img.forward with flux_flag=False (geometric_model.py:275-381):
+    params [B, 6 + 6 g] in (0, 1) -> unit-flux images [B, npix, npix]."""
+    R = CRESCENT_RANGES
+    hf = 0.5 * fov
+    grid_x, grid_y, grid_r, grid_th = crescent_grids(npix, params.dtype)
+    col = lambda i: params[:, i].unsqueeze(-1).unsqueeze(-1)
+    r = R["r_range"][0] / hf + col(0) * (R["r_range"][1] - R["r_range"][0]) / hf
+    sigma = R["width_range"][0] / hf + col(1) * (R["width_range"][1] - R["width_range"][0]) / hf
+    s = R["asym_range"][0] + col(2) * (R["asym_range"][1] - R["asym_range"][0])
+    eta = 181 / 180 * np.pi * (2.0 * col(3) - 1.0)
+    floor = R["floor_range"][0] + (R["floor_range"][1] - R["floor_range"][0]) * col(4 + n_gaussian * 6)
+    cflux = R["crescent_flux_range"][0] + (R["crescent_flux_range"][1] - R["crescent_flux_range"][0]) * col(5 + n_gaussian * 6)
+    ring = torch.exp(-0.5 * (grid_r - r) ** 2 / sigma ** 2)
+    S = 1 + s * torch.cos(grid_th - eta)
+    crescent = S * ring
+    disk = 0.5 * (1 + torch.erf((r - grid_r) / (np.sqrt(2) * sigma)))
+    crescent = crescent / (torch.sum(crescent, (-1, -2)).unsqueeze(-1).unsqueeze(-1) + eps)
+    disk = disk / (torch.sum(disk, (-1, -2)).unsqueeze(-1).unsqueeze(-1) + eps)
+    crescent = cflux * ((1 - floor) * crescent + floor * disk)
+    for k in range(n_gaussian):
+        sh = R["shift_range"]
+        x_shift = sh[0] / hf + col(4 + k * 6) * (sh[1] - sh[0]) / hf
+        y_shift = sh[0] / hf + col(5 + k * 6) * (sh[1] - sh[0]) / hf
+        scale = R["gaussian_scale_range"][0] + col(6 + k * 6) * (R["gaussian_scale_range"][1] - R["gaussian_scale_range"][0])
+        sigma_x = R["sigma_range"][0] / hf + col(7 + k * 6) * (R["sigma_range"][1] - R["sigma_range"][0]) / hf
+        sigma_y = R["sigma_range"][0] / hf + col(8 + k * 6) * (R["sigma_range"][1] - R["sigma_range"][0]) / hf
+        theta = 181 / 180 * 0.5 * np.pi * col(9 + k * 6)
+        x_c, y_c = grid_x - x_shift, grid_y - y_shift
+        x_rot = x_c * torch.cos(theta) + y_c * torch.sin(theta)
+        y_rot = -x_c * torch.sin(theta) + y_c * torch.cos(theta)
+        delta = 0.5 * (x_rot ** 2 / sigma_x ** 2 + y_rot ** 2 / sigma_y ** 2)
+        nuis = 1 / (2 * np.pi * sigma_x * sigma_y) * torch.exp(-delta)
+        nuis = nuis / (torch.sum(nuis, (-1, -2)).unsqueeze(-1).unsqueeze(-1) + eps)
+        crescent = crescent + scale * nuis
+    return crescent / (torch.sum(crescent, (-1, -2)).unsqueeze(-1).unsqueeze(-1) + eps)
+
+
+def dpix_weights(n_cp: int, n_ca: int, logdet: float = 1.0):
+    """data_product 'cphase_logcamp' (DPIx_interferometry.py:268-274)."""
+    return dict(camp=1.0, cphase=n_cp / n_ca, logdet=2.0 * logdet / n_ca, scale_factor=1.0 / n_ca)
+
+
+def dpix_loss(sd: State, z: Tensor, c: dict, data_weight: float = 1.0, train: bool = True):
+    """Loop body DPIx_interferometry.py:336-380 for data_product 'cphase_logcamp'. `c`: npix, fov, n_gaussian,
+    dft_mat, cphase_ind/sign, camp_ind, cphase_true, logcamp_true, sigma_cp, sigma_ca, w, alpha ('KL' when 1)."""
+    w, sf, alpha = c["w"], c["w"]["scale_factor"], c["alpha"]
+    ps, logdet = realnvp_reverse(sd, z, train)
+    params = torch.sigmoid(ps)
+    img = crescent_render(params, c["npix"], c["fov"], c["n_gaussian"])
+    det_sigmoid = torch.sum(-ps - 2 * torch.nn.functional.softplus(-ps), -1)
+    logdet = logdet + det_sigmoid
+    vis, amp, cphase, logcamp = eht_observe(img, c["dft_mat"], c["cphase_ind"], c["cphase_sign"], c["camp_ind"])
+    l_cp = loss_angle_diff(c["sigma_cp"], c["cphase_true"], cphase)
+    l_ca = loss_logca_diff2(c["sigma_ca"], c["logcamp_true"], logcamp)
+    loss_data = 0.5 * (w["camp"] * l_ca + w["cphase"] * l_cp) / sf
+    logprob = -logdet - 0.5 * torch.sum(z ** 2, 1)
+    li = data_weight * loss_data + logprob
+    lo = loss_data + logprob
+    if alpha == 1:
+        loss = torch.mean(sf * li)
+        loss_orig = torch.mean(sf * lo)
+    else:
+        rej = torch.softmax(-(1 - alpha) * li, 0).detach()
+        loss = torch.sum(rej * sf * li)
+        loss_orig = sf * torch.log(torch.mean(torch.exp(-(1 - alpha) * lo))) / (alpha - 1)
+    terms = dict(loss=loss, loss_orig=loss_orig, cphase=l_cp.mean(), logca=l_ca.mean(), logdet=logdet.mean(),
+                 img=img, params=params, logdet_vec=logdet, loss_i=li)
+    return loss, terms
+
+
+# ----------------------------------------------------------------------------------------------
 # MRI forward model + losses (DPItorch/DPI_MRI.py, MRI_helpers.py)
 # ----------------------------------------------------------------------------------------------
 def fft2c(img: Tensor) -> Tensor:
@@ -452,6 +540,8 @@ class OracleTrainer:
         self.opt.zero_grad()
         if self.log_scale is not None:
             loss, terms = self.loss_fn(self.sd, self.log_scale, z, self.consts)
+        elif self.loss_fn is dpix_loss:
+            loss, terms = self.loss_fn(self.sd, z, self.consts, data_weight=getattr(self, "data_weight", 1.0))
         else:
             loss, terms = self.loss_fn(self.sd, z, **self.consts)
         loss.backward()

@@ -220,6 +220,81 @@ def mri_case(name, npix, NF, B, seed, steps=3):
     print(name, "ok", hist[-1])
 
 
+def dpix_case(name, npix, NF, B, seed, alpha, n_stations=5, n_scans=8, steps=3):
+    """DPIx_interferometry.py:329-386 (cphase_logcamp, simple_crescent_floor_nuisance) assembled from the
+    reference modules: RealNVP(18, NF, seqfrac=1/16), SimpleCrescentNuisanceFloor_Param2Img, eht closure operator."""
+    from dpi_b200.workloads import dpix_workload
+    wl = dpix_workload(npix=npix, seed=seed, n_stations=n_stations, n_scans=n_scans, alpha=alpha)
+    obs = syn.SyntheticObs(n_stations=n_stations, n_scans=n_scans, seed=seed, min_vis=2)
+    dft, ktraj, pf, cpi, cps, cai = IH.Obs_params_torch(obs, syn.SimImage(npix, 160.0), ttype="direct")
+    dev = torch.device("cpu")
+    eht = IH.eht_observation_pytorch(npix, ref_shim.types.SimpleNamespace(to=lambda **k: None), dft, ktraj, pf, cpi, cps,
+                                     cai, dev, ttype="direct")
+    GM = R["geometric"]
+    conv = GM.SimpleCrescentNuisanceFloor_Param2Img(npix, r_range=[10.0, 40.0], fov=160.0, n_gaussian=2, flux_flag=False)
+    nparams = conv.nparams
+    w, sf = wl["w"], wl["w"]["scale_factor"]
+    torch.manual_seed(seed)
+    gen = RealNVP(nparams, NF, seqfrac=1 / 16)
+    sd = init_state(nparams, NF, seqfrac=1 / 16, seed=seed, randomize=True)
+    gen.load_state_dict(sd)
+    L_cp = IH.Loss_angle_diff(wl["sigma_cp"].numpy(), dev)
+    L_ca = IH.Loss_logca_diff2(wl["sigma_ca"].numpy(), dev)
+    params_l = list(gen.parameters())
+    opt = torch.optim.Adam(params_l, lr=1e-4)
+    out = dict(npix=npix, NF=NF, B=B, seed=seed, n_stations=n_stations, n_scans=n_scans, steps=steps, lr=1e-4,
+               clip=1e-4, alpha=alpha, start_order=4, decay_rate=2000)
+    out.update(sd_to_np(sd))
+    # renderer alone: image and parameter gradient of a random linear functional
+    p0 = torch.rand(B, nparams, generator=torch.Generator().manual_seed(seed)).requires_grad_(True)
+    cimg = torch.randn(B, npix, npix, generator=torch.Generator().manual_seed(seed + 1))
+    im0 = conv.forward(p0)
+    (im0 * cimg).sum().backward()
+    out.update(render_params=p0.detach().numpy(), render_cimg=cimg.numpy(), render_img=im0.detach().numpy(),
+               render_gparams=p0.grad.numpy().copy())
+    zs, hist = [], []
+    for k in range(steps):
+        data_weight = min(10 ** (-4 + k / 2000), 1.0)
+        z = torch.randn(B, nparams)
+        zs.append(z.numpy())
+        ps, logdet = gen.reverse(z)
+        prm = torch.sigmoid(ps)
+        img = conv.forward(prm)
+        det_sigmoid = torch.sum(-ps - 2 * torch.nn.Softplus()(-ps), -1)
+        logdet = logdet + det_sigmoid
+        vis, visamp, cphase, logcamp = eht(img)
+        l_cp = L_cp(wl["cphase_true"], cphase)
+        l_ca = L_ca(wl["logcamp_true"], logcamp)
+        loss_data = 0.5 * (w["camp"] * l_ca + w["cphase"] * l_cp) / sf
+        logprob = -logdet - 0.5 * torch.sum(z ** 2, 1)
+        loss = data_weight * loss_data + logprob
+        if alpha == 1:
+            loss = torch.mean(sf * loss)
+        else:
+            rej = torch.nn.Softmax(dim=0)(-(1 - alpha) * loss).detach()
+            loss = torch.sum(rej * sf * loss)
+        loss_orig = loss_data + logprob
+        if alpha == 1:
+            loss_orig = torch.mean(sf * loss_orig)
+        else:
+            loss_orig = sf * torch.log(torch.mean(torch.exp(-(1 - alpha) * loss_orig))) / (alpha - 1)
+        opt.zero_grad()
+        loss.backward()
+        if k == 0:
+            out.update(img0=img.detach().numpy(), params0=prm.detach().numpy(), logdet0=logdet.detach().numpy(),
+                       l_cp0=l_cp.detach().numpy(), l_ca0=l_ca.detach().numpy())
+            for kk, p in gen.named_parameters():
+                out["grad0." + kk] = p.grad.detach().numpy().copy()
+        norm = torch.nn.utils.clip_grad_norm_(params_l, 1e-4)
+        opt.step()
+        hist.append([float(loss), float(loss_orig), float(l_cp.mean()), float(l_ca.mean()), float(logdet.mean()), float(norm)])
+    out["z"] = np.stack(zs)
+    out["hist"] = np.array(hist, dtype=np.float64)
+    out.update(sd_to_np(gen.state_dict(), "sd_final."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", hist[-1])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     flow_case("flow_even", D=20, NF=2, B=6, seqfrac=1, seed=11)          # H=10, one row tile
@@ -231,3 +306,5 @@ if __name__ == "__main__":
     closure_map_case("closure_eht", n_stations=7, n_scans=100, seed=190, npix=32)
     interferometry_case("interferometry_small", npix=8, NF=2, B=6, seed=3)
     mri_case("mri_small", npix=8, NF=2, B=6, seed=5)
+    dpix_case("dpix_small", npix=16, NF=2, B=12, seed=9, alpha=0.95)
+    dpix_case("dpix_kl", npix=16, NF=2, B=12, seed=10, alpha=1.0)

@@ -126,3 +126,43 @@ def test_adam_restatement_matches_torch():
         opt.step()
         O.adam_update(p, g, m, v, step, 1e-3)
         assert rel_err(p, p2.detach()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- alpha-DPI (DPIx)
+@pytest.mark.parametrize("name", ["dpix_small", "dpix_kl"])
+def test_dpix_renderer_and_trajectory_match_reference_run(name):
+    """Crescent renderer (geometric_model.py:333-381) and the alpha-divergence loop (DPIx_interferometry.py:329-386)
+    of the oracle against the fixtures generated from the unmodified reference modules."""
+    from dpi_b200.workloads import dpix_workload
+    g = load_golden(name)
+    npix, NF, B = int(g["npix"]), int(g["NF"]), int(g["B"])
+    p0 = torch.from_numpy(g["render_params"]).requires_grad_(True)
+    im = O.crescent_render(p0, npix, 160.0, 2)
+    (im * torch.from_numpy(g["render_cimg"])).sum().backward()
+    assert rel_err(im, g["render_img"]) < 1e-5
+    assert rel_err(p0.grad, g["render_gparams"]) < 1e-4
+    wl = dpix_workload(npix=npix, seed=int(g["seed"]), n_stations=int(g["n_stations"]), n_scans=int(g["n_scans"]),
+                       alpha=float(g["alpha"]))
+    c = dict(npix=npix, fov=160.0, n_gaussian=2, dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"],
+             cphase_sign=wl["cphase_sign"], camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"],
+             logcamp_true=wl["logcamp_true"], sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], w=wl["w"],
+             alpha=float(g["alpha"]))
+    sd = split_sd(g)
+    tr = O.OracleTrainer(sd, None, O.dpix_loss, c, lr=float(g["lr"]), clip=float(g["clip"]))
+    for k in range(int(g["steps"])):
+        tr.data_weight = min(10 ** (-int(g["start_order"]) + k / int(g["decay_rate"])), 1.0)
+        z = torch.from_numpy(g["z"][k])
+        if k == 0:
+            bn = {kk: v.clone() for kk, v in sd.items() if "running" in kk or "num_batches" in kk}
+            loss, t = tr.loss_and_grads(z)
+            assert rel_err(t["img"], g["img0"]) < 1e-5 and rel_err(t["logdet_vec"], g["logdet0"]) < 1e-5
+            for kk in tr.keys:
+                assert rel_err(sd[kk].grad, g["grad0." + kk]) < 2e-4, kk
+            for kk, v in bn.items():          # the extra forward pass must not count as a training step
+                sd[kk].copy_(v)
+        loss, t = tr.step(z)
+        got = [float(loss), float(t["loss_orig"]), float(t["cphase"]), float(t["logca"]), float(t["logdet"]),
+               float(t["grad_norm"])]
+        assert np.allclose(got, g["hist"][k], rtol=2e-4, atol=1e-6), (k, got, g["hist"][k])
+    for k, v in split_sd(g, "sd_final.").items():
+        assert rel_err(sd[k].detach().float(), v.float()) < 1e-4, k

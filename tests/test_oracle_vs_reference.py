@@ -96,3 +96,21 @@ def test_vectorised_closure_maps_equal_reference_loops(R):
         for la, lb in zip(a[3:], b[3:]):
             for x, y in zip(la, lb):
                 assert x.dtype == y.dtype and torch.equal(x, y)
+
+
+@pytest.mark.parametrize("npix,B,ng", [(16, 6, 2), (64, 4, 2), (32, 5, 1)])
+def test_crescent_renderer_matches_reference_class(R, npix, B, ng):
+    """geometric_model.SimpleCrescentNuisanceFloor_Param2Img (flux_flag=False) vs the oracle restatement."""
+    from oracle import dpi_oracle as O
+    conv = R["geometric"].SimpleCrescentNuisanceFloor_Param2Img(npix, r_range=[10.0, 40.0], fov=160.0, n_gaussian=ng,
+                                                                flux_flag=False)
+    torch.manual_seed(npix)
+    p = torch.rand(B, conv.nparams)
+    c = torch.randn(B, npix, npix)
+    pr = p.clone().requires_grad_(True)
+    ir = conv.forward(pr)
+    (ir * c).sum().backward()
+    po = p.clone().requires_grad_(True)
+    io = O.crescent_render(po, npix, 160.0, ng)
+    (io * c).sum().backward()
+    assert rel_err(io, ir) < 1e-6 and rel_err(po.grad, pr.grad) < 1e-5
