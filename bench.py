@@ -36,14 +36,17 @@ WORKLOADS = {
            "sigma=5e-7"),
     "c4": ("interferometry", 64, 32, 1024, 1e-4, 1e-3,
            "DPI_interferometry scale-up npix=64 n_flow=32 batch=1024/GPU (weak scaling), synthetic EHT uv-coverage"),
+    "c3": ("dpix", 64, 16, 2048, 1e-4, 1e-4,
+           "DPIx_interferometry crescent + 2 Gaussians (18 parameters, npix=64, fov=160), alpha-divergence 0.95, "
+           "batch=2048/GPU, synthetic M87-like uv-coverage (7 stations, 25 scans), closure phase + log closure amp"),
 }
 METRIC = "DPI train samples/sec (flow+logdet+fwd-model, fwd+bwd)"
 
 
 def build_workload(name):
-    from dpi_b200.workloads import interferometry_workload, mri_workload
+    from dpi_b200.workloads import dpix_workload, interferometry_workload, mri_workload
     kind, npix, nf, B, lr, clip, desc = WORKLOADS[name]
-    wl = interferometry_workload(npix=npix) if kind == "interferometry" else mri_workload(npix=npix)
+    wl = {"interferometry": interferometry_workload, "mri": mri_workload, "dpix": dpix_workload}[kind](npix=npix)
     return wl, kind, npix, nf, B, lr, clip, desc
 
 
@@ -56,14 +59,27 @@ def cpu_reference_run(name, steps, warmup, max_seconds=25.0):
     wl, kind, npix, nf, B, lr, clip, desc = build_workload(name)
     torch.set_num_threads(os.cpu_count() or 1)
     D = npix * npix
-    sd = O.init_state(D, nf, seed=0, randomize=False)
-    ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
-    if kind == "interferometry":
+    if kind == "dpix":
+        D = wl["nparams"]
+        sd = O.init_state(D, nf, seqfrac=1 / 16, seed=0, randomize=False)
+        c = dict(npix=npix, fov=wl["fov"], n_gaussian=wl["n_gaussian"], dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"],
+                 cphase_sign=wl["cphase_sign"], camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"],
+                 logcamp_true=wl["logcamp_true"], sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], w=wl["w"],
+                 alpha=wl["alpha"])
+        tr = O.OracleTrainer(sd, None, O.dpix_loss, c, lr=lr, clip=clip)
+        tr.data_weight = 1e-4
+        ls = None
+    else:
+        sd = O.init_state(D, nf, seed=0, randomize=False)
+        ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
+    if kind == "dpix":
+        pass
+    elif kind == "interferometry":
         c = dict(npix=npix, dft_mat=wl["dft_mat"], cphase_ind=wl["cphase_ind"], cphase_sign=wl["cphase_sign"],
                  camp_ind=wl["camp_ind"], cphase_true=wl["cphase_true"], logcamp_true=wl["logcamp_true"],
                  sigma_cp=wl["sigma_cp"], sigma_ca=wl["sigma_ca"], prior=wl["prior"], flux=wl["flux"], w=wl["w"])
         tr = O.OracleTrainer(sd, ls, O.interferometry_loss, c, lr=lr, clip=clip)
-    else:
+    elif kind == "mri":
         c = dict(npix=npix, mask=wl["mask"], kspace_true=wl["kspace_true"], sigma=wl["sigma"], w=wl["w"])
         tr = O.OracleTrainer(sd, ls, O.mri_loss, c, lr=lr, clip=clip)
     torch.manual_seed(1234)
@@ -133,7 +149,7 @@ def gpu_run(args):
     import torch.distributed as dist
     from dpi_b200 import _lib
     from dpi_b200.generative_model.realnvpfc_model import RealNVP
-    from dpi_b200.trainer import InterferometryTrainer, MRITrainer
+    from dpi_b200.trainer import DPIxTrainer, InterferometryTrainer, MRITrainer
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -148,9 +164,14 @@ def gpu_run(args):
     wl, kind, npix, nf, B, lr, clip, desc = build_workload(args.workload)
     D = npix * npix
     torch.manual_seed(0)                      # identical initial weights on every rank
-    flow = RealNVP(D, nf)
-    T = InterferometryTrainer if kind == "interferometry" else MRITrainer
-    tr = T(flow, wl, B, lr=lr, clip=clip, device=dev, use_graph=not args.no_graph)
+    if kind == "dpix":
+        D = wl["nparams"]
+        flow = RealNVP(D, nf, seqfrac=1 / 16)
+        tr = DPIxTrainer(flow, wl, B, lr=lr, clip=clip, device=dev)
+    else:
+        flow = RealNVP(D, nf)
+        T = InterferometryTrainer if kind == "interferometry" else MRITrainer
+        tr = T(flow, wl, B, lr=lr, clip=clip, device=dev, use_graph=not args.no_graph)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)              # per-rank z stream
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -187,7 +208,7 @@ def gpu_run(args):
 
     # ---- end-to-end through the public step API with host buffers: pinned z -> H2D, loss -> D2H
     zs = [torch.randn(B, D).pin_memory() for _ in range(4)]
-    host_terms = torch.empty(16, dtype=torch.float32).pin_memory()
+    host_terms = torch.empty(tr.terms.numel(), dtype=torch.float32).pin_memory()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -200,7 +221,13 @@ def gpu_run(args):
     e2e_s = float(e2e_s)
 
     # ---- per-kernel timing of the dominant kernels (eager launches, CUDA events on the launch stream)
-    prof = tr.profile_kernels(steps=min(args.steps, 10), flush=None if args.no_flush else l2_flush)
+    if hasattr(tr, "profile_kernels"):
+        prof = tr.profile_kernels(steps=min(args.steps, 10), flush=None if args.no_flush else l2_flush)
+        step_bytes = tr.algorithmic_bytes_per_step()
+    else:   # DPIx: the step is reported as one unit (parameter state + per-sample images + DFT matrix)
+        P_ = int(flow.flat.numel())
+        step_bytes = 40 * P_ + 4 * B * (npix * npix) * 4 + 2 * 4 * npix * npix * 2 * wl["n_vis"]
+        prof = {"dpix_step": dict(ms=total_ms / args.steps, bytes=step_bytes)}
     barrier()
     if rank != 0:
         if world > 1:
@@ -215,8 +242,7 @@ def gpu_run(args):
     roof = dict(bound="hbm", kernel=dom, achieved=prof[dom]["bytes"] / (prof[dom]["ms"] * 1e-3) / 1e9, peak=hbm_peak,
                 peak_source=peak_src, unit="GB/s", traffic=None, algorithmic_bytes=prof[dom]["bytes"],
                 ms_per_launch=prof[dom]["ms"],
-                step=dict(algorithmic_bytes=tr.algorithmic_bytes_per_step(),
-                          achieved=tr.algorithmic_bytes_per_step() / (total_ms / args.steps * 1e-3) / 1e9),
+                step=dict(algorithmic_bytes=step_bytes, achieved=step_bytes / (total_ms / args.steps * 1e-3) / 1e9),
                 kernels={k: dict(ms=round(v["ms"], 5), gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)) for k, v in prof.items()})
     roof["frac"] = roof["achieved"] / hbm_peak
     roof["step"]["frac"] = roof["step"]["achieved"] / hbm_peak
@@ -226,7 +252,7 @@ def gpu_run(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "name": args.workload, "global_batch": world * B, "batch_per_gpu": B,
-                   "params": int(flow.flat.numel()), "cuda_graph": not args.no_graph,
+                   "params": int(flow.flat.numel()), "cuda_graph": (not args.no_graph) and kind != "dpix",
                    "l2": "flushed between timed steps (192 MiB fill)" if not args.no_flush else "not flushed",
                    "bn": "per-replica batch statistics", "wall_s_timed_region": round(t_wall, 4)},
         "clocks": clocks.summary(),

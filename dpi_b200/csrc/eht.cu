@@ -26,7 +26,7 @@ struct dpi_eht_s {
 namespace dpi {
 namespace {
 
-constexpr int kCtrl = 1024;  // uint32 words at the start of the workspace (split-K counters)
+constexpr int kCtrl = 8192;  // uint32 words at the start of the workspace (split-K counters)
 
 struct DftPlan { int tiles_m, tiles_n, splits, kchunk; };
 
@@ -291,7 +291,7 @@ int run_dft_fwd(dpi_eht_s* h, int batch, const float* img, float* vis, void* ws,
   eht_ws_floats(h, batch, &pf, nullptr);
   unsigned* ctr = (unsigned*)ws;
   float* part = (float*)((char*)ws + kCtrl * sizeof(unsigned)) + (size_t)batch * 2 * h->n_vis;
-  DPI_REQUIRE(pf.tiles_m * pf.tiles_n <= kCtrl, "eht: too many tiles");
+  DPI_REQUIRE(pf.splits == 1 || pf.tiles_m * pf.tiles_n <= kCtrl, "eht: too many tiles");
   DPI_CUDA(cudaMemsetAsync(ctr, 0, kCtrl * sizeof(unsigned), st));
   dft_gemm_kernel<false><<<pf.tiles_m * pf.tiles_n * pf.splits, kThreads, 0, st>>>(
       batch, 2 * h->n_vis, h->P, img, h->d_F, vis, 0, pf, part, ctr);
@@ -305,7 +305,7 @@ int run_dft_bwd(dpi_eht_s* h, int batch, float* g_img, void* ws, cudaStream_t st
   unsigned* ctr = (unsigned*)ws;
   float* gvis = (float*)((char*)ws + kCtrl * sizeof(unsigned));
   float* part = gvis + (size_t)batch * 2 * h->n_vis;
-  DPI_REQUIRE(pb.tiles_m * pb.tiles_n <= kCtrl, "eht: too many tiles");
+  DPI_REQUIRE(pb.splits == 1 || pb.tiles_m * pb.tiles_n <= kCtrl, "eht: too many tiles");
   DPI_CUDA(cudaMemsetAsync(ctr, 0, kCtrl * sizeof(unsigned), st));
   dft_gemm_kernel<true><<<pb.tiles_m * pb.tiles_n * pb.splits, kThreads, 0, st>>>(
       batch, h->P, 2 * h->n_vis, gvis, h->d_F, g_img, 1, pb, part, ctr);
