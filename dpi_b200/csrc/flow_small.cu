@@ -898,8 +898,10 @@ __device__ __noinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int
   int jq, iq, mp;
   if (MS == 4) { jq = lane & 15; iq = (lane >> 4) + 2 * (warp & 1); mp = warp >> 1; }
   else { jq = lane; iq = warp; mp = 0; }
+  // tiles are dealt from the LAST CTA downwards: the GEMM phases deal theirs from CTA 0 upwards, so CTAs that idle
+  // in a phase's critical part take the weight-gradient tiles and run them concurrently with it
 #pragma unroll 1
-  for (int t = blockIdx.x; t < tiles_i * tiles_j; t += A.sp.NC) {
+  for (int t = A.sp.NC - 1 - (int)blockIdx.x; t < tiles_i * tiles_j; t += A.sp.NC) {
     const int ti = t / tiles_j, tj = t - ti * tiles_j;
     const int i0 = ti * TI, j0 = tj * TJ;
     __syncthreads();   // previous users of the X region are done
@@ -1084,13 +1086,32 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
       }
       prefetch_gemm(A, s, pd[p + 1 - a.phase_begin]);   // next hop's weights / indices / parameters -> shared memory
     }
+    if (real && (kind == K_F1 || kind == K_B0)) {
+      // L2 prefetch of the parameter block of the stage that runs next (parameters of a stage are contiguous in the
+      // flat buffer, net.0.weight .. net.6.fc.bias): its weights are then L2 hits when the shadow prefetch of the
+      // coming phases copies them into shared memory. One 128-byte line per thread and step.
+      const int en = kind == K_F1 ? e + 1 : e - 1;
+      if (en >= 0 && en < a.S) {
+        const StageTab& sn = s.st[a.dir ? a.S - 1 - en : en];
+        const char* lo = reinterpret_cast<const char*>(a.P + sn.p[P_W1]);
+        const long long bytes = (sn.p[P_B3] + a.Dout - sn.p[P_W1]) * 4;
+        for (long long off = ((long long)blockIdx.x * kT + threadIdx.x) * 128; off < bytes; off += (long long)gridDim.x * kT * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(lo + off));
+      }
+    }
     if (real) {
       STAMP(6);
       // shadow of the barrier: weight gradients of this stage (inputs complete since the previous barrier)
-      if (kind == K_DG2 || kind == K_DG1 || kind == K_DGIN) {
-        const int which = kind == K_DG2 ? 3 : (kind == K_DG1 ? 2 : 1);
-        if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, e, which);
-        else wgrad_tiles<32, 128, 1>(A, s, e, which);
+      // net.6.fc.weight with DG2, net.3.weight with DG1; net.0.weight of stage e + 1 rides with B0 of stage e
+      // (B0 keeps only Db / 8 CTAs busy; DGIN keeps all of them busy), the first stage's with its own DGIN
+      int which = 0, we = e;
+      if (kind == K_DG2) which = 3;
+      else if (kind == K_DG1) which = 2;
+      else if (kind == K_B0 && e + 1 < a.S) { which = 1; we = e + 1; }
+      else if (kind == K_DGIN && e == 0) which = 1;
+      if (which) {
+        if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, we, which);
+        else wgrad_tiles<32, 128, 1>(A, s, we, which);
       }
       STAMP(7);
     }
@@ -1263,7 +1284,11 @@ int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStre
     at[na].val.clusterDim.x = bp.small.cl; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (h->persistent) {
+  // DPI_B200_SMALL_COOP=0: plain (non-cooperative) launch of the persistent kernel. The grid never exceeds the
+  // co-resident capacity, so this is safe on an otherwise idle GPU; it exists because Nsight Compute cannot
+  // launch a cooperative kernel with a cluster dimension ("LaunchFailed").
+  static const bool coop = []() { const char* e = getenv("DPI_B200_SMALL_COOP"); return !(e && e[0] == '0'); }();
+  if (h->persistent && coop) {
     at[na].id = cudaLaunchAttributeCooperative;
     at[na].val.cooperative = 1;
     ++na;
