@@ -41,6 +41,9 @@ WORKLOADS = {
            "batch=2048/GPU, synthetic M87-like uv-coverage (7 stations, 25 scans), closure phase + log closure amp"),
 }
 METRIC = "DPI train samples/sec (flow+logdet+fwd-model, fwd+bwd)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same workload
+# (profiles/ncu_small_persistent_r01.txt; bench.py cannot run ncu itself). Keyed by workload and launch group.
+NCU_TRAFFIC = {"c1": {"flow_reverse_fwd": 28.19e6 + 0.02e6, "flow_reverse_bwd": 49.42e6 + 4.05e6}}
 
 
 def build_workload(name):
@@ -240,7 +243,8 @@ def gpu_run(args):
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     dom = max(prof, key=lambda k: prof[k]["ms"])
     roof = dict(bound="hbm", kernel=dom, achieved=prof[dom]["bytes"] / (prof[dom]["ms"] * 1e-3) / 1e9, peak=hbm_peak,
-                peak_source=peak_src, unit="GB/s", traffic=None, algorithmic_bytes=prof[dom]["bytes"],
+                peak_source=peak_src, unit="GB/s", traffic=NCU_TRAFFIC.get(args.workload, {}).get(dom),
+                algorithmic_bytes=prof[dom]["bytes"],
                 ms_per_launch=prof[dom]["ms"],
                 step=dict(algorithmic_bytes=step_bytes, achieved=step_bytes / (total_ms / args.steps * 1e-3) / 1e9),
                 kernels={k: dict(ms=round(v["ms"], 5), gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)) for k, v in prof.items()})

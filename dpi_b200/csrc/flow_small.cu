@@ -879,7 +879,7 @@ __device__ __forceinline__ void run_b0(const SArgs& A, const Sm& s, int e) {
 // Weight gradients gW[i][j] = sum_m g^T[i][m] * act^T[j][m]  (which = 3: fc.weight, 2: net.3, 1: net.0), computed
 // in the shadow of the grid barrier. Tile TI x TJ, thread tile 4 x 4 (rows 4 iq + a, columns jq + (TJ/4) b).
 template <int TI, int TJ, int MS>
-__device__ __noinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int which) {
+__device__ __noinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int which, int busy) {
   const KArgs& a = A.k;
   Cx c(a, s.st, e);
   const int I = which == 3 ? a.Dout : a.H;
@@ -898,10 +898,20 @@ __device__ __noinline__ void wgrad_tiles(const SArgs& A, const Sm& s, int e, int
   int jq, iq, mp;
   if (MS == 4) { jq = lane & 15; iq = (lane >> 4) + 2 * (warp & 1); mp = warp >> 1; }
   else { jq = lane; iq = warp; mp = 0; }
-  // tiles are dealt from the LAST CTA downwards: the GEMM phases deal theirs from CTA 0 upwards, so CTAs that idle
-  // in a phase's critical part take the weight-gradient tiles and run them concurrently with it
+  // The critical part of a phase deals its tiles from CTA 0 upwards and keeps `busy` CTAs occupied. If the other
+  // CTAs can absorb all weight-gradient tiles with at most three each they take all of them (they run concurrently
+  // with the critical part); otherwise the tiles are dealt over all CTAs from the last one downwards.
+  const int n_tiles = tiles_i * tiles_j, idle = A.sp.NC - busy;
+  int t0, tstep;
+  if (idle > 0 && n_tiles <= 3 * idle) {
+    t0 = (int)blockIdx.x >= busy ? (int)blockIdx.x - busy : n_tiles;
+    tstep = idle;
+  } else {
+    t0 = A.sp.NC - 1 - (int)blockIdx.x;
+    tstep = A.sp.NC;
+  }
 #pragma unroll 1
-  for (int t = A.sp.NC - 1 - (int)blockIdx.x; t < tiles_i * tiles_j; t += A.sp.NC) {
+  for (int t = t0; t < n_tiles; t += tstep) {
     const int ti = t / tiles_j, tj = t - ti * tiles_j;
     const int i0 = ti * TI, j0 = tj * TJ;
     __syncthreads();   // previous users of the X region are done
@@ -1110,8 +1120,13 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
       else if (kind == K_B0 && e + 1 < a.S) { which = 1; we = e + 1; }
       else if (kind == K_DGIN && e == 0) which = 1;
       if (which) {
-        if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, we, which);
-        else wgrad_tiles<32, 128, 1>(A, s, we, which);
+        // CTAs occupied by this phase's critical part
+        const PD& dc = pd[p - a.phase_begin];
+        int busy;
+        if (kind == K_B0) busy = min(A.sp.red_tiles, A.sp.NC);
+        else busy = dc.split ? min(dc.n_tiles, A.sp.G) * A.sp.cl : min(dc.n_tiles, A.sp.NC);
+        if (A.sp.wgv == 0) wgrad_tiles<16, 64, 4>(A, s, we, which, busy);
+        else wgrad_tiles<32, 128, 1>(A, s, we, which, busy);
       }
       STAMP(7);
     }
