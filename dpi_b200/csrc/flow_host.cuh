@@ -36,7 +36,8 @@ struct dpi_flow_s {
   int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
   int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   int small_mode = 1;                         // 0: never use the small-batch kernel
-  int small_clusters = 0, small_cl = 1;       // co-resident clusters and cluster size (8, or 1 without cluster launch)
+  int small_clusters = 0, small_cl = 1;       // CTAs without clusters; small_cl > 1: cluster launches are available
+  int small_G[3] = {0, 0, 0};                 // co-resident clusters of 8, 4, 2 CTAs
   int small_ksplit_min = 512;                 // GEMMs with K >= this are split over the ranks of a cluster
   long long n_params = 0, n_bn = 0;
   std::vector<dpi::StageTab> stages;          // reverse execution order

@@ -213,7 +213,7 @@ template <bool WK>
 __device__ __forceinline__ void act_mac(float (&acc)[4][4], const float* X_s, const float* W_s, int ldw, int knp, int sq,
                                         int fq, int kp, int KP) {
   if (WK) {
-#pragma unroll 1
+#pragma unroll 2
     for (int k4 = 4 * kp; k4 < knp; k4 += 4 * KP) {
       float4 x[4], w[4];
 #pragma unroll
@@ -406,7 +406,7 @@ __device__ __forceinline__ void issue_params(const Sm& s, const PD& d, int tile)
     }                                                                                   \
   } while (0)
 
-// sum over the ranks of the cluster (fixed order) of R_s[nl][lane], R_s[nl][lane + 32]
+// sum over the nr (<= 8) ranks of the cluster, in rank order, of R_s[nl][lane], R_s[nl][lane + 32]
 __device__ __forceinline__ void combine(const Sm& s, int nl, int lane, int nr, float& s0, float& s1) {
   const float* p = s.R + nl * kMB + lane;
   if (nr == 1) {
@@ -414,7 +414,10 @@ __device__ __forceinline__ void combine(const Sm& s, int nl, int lane, int nr, f
   } else {
     float v0[8], v1[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { v0[r] = ld_dsmem(p, r); v1[r] = ld_dsmem(p + 32, r); }
+    for (int r = 0; r < 8; ++r) {
+      v0[r] = r < nr ? ld_dsmem(p, r) : 0.f;
+      v1[r] = r < nr ? ld_dsmem(p + 32, r) : 0.f;
+    }
     s0 = 0.f; s1 = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; ++r) { s0 += v0[r]; s1 += v1[r]; }
@@ -1187,33 +1190,43 @@ int small_query(dpi_flow_s* h) {
     return DPI_OK;
   }
   const char* nocl = getenv("DPI_B200_SMALL_NOCLUSTER");
+  for (int i = 0; i < 3; ++i) h->small_G[i] = 0;
   if (!(nocl && nocl[0] == '1')) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(8 * 18); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = max_smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, (const void*)flow_small_kernel, &cfg) == cudaSuccess && nc >= 4) {
-      h->small_clusters = nc;
-      h->small_cl = 8;
-    } else {
-      cudaGetLastError();
+    const char* want = getenv("DPI_B200_SMALL_CL");    // force one cluster size (8, 4 or 2)
+    for (int i = 0; i < 3; ++i) {
+      const int cl = 8 >> i;
+      if (want && atoi(want) != cl) continue;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(cl * (h->n_sm / cl)); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = max_smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, (const void*)flow_small_kernel, &cfg) == cudaSuccess && nc >= 2) {
+        h->small_G[i] = std::min(nc, h->n_sm / cl);
+        h->small_cl = 8;      // "cluster launch available"
+      } else {
+        cudaGetLastError();
+      }
     }
   }
-  if (h->small_cl == 1) h->small_clusters = h->n_sm;   // plain cooperative launch, one CTA per SM
+  h->small_clusters = h->n_sm;   // without clusters: plain cooperative launch, one CTA per SM
   return DPI_OK;
 }
 
-void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
-  SmallPlan& sp = bp.small;
-  sp = SmallPlan{};
-  if (!h->small_mode || bp.B > kMB || h->H > 512 || (h->H & 3) || (h->Da & 3)) return;
-  const int cl = h->small_cl, G = h->small_clusters, NC = cl == 8 ? 8 * G : G;
-  sp.NC = NC; sp.G = cl == 8 ? G : NC; sp.cl = cl;
+namespace {
+// FMA on the busiest CTA of a hop (rounds x features per tile x K extent per rank), the quantity the hop's
+// critical path scales with
+long long hop_cost(const ActPlan& p, int units) {
+  const int rounds = (p.n_tiles + units - 1) / units;
+  return (long long)rounds * p.NT * p.KC;
+}
+void plan_hops(const dpi_flow_s* h, SmallPlan& sp, int cl, int G) {
+  const int NC = cl > 1 ? cl * G : G;
+  sp.NC = NC; sp.G = cl > 1 ? G : NC; sp.cl = cl;
   const int H = h->H, Da = h->Da, Db = h->Db, Dout = h->Dout;
-  auto split = [&](int K) { return cl == 8 && K >= h->small_ksplit_min; };
+  auto split = [&](int K) { return cl > 1 && K >= h->small_ksplit_min; };
   sp.f1 = plan_act(H, Da, split(Da), sp.G, NC, cl, true, 0);
   sp.f2 = plan_act(H, H, split(H), sp.G, NC, cl, true, 0);
   {  // output layer: tiles of NP column pairs -> 2 NP weight rows, never split (N large, K = H small)
@@ -1232,6 +1245,40 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
   sp.dg2 = plan_act(H, Dout, split(Dout), sp.G, NC, cl, false, 0);
   sp.dg1 = plan_act(H, H, split(H), sp.G, NC, cl, false, 0);
   sp.dgin = plan_act(Da, H, false, sp.G, NC, cl, false, 0);
+}
+long long plan_cost(const SmallPlan& sp) {
+  auto u = [&](const ActPlan& p) { return p.ksplit ? sp.G : sp.NC; };
+  return hop_cost(sp.f1, u(sp.f1)) + hop_cost(sp.f2, u(sp.f2)) + hop_cost(sp.f3, u(sp.f3)) + hop_cost(sp.dg2, u(sp.dg2)) +
+         hop_cost(sp.dg1, u(sp.dg1)) + hop_cost(sp.dgin, u(sp.dgin));
+}
+}  // namespace
+
+void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
+  SmallPlan& sp = bp.small;
+  sp = SmallPlan{};
+  if (!h->small_mode || bp.B > kMB || h->H > 512 || (h->H & 3) || (h->Da & 3)) return;
+  const int H = h->H, Dout = h->Dout, Db = h->Db;
+  // cluster size: the largest of 8, 4, 2 CTAs the device can co-schedule (DPI_B200_SMALL_CL forces one). Measured
+  // on C1 / C2 (tools/cl_sweep.sh): 8 x 15 clusters beats 4 x 33 and 2 x 74 although the busiest CTA does up to twice
+  // the FMA work - the CTAs left idle by a hop absorb the weight-gradient tiles. No cluster launch available ->
+  // single CTAs, K never split.
+  long long best = -1;
+  for (int i = 0; i < 3 && best < 0; ++i) {
+    if (h->small_G[i] <= 0) continue;
+    plan_hops(h, sp, 8 >> i, h->small_G[i]);
+    best = plan_cost(sp);
+  }
+  if (best < 0) plan_hops(h, sp, 1, h->small_clusters);
+  if (getenv("DPI_B200_SMALL_VERBOSE")) {
+    const ActPlan* all[6] = {&sp.f1, &sp.f2, &sp.f3, &sp.dg2, &sp.dg1, &sp.dgin};
+    const char* nm[6] = {"f1", "f2", "f3", "dg2", "dg1", "dgin"};
+    fprintf(stderr, "dpi_b200 small plan: B=%d cluster=%d G=%d NC=%d (available: 8x%d 4x%d 2x%d) cost=%lld\n", bp.B, sp.cl,
+            sp.G, sp.NC, h->small_G[0], h->small_G[1], h->small_G[2], best);
+    for (int i = 0; i < 6; ++i)
+      fprintf(stderr, "   %-4s N=%d K=%d NT=%d tiles=%d split=%d KC=%d KS=%d\n", nm[i], all[i]->N, all[i]->K, all[i]->NT,
+              all[i]->n_tiles, all[i]->ksplit, all[i]->KC, all[i]->KS);
+  }
+  const int NC = sp.NC;
   const long long wg3 = ((long long)Dout + 15) / 16 * ((H + 63) / 64);
   sp.wgv = wg3 > 4LL * NC ? 1 : 0;
   sp.ldp_tiles = std::max(sp.f3.n_tiles, (NC + h->S - 1) / h->S);   // workspace rows: one logdet partial per CTA

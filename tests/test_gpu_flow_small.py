@@ -107,6 +107,13 @@ def test_small_kernel_without_clusters(D, NF, B, seqfrac):
     _check(_run(D, NF, B, seqfrac, {"DPI_B200_SMALL": "1", "DPI_B200_SMALL_NOCLUSTER": "1"}))
 
 
+@pytest.mark.parametrize("cl", ["8", "4", "2"])
+@pytest.mark.parametrize("D,NF,B,seqfrac", [SHAPES[0], SHAPES[5]])
+def test_small_kernel_every_cluster_size(D, NF, B, seqfrac, cl):
+    """Cluster sizes 8 / 4 / 2 (the planner normally picks the cheapest per shape), K split from 8 up."""
+    _check(_run(D, NF, B, seqfrac, {"DPI_B200_SMALL": "1", "DPI_B200_SMALL_CL": cl, "DPI_B200_SMALL_KSPLIT_MIN": "8"}))
+
+
 def test_small_kernel_no_batchnorm():
     _check(_run(64, 2, 8, 1, {"DPI_B200_SMALL": "1"}, bn=False), bn=False)
 
