@@ -10,11 +10,16 @@
 #include <memory>
 #include <vector>
 
+#include "dft_tc.cuh"
 #include "gemm_tile.cuh"
 
 struct dpi_eht_s {
   int device = 0, npix = 0, P = 0, n_vis = 0, n_cp = 0, n_ca = 0, n_sm = 0;
   float* d_F = nullptr;            // [P, 2*n_vis]
+  // tcgen05 DFT (dft_tc.cuh): F split into TF32 hi / lo and tiled as K-major UMMA operands, for the forward
+  // GEMM (B[n][k] = F[k][n]) and for the adjoint (B[n][k] = F[n][k])
+  int use_tc = 1;
+  float* d_Bf = nullptr; float* d_Bb = nullptr;
   int* d_cp_ind = nullptr;         // [3, n_cp]
   double* d_cp_sign = nullptr;     // [3, n_cp]
   int* d_ca_ind = nullptr;         // [4, n_ca]
@@ -285,8 +290,23 @@ size_t eht_ws_floats(const dpi_eht_s* h, int batch, DftPlan* f, DftPlan* bw) {
   size_t part_b = pb.splits > 1 ? (size_t)pb.tiles_m * pb.tiles_n * pb.splits * kBM * 64 : 0;
   return std::max(part_f, part_b) + (size_t)batch * 2 * h->n_vis + 64;
 }
+// scratch of the tcgen05 DFT (packed A + split partials), placed behind the region above
+size_t eht_tc_floats(const dpi_eht_s* h, int batch) {
+  if (!h->use_tc) return 0;
+  const tc::Plan f = tc::make_plan(batch, 2 * h->n_vis, h->P, h->n_sm), b = tc::make_plan(batch, h->P, 2 * h->n_vis, h->n_sm);
+  return std::max(tc::a_pack_floats(f) + tc::part_floats(f), tc::a_pack_floats(b) + tc::part_floats(b)) + 256;
+}
+float* eht_tc_base(const dpi_eht_s* h, int batch, void* ws) {
+  float* base = (float*)((char*)ws + kCtrl * sizeof(unsigned)) + eht_ws_floats(h, batch, nullptr, nullptr);
+  return (float*)(((uintptr_t)base + 1023) & ~(uintptr_t)1023);
+}
 
 int run_dft_fwd(dpi_eht_s* h, int batch, const float* img, float* vis, void* ws, cudaStream_t st) {
+  if (h->use_tc) {
+    const tc::Plan p = tc::make_plan(batch, 2 * h->n_vis, h->P, h->n_sm);
+    float* a_pack = eht_tc_base(h, batch, ws);
+    return tc::gemm(p, img, h->P, h->d_Bf, a_pack, a_pack + tc::a_pack_floats(p), vis, 0, st);
+  }
   DftPlan pf;
   eht_ws_floats(h, batch, &pf, nullptr);
   unsigned* ctr = (unsigned*)ws;
@@ -300,6 +320,12 @@ int run_dft_fwd(dpi_eht_s* h, int batch, const float* img, float* vis, void* ws,
 }
 
 int run_dft_bwd(dpi_eht_s* h, int batch, float* g_img, void* ws, cudaStream_t st) {
+  if (h->use_tc) {
+    const tc::Plan p = tc::make_plan(batch, h->P, 2 * h->n_vis, h->n_sm);
+    const float* gvis_tc = (const float*)((char*)ws + kCtrl * sizeof(unsigned));
+    float* a_pack = eht_tc_base(h, batch, ws);
+    return tc::gemm(p, gvis_tc, 2 * h->n_vis, h->d_Bb, a_pack, a_pack + tc::a_pack_floats(p), g_img, 1, st);
+  }
   DftPlan pb;
   eht_ws_floats(h, batch, nullptr, &pb);
   unsigned* ctr = (unsigned*)ws;
@@ -342,6 +368,22 @@ int dpi_eht_create(dpi_eht_t* out, int device, int npix, int n_vis, const float*
   const size_t nF = (size_t)h->P * 2 * n_vis;
   DPI_CUDA(cudaMalloc(&h->d_F, nF * sizeof(float)));
   DPI_CUDA(cudaMemcpy(h->d_F, dft_mat, nF * sizeof(float), cudaMemcpyHostToDevice));
+  {  // DPI_B200_DFT=simt selects the fp32 SIMT GEMM instead of the tcgen05 one
+    const char* e = getenv("DPI_B200_DFT");
+    h->use_tc = (e && e[0] == 's') ? 0 : 1;
+  }
+  if (h->use_tc) {
+    const int N2 = 2 * n_vis;
+    int rc = tc::init();
+    if (rc) return rc;
+    DPI_CUDA(cudaMalloc(&h->d_Bf, tc::b_pack_floats(N2, h->P) * sizeof(float)));
+    DPI_CUDA(cudaMalloc(&h->d_Bb, tc::b_pack_floats(h->P, N2) * sizeof(float)));
+    rc = tc::pack_b(h->d_F, 1, N2, N2, h->P, h->d_Bf, 0);        // forward: B[n][k] = F[k][n]
+    if (rc) return rc;
+    rc = tc::pack_b(h->d_F, N2, 1, h->P, N2, h->d_Bb, 0);        // adjoint: B[n][k] = F[n][k]
+    if (rc) return rc;
+    DPI_CUDA(cudaDeviceSynchronize());
+  }
   std::vector<int> cpi(3 * (size_t)n_cp), cai(4 * (size_t)n_ca);
   std::vector<double> cps(cp_sign, cp_sign + 3 * (size_t)n_cp);
   for (size_t i = 0; i < cpi.size(); ++i) cpi[i] = (int)cp_ind[i];
@@ -386,7 +428,9 @@ int dpi_eht_create(dpi_eht_t* out, int device, int npix, int n_vis, const float*
 int dpi_eht_destroy(dpi_eht_t h) {
   if (!h) return DPI_OK;
   DeviceGuard g(h->device);
-  cudaFree(h->d_F); cudaFree(h->d_cp_ind); cudaFree(h->d_cp_sign); cudaFree(h->d_ca_ind);
+  cudaFree(h->d_F);
+  cudaFree(h->d_Bf);
+  cudaFree(h->d_Bb); cudaFree(h->d_cp_ind); cudaFree(h->d_cp_sign); cudaFree(h->d_ca_ind);
   cudaFree(h->d_cp_ptr); cudaFree(h->d_cp_adj); cudaFree(h->d_cp_adj_sign);
   cudaFree(h->d_ca_ptr); cudaFree(h->d_ca_adj); cudaFree(h->d_ca_adj_sign);
   delete h;
@@ -395,7 +439,7 @@ int dpi_eht_destroy(dpi_eht_t h) {
 
 size_t dpi_eht_workspace_bytes(dpi_eht_t h, int batch) {
   if (!h || batch < 1) return 0;
-  return kCtrl * sizeof(unsigned) + eht_ws_floats(h, batch, nullptr, nullptr) * sizeof(float);
+  return kCtrl * sizeof(unsigned) + (eht_ws_floats(h, batch, nullptr, nullptr) + eht_tc_floats(h, batch)) * sizeof(float) + 1024;
 }
 
 int dpi_eht_forward(dpi_eht_t h, int batch, const float* img, float* vis, float* visamp, double* cphase,

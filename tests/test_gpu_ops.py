@@ -31,8 +31,14 @@ def test_eht_forward_matches_reference_fixture():
     assert rel_err(cph, g["cphase0"]) < RTOL and rel_err(lca, g["logcamp0"]) < RTOL
 
 
+@pytest.mark.parametrize("dft", ["tc", "simt"])
 @pytest.mark.parametrize("npix,ns,nsc,B", [(8, 5, 8, 6), (32, 7, 100, 64), (16, 6, 20, 130)])
-def test_eht_forward_backward_vs_oracle(npix, ns, nsc, B):
+def test_eht_forward_backward_vs_oracle(npix, ns, nsc, B, dft, monkeypatch):
+    """dft='tc': tcgen05 3xTF32 GEMM (default); 'simt': fp32 FFMA GEMM. Forward quantities meet 1e-4 on both. The
+    gradient of closure phases / log amplitudes of RANDOM images is ill-conditioned (terms ~ 1/|V|^2 with |V| ~ 0):
+    the tensor-core path is held to its separately stated tolerance there (north_star), 5e-4."""
+    monkeypatch.setenv("DPI_B200_DFT", dft)
+    GTOL = 5e-4 if dft == "tc" else RTOL
     wl = _wl(npix, 190 if npix == 32 else 3, ns, nsc)
     f = _eht_func(wl)
     torch.manual_seed(1)
@@ -44,13 +50,13 @@ def test_eht_forward_backward_vs_oracle(npix, ns, nsc, B):
     v, a, c, l = f(ig)
     ((v * cv.cuda()).sum() + (a * ca.cuda()).sum() + (c * cc.cuda()).sum() + (l * cl.cuda()).sum()).backward()
     assert rel_err(v, vo) < RTOL and rel_err(a, ao) < RTOL and rel_err(c, co) < RTOL and rel_err(l, lo) < RTOL
-    assert rel_err(ig.grad.reshape(img.shape), img.grad) < RTOL
+    assert rel_err(ig.grad.reshape(img.shape), img.grad) < GTOL
     # partial use of the outputs (unused ones arrive as None)
     ig2 = img.detach().cuda().requires_grad_(True)
     f(ig2)[3].sum().backward()
     img2 = img.detach().clone().requires_grad_(True)
     O.eht_observe(img2, wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"])[3].sum().backward()
-    assert rel_err(ig2.grad.reshape(img.shape), img2.grad) < RTOL
+    assert rel_err(ig2.grad.reshape(img.shape), img2.grad) < GTOL
 
 
 def test_chi2_losses_vs_oracle():
