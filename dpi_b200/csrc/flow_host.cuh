@@ -27,7 +27,8 @@ struct BatchPlan {
   Program fwd[2][2];
   Program bwd[2];   // [1]: also produces the gradient wrt the flow input
   // small-batch cluster kernel (batch <= 64): decomposition + shared-memory layout, or small.ok == 0
-  SmallPlan small;
+  SmallPlan small;       // backward pass (and the shared facts: ok, workspace rows)
+  SmallPlan small_fwd;   // forward pass (may use a different cluster size)
 };
 
 }  // namespace dpi
@@ -57,6 +58,6 @@ struct dpi_flow_s {
 namespace dpi {
 // flow_small.cu
 int small_query(dpi_flow_s* h);                                        // fills small_clusters / small_cl
-void small_plan(const dpi_flow_s* h, BatchPlan& bp);                   // fills bp.small (ok = 0 if unsupported)
+void small_plan(const dpi_flow_s* h, BatchPlan& bp);                   // fills bp.small / small_fwd (ok = 0 if unsupported)
 int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream);
 }  // namespace dpi

@@ -1148,21 +1148,20 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
 namespace {
 
 inline int up4(int x) { return (x + 3) & ~3; }
+constexpr int kSmallSmemMax = 214 * 1024;   // dynamic shared memory ceiling (232,448 B per block minus ~14 KB static)
 
-ActPlan plan_act(int N, int K, bool split, int G, int NC, int cl, bool wk, int max_nt_log) {
+ActPlan plan_act(int N, int K, bool split, int G, int NC, int cl, bool wk, int wmax) {
   ActPlan p{};
   p.N = N; p.K = K;
   p.ksplit = split ? 1 : 0;
   const int units = split ? G : NC;
   int nt = 4;
   while (nt < 64 && (N + nt - 1) / nt > units) nt *= 2;
-  (void)max_nt_log;
   p.NT = nt;
   p.n_tiles = (N + nt - 1) / nt;
   const int nr = split ? cl : 1;
   p.KC = up4((K + nr - 1) / nr);
   p.KS = std::min(p.KC, 512);
-  const int wmax = 36 * 1024;
   auto wbytes = [&](int ks) { return wk ? nt * (ks + 4) * 4 : ks * (nt + 4) * 4; };
   while (p.KS > 4 && wbytes(p.KS) > wmax) p.KS = up4(p.KS / 2);
   p.nq = nt / 4;
@@ -1183,7 +1182,7 @@ int small_query(dpi_flow_s* h) {
   const char* ks = getenv("DPI_B200_SMALL_KSPLIT_MIN");
   h->small_ksplit_min = ks ? std::max(8, atoi(ks)) : 512;
   if (!h->small_mode) return DPI_OK;
-  const int max_smem = 200 * 1024;
+  const int max_smem = kSmallSmemMax;
   if (cudaFuncSetAttribute((const void*)flow_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
     cudaGetLastError();
     h->small_mode = 0;
@@ -1222,29 +1221,29 @@ long long hop_cost(const ActPlan& p, int units) {
   const int rounds = (p.n_tiles + units - 1) / units;
   return (long long)rounds * p.NT * p.KC;
 }
-void plan_hops(const dpi_flow_s* h, SmallPlan& sp, int cl, int G) {
+void plan_hops(const dpi_flow_s* h, SmallPlan& sp, int cl, int G, int wmax) {
   const int NC = cl > 1 ? cl * G : G;
   sp.NC = NC; sp.G = cl > 1 ? G : NC; sp.cl = cl;
   const int H = h->H, Da = h->Da, Db = h->Db, Dout = h->Dout;
   auto split = [&](int K) { return cl > 1 && K >= h->small_ksplit_min; };
-  sp.f1 = plan_act(H, Da, split(Da), sp.G, NC, cl, true, 0);
-  sp.f2 = plan_act(H, H, split(H), sp.G, NC, cl, true, 0);
+  sp.f1 = plan_act(H, Da, split(Da), sp.G, NC, cl, true, wmax);
+  sp.f2 = plan_act(H, H, split(H), sp.G, NC, cl, true, wmax);
   {  // output layer: tiles of NP column pairs -> 2 NP weight rows, never split (N large, K = H small)
     int np = 2;
     while (np < 32 && (Db + np - 1) / np > NC) np *= 2;
-    ActPlan p = plan_act(2 * np, H, false, sp.G, NC, cl, true, 0);
+    ActPlan p = plan_act(2 * np, H, false, sp.G, NC, cl, true, wmax);
     p.NT = 2 * np; p.nq = p.NT / 4; p.kp = 16 / p.nq;
     p.nt_log = 0;
     while ((1 << p.nt_log) < p.NT) ++p.nt_log;
     p.nq_log = p.nt_log - 2;
     p.N = Db; p.n_tiles = (Db + np - 1) / np;
     p.KS = std::min(p.KC, 512);
-    while (p.KS > 4 && p.NT * (p.KS + 4) * 4 > 36 * 1024) p.KS = up4(p.KS / 2);
+    while (p.KS > 4 && p.NT * (p.KS + 4) * 4 > wmax) p.KS = up4(p.KS / 2);
     sp.f3 = p;
   }
-  sp.dg2 = plan_act(H, Dout, split(Dout), sp.G, NC, cl, false, 0);
-  sp.dg1 = plan_act(H, H, split(H), sp.G, NC, cl, false, 0);
-  sp.dgin = plan_act(Da, H, false, sp.G, NC, cl, false, 0);
+  sp.dg2 = plan_act(H, Dout, split(Dout), sp.G, NC, cl, false, wmax);
+  sp.dg1 = plan_act(H, H, split(H), sp.G, NC, cl, false, wmax);
+  sp.dgin = plan_act(Da, H, false, sp.G, NC, cl, false, wmax);
 }
 long long plan_cost(const SmallPlan& sp) {
   auto u = [&](const ActPlan& p) { return p.ksplit ? sp.G : sp.NC; };
@@ -1253,22 +1252,20 @@ long long plan_cost(const SmallPlan& sp) {
 }
 }  // namespace
 
-void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
-  SmallPlan& sp = bp.small;
+namespace {
+// One pass's plan. `pref`: cluster-size preference order as indices into small_G (0: 8 CTAs, 1: 4, 2: 2).
+void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, const int (&pref)[3], int wmax) {
   sp = SmallPlan{};
   if (!h->small_mode || bp.B > kMB || h->H > 512 || (h->H & 3) || (h->Da & 3)) return;
   const int H = h->H, Dout = h->Dout, Db = h->Db;
-  // cluster size: the largest of 8, 4, 2 CTAs the device can co-schedule (DPI_B200_SMALL_CL forces one). Measured
-  // on C1 / C2 (tools/cl_sweep.sh): 8 x 15 clusters beats 4 x 33 and 2 x 74 although the busiest CTA does up to twice
-  // the FMA work - the CTAs left idle by a hop absorb the weight-gradient tiles. No cluster launch available ->
-  // single CTAs, K never split.
   long long best = -1;
-  for (int i = 0; i < 3 && best < 0; ++i) {
+  for (int q = 0; q < 3 && best < 0; ++q) {
+    const int i = pref[q];
     if (h->small_G[i] <= 0) continue;
-    plan_hops(h, sp, 8 >> i, h->small_G[i]);
+    plan_hops(h, sp, 8 >> i, h->small_G[i], wmax);
     best = plan_cost(sp);
   }
-  if (best < 0) plan_hops(h, sp, 1, h->small_clusters);
+  if (best < 0) plan_hops(h, sp, 1, h->small_clusters, wmax);   // no cluster launch: single CTAs, K never split
   if (getenv("DPI_B200_SMALL_VERBOSE")) {
     const ActPlan* all[6] = {&sp.f1, &sp.f2, &sp.f3, &sp.dg2, &sp.dg1, &sp.dgin};
     const char* nm[6] = {"f1", "f2", "f3", "dg2", "dg1", "dgin"};
@@ -1307,20 +1304,42 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
   const int n_ph = 4 * h->S + 2;                       // backward pass has the most phases
   sp.oPD = o; o += al(n_ph * (int)sizeof(PD));
   sp.smem_bytes = o;
-  sp.ok = o <= 200 * 1024 ? 1 : 0;
+  sp.ok = o <= kSmallSmemMax ? 1 : 0;
+}
+// weight slices up to 70 KB keep the K loop of the MRI-sized layers at two chunks; smaller budget when that overflows
+void small_plan_pass(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, const int (&pref)[3]) {
+  small_plan_pass_w(h, bp, sp, pref, 70 * 1024);
+  if (!sp.ok) small_plan_pass_w(h, bp, sp, pref, 36 * 1024);
+}
+}  // namespace
+
+// Cluster size per pass (DPI_B200_SMALL_CL forces one size for both). Measured on C1 / C2 (tools/cl_sweep.sh): the
+// backward pass is fastest with 15 clusters of 8 - the CTAs a hop leaves idle absorb the weight-gradient tiles -
+// while the forward pass, which has no such side work, is fastest with 33 clusters of 4 (more CTAs busy per hop).
+void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
+  // ... as long as the hops are latency-bound (C1: 14 MFMA per stage); at MRI sizes (C2: 218 MFMA per stage) the
+  // hops are FFMA-bound and 8 x 15 wins for both passes.
+  const long long stage_fma = 64LL * ((long long)h->Da * h->H + (long long)h->H * h->H + (long long)h->H * h->Dout);
+  const int pref_bwd[3] = {0, 1, 2}, pref_fwd4[3] = {1, 0, 2};
+  small_plan_pass(h, bp, bp.small, pref_bwd);
+  small_plan_pass(h, bp, bp.small_fwd, stage_fma < 50000000LL ? pref_fwd4 : pref_bwd);
+  if (!bp.small.ok || !bp.small_fwd.ok) { bp.small.ok = 0; bp.small_fwd.ok = 0; }
+  // the logdet partial rows (one per forward CTA) live in the workspace sized from bp.small
+  bp.small.ldp_tiles = std::max(bp.small.ldp_tiles, bp.small_fwd.ldp_tiles);
 }
 
 int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream) {
+  const SmallPlan& plan = bwd ? bp.small : bp.small_fwd;
   SArgs A{};
   A.k = a;
-  A.sp = bp.small;
+  A.sp = plan;
   A.bwd = bwd;
   A.k.phases = nullptr;
   A.k.use_tc = 0;
   A.k.tbuf = nullptr;
   A.k.tiles_m = 1;
-  A.k.ldp_tiles = bp.small.ldp_tiles;
-  A.k.red_tiles = bp.small.red_tiles;
+  A.k.ldp_tiles = plan.ldp_tiles;
+  A.k.red_tiles = plan.red_tiles;
   const int n_phases = bwd ? 4 * h->S + 2 : 3 * h->S + 2;
   if (h->d_tbuf && n_phases <= 4096) {
     A.k.tbuf = h->d_tbuf;
@@ -1335,15 +1354,15 @@ int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStre
   }
   DPI_CUDA(cudaMemsetAsync(A.k.ctrl, 0, kCtrlWords * sizeof(unsigned), stream));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(bp.small.NC);
+  cfg.gridDim = dim3(plan.NC);
   cfg.blockDim = dim3(kT);
-  cfg.dynamicSmemBytes = bp.small.smem_bytes;
+  cfg.dynamicSmemBytes = plan.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
   int na = 0;
-  if (bp.small.cl > 1) {
+  if (plan.cl > 1) {
     at[na].id = cudaLaunchAttributeClusterDimension;
-    at[na].val.clusterDim.x = bp.small.cl; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    at[na].val.clusterDim.x = plan.cl; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
     ++na;
   }
   // DPI_B200_SMALL_COOP=0: plain (non-cooperative) launch of the persistent kernel. The grid never exceeds the
