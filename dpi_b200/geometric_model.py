@@ -8,6 +8,7 @@ flux_flag=False and the constructor's default parameter ranges (r_range [10, 40]
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -68,7 +69,26 @@ class SimpleCrescentNuisanceFloor_Param2Img(nn.Module):
         self.eps = 1e-4
 
     def compute_features(self, params):
-        raise NotImplementedError("dpi_b200: features are computed inside the CUDA kernel")
+        """Physical features of each sample (geometric_model.py:275-321), same return tuple as the reference with
+        flux_flag=False. Offline analysis helper (posterior summaries, DPIx_interferometry.py:492-520): plain
+        elementwise torch on whatever device `params` lives on; the renderer kernel recomputes them internally."""
+        hf = 0.5 * self.fov
+        col = lambda i: params[:, i].unsqueeze(-1).unsqueeze(-1)
+        r = 10.0 / hf + col(0) * 30.0 / hf
+        sigma = 1.0 / hf + col(1) * 39.0 / hf
+        s = 1e-3 + col(2) * (0.99 - 1e-3)
+        eta = 181 / 180 * np.pi * (2.0 * col(3) - 1.0)
+        scale, xs, ys, sx, sy, th = [], [], [], [], [], []
+        for k in range(self.n_gaussian):
+            xs.append(-200.0 / hf + col(4 + k * 6) * 400.0 / hf)
+            ys.append(-200.0 / hf + col(5 + k * 6) * 400.0 / hf)
+            scale.append(1e-3 + col(6 + k * 6) * (2.0 - 1e-3))
+            sx.append(1.0 / hf + col(7 + k * 6) * 99.0 / hf)
+            sy.append(1.0 / hf + col(8 + k * 6) * 99.0 / hf)
+            th.append(181 / 180 * 0.5 * np.pi * col(9 + k * 6))
+        floor = col(4 + self.n_gaussian * 6)
+        crescent_flux = 1e-3 + (2.0 - 1e-3) * col(5 + self.n_gaussian * 6)
+        return r, sigma, s, eta, crescent_flux, floor, scale, xs, ys, sx, sy, th
 
     def forward(self, params):
         return _CrescentFunction.apply(params, self.npix, self.n_gaussian, self.fov)

@@ -496,3 +496,60 @@ class DPIxTrainer:
         self.k += 1
         self.launches_per_step = _lib.launch_count() - n0
         return self.terms
+
+    # ------------------------------------------------------------------ posterior sampling
+    @torch.no_grad()
+    def sample_posterior(self, n_concat=1, rejsamp=True, generator=None, z=None):
+        """`Gen_samples` of DPIx_interferometry.py:433-470: draw z, run the trained flow in reverse with the BatchNorm
+        running statistics (the script calls `.eval()` first, :899), render, evaluate loss_orig = 0.5 loss_data +
+        logprob per sample, importance weights softmax_i(-loss_orig), rejection step U < w / max w. Forward-only reuse
+        of the training kernels. Returns dict(params, img, weights, accepted (bool), img_mean, img_std, img_map)."""
+        lib, B, st = self.lib, self.B, None
+        was_training = self.flow.training
+        self.flow.eval()
+        out = dict(params=[], img=[], weights=[], accepted=[], loss_data=[])
+        try:
+            for k in range(n_concat):
+                if z is not None:
+                    self.z.copy_(z[k] if z.dim() == 3 else z)
+                else:
+                    self.sample_z(generator)
+                with torch.cuda.device(self.device):
+                    st = _lib.stream_ptr()
+                    _lib.check(lib.dpi_flow_run(self.handle, 0, 0, B, self.params.data_ptr(), self.flow.bn_running.data_ptr(),
+                                                self.z.data_ptr(), self.ps.data_ptr(), self.logdet_flow.data_ptr(),
+                                                self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
+                    _lib.check(lib.dpi_sigmoid_forward(B, self.np_, self.ps.data_ptr(), self.prm.data_ptr(),
+                                                       self.det.data_ptr(), st), "dpi_sigmoid_forward")
+                    _lib.check(lib.dpi_crescent_forward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(),
+                                                        self.img.data_ptr(), st), "dpi_crescent_forward")
+                    _lib.check(lib.dpi_eht_forward(self.op.handle, B, self.img.data_ptr(), self.vis.data_ptr(), None, None,
+                                                   None, self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_forward")
+                    _lib.check(lib.dpi_eht_data_grad(self.op.handle, B, self.vis.data_ptr(), self.cphase_true.data_ptr(),
+                                                     self.sigma_cp.data_ptr(), self.logcamp_true.data_ptr(),
+                                                     self.sigma_ca.data_ptr(), self.w["cphase"], self.w["camp"],
+                                                     self.loss_cp.data_ptr(), self.loss_ca.data_ptr(), self.g_img.data_ptr(),
+                                                     self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_data_grad")
+                    # loss_orig = 0.5 * loss_data + logprob (:466): scale_factor 1, data weight 1; softmax(-loss_orig) = alpha 0
+                    _lib.check(lib.dpi_alpha_objective(B, self.np_, self.z.data_ptr(), self.loss_cp.data_ptr(),
+                                                       self.loss_ca.data_ptr(), self.logdet_flow.data_ptr(), self.det.data_ptr(),
+                                                       self.w["cphase"], self.w["camp"], 1.0, 1.0, 0.0, 0, B,
+                                                       self.loss_i.data_ptr(), self.gscale.data_ptr(), self.g_logdet.data_ptr(),
+                                                       self.terms.data_ptr(), self.stats.data_ptr(), st), "dpi_alpha_objective")
+                w = -self.g_logdet.clone()                       # g_logdet = -w_i * scale_factor (= 1)
+                out["weights"].append(w)
+                out["params"].append(self.prm.clone())
+                out["img"].append(self.img.view(B, self.npix, self.npix).clone())
+                out["loss_data"].append(self.w["camp"] * self.loss_ca + self.w["cphase"] * self.loss_cp.float())
+                if rejsamp:
+                    u = torch.rand(B, device=self.device, generator=generator)
+                    out["accepted"].append(w / w.max() > u)                   # rej_prob / max(rej_prob) > U (:471-474)
+                else:
+                    out["accepted"].append(torch.ones(B, dtype=torch.bool, device=self.device))
+        finally:
+            if was_training:
+                self.flow.train()
+        res = {k: torch.cat(v) for k, v in out.items()}
+        res["img_mean"], res["img_std"] = res["img"].mean(0), res["img"].std(0)
+        res["img_map"] = res["img"][torch.argmin(res["loss_data"])]
+        return res

@@ -104,3 +104,44 @@ def test_dpix_config_size_step_vs_oracle():
     mine = tr.flow.state_dict()
     worst = max(rel_err(mine[k].cpu(), sd[k].detach()) for k in ot.keys)
     assert worst < 2 * RTOL, worst
+
+
+def test_posterior_sampling_weights_vs_oracle():
+    """SURVEY 8(f) n1, `Gen_samples` (DPIx_interferometry.py:433-474): eval-mode flow, importance weights
+    softmax(-(0.5 loss_data + logprob)) and the feature extraction used for the posterior summaries."""
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    from dpi_b200.geometric_model import SimpleCrescentNuisanceFloor_Param2Img
+    from dpi_b200.trainer import DPIxTrainer
+    from dpi_b200.workloads import dpix_workload
+    wl = dpix_workload(npix=32, n_scans=12)
+    B, NF = 128, 3
+    sd = O.init_state(18, NF, seqfrac=1 / 16, seed=8, randomize=True)
+    for k in sd:                                    # non-trivial running statistics for the eval-mode pass
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn_like(sd[k]) * 0.05
+        if k.endswith("running_var"):
+            sd[k] = 1 + 0.2 * torch.rand_like(sd[k])
+    flow = RealNVP(18, NF, seqfrac=1 / 16)
+    flow.load_state_dict({k: v.clone() for k, v in sd.items()})
+    tr = DPIxTrainer(flow, wl, B)
+    torch.manual_seed(4)
+    z = torch.randn(B, 18)
+    res = tr.sample_posterior(z=z.cuda(), rejsamp=True)
+    with torch.no_grad():
+        ps, logdet = O.realnvp_reverse({k: v.clone() for k, v in sd.items()}, z, train=False)
+        prm = torch.sigmoid(ps)
+        img = O.crescent_render(prm, 32, 160.0, 2)
+        logdet = logdet + torch.sum(-ps - 2 * torch.nn.functional.softplus(-ps), -1)
+        _, _, cph, lca = O.eht_observe(img, wl["dft_mat"], wl["cphase_ind"], wl["cphase_sign"], wl["camp_ind"])
+        ld = wl["w"]["camp"] * O.loss_logca_diff2(wl["sigma_ca"], wl["logcamp_true"], lca) \
+            + wl["w"]["cphase"] * O.loss_angle_diff(wl["sigma_cp"], wl["cphase_true"], cph)
+        lo = 0.5 * ld + (-logdet - 0.5 * (z ** 2).sum(1))
+        w = torch.softmax(-lo.double(), 0)
+    assert rel_err(res["params"], prm) < RTOL and rel_err(res["img"], img) < RTOL
+    assert rel_err(res["weights"], w) < 5e-3          # exp() of O(1e2) exponents amplifies 1e-5 input differences
+    assert bool(res["accepted"][torch.argmax(res["weights"])])
+    assert res["img_mean"].shape == (32, 32) and res["img_std"].shape == (32, 32)
+    conv = SimpleCrescentNuisanceFloor_Param2Img(32, n_gaussian=2, fov=160)
+    feats = conv.compute_features(res["params"])
+    assert len(feats) == 12 and feats[0].shape == (B, 1, 1)
+    assert float(feats[0].min()) >= 10.0 / 80.0 - 1e-6 and float(feats[0].max()) <= 40.0 / 80.0 + 1e-6
