@@ -39,6 +39,7 @@ enum Kind { K_TIN = 0, K_F1, K_F2, K_F3, K_FFIN, K_B0, K_DG2, K_DG1, K_DGIN, K_B
 
 struct Sm {
   float *X, *W, *E, *P, *R, *Pm;
+  float *X2, *W2;         // second halves of the K-chunk ring (== X / W when every hop is a single chunk)
   int *idx, *idx2;
   float* red;             // 8 * 64 + 128 floats (static)
   float* ldacc;           // this CTA's running logdet partial over the stages of the pass (64 floats, static)
@@ -365,19 +366,23 @@ __device__ __noinline__ PD make_desc(const SArgs& A, const StageTab* stb, int ki
   return d;
 }
 
-// weights + row indices of one k-chunk of `tile`
-__device__ __forceinline__ void issue_weights(const Sm& s, const PD& d, int tile, int kb, int knp, int k_hi) {
+// weight slice of one k-chunk of `tile` -> Wdst; with_idx: also the row indices of this rank's whole K range
+// [k_lo, k_hi) -> s.idx (chunks index it at kb - k_lo), so that later chunks can be issued without waiting for them
+__device__ __forceinline__ void issue_weights(const Sm& s, const PD& d, float* Wdst, int tile, int kb, int knp, int k_hi,
+                                              bool with_idx, int k_lo) {
   if (d.wk) {
-    if (d.np_log >= 0) load_w_k(s.W, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.np_log, d.pair_db, d.np_log);
-    else load_w_k(s.W, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.nt_log, d.N, -1);
+    if (d.np_log >= 0) load_w_k(Wdst, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.np_log, d.pair_db, d.np_log);
+    else load_w_k(Wdst, d.KS + 4, d.Wg, d.K, d.NT, kb, knp, k_hi, tile << d.nt_log, d.N, -1);
   } else {
-    load_w_n(s.W, d.NT + 4, d.Wg, d.w_ld, kb, knp, k_hi, tile << d.nt_log, d.nt_log - 2, d.N);
+    load_w_n(Wdst, d.NT + 4, d.Wg, d.w_ld, kb, knp, k_hi, tile << d.nt_log, d.nt_log - 2, d.N);
   }
-  if (d.xmap)
-    for (int t = threadIdx.x; t < knp; t += kT) {
-      const bool ok = kb + t < k_hi;
-      cp_async4(reinterpret_cast<float*>(s.idx + t), reinterpret_cast<const float*>(ok ? d.xmap + kb + t : d.xmap), ok);
+  if (with_idx && d.xmap) {
+    const int cnt = (k_hi - k_lo + 3) & ~3;
+    for (int t = threadIdx.x; t < cnt; t += kT) {
+      const bool ok = k_lo + t < k_hi;
+      cp_async4(reinterpret_cast<float*>(s.idx + t), reinterpret_cast<const float*>(ok ? d.xmap + k_lo + t : d.xmap), ok);
     }
+  }
 }
 // per-tile parameter / index vectors
 __device__ __forceinline__ void issue_params(const Sm& s, const PD& d, int tile) {
@@ -433,7 +438,7 @@ __device__ __forceinline__ void prefetch_gemm(const SArgs& A, const Sm& s, const
     if (unit < d.n_tiles) {
       const int k_lo = rank * d.KC, k_hi = min(d.K, k_lo + d.KC);
       const int kn = max(0, min(d.KS, k_hi - k_lo)), knp = (kn + 3) & ~3;
-      issue_weights(s, d, unit, k_lo, knp, k_hi);
+      issue_weights(s, d, s.W, unit, k_lo, knp, k_hi, true, k_lo);
       issue_params(s, d, unit);
     }
   }
@@ -467,20 +472,21 @@ __device__ __forceinline__ void run_gemm(const SArgs& A, const Sm& s, const PD& 
     for (int f = 0; f < 4; ++f)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[f][i] = 0.f;
-    bool first = true;
-#pragma unroll 1
-    for (int kb = k_lo; first || kb < k_hi; kb += d.KS) {
-      const int kn = max(0, min(d.KS, k_hi - kb)), knp = (kn + 3) & ~3;
-      if (!(pf && first)) {
-        __syncthreads();   // earlier readers of W / idx / X are done
-        issue_weights(s, d, tile, kb, knp, k_hi);
-        cp_async_commit();
-      }
-      cp_async_wait<0>();
-      __syncthreads();     // weights + indices + parameters landed (and X of the previous chunk is free)
-      if (first) STAMP(1);
-      load_rows(s.X, kMB, d.Xbase, s.idx, d.xmap ? 1 : 0, kb, k_hi, 0, LB, a.B, knp);
-      if (first && d.emode) {
+    // K range of this rank in chunks of KS rows through a two-buffer ring (s.X / s.X2, s.W / s.W2): chunk c + 1 is
+    // in flight while chunk c is multiplied. Single-chunk hops (C1) take exactly one pass.
+    if (!pf) {
+      __syncthreads();     // earlier readers of W / idx / X are done
+      const int kn0 = max(0, min(d.KS, k_hi - k_lo));
+      issue_weights(s, d, s.W, tile, k_lo, (kn0 + 3) & ~3, k_hi, true, k_lo);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncthreads();       // first weight chunk + all row indices + parameters landed
+    STAMP(1);
+    {
+      const int kn0 = max(0, min(d.KS, k_hi - k_lo));
+      load_rows(s.X, kMB, d.Xbase, s.idx, d.xmap ? 1 : 0, k_lo, k_hi, 0, LB, a.B, (kn0 + 3) & ~3);
+      if (d.emode) {
         if (d.emode == 3) {      // saved LeakyReLU outputs of the features this rank finalises
           const int nslots = max(0, (NT - rank + nr - 1) / nr);
           const int r = threadIdx.x >> 4;
@@ -493,17 +499,41 @@ __device__ __forceinline__ void run_gemm(const SArgs& A, const Sm& s, const PD& 
             cp_async16(s.E + i * kMB + m4, v ? d.Ebase + (size_t)n * LB + m4 : d.Ebase, v ? bytes : 0);
           }
         } else {
-          load_rows(s.E, kMB, d.Ebase, s.idx2, d.emode == 2 ? 2 : 0, n0, d.elim, d.np_log, LB, a.B,
-                    d.emode == 2 ? NT : NT);
+          load_rows(s.E, kMB, d.Ebase, s.idx2, d.emode == 2 ? 2 : 0, n0, d.elim, d.np_log, LB, a.B, NT);
         }
       }
       cp_async_commit();
-      cp_async_wait<0>();
+    }
+    int ch = 0;
+    const bool ring = s.X2 != s.X;       // false: shared memory only allowed one buffer -> chunks strictly in turn
+#pragma unroll 1
+    for (int kb = k_lo; ch == 0 || kb < k_hi; kb += d.KS, ++ch) {
+      const int kn = max(0, min(d.KS, k_hi - kb)), knp = (kn + 3) & ~3;
+      const int kb2 = kb + d.KS;
+      float* Xc = (ch & 1) ? s.X2 : s.X;
+      float* Wc = (ch & 1) ? s.W2 : s.W;
+      if (!ring) {
+        if (ch > 0) {
+          __syncthreads();
+          issue_weights(s, d, s.W, tile, kb, knp, k_hi, false, k_lo);
+          load_rows(s.X, kMB, d.Xbase, s.idx + (kb - k_lo), d.xmap ? 1 : 0, kb, k_hi, 0, LB, a.B, knp);
+          cp_async_commit();
+        }
+        cp_async_wait<0>();
+      } else if (kb2 < k_hi) {      // next chunk -> the other buffers (free since the barrier that ended chunk ch - 1)
+        const int kn2 = min(d.KS, k_hi - kb2), knp2 = (kn2 + 3) & ~3;
+        issue_weights(s, d, (ch & 1) ? s.W : s.W2, tile, kb2, knp2, k_hi, false, k_lo);
+        load_rows((ch & 1) ? s.X : s.X2, kMB, d.Xbase, s.idx + (kb2 - k_lo), d.xmap ? 1 : 0, kb2, k_hi, 0, LB, a.B, knp2);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
       __syncthreads();
-      if (first) STAMP(2);
-      if (d.wk) act_mac<true>(acc, s.X, s.W, ldw, knp, sq, fq, kp, d.kpn);
-      else act_mac<false>(acc, s.X, s.W, ldw, knp, sq, fq, kp, d.kpn);
-      first = false;
+      if (ch == 0) STAMP(2);
+      if (d.wk) act_mac<true>(acc, Xc, Wc, ldw, knp, sq, fq, kp, d.kpn);
+      else act_mac<false>(acc, Xc, Wc, ldw, knp, sq, fq, kp, d.kpn);
+      if (ring && kb2 < k_hi) __syncthreads();   // everyone is done with this chunk's buffers before they are refilled
     }
     pf = false;
     // ---- k-part partials -> P_s[kp][n][m] -> R_s[n][m]
@@ -1022,6 +1052,8 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
   Sm s;
   s.X = reinterpret_cast<float*>(smem_raw + A.sp.oX);
   s.W = reinterpret_cast<float*>(smem_raw + A.sp.oW);
+  s.X2 = reinterpret_cast<float*>(smem_raw + A.sp.oX2);
+  s.W2 = reinterpret_cast<float*>(smem_raw + A.sp.oW2);
   s.E = reinterpret_cast<float*>(smem_raw + A.sp.oE);
   s.P = reinterpret_cast<float*>(smem_raw + A.sp.oP);
   s.R = reinterpret_cast<float*>(smem_raw + A.sp.oR);
@@ -1254,7 +1286,7 @@ long long plan_cost(const SmallPlan& sp) {
 
 namespace {
 // One pass's plan. `pref`: cluster-size preference order as indices into small_G (0: 8 CTAs, 1: 4, 2: 2).
-void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, const int (&pref)[3], int wmax) {
+void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, const int (&pref)[3], int wmax, bool allow_ring) {
   sp = SmallPlan{};
   if (!h->small_mode || bp.B > kMB || h->H > 512 || (h->H & 3) || (h->Da & 3)) return;
   const int H = h->H, Dout = h->Dout, Db = h->Db;
@@ -1282,12 +1314,16 @@ void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, 
   sp.red_tiles = (Db + 7) / 8;
   const ActPlan* all[6] = {&sp.f1, &sp.f2, &sp.f3, &sp.dg2, &sp.dg1, &sp.dgin};
   int xb = 0, wb = 0, ib = 0;
+  bool multi = false;
+  int xb_gemm = 0;
   for (int i = 0; i < 6; ++i) {
     const ActPlan& p = *all[i];
     const bool wk = i < 3;
     xb = std::max(xb, p.KS * kMB * 4);
+    xb_gemm = xb;
     wb = std::max(wb, wk ? p.NT * (p.KS + 4) * 4 : p.KS * (p.NT + 4) * 4);
-    ib = std::max(ib, p.KS * 4);
+    ib = std::max(ib, (p.KC + 4) * 4);
+    if (p.KS < p.KC && allow_ring) multi = true;
   }
   const int wg_bytes = sp.wgv == 0 ? (16 + 64) * kLdG * 4 + 16 * 1024 : (32 + 128) * kLdG * 4 + 1024;
   xb = std::max(xb, std::max(wg_bytes, 33 * 32 * 4));
@@ -1295,6 +1331,11 @@ void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, 
   int o = 0;
   sp.oX = o; o += al(xb);
   sp.oW = o; o += al(wb);
+  sp.oX2 = sp.oX; sp.oW2 = sp.oW;
+  if (multi) {            // second halves of the K-chunk ring
+    sp.oX2 = o; o += al(xb_gemm);
+    sp.oW2 = o; o += al(wb);
+  }
   sp.oE = o; o += 64 * kMB * 4;
   sp.oP = o; o += 16 * 4 * kMB * 4;
   sp.oR = o; o += 64 * kMB * 4;
@@ -1308,8 +1349,9 @@ void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, 
 }
 // weight slices up to 70 KB keep the K loop of the MRI-sized layers at two chunks; smaller budget when that overflows
 void small_plan_pass(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, const int (&pref)[3]) {
-  small_plan_pass_w(h, bp, sp, pref, 70 * 1024);
-  if (!sp.ok) small_plan_pass_w(h, bp, sp, pref, 36 * 1024);
+  small_plan_pass_w(h, bp, sp, pref, 70 * 1024, true);
+  if (!sp.ok) small_plan_pass_w(h, bp, sp, pref, 36 * 1024, true);
+  if (!sp.ok) small_plan_pass_w(h, bp, sp, pref, 36 * 1024, false);
 }
 }  // namespace
 

@@ -30,7 +30,7 @@ struct SmallPlan {
   int wgv;                     // weight-gradient tile variant: 0 = 16 x 64 (4-way sample split), 1 = 32 x 128
   int ldp_tiles, red_tiles;    // logdet partial slots per stage, ActNorm partial slots per stage
   // dynamic shared memory layout (byte offsets)
-  int oX, oW, oE, oP, oR, oPm, oIdx, oIdx2, oPD, smem_bytes;
+  int oX, oW, oX2, oW2, oE, oP, oR, oPm, oIdx, oIdx2, oPD, smem_bytes;
 };
 
 }  // namespace dpi
