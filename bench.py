@@ -233,8 +233,7 @@ def gpu_run(args):
         prof = {"dpix_step": dict(ms=total_ms / args.steps, bytes=step_bytes)}
     barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _teardown(tr, world)
         return
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -269,9 +268,28 @@ def gpu_run(args):
                                    f"{cpu['ms_per_step']:.1f} ms/step, torch {torch.__version__} CPU"},
         "loss": float(host_terms[0]),
     }
-    print(json.dumps(out))
-    if world > 1:
+    print(json.dumps(out), flush=True)
+    _teardown(tr, world)
+
+
+def _teardown(tr, world):
+    """Multi-rank exit. The step graph holds a captured NCCL all-reduce, and NCCL will not destroy a communicator a
+    live graph still references: release the graphs first, then destroy the group under a watchdog, then leave
+    without running interpreter finalisers (rank 0 has already printed and flushed its line)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    if hasattr(tr, "close"):
+        tr.close()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(10.0, lambda: os._exit(0)).start()
+    try:
         dist.destroy_process_group()
+    except Exception:
+        pass
+    os._exit(0)
 
 
 def reference_run(args):

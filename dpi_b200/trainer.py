@@ -181,6 +181,8 @@ class _FusedTrainer:
                 self._warm += 1
                 if self._warm >= 2:
                     self._capture()
+            elif self._graphs[1] is None:   # one graph holds the whole step, the NCCL all-reduce included
+                self._graphs[0].replay()
             else:
                 ga, gb = self._graphs
                 ga.replay()
@@ -197,17 +199,43 @@ class _FusedTrainer:
                                      self.flow.bn_running)]
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            with torch.cuda.graph(ga, stream=s):
-                self._enqueue_loss_grad()
-            with torch.cuda.graph(gb, stream=s):
-                self._enqueue_update()
+        single = None
+        if self.world > 1:
+            # Data parallel: try to capture the gradient all-reduce inside ONE graph with both halves of the step (no
+            # host round trip between backward and Adam). NCCL collectives are capturable; if this build refuses,
+            # fall back to two graphs with the all-reduce issued eagerly between them.
+            try:
+                single = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(single, stream=s):
+                        self._enqueue_loss_grad()
+                        self._allreduce_impl()
+                        self._enqueue_update()
+            except Exception:
+                single = None
+                torch.cuda.synchronize(self.device)
+        if single is not None:
+            ga, gb = single, None
+        else:
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(ga, stream=s):
+                    self._enqueue_loss_grad()
+                with torch.cuda.graph(gb, stream=s):
+                    self._enqueue_update()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         for t, sv in zip((self.params, self.log_scale, self.m, self.v, self.m_ls, self.v_ls, self.step_dev,
                           self.flow.bn_running), saved):
             t.copy_(sv)
         self._graphs = (ga, gb)
+
+    def close(self):
+        """Drop the captured step graphs (they pin the NCCL communicator under data parallel); the next step() would
+        re-warm and re-capture."""
+        if self._graphs is not None:
+            torch.cuda.synchronize(self.device)
+            self._graphs = None
+            self._warm = 0
 
     # -- conveniences ---------------------------------------------------------------------------
     def sample_z(self, generator=None):
