@@ -193,7 +193,57 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   }
 
   small_plan(h, bp);
-  const int ldp_slots = std::max(bp.ldp_tiles, bp.small.ok ? bp.small.ldp_tiles : 0);
+  int ldp_slots = std::max(bp.ldp_tiles, bp.small.ok ? bp.small.ldp_tiles : 0);
+
+  // ---- tensor-core path: strip-op programs between the tcgen05 GEMMs (flow_tc.cu)
+  bp.tc_ok = (!bp.small.ok && h->tc_min_batch > 0 && B >= h->tc_min_batch) ? 1 : 0;
+  if (bp.tc_ok) {
+    const int cols = 16;                                   // coupling columns per tail strip
+    const int chunks = (Db + cols - 1) / cols, mblocks = (B + kThreads - 1) / kThreads;
+    bp.tc_ldp_tiles = chunks;
+    ldp_slots = std::max(ldp_slots, chunks);
+    for (int dir = 0; dir < 2; ++dir)
+      for (int train = 0; train < 2; ++train) {
+        Builder b;
+        b.add(0, strip_subop(OP_TRANSPOSE, 0, tr_tiles));
+        for (int e = 0; e < S; ++e) {
+          if (h->has_bn && train) {
+            b.add(e, strip_subop(OP_BN_STATS, 1, (H + 7) / 8));
+            b.add(e, strip_subop(OP_BN_STATS, 2, (H + 7) / 8));
+          }
+          SubOp tl = strip_subop(OP_TAIL, 0, chunks * mblocks);
+          tl.tiles_n = chunks; tl.tiles_m = mblocks; tl.kchunk = cols;
+          b.add(e, tl);
+        }
+        b.add(S - 1, strip_subop(OP_LOGDET_FINAL, 0, (B + 31) / 32), strip_subop(OP_TRANSPOSE, dir == 0 ? 2 : 3, tr_tiles));
+        int rc = upload(b, bp.tc_fwd[dir][train]);
+        if (rc) return rc;
+      }
+    for (int want_gin = 0; want_gin < 2; ++want_gin) {
+      Builder b;
+      b.add(S - 1, strip_subop(OP_TRANSPOSE, 1, tr_tiles));
+      for (int e = S - 1; e >= 0; --e) {
+        b.add(e, strip_subop(OP_B0, 0, bp.red_tiles));
+        b.add(e, strip_subop(OP_BNBWD, 2, (H + 7) / 8));
+        b.add(e, strip_subop(OP_BNBWD, 1, (H + 7) / 8));
+      }
+      if (want_gin) b.add(0, strip_subop(OP_BWD_FINAL, 0, 1), strip_subop(OP_TRANSPOSE, 4, tr_tiles));
+      else b.add(0, strip_subop(OP_BWD_FINAL, 0, 1));
+      int rc = upload(b, bp.tc_bwd[want_gin]);
+      if (rc) return rc;
+    }
+    const int sm = h->n_sm;
+    ftc::configure();
+    bp.g_f1 = ftc::make_gemm(B, H, Da, sm);
+    bp.g_f2 = ftc::make_gemm(B, H, H, sm);
+    bp.g_f3 = ftc::make_gemm(B, Dout, H, sm);
+    bp.g_dg2 = ftc::make_gemm(B, H, Dout, sm);
+    bp.g_wg3 = ftc::make_gemm(Dout, H, B, sm);
+    bp.g_dg1 = ftc::make_gemm(B, H, H, sm);
+    bp.g_wg2 = ftc::make_gemm(H, H, B, sm);
+    bp.g_dgin = ftc::make_gemm(B, Da, H, sm);
+    bp.g_wg1 = ftc::make_gemm(H, Da, B, sm);
+  }
 
   const long long LB = bp.small.ok ? (B + 3) / 4 * 4 : B;   // workspace row stride
   bp.ldb = (int)LB;
@@ -215,6 +265,19 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.oGP2T = take((long long)H * LB);
   bp.oPART = take(std::max(32LL, max_part));
   bp.oRED = take((long long)S * bp.red_tiles * 2);
+  if (bp.tc_ok) {
+    const ftc::Gemm* gs[9] = {&bp.g_f1, &bp.g_f2, &bp.g_f3, &bp.g_dg2, &bp.g_wg3, &bp.g_dg1, &bp.g_wg2, &bp.g_dgin, &bp.g_wg1};
+    size_t ma = 0, mb = 0, mp = 0;
+    for (const ftc::Gemm* g : gs) {
+      ma = std::max(ma, ftc::a_pack_floats(*g));
+      mb = std::max(mb, ftc::b_pack_floats(*g));
+      mp = std::max(mp, ftc::part_floats(*g));
+    }
+    o = (o + 255) / 256 * 256;                // packed tiles are fetched with cp.async.bulk: keep them 1 KB aligned
+    bp.oTCA = take((long long)ma);
+    bp.oTCB = take((long long)mb);
+    bp.oTCP = take((long long)mp);
+  }
   bp.total_floats = o;
   return DPI_OK;
 }
@@ -272,6 +335,149 @@ int launch_program(dpi_flow_s* h, const Program& prog, KArgs& a, cudaStream_t st
   return DPI_OK;
 }
 
+int launch_phase(const Program& prog, KArgs& a, int p, cudaStream_t stream) {
+  a.phases = prog.d_phases;
+  a.persistent = 0; a.phase_begin = p; a.phase_end = p + 1;
+  void* params[] = {&a};
+  DPI_CUDA(cudaLaunchKernel(flow_strip_kernel_ptr(), dim3(prog.phase_tiles[p]), dim3(kThreads), params, 0, stream));
+  count_launch();
+  return DPI_OK;
+}
+
+#define DPI_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+struct TcBufs {
+  float *apack, *bpack, *part;
+};
+
+int tc_gemm(const ftc::Gemm& g, const ftc::Pack& pa, const ftc::Pack& pb, const ftc::Epi& ep, const TcBufs& tb,
+            cudaStream_t st) {
+  DPI_TRY(ftc::pack(pa, ftc::kM, tb.apack, st));
+  DPI_TRY(ftc::pack(pb, g.TN, tb.bpack, st));
+  return ftc::run(g, tb.apack, tb.bpack, tb.part, ep, st);
+}
+
+// RealNVP.reverse / .forward (:594-603 / :583-592) with the three Linear layers of every coupling net on tcgen05.
+int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
+  const Program& prog = bp.tc_fwd[a.dir][a.train];
+  const int D = h->D, Da = h->Da, Dout = h->Dout, H = h->H, S = h->S, B = bp.B;
+  const long long LB = bp.ldb;
+  a.ldp_tiles = bp.tc_ldp_tiles;
+  a.use_tc = 0; a.tbuf = nullptr;
+  DPI_TRY(ftc::init());
+  DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), st));
+  float* W = a.W;
+  const TcBufs tb{W + bp.oTCA, W + bp.oTCB, W + bp.oTCP};
+  const bool bn_phase = h->has_bn && a.train;
+  int pi = 0;
+  DPI_TRY(launch_phase(prog, a, pi++, st));
+  for (int e = 0; e < S; ++e) {
+    const StageTab& sg = h->stages[a.dir ? S - 1 - e : e];
+    const int* gmap = h->d_gmaps + ((size_t)a.dir * S + e) * D;
+    const float* yprev = e == 0 ? W + bp.oZT : W + bp.oYT + (long long)(e - 1) * D * LB;
+    float* L1 = W + bp.oL1T + (long long)e * H * LB;
+    float* L2 = W + bp.oL2T + (long long)e * H * LB;
+    float* N1 = W + bp.oN1T + (long long)e * H * LB;
+    float* N2 = W + bp.oN2T + (long long)e * H * LB;
+    float* O = W + bp.oOT + (long long)e * Dout * LB;
+    for (int which = 1; which <= 2; ++which) {
+      ftc::Epi ep{};
+      ep.mode = ftc::EPI_T_HID; ep.out = which == 1 ? L1 : L2; ep.ldo = LB; ep.bias = a.P + sg.p[which == 1 ? P_B1 : P_B2];
+      const bool fused_bn = bn_phase && B <= ftc::kEpiMaxM;   // batch statistics inside the GEMM epilogue
+      if (!bn_phase || fused_bn) {
+        ep.out2 = which == 1 ? N1 : N2;
+        ep.bn_mode = !h->has_bn ? 0 : (a.train ? 1 : 2);
+        if (h->has_bn) {
+          ep.gamma = a.P + sg.p[which == 1 ? P_G1 : P_G2]; ep.beta = a.P + sg.p[which == 1 ? P_BE1 : P_BE2];
+          ep.rmean = a.R + sg.r[(which - 1) * 2]; ep.rvar = a.R + sg.r[(which - 1) * 2 + 1];
+          ep.mean = W + bp.oST + ((long long)e * 4 + (which - 1) * 2) * H;
+          ep.rstd = ep.mean + H;
+        }
+      }
+      if (which == 1)
+        DPI_TRY(tc_gemm(bp.g_f1, ftc::Pack{yprev, LB, 0, gmap, B, Da}, ftc::Pack{a.P + sg.p[P_W1], Da, 1, nullptr, H, Da}, ep, tb, st));
+      else
+        DPI_TRY(tc_gemm(bp.g_f2, ftc::Pack{N1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 1, nullptr, H, H}, ep, tb, st));
+      if (bn_phase) {
+        if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));
+        ++pi;
+      }
+    }
+    ftc::Epi ep{};
+    ep.mode = ftc::EPI_T_RAW; ep.out = O; ep.ldo = LB;
+    DPI_TRY(tc_gemm(bp.g_f3, ftc::Pack{N2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W3], H, 1, nullptr, Dout, H}, ep, tb, st));
+    DPI_TRY(launch_phase(prog, a, pi++, st));   // tail
+  }
+  return launch_phase(prog, a, pi++, st);
+}
+
+// Backward of RealNVP.reverse: data gradients and weight gradients of the coupling nets on tcgen05.
+int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
+  const Program& prog = bp.tc_bwd[a.g_in ? 1 : 0];
+  const int D = h->D, Da = h->Da, Dout = h->Dout, H = h->H, S = h->S, B = bp.B;
+  const long long LB = bp.ldb;
+  a.ldp_tiles = bp.tc_ldp_tiles;
+  a.use_tc = 0; a.tbuf = nullptr;
+  DPI_TRY(ftc::init());
+  DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), st));
+  float* W = a.W;
+  const TcBufs tb{W + bp.oTCA, W + bp.oTCB, W + bp.oTCP};
+  float* GPRE = W + bp.oGPRET;
+  float* GN = W + bp.oGNT;
+  float* GP1 = W + bp.oGP1T;
+  float* GP2 = W + bp.oGP2T;
+  int pi = 0;
+  DPI_TRY(launch_phase(prog, a, pi++, st));
+  for (int e = S - 1; e >= 0; --e) {
+    const StageTab& sg = h->stages[e];
+    const int* gmap = h->d_gmaps + (size_t)e * D;
+    const float* yprev = e == 0 ? W + bp.oZT : W + bp.oYT + (long long)(e - 1) * D * LB;
+    const float* N1 = W + bp.oN1T + (long long)e * H * LB;
+    const float* N2 = W + bp.oN2T + (long long)e * H * LB;
+    const float* gy = W + bp.oGYT + (long long)(e & 1) * D * LB;
+    float* gyprev = W + bp.oGYT + (long long)((e - 1) & 1) * D * LB;
+    DPI_TRY(launch_phase(prog, a, pi++, st));   // B0
+    const bool fused_bn = B <= ftc::kEpiMaxM;   // BatchNorm + LeakyReLU backward inside the dgrad epilogue
+    auto hid_epi = [&](int which) {
+      ftc::Epi ep{};
+      ep.ldo = LB;
+      if (!fused_bn) { ep.mode = ftc::EPI_T_RAW; ep.out = GN; return ep; }
+      ep.mode = ftc::EPI_T_BNBWD; ep.out = which == 2 ? GP2 : GP1; ep.bn_mode = h->has_bn;
+      ep.lsaved = W + (which == 1 ? bp.oL1T : bp.oL2T) + (long long)e * H * LB;
+      if (h->has_bn) {
+        ep.mean = W + bp.oST + ((long long)e * 4 + (which - 1) * 2) * H;
+        ep.rstd = ep.mean + H;
+        ep.gamma = a.P + sg.p[which == 1 ? P_G1 : P_G2];
+        ep.g_gamma = a.G + sg.p[which == 1 ? P_G1 : P_G2];
+        ep.g_beta = a.G + sg.p[which == 1 ? P_BE1 : P_BE2];
+      }
+      ep.g_bias = a.G + sg.p[which == 1 ? P_B1 : P_B2];
+      return ep;
+    };
+    ftc::Epi wg{};
+    wg.mode = ftc::EPI_ROWMAJOR;
+    // through net.6.fc: g_n2[m][n] = sum_k g_pre[k][m] W3[k][n];  gW3[i][j] = sum_m g_pre[i][m] n2[j][m]
+    DPI_TRY(tc_gemm(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, ftc::Pack{a.P + sg.p[P_W3], H, 0, nullptr, H, Dout}, hid_epi(2), tb, st));
+    wg.out = a.G + sg.p[P_W3]; wg.ldo = H;
+    DPI_TRY(tc_gemm(bp.g_wg3, ftc::Pack{GPRE, LB, 1, nullptr, Dout, B}, ftc::Pack{N2, LB, 1, nullptr, H, B}, wg, tb, st));
+    if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // BatchNorm + LeakyReLU backward of hidden layer 2 -> GP2
+    ++pi;
+    // through net.3
+    DPI_TRY(tc_gemm(bp.g_dg1, ftc::Pack{GP2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 0, nullptr, H, H}, hid_epi(1), tb, st));
+    wg.out = a.G + sg.p[P_W2]; wg.ldo = H;
+    DPI_TRY(tc_gemm(bp.g_wg2, ftc::Pack{GP2, LB, 1, nullptr, H, B}, ftc::Pack{N1, LB, 1, nullptr, H, B}, wg, tb, st));
+    if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // hidden layer 1 -> GP1
+    ++pi;
+    // through net.0, written through the fused permutation, plus the ActNorm pass-through of the a-half
+    ftc::Epi sc{};
+    sc.mode = ftc::EPI_T_SCATTER; sc.out = gyprev; sc.ldo = LB; sc.rowmap = gmap; sc.add = gy; sc.lsi = a.P + sg.lsi;
+    DPI_TRY(tc_gemm(bp.g_dgin, ftc::Pack{GP1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W1], Da, 0, nullptr, Da, H}, sc, tb, st));
+    wg.out = a.G + sg.p[P_W1]; wg.ldo = Da;
+    DPI_TRY(tc_gemm(bp.g_wg1, ftc::Pack{GP1, LB, 1, nullptr, H, B}, ftc::Pack{yprev, LB, 1, gmap, Da, B}, wg, tb, st));
+  }
+  return launch_phase(prog, a, pi++, st);
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -301,6 +507,8 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   const char* tile = getenv("DPI_B200_TILE");
   h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
   small_query(h.get());
+  const char* tcm = getenv("DPI_B200_FLOW_TC");          // minimum batch of the tcgen05 GEMM path; 0 disables it
+  if (tcm) h->tc_min_batch = std::max(0, atoi(tcm));
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
   h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
 
@@ -385,6 +593,10 @@ int dpi_flow_destroy(dpi_flow_t h) {
       for (int t = 0; t < 2; ++t) cudaFree(kv.second->fwd[d][t].d_phases);
     cudaFree(kv.second->bwd[0].d_phases);
     cudaFree(kv.second->bwd[1].d_phases);
+    for (int d = 0; d < 2; ++d)
+      for (int t = 0; t < 2; ++t) cudaFree(kv.second->tc_fwd[d][t].d_phases);
+    cudaFree(kv.second->tc_bwd[0].d_phases);
+    cudaFree(kv.second->tc_bwd[1].d_phases);
   }
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
@@ -516,6 +728,7 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
   a.P = params; a.G = nullptr; a.R = bn_running; a.in = in; a.out = out; a.logdet = logdet;
   a.g_out = nullptr; a.g_ld = nullptr; a.g_in = nullptr;
   if (bp->small.ok) return small_launch(h, *bp, a, 0, (cudaStream_t)stream);
+  if (bp->tc_ok) return tc_forward(h, *bp, a, (cudaStream_t)stream);
   return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
 }
 
@@ -538,6 +751,7 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
   if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
+  if (bp->tc_ok) return tc_backward(h, *bp, a, (cudaStream_t)stream);
   return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
 }
 

@@ -38,7 +38,8 @@ enum Op : int {
   OP_WGRAD,          // weight gradients
   OP_DGRAD_IN,       // dgrad through W1, written through the fused permutation
   OP_BNBWD,          // BatchNorm/LeakyReLU backward for large batches
-  OP_BWD_FINAL       // ActNorm gradients from per-tile partials
+  OP_BWD_FINAL,      // ActNorm gradients from per-tile partials
+  OP_TAIL            // tensor-core path: ZeroFC bias/scale + coupling + ActNorm + logdet partials on the raw GEMM output
 };
 
 struct SubOp {

@@ -8,9 +8,11 @@
 
 #include "flow.cuh"
 #include "flow_small.cuh"
+#include "flow_tc.cuh"
 
 namespace dpi {
 void* flow_kernel_ptr();
+void* flow_strip_kernel_ptr();
 
 struct Program {
   Phase* d_phases = nullptr;
@@ -29,6 +31,12 @@ struct BatchPlan {
   // small-batch cluster kernel (batch <= 64): decomposition + shared-memory layout, or small.ok == 0
   SmallPlan small;       // backward pass (and the shared facts: ok, workspace rows)
   SmallPlan small_fwd;   // forward pass (may use a different cluster size)
+  // tensor-core path (flow_tc.cu): GEMM plans, the strip-op programs that run between the GEMMs, pack / partial areas
+  int tc_ok = 0, tc_ldp_tiles = 0;
+  ftc::Gemm g_f1, g_f2, g_f3, g_dg2, g_wg3, g_dg1, g_wg2, g_dgin, g_wg1;
+  Program tc_fwd[2][2];
+  Program tc_bwd[2];
+  long long oTCA = 0, oTCB = 0, oTCP = 0;
 };
 
 }  // namespace dpi
@@ -37,6 +45,7 @@ struct dpi_flow_s {
   int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
   int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   int small_mode = 1;                         // 0: never use the small-batch kernel
+  int tc_min_batch = 96;                      // batches >= this run the coupling GEMMs on tcgen05 (0: never)
   int small_clusters = 0, small_cl = 1;       // CTAs without clusters; small_cl > 1: cluster launches are available
   int small_G[3] = {0, 0, 0};                 // co-resident clusters of 8, 4, 2 CTAs
   int small_ksplit_min = 512;                 // GEMMs with K >= this are split over the ranks of a cluster

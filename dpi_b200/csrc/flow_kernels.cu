@@ -357,6 +357,47 @@ __device__ __noinline__ void op_fwd_out(const KArgs& a, int e, const SubOp& so, 
   }
 }
 
+// Tensor-core path (flow_tc.cu): the ZeroFC GEMM leaves its raw output in O^T; this strip op applies what
+// op_fwd_out's epilogue applies (ZeroFC bias and exp(3 scale) :137-141, tanh/exp coupling :244-249 / :226-231,
+// ActNorm :66 / :45) with one thread per sample over a chunk of so.kchunk coupling columns (every access is a
+// coalesced row segment) and writes that chunk's logdet partial.
+__device__ __noinline__ void op_tail(const KArgs& a, int e, const SubOp& so, int t) {
+  Ctx c(a, e);
+  const int chunks = so.tiles_n, chunk = t % chunks, mb = t / chunks;
+  const int m = mb * kThreads + threadIdx.x;
+  if (m >= a.B) return;
+  float qa, qc;
+  c.post_affine(qa, qc);
+  const float* yp = c.yprev();
+  float* O = c.O();
+  float* y = c.y();
+  const size_t B = a.B;
+  const int j0 = chunk * so.kchunk, j1 = min(a.Db, j0 + so.kchunk);
+  float ld = 0.f;
+#pragma unroll 2
+  for (int j = j0; j < j1; ++j) {
+    const float e_ls = expf(3.f * __ldg(c.P(P_SCALE) + j)), e_t = expf(3.f * __ldg(c.P(P_SCALE) + a.Db + j));
+    const float b_ls = __ldg(c.P(P_B3) + j), b_t = __ldg(c.P(P_B3) + a.Db + j);
+    const int gb = __ldg(c.gmap + a.Da + j), ga = __ldg(c.gmap + j);
+    const float bv = __ldcg(yp + (size_t)gb * B + m), av = __ldcg(yp + (size_t)ga * B + m);
+    const float ols = (__ldcg(O + (size_t)j * B + m) + b_ls) * e_ls;
+    const float ot = (__ldcg(O + (size_t)(a.Db + j) * B + m) + b_t) * e_t;
+    const float ls = tanhf(ols);
+    float bp;
+    if (a.dir == 0) { bp = bv / expf(ls) - ot; ld -= ls; }
+    else            { bp = (bv + ot) * expf(ls); ld += ls; }
+    __stcg(O + (size_t)j * B + m, ols);
+    __stcg(O + (size_t)(a.Db + j) * B + m, ot);
+    __stcg(y + (size_t)(a.Da + j) * B + m, fmaf(bp, qa, qc));
+    __stcg(y + (size_t)j * B + m, fmaf(av, qa, qc));
+  }
+  if (a.Da > a.Db && chunk == 0) {   // odd D: the a-half has one more row (chunk(2,1) semantics, :241)
+    const int col = a.Da - 1;
+    __stcg(y + (size_t)col * B + m, fmaf(__ldcg(yp + (size_t)__ldg(c.gmap + col) * B + m), qa, qc));
+  }
+  __stcg(a.W + a.oLDP + ((size_t)e * a.ldp_tiles + chunk) * B + m, ld);
+}
+
 // logdet[m] = sum over stages/tiles of the coupling partials + sum_s (+-) D * log_scale_inv_s.
 // One CTA per 32 samples: lane = sample (coalesced), 8 warps each sum a fixed slice of the S*tiles
 // partials with independent loads in flight; slices are combined in a fixed order (deterministic).
@@ -767,6 +808,7 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
         case OP_B0: op_b0(a, ph.stage, so, t, sRed); break;
         case OP_BNBWD: op_bnbwd(a, ph.stage, so, t); break;
         case OP_BWD_FINAL: op_bwd_final(a, sRed); break;
+        case OP_TAIL: op_tail(a, ph.stage, so, t); break;
         default:
           if (so.bn == 64) run_gemm_op<64>(a, ph.stage, so, t, smem, &sFlag, tc);
           else if (so.bn == 32) run_gemm_op<32>(a, ph.stage, so, t, smem, &sFlag, tc);
@@ -789,6 +831,32 @@ __global__ void __launch_bounds__(kThreads) flow_program_kernel(KArgs a) {
   }
 }
 
+// One phase of strip ops only (no GEMM tiles): the launches between the tcgen05 GEMMs of the tensor-core path.
+// Small static shared memory and a register cap, so several CTAs are resident per SM (these ops are HBM-bound).
+__global__ void __launch_bounds__(kThreads, 3) flow_strip_kernel(KArgs a) {
+  __shared__ float sRed[1024 + 128];
+  __shared__ float sT[32 * 33];
+  const Phase& ph = a.phases[a.phase_begin];
+  const int n0 = ph.sub[0].ntiles;
+  const int total = n0 + (ph.nsub > 1 ? ph.sub[1].ntiles : 0);
+  for (int tt = blockIdx.x; tt < total; tt += gridDim.x) {
+    const SubOp& so = tt < n0 ? ph.sub[0] : ph.sub[1];
+    const int t = tt < n0 ? tt : tt - n0;
+    switch (so.op) {
+      case OP_TRANSPOSE: op_transpose(a, so, t, sT); break;
+      case OP_BN_STATS: op_bn_stats(a, ph.stage, so, t); break;
+      case OP_LOGDET_FINAL: op_logdet_final(a, t, sRed); break;
+      case OP_B0: op_b0(a, ph.stage, so, t, sRed); break;
+      case OP_BNBWD: op_bnbwd(a, ph.stage, so, t); break;
+      case OP_BWD_FINAL: op_bwd_final(a, sRed); break;
+      case OP_TAIL: op_tail(a, ph.stage, so, t); break;
+      default: break;
+    }
+    __syncthreads();
+  }
+}
+
 void* flow_kernel_ptr() { return (void*)flow_program_kernel; }
+void* flow_strip_kernel_ptr() { return (void*)flow_strip_kernel; }
 
 }  // namespace dpi

@@ -1,0 +1,82 @@
+// flow_tc.cuh - the coupling-net GEMMs of the RealNVP flow (generative_model/realnvpfc_model.py:171-187,
+// AffineCoupling.net: Linear(Da->H), Linear(H->H), ZeroFC(H->Dout)) and their data / weight gradients on the
+// 5th-generation tensor cores, for batches that span at least one 128-row UMMA tile.
+//
+//   C[M, N] = A[M, K] * B[N, K]^T      fp32 in / out, 3xTF32 (hi/lo split, three tcgen05.mma per k-step, fp32
+//                                      accumulation in TMEM): fp32-level accuracy, ~2^-21 per product
+//
+// Both operands reach shared memory as pre-split, pre-tiled K-major tiles (canonical no-swizzle UMMA layout:
+// core matrix 8 rows x 16 B, LBO 128 B, SBO 1024 B), one cp.async.bulk per tile and stage, mbarrier expect_tx
+// ring; one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M 128, N 64, K 8); the accumulator is read
+// back with tcgen05.ld 32x32b. The flow keeps its activations FEATURE-major (X^T[feature][sample], see flow.cuh),
+// so the pack pre-pass is also where the layout turns K-major, where the fixed permutations of the flow are
+// applied (a row map on the feature index) and where fp32 is split into TF32 hi / lo.
+//
+//   forward  : samples are the UMMA M (TMEM lane = sample -> feature-major stores are coalesced along samples)
+//   dgrad    : same, with B[n][k] = W[k][n] (transposing pack of the weight)
+//   wgrad    : gW[i][j] = sum_m G^T[i][m] X^T[j][m]: both operands are already K-major (K = batch)
+//
+// Split-K partial tiles are summed in split order by the epilogue kernel (deterministic), which also applies
+// the per-layer epilogue (bias + LeakyReLU [+ eval-mode BatchNorm], row-mapped scatter with the ActNorm
+// pass-through term, or the row-major weight-gradient store).
+#pragma once
+#include "common.cuh"
+
+namespace dpi {
+namespace ftc {
+
+constexpr int kM = 128;   // UMMA M
+constexpr int kK = 32;    // k per pipeline stage = 4 UMMA k-steps of 8
+constexpr int kMaxStages = 6;
+
+struct Gemm {
+  int M, N, K, TN, m_tiles, n_tiles, k_tiles, splits, kt_per_split, stages;
+};
+Gemm make_gemm(int M, int N, int K, int n_sm);
+inline size_t a_pack_floats(const Gemm& g) { return (size_t)g.m_tiles * g.k_tiles * 2 * kM * kK; }
+inline size_t b_pack_floats(const Gemm& g) { return (size_t)g.n_tiles * g.k_tiles * 2 * g.TN * kK; }
+inline size_t part_floats(const Gemm& g) { return (size_t)g.splits * g.m_tiles * g.n_tiles * kM * g.TN; }
+
+// element(r, k) of the operand = k_contig ? src[(map ? map[r] : r) * ld + k] : src[(map ? map[k] : k) * ld + r];
+// zero outside rows x K. dst: [row tiles][k tiles][hi, lo][R x 32 canonical].
+struct Pack {
+  const float* src;
+  long long ld;
+  int k_contig;
+  const int* map;
+  int rows, K;
+};
+int pack(const Pack& p, int R, float* dst, cudaStream_t st);
+
+enum EpiMode {
+  EPI_T_RAW = 0,   // out[n * ldo + m] = c
+  EPI_T_HID,       // out[n * ldo + m] = v = lrelu(c + bias[n]); out2 = v (bn_mode 0), BatchNorm with batch statistics
+                   // (bn_mode 1: statistics saved, running statistics updated) or with running statistics (bn_mode 2)
+  EPI_T_SCATTER,   // out[rowmap[n] * ldo + m] = c + add[n * ldo + m] * exp(*lsi)
+  EPI_T_BNBWD,     // out[n * ldo + m] = LeakyReLU'(l) * BatchNorm-backward(c) (bn_mode 1) or LeakyReLU'(l) * c (bn_mode 0),
+                   // plus the gradients of gamma / beta / the Linear bias of that feature row
+  EPI_ROWMAJOR     // out[m * ldo + n] = c
+};
+constexpr int kEpiMaxM = 4096;   // the fused BatchNorm epilogues keep one feature row (all samples) in registers
+struct Epi {
+  int mode;
+  float* out;
+  long long ldo;
+  const float* bias;
+  float* out2;
+  int bn_mode;
+  const float *gamma, *beta;
+  float *rmean, *rvar;          // running statistics (bn_mode 1: updated, 2: read)
+  float *mean, *rstd;           // batch statistics of the row (HID bn_mode 1: written, BNBWD: read)
+  const int* rowmap;
+  const float* add;
+  const float* lsi;
+  const float* lsaved;          // BNBWD: the saved LeakyReLU output L^T
+  float *g_gamma, *g_beta, *g_bias;
+};
+int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st);
+int init();
+void configure();   // reads DPI_B200_TC_TN (call before make_gemm)
+
+}  // namespace ftc
+}  // namespace dpi

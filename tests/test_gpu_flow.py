@@ -146,3 +146,49 @@ def test_reverse_requires_two_samples_in_train_mode():
         m.reverse(torch.randn(1, 16, device="cuda"))
     m.eval()
     m.reverse(torch.randn(1, 16, device="cuda"))
+
+
+@pytest.mark.parametrize("D,NF,B,seqfrac,bn", [(64, 2, 130, 1, True), (64, 2, 130, 1, False), (9, 2, 97, 0.25, True),
+                                                (512, 2, 384, 4, True)])
+def test_tensor_core_path_train_eval_nobn_odd(D, NF, B, seqfrac, bn, monkeypatch):
+    """Batches >= 96 run the coupling GEMMs on tcgen05 (flow_tc.cu, 3xTF32): training-mode pass + all gradients,
+    eval-mode (running statistics) reverse/forward, the batch_norm=False variant and an odd ndim, against the oracle;
+    and the same pass with the tensor-core path switched off (mma.sync tile program) as a second witness."""
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    sd = O.init_state(D, NF, seqfrac=seqfrac, seed=21, randomize=True, batch_norm=bn)
+    sd0 = {k: v.detach().clone() for k, v in sd.items()}
+    torch.manual_seed(5)
+    z, cx, cl = torch.randn(B, D), torch.randn(B, D), torch.randn(B)
+
+    def run(tc_min):
+        monkeypatch.setenv("DPI_B200_FLOW_TC", str(tc_min))
+        m = RealNVP(D, NF, seqfrac=seqfrac, batch_norm=bn)
+        m.load_state_dict({k: v.clone() for k, v in sd0.items()})
+        m = m.cuda()
+        zg = z.cuda().requires_grad_(True)
+        x, ld = m.reverse(zg)
+        ((x * cx.cuda()).sum() + (ld * cl.cuda()).sum()).backward()
+        grads = {k: gv.detach().cpu().clone() for k, gv in m.named_grad_views()}
+        with torch.no_grad():
+            zb, ldb = m.forward(x.detach())
+            m.eval()
+            xe, lde = m.reverse(z.cuda())
+        return x.detach().cpu(), ld.detach().cpu(), zg.grad.cpu(), grads, zb.cpu(), ldb.cpu(), xe.cpu(), lde.cpu(), m
+
+    x, ld, gz, grads, zb, ldb, xe, lde, m = run(96)
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    zo = z.clone().requires_grad_(True)
+    xo, ldo = O.realnvp_reverse(sd, zo, train=True)
+    ((xo * cx).sum() + (ldo * cl).sum()).backward()
+    assert rel_err(x, xo) < RTOL and rel_err(ld, ldo) < RTOL
+    assert rel_err(gz, zo.grad) < RTOL
+    worst = max(((rel_err(gv, sd[k].grad), k) for k, gv in grads.items() if "actnorm" not in k))
+    assert worst[0] < 3 * RTOL, worst
+    assert float((zb - z).abs().max()) < 5e-4
+    assert float((ldb + ld).abs().max()) < 1e-3 * max(1.0, float(ld.abs().max()))
+    x2, ld2, gz2, grads2, _, _, xe2, lde2, _ = run(0)
+    assert rel_err(x, x2) < RTOL and rel_err(ld, ld2) < RTOL and rel_err(gz, gz2) < RTOL
+    assert rel_err(xe, xe2) < RTOL and rel_err(lde, lde2) < RTOL
+    worst = max(((rel_err(gv, grads2[k]), k) for k, gv in grads.items() if "actnorm" not in k))
+    assert worst[0] < 3 * RTOL, worst
