@@ -198,7 +198,7 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   // ---- tensor-core path: strip-op programs between the tcgen05 GEMMs (flow_tc.cu)
   bp.tc_ok = (!bp.small.ok && h->tc_min_batch > 0 && B >= h->tc_min_batch) ? 1 : 0;
   if (bp.tc_ok) {
-    const int cols = 16;                                   // coupling columns per tail strip
+    const int cols = ftc::kTailCols;                       // coupling columns per logdet partial
     const int chunks = (Db + cols - 1) / cols, mblocks = (B + kThreads - 1) / kThreads;
     bp.tc_ldp_tiles = chunks;
     ldp_slots = std::max(ldp_slots, chunks);
@@ -403,10 +403,18 @@ int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
         ++pi;
       }
     }
+    // net.6 (ZeroFC) with the coupling tail as its epilogue
     ftc::Epi ep{};
-    ep.mode = ftc::EPI_T_RAW; ep.out = O; ep.ldo = LB;
+    ep.mode = ftc::EPI_T_TAIL; ep.out = O; ep.ldo = LB;
+    ep.yprev = yprev; ep.y = W + bp.oYT + (long long)e * D * LB; ep.gmap = gmap;
+    ep.scale = a.P + sg.p[P_SCALE]; ep.b3 = a.P + sg.p[P_B3];
+    ep.dir = a.dir; ep.Da = Da; ep.Db = h->Db;
+    if (a.dir == 0) { ep.post_mode = 0; ep.post_lsi = a.P + sg.lsi; ep.post_loc = a.P + sg.loc; }
+    else if (e + 1 < S) { const StageTab& nx = h->stages[S - 2 - e]; ep.post_mode = 1; ep.post_lsi = a.P + nx.lsi; ep.post_loc = a.P + nx.loc; }
+    else ep.post_mode = 2;
+    ep.ldp = W + bp.oLDP + (long long)e * bp.tc_ldp_tiles * LB;
     DPI_TRY(tc_gemm(bp.g_f3, ftc::Pack{N2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W3], H, 1, nullptr, Dout, H}, ep, tb, st));
-    DPI_TRY(launch_phase(prog, a, pi++, st));   // tail
+    ++pi;   // the strip-op tail of the program is not needed
   }
   return launch_phase(prog, a, pi++, st);
 }

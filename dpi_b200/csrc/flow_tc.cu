@@ -32,12 +32,49 @@ __device__ __forceinline__ void tmem_dealloc_n(unsigned taddr) {
 // through shared memory, TF32 hi / lo split, float4 stores of the canonical K-major tile (position of element
 // (r, kk) in floats: (r >> 3) * 256 + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3)).
 template <int R>
-__global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, float* __restrict__ dst) {
+__global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, int vec, float* __restrict__ dst) {
   __shared__ float s[kK][R + 1];
   const int kt = blockIdx.x % k_tiles, rt = blockIdx.x / k_tiles;
   const int r0 = rt * R, k0 = kt * kK;
   const int tid = threadIdx.x;
-  if (p.k_contig) {
+  constexpr int NI = R / 32;          // float4 items per thread (kK * R / 4 / 256)
+  if (vec) {
+    // every load of the tile is issued before the first shared-memory store: the CTA is one latency, not NI of them
+    float4 v[NI];
+    if (p.k_contig) {
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int i = tid + 256 * u, r = i >> 3, k4 = (i & 7) * 4;
+        const int row = r0 + r, k = k0 + k4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.rows && k < p.K) {
+          const int rr = p.map ? __ldg(p.map + row) : row;
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.src + (long long)rr * p.ld + k));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int i = tid + 256 * u, r = i >> 3, k4 = (i & 7) * 4;
+        s[k4][r] = v[u].x; s[k4 + 1][r] = v[u].y; s[k4 + 2][r] = v[u].z; s[k4 + 3][r] = v[u].w;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int i = tid + 256 * u, kk = i / (R / 4), r4 = (i % (R / 4)) * 4;
+        const int row = r0 + r4, k = k0 + kk;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < p.rows && k < p.K) {
+          const int kr = p.map ? __ldg(p.map + k) : k;
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.src + (long long)kr * p.ld + row));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int i = tid + 256 * u, kk = i / (R / 4), r4 = (i % (R / 4)) * 4;
+        s[kk][r4] = v[u].x; s[kk][r4 + 1] = v[u].y; s[kk][r4 + 2] = v[u].z; s[kk][r4 + 3] = v[u].w;
+      }
+    }
+  } else if (p.k_contig) {
     const int lane = tid & 31, w = tid >> 5;
     const int k = k0 + lane;
 #pragma unroll 8
@@ -65,17 +102,18 @@ __global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, float* _
   }
   __syncthreads();
   float* t = dst + (size_t)blockIdx.x * (2 * R * kK);
-  for (int q = tid; q < R * kK / 4; q += 256) {
-    const int within = q * 4;
+#pragma unroll
+  for (int u = 0; u < NI; ++u) {
+    const int within = (tid + 256 * u) * 4;
     const int rg = within >> 8, rem = within & 255, kc = rem >> 5, rr = (rem & 31) >> 2;
     const int r = rg * 8 + rr, kk = kc * 4;
     unsigned h[4], l[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) split_tf32(s[kk + u][r], h[u], l[u]);
-    *reinterpret_cast<float4*>(t + within) =
-        make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-    *reinterpret_cast<float4*>(t + R * kK + within) =
-        make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+    for (int q = 0; q < 4; ++q) split_tf32(s[kk + q][r], h[q], l[q]);
+    __stcg(reinterpret_cast<float4*>(t + within),
+           make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3])));
+    __stcg(reinterpret_cast<float4*>(t + R * kK + within),
+           make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3])));
   }
 }
 
@@ -179,65 +217,110 @@ __global__ void __launch_bounds__(128) gemm_kernel(Gemm g, const float* __restri
 
 // ------------------------------------------------------------------------------------------- epilogue
 // One CTA per output row: a feature row n (all samples m; transposed partial tiles, coalesced along m) for the
-// feature-major modes, a gradient row for EPI_ROWMAJOR. Split partials are summed in split order.
+// feature-major modes, a gradient row for EPI_ROWMAJOR. Split partials are summed in split order. V = 4: 16-byte
+// accesses (sample count and row stride multiples of 4), V = 1: scalar fallback.
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float (&x)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+  } else {
+    x[0] = __ldcg(p);
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const float (&x)[V]) {
+  if constexpr (V == 4) __stcg(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+  else __stcg(p, x[0]);
+}
+// sum over the K splits of V consecutive elements of one partial-tile row
+template <int V>
+__device__ __forceinline__ void fetchv(const float* p, int splits, size_t sstride, float (&c)[V]) {
+#pragma unroll
+  for (int q = 0; q < V; ++q) c[q] = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < splits; ++s) {
+    float t[V];
+    ldv<V>(p + s * sstride, t);
+#pragma unroll
+    for (int q = 0; q < V; ++q) c[q] += t[q];
+  }
+}
+
+template <int MODE, int V, int PER>
 __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restrict__ part, Epi e) {
   __shared__ float red[32];
   const size_t tile = (size_t)kM * g.TN;
   const size_t sstride = (size_t)g.m_tiles * g.n_tiles * tile;
   const int tid = threadIdx.x;
-  if (e.mode == EPI_ROWMAJOR) {
+  if constexpr (MODE == EPI_ROWMAJOR) {
     const int m = blockIdx.x;
     const float* row = part + (size_t)(m / kM) * g.n_tiles * tile + (size_t)(m % kM) * g.TN;
-    for (int n = tid; n < g.N; n += 256) {
-      const float* p = row + (size_t)(n / g.TN) * tile + n % g.TN;
-      float c = 0.f;
-      for (int s = 0; s < g.splits; ++s) c += __ldcg(p + s * sstride);
-      __stcg(e.out + (long long)m * e.ldo + n, c);
+    for (int n = tid * V; n < g.N; n += 256 * V) {
+      float c[V];
+      fetchv<V>(row + (size_t)(n / g.TN) * tile + n % g.TN, g.splits, sstride, c);
+      stv<V>(e.out + (long long)m * e.ldo + n, c);
     }
     return;
   }
   const int n = blockIdx.x;
   const float* row = part + (size_t)(n / g.TN) * tile + (size_t)(n % g.TN) * kM;
-  auto fetch = [&](int m) {
-    const float* p = row + (size_t)(m >> 7) * g.n_tiles * tile + (m & 127);
-    float c = 0.f;
-    for (int s = 0; s < g.splits; ++s) c += __ldcg(p + s * sstride);
-    return c;
-  };
-  constexpr int kPer = kEpiMaxM / 256;
-  if (e.mode == EPI_T_RAW) {
-    for (int m = tid; m < g.M; m += 256) __stcg(e.out + (long long)n * e.ldo + m, fetch(m));
-  } else if (e.mode == EPI_T_SCATTER) {
+  auto src = [&](int m) { return row + (size_t)(m >> 7) * g.n_tiles * tile + (m & 127); };
+  const long long orow = (long long)n * e.ldo;
+  if constexpr (MODE == EPI_T_RAW) {
+    for (int m = tid * V; m < g.M; m += 256 * V) {
+      float c[V];
+      fetchv<V>(src(m), g.splits, sstride, c);
+      stv<V>(e.out + orow + m, c);
+    }
+  } else if constexpr (MODE == EPI_T_SCATTER) {
     const float sc = expf(__ldg(e.lsi));
     const int r = __ldg(e.rowmap + n);
-    for (int m = tid; m < g.M; m += 256)
-      __stcg(e.out + (long long)r * e.ldo + m, fmaf(__ldcg(e.add + (long long)n * e.ldo + m), sc, fetch(m)));
-  } else if (e.mode == EPI_T_HID) {
+    for (int m = tid * V; m < g.M; m += 256 * V) {
+      float c[V], ad[V];
+      ldv<V>(e.add + orow + m, ad);
+      fetchv<V>(src(m), g.splits, sstride, c);
+#pragma unroll
+      for (int q = 0; q < V; ++q) c[q] = fmaf(ad[q], sc, c[q]);
+      stv<V>(e.out + (long long)r * e.ldo + m, c);
+    }
+  } else if constexpr (MODE == EPI_T_HID) {
     const float bias = __ldg(e.bias + n);
     if (e.bn_mode == 1) {   // BatchNorm1d in training mode (realnvpfc_model.py:178,185): biased batch variance, eps 1e-2
-      float v[kPer];
+      float v[PER][V];
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < kPer; ++i) {
-        const int m = tid + 256 * i;
-        v[i] = 0.f;
-        if (m < g.M) { v[i] = lrelu_f(fetch(m) + bias); s += v[i]; }
+      for (int i = 0; i < PER; ++i) {
+        const int m = (tid + 256 * i) * V;
+#pragma unroll
+        for (int q = 0; q < V; ++q) v[i][q] = 0.f;
+        if (m < g.M) {
+          fetchv<V>(src(m), g.splits, sstride, v[i]);
+#pragma unroll
+          for (int q = 0; q < V; ++q) { v[i][q] = lrelu_f(v[i][q] + bias); s += v[i][q]; }
+        }
       }
       const float invB = 1.0f / (float)g.M;
       const float mean = block_sum(s, red) * invB;
-      float q = 0.f;
+      float qq = 0.f;
 #pragma unroll
-      for (int i = 0; i < kPer; ++i)
-        if (tid + 256 * i < g.M) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-      const float var = block_sum(q, red) * invB;
+      for (int i = 0; i < PER; ++i)
+        if ((tid + 256 * i) * V < g.M) {
+#pragma unroll
+          for (int q = 0; q < V; ++q) { const float d = v[i][q] - mean; qq = fmaf(d, d, qq); }
+        }
+      const float var = block_sum(qq, red) * invB;
       const float rstd = 1.0f / sqrtf(var + kBnEps);
       const float ga = __ldg(e.gamma + n) * rstd, be = __ldg(e.beta + n);
 #pragma unroll
-      for (int i = 0; i < kPer; ++i) {
-        const int m = tid + 256 * i;
+      for (int i = 0; i < PER; ++i) {
+        const int m = (tid + 256 * i) * V;
         if (m < g.M) {
-          __stcg(e.out + (long long)n * e.ldo + m, v[i]);
-          __stcg(e.out2 + (long long)n * e.ldo + m, fmaf(v[i] - mean, ga, be));
+          float nv[V];
+#pragma unroll
+          for (int q = 0; q < V; ++q) nv[q] = fmaf(v[i][q] - mean, ga, be);
+          stv<V>(e.out + orow + m, v[i]);
+          stv<V>(e.out2 + orow + m, nv);
         }
       }
       if (tid == 0) {
@@ -253,25 +336,29 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
         ga = __ldg(e.gamma + n) * rs;
         be = __ldg(e.beta + n) - e.rmean[n] * ga;
       }
-      for (int m = tid; m < g.M; m += 256) {
-        const float v = lrelu_f(fetch(m) + bias);
-        __stcg(e.out + (long long)n * e.ldo + m, v);
-        if (e.out2) __stcg(e.out2 + (long long)n * e.ldo + m, e.bn_mode == 2 ? fmaf(v, ga, be) : v);
+      for (int m = tid * V; m < g.M; m += 256 * V) {
+        float c[V], nv[V];
+        fetchv<V>(src(m), g.splits, sstride, c);
+#pragma unroll
+        for (int q = 0; q < V; ++q) { c[q] = lrelu_f(c[q] + bias); nv[q] = e.bn_mode == 2 ? fmaf(c[q], ga, be) : c[q]; }
+        stv<V>(e.out + orow + m, c);
+        if (e.out2) stv<V>(e.out2 + orow + m, nv);
       }
     }
   } else {   // EPI_T_BNBWD
-    float gv[kPer], l[kPer];
+    float gv[PER][V], l[PER][V];
     float mean = 0.f, rstd = 1.f, gam = 1.f, s1 = 0.f, s2 = 0.f;
     if (e.bn_mode) { mean = e.mean[n]; rstd = e.rstd[n]; gam = __ldg(e.gamma + n); }
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-      const int m = tid + 256 * i;
-      gv[i] = 0.f; l[i] = 0.f;
+    for (int i = 0; i < PER; ++i) {
+      const int m = (tid + 256 * i) * V;
+#pragma unroll
+      for (int q = 0; q < V; ++q) { gv[i][q] = 0.f; l[i][q] = 0.f; }
       if (m < g.M) {
-        gv[i] = fetch(m);
-        l[i] = __ldcg(e.lsaved + (long long)n * e.ldo + m);
-        s1 += gv[i];
-        s2 = fmaf(gv[i], (l[i] - mean) * rstd, s2);
+        ldv<V>(e.lsaved + orow + m, l[i]);
+        fetchv<V>(src(m), g.splits, sstride, gv[i]);
+#pragma unroll
+        for (int q = 0; q < V; ++q) { s1 += gv[i][q]; s2 = fmaf(gv[i][q], (l[i][q] - mean) * rstd, s2); }
       }
     }
     float gbeta = 0.f, ggamma = 0.f;
@@ -279,14 +366,18 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
     const float invB = 1.0f / (float)g.M;
     float s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-      const int m = tid + 256 * i;
+    for (int i = 0; i < PER; ++i) {
+      const int m = (tid + 256 * i) * V;
       if (m < g.M) {
-        float gl = gv[i];
-        if (e.bn_mode) gl = gam * rstd * (gv[i] - gbeta * invB - (l[i] - mean) * rstd * ggamma * invB);
-        const float v = gl * (l[i] > 0.f ? 1.f : kLreluSlope);
-        __stcg(e.out + (long long)n * e.ldo + m, v);
-        s3 += v;
+        float o[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          float gl = gv[i][q];
+          if (e.bn_mode) gl = gam * rstd * (gl - gbeta * invB - (l[i][q] - mean) * rstd * ggamma * invB);
+          o[q] = gl * (l[i][q] > 0.f ? 1.f : kLreluSlope);
+          s3 += o[q];
+        }
+        stv<V>(e.out + orow + m, o);
       }
     }
     s3 = block_sum(s3, red);
@@ -294,6 +385,76 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
       if (e.bn_mode) { e.g_gamma[n] = ggamma; e.g_beta[n] = gbeta; }
       e.g_bias[n] = s3;
     }
+  }
+}
+
+// The coupling tail on the raw ZeroFC result. CTA = 4 column lanes x 64 sample items: kTailCols coupling columns of
+// 64 * V samples; the four lanes' logdet partial sums are combined in lane order (deterministic).
+template <int V>
+__global__ void __launch_bounds__(256) epi_tail_kernel(Gemm g, const float* __restrict__ part, Epi e, int m_blocks) {
+  __shared__ float sld[4][64 * V];
+  const size_t tile = (size_t)kM * g.TN;
+  const size_t sstride = (size_t)g.m_tiles * g.n_tiles * tile;
+  const int chunk = blockIdx.x / m_blocks, mb = blockIdx.x % m_blocks;
+  const int cl = threadIdx.x >> 6, mi = threadIdx.x & 63;
+  const int m = (mb * 64 + mi) * V;
+  const bool okm = m < g.M;
+  float qa = 1.f, qc = 0.f;
+  if (e.post_mode == 0) { qa = expf(__ldg(e.post_lsi)); qc = -__ldg(e.post_loc); }
+  else if (e.post_mode == 1) { const float inv = 1.0f / expf(__ldg(e.post_lsi)); qa = inv; qc = __ldg(e.post_loc) * inv; }
+  float ld[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) ld[q] = 0.f;
+  auto src = [&](int n) {
+    return part + (size_t)(n / g.TN) * tile + (size_t)(n % g.TN) * kM + (size_t)(m >> 7) * g.n_tiles * tile + (m & 127);
+  };
+  if (okm) {
+#pragma unroll 2
+    for (int q4 = 0; q4 < kTailCols / 4; ++q4) {
+      const int j = chunk * kTailCols + cl * (kTailCols / 4) + q4;
+      if (j >= e.Db) break;
+      const float e_ls = expf(3.f * __ldg(e.scale + j)), e_t = expf(3.f * __ldg(e.scale + e.Db + j));
+      const float b_ls = __ldg(e.b3 + j), b_t = __ldg(e.b3 + e.Db + j);
+      const int gb = __ldg(e.gmap + e.Da + j), ga = __ldg(e.gmap + j);
+      float bv[V], av[V], cls[V], ct[V];
+      ldv<V>(e.yprev + (long long)gb * e.ldo + m, bv);
+      ldv<V>(e.yprev + (long long)ga * e.ldo + m, av);
+      fetchv<V>(src(j), g.splits, sstride, cls);
+      fetchv<V>(src(e.Db + j), g.splits, sstride, ct);
+      float ols[V], ot[V], yb[V], ya[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        ols[q] = (cls[q] + b_ls) * e_ls;
+        ot[q] = (ct[q] + b_t) * e_t;
+        const float ls = tanhf(ols[q]);
+        float bp;
+        if (e.dir == 0) { bp = bv[q] / expf(ls) - ot[q]; ld[q] -= ls; }
+        else            { bp = (bv[q] + ot[q]) * expf(ls); ld[q] += ls; }
+        yb[q] = fmaf(bp, qa, qc);
+        ya[q] = fmaf(av[q], qa, qc);
+      }
+      stv<V>(e.out + (long long)j * e.ldo + m, ols);
+      stv<V>(e.out + (long long)(e.Db + j) * e.ldo + m, ot);
+      stv<V>(e.y + (long long)(e.Da + j) * e.ldo + m, yb);
+      stv<V>(e.y + (long long)j * e.ldo + m, ya);
+    }
+    if (e.Da > e.Db && chunk == 0 && cl == 0) {   // odd D: the a-half has one more row (chunk(2,1) semantics, :241)
+      const int col = e.Da - 1;
+      float av[V];
+      ldv<V>(e.yprev + (long long)__ldg(e.gmap + col) * e.ldo + m, av);
+#pragma unroll
+      for (int q = 0; q < V; ++q) av[q] = fmaf(av[q], qa, qc);
+      stv<V>(e.y + (long long)col * e.ldo + m, av);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < V; ++q) sld[cl][mi * V + q] = ld[q];
+  __syncthreads();
+  if (cl == 0 && okm) {
+    float o[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) o[q] = ((sld[0][mi * V + q] + sld[1][mi * V + q]) + sld[2][mi * V + q]) + sld[3][mi * V + q];
+    stv<V>(e.ldp + (long long)chunk * e.ldo + m, o);
   }
 }
 
@@ -352,9 +513,11 @@ void configure() {
 
 int pack(const Pack& p, int R, float* dst, cudaStream_t st) {
   const int r_tiles = (p.rows + R - 1) / R, k_tiles = (p.K + kK - 1) / kK;
-  if (R == 128) pack_kernel<128><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, dst);
-  else if (R == 256) pack_kernel<256><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, dst);
-  else if (R == 64) pack_kernel<64><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, dst);
+  // 16-byte loads need an aligned base, a row stride that keeps rows aligned, and the contiguous extent a multiple of 4
+  const int vec = ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
+  if (R == 128) pack_kernel<128><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
+  else if (R == 256) pack_kernel<256><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
+  else if (R == 64) pack_kernel<64><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
   else { set_error("ftc::pack: unsupported tile rows %d", R); return DPI_ERR_INVALID; }
   DPI_LAUNCH_CHECK();
   return DPI_OK;
@@ -366,11 +529,41 @@ int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, co
   else if (g.TN == 128) gemm_kernel<128><<<grid, 128, smem_for<128>(), st>>>(g, a_pack, b_pack, part, tr);
   else gemm_kernel<256><<<grid, 128, smem_for<256>(), st>>>(g, a_pack, b_pack, part, tr);
   DPI_LAUNCH_CHECK();
-  if ((e.mode == EPI_T_BNBWD || (e.mode == EPI_T_HID && e.bn_mode == 1)) && g.M > kEpiMaxM) {
+  const bool fused = e.mode == EPI_T_BNBWD || (e.mode == EPI_T_HID && e.bn_mode == 1);
+  if (fused && g.M > kEpiMaxM) {
     set_error("ftc::run: fused BatchNorm epilogue supports at most %d samples (got %d)", kEpiMaxM, g.M);
     return DPI_ERR_UNSUPPORTED;
   }
-  epi_kernel<<<e.mode == EPI_ROWMAJOR ? g.M : g.N, 256, 0, st>>>(g, part, e);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int ext = e.mode == EPI_ROWMAJOR ? g.N : g.M;   // the contiguous extent of an output row
+  const bool vec = (ext & 3) == 0 && (e.ldo & 3) == 0 && al(e.out) && al(e.out2) && al(e.add) && al(e.lsaved) && al(e.yprev) &&
+                   al(e.y) && al(e.ldp) && al(part);
+#define DPI_EPI(MODE, PER)                                                                       \
+  do {                                                                                           \
+    if (vec) epi_kernel<MODE, 4, PER><<<e.mode == EPI_ROWMAJOR ? g.M : g.N, 256, 0, st>>>(g, part, e); \
+    else epi_kernel<MODE, 1, 4 * PER><<<e.mode == EPI_ROWMAJOR ? g.M : g.N, 256, 0, st>>>(g, part, e); \
+  } while (0)
+  switch (e.mode) {
+    case EPI_T_RAW: DPI_EPI(EPI_T_RAW, 1); break;
+    case EPI_T_SCATTER: DPI_EPI(EPI_T_SCATTER, 1); break;
+    case EPI_ROWMAJOR: DPI_EPI(EPI_ROWMAJOR, 1); break;
+    case EPI_T_HID:
+      if (g.M <= 1024) DPI_EPI(EPI_T_HID, 1); else DPI_EPI(EPI_T_HID, 4);
+      break;
+    case EPI_T_BNBWD:
+      if (g.M <= 1024) DPI_EPI(EPI_T_BNBWD, 1); else DPI_EPI(EPI_T_BNBWD, 4);
+      break;
+    case EPI_T_TAIL: {
+      const int chunks = (e.Db + kTailCols - 1) / kTailCols;
+      if (vec) { const int mbk = (g.M + 255) / 256; epi_tail_kernel<4><<<chunks * mbk, 256, 0, st>>>(g, part, e, mbk); }
+      else { const int mbk = (g.M + 63) / 64; epi_tail_kernel<1><<<chunks * mbk, 256, 0, st>>>(g, part, e, mbk); }
+      break;
+    }
+    default:
+      set_error("ftc::run: unknown epilogue mode %d", e.mode);
+      return DPI_ERR_INVALID;
+  }
+#undef DPI_EPI
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

@@ -55,7 +55,9 @@ enum EpiMode {
   EPI_T_SCATTER,   // out[rowmap[n] * ldo + m] = c + add[n * ldo + m] * exp(*lsi)
   EPI_T_BNBWD,     // out[n * ldo + m] = LeakyReLU'(l) * BatchNorm-backward(c) (bn_mode 1) or LeakyReLU'(l) * c (bn_mode 0),
                    // plus the gradients of gamma / beta / the Linear bias of that feature row
-  EPI_ROWMAJOR     // out[m * ldo + n] = c
+  EPI_ROWMAJOR,    // out[m * ldo + n] = c
+  EPI_T_TAIL       // ZeroFC bias / exp(3 scale), tanh-exp affine coupling, ActNorm, logdet partials (AffineCoupling
+                   // .reverse / .forward, realnvpfc_model.py:240-249 / :222-231) on the raw ZeroFC GEMM result
 };
 constexpr int kEpiMaxM = 4096;   // the fused BatchNorm epilogues keep one feature row (all samples) in registers
 struct Epi {
@@ -73,7 +75,18 @@ struct Epi {
   const float* lsi;
   const float* lsaved;          // BNBWD: the saved LeakyReLU output L^T
   float *g_gamma, *g_beta, *g_bias;
+  // TAIL: out = O^T (rows j: log_s pre-tanh, rows Db + j: t), y = stage output, yprev = stage input (rows through gmap)
+  const float* yprev;
+  float* y;
+  const int* gmap;
+  const float *scale, *b3;      // net.6.scale, net.6.fc.bias
+  const float *post_lsi, *post_loc;
+  int post_mode;                // 0: y = w * exp(lsi) - loc (reverse); 1: y = (w + loc) / exp(lsi) (forward, next stage's
+                                // ActNorm); 2: identity
+  int dir, Da, Db;
+  float* ldp;                   // logdet partials of this stage: [Db / 16 chunks][ldo]
 };
+constexpr int kTailCols = 16;   // coupling columns per logdet partial
 int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st);
 int init();
 void configure();   // reads DPI_B200_TC_TN (call before make_gemm)
