@@ -170,7 +170,7 @@ def gpu_run(args):
     if kind == "dpix":
         D = wl["nparams"]
         flow = RealNVP(D, nf, seqfrac=1 / 16)
-        tr = DPIxTrainer(flow, wl, B, lr=lr, clip=clip, device=dev)
+        tr = DPIxTrainer(flow, wl, B, lr=lr, clip=clip, device=dev, use_graph=not args.no_graph)
     else:
         flow = RealNVP(D, nf)
         T = InterferometryTrainer if kind == "interferometry" else MRITrainer
@@ -255,7 +255,7 @@ def gpu_run(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "name": args.workload, "global_batch": world * B, "batch_per_gpu": B,
-                   "params": int(flow.flat.numel()), "cuda_graph": (not args.no_graph) and kind != "dpix",
+                   "params": int(flow.flat.numel()), "cuda_graph": not args.no_graph,
                    "l2": "flushed between timed steps (192 MiB fill)" if not args.no_flush else "not flushed",
                    "bn": "per-replica batch statistics", "wall_s_timed_region": round(t_wall, 4)},
         "clocks": clocks.summary(),

@@ -485,9 +485,10 @@ Gemm make_gemm(int M, int N, int K, int n_sm) {
     if ((long long)g.m_tiles * ((N + tn - 1) / tn) * max_splits >= (3LL * n_sm) / 4) break;
   }
   g.n_tiles = (N + g.TN - 1) / g.TN;
+  // one CTA per SM (the stage ring takes the whole shared memory): split K so the grid is as close to one full
+  // wave as possible without spilling into a second, nearly empty one
   const int mn = g.m_tiles * g.n_tiles;
-  int want = std::max(1, (n_sm + mn - 1) / std::max(1, mn));
-  if (mn >= (3 * n_sm) / 4) want = 1;
+  int want = std::max(1, n_sm / std::max(1, mn));
   want = std::min(want, max_splits);
   g.kt_per_split = (g.k_tiles + want - 1) / want;
   g.splits = (g.k_tiles + g.kt_per_split - 1) / g.kt_per_split;

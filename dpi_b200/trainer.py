@@ -393,8 +393,9 @@ class DPIxTrainer:
     and the flat gradient are all-reduced."""
 
     def __init__(self, flow: RealNVP, wl: dict, batch: int, lr=1e-4, clip=1e-4, device="cuda", start_order=4,
-                 decay_rate=2000, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+                 decay_rate=2000, betas=(0.9, 0.999), eps=1e-8, process_group=None, use_graph=True):
         from dpi_b200.interferometry_helpers import _EhtOp
+        self.use_graph, self._graphs, self._warm = use_graph, None, 0
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -465,65 +466,123 @@ class DPIxTrainer:
                                                 self.g_logdet.data_ptr(), self.terms.data_ptr(), self.stats.data_ptr(), st),
                    "dpi_alpha_objective")
 
+    # -- the step in three enqueue parts: [flow -> renderer -> closure operator and its unit-weight gradient],
+    #    the objective (takes the annealed data weight as a host scalar, and two scalar all-reduces under data
+    #    parallel), [renderer / flow backward], then the update. Parts 1, 3 and the update are CUDA-graph replays
+    #    after warm-up.
+    def _enqueue_forward(self):
+        lib, B, st, fl = self.lib, self.B, _lib.stream_ptr(), self.flow
+        _lib.check(lib.dpi_flow_run(self.handle, 0, 1, B, self.params.data_ptr(), fl.bn_running.data_ptr(),
+                                    self.z.data_ptr(), self.ps.data_ptr(), self.logdet_flow.data_ptr(),
+                                    self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
+        _lib.check(lib.dpi_sigmoid_forward(B, self.np_, self.ps.data_ptr(), self.prm.data_ptr(), self.det.data_ptr(), st),
+                   "dpi_sigmoid_forward")
+        _lib.check(lib.dpi_crescent_forward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.img.data_ptr(), st),
+                   "dpi_crescent_forward")
+        _lib.check(lib.dpi_eht_forward(self.op.handle, B, self.img.data_ptr(), self.vis.data_ptr(), None, None, None,
+                                       self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_forward")
+        # unit-weight data gradient d(w_ca l_ca + w_cp l_cp)/d img; the per-sample importance weight enters as gscale
+        _lib.check(lib.dpi_eht_data_grad(self.op.handle, B, self.vis.data_ptr(), self.cphase_true.data_ptr(),
+                                         self.sigma_cp.data_ptr(), self.logcamp_true.data_ptr(), self.sigma_ca.data_ptr(),
+                                         self.w["cphase"], self.w["camp"], self.loss_cp.data_ptr(), self.loss_ca.data_ptr(),
+                                         self.g_img.data_ptr(), self.ws_eht.data_ptr(), self.ws_eht.numel(), st),
+                   "dpi_eht_data_grad")
+
+    def _enqueue_objective(self, dw):
+        st = _lib.stream_ptr()
+        if self.world > 1 and self.alpha != 1.0:
+            import torch.distributed as dist
+            self._objective(1, dw, st)
+            dist.all_reduce(self.stats[0:1], op=dist.ReduceOp.MAX, group=self.pg)
+            self._objective(2, dw, st)
+            dist.all_reduce(self.stats[1:2], op=dist.ReduceOp.SUM, group=self.pg)
+            self._objective(3, dw, st)
+        else:
+            self._objective(0, dw, st)
+
+    def _enqueue_backward(self):
+        lib, B, st = self.lib, self.B, _lib.stream_ptr()
+        _lib.check(lib.dpi_crescent_backward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.g_img.data_ptr(),
+                                             self.gscale.data_ptr(), self.g_prm.data_ptr(), st), "dpi_crescent_backward")
+        _lib.check(lib.dpi_sigmoid_backward(B, self.np_, self.ps.data_ptr(), self.g_prm.data_ptr(), self.g_logdet.data_ptr(),
+                                            self.g_ps.data_ptr(), st), "dpi_sigmoid_backward")
+        _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(), self.z.data_ptr(),
+                                         self.g_ps.data_ptr(), self.g_logdet.data_ptr(), None, self.ws_flow.data_ptr(),
+                                         self.ws_flow.numel(), st), "dpi_flow_backward")
+
+    def _enqueue_update(self):
+        lib, st = self.lib, _lib.stream_ptr()
+        b1, b2 = self.betas
+        _lib.check(lib.dpi_grad_sqnorm(self.P, self.grads.data_ptr(), self.sq.data_ptr(), self.ws_opt.data_ptr(),
+                                       self.ws_opt.numel(), st), "dpi_grad_sqnorm")
+        _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
+        # under data parallel every rank's weights already sum to 1 over the GLOBAL batch: plain sum of gradients
+        _lib.check(lib.dpi_clip_adam(self.P, self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
+                                     self.v.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
+                                     self.step_dev.data_ptr(), 1.0, self.norm_out.data_ptr(), st), "dpi_clip_adam")
+
     def loss_and_grad(self, z=None, data_weight=None):
         if z is not None:
             self.z.copy_(z, non_blocking=True)
-        lib, B, st, fl = self.lib, self.B, _lib.stream_ptr(), self.flow
         dw = self.data_weight() if data_weight is None else float(data_weight)
         with torch.cuda.device(self.device):
-            _lib.check(lib.dpi_flow_run(self.handle, 0, 1, B, self.params.data_ptr(), fl.bn_running.data_ptr(),
-                                        self.z.data_ptr(), self.ps.data_ptr(), self.logdet_flow.data_ptr(),
-                                        self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_run")
-            _lib.check(lib.dpi_sigmoid_forward(B, self.np_, self.ps.data_ptr(), self.prm.data_ptr(), self.det.data_ptr(), st),
-                       "dpi_sigmoid_forward")
-            _lib.check(lib.dpi_crescent_forward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.img.data_ptr(), st),
-                       "dpi_crescent_forward")
-            _lib.check(lib.dpi_eht_forward(self.op.handle, B, self.img.data_ptr(), self.vis.data_ptr(), None, None, None,
-                                           self.ws_eht.data_ptr(), self.ws_eht.numel(), st), "dpi_eht_forward")
-            # unit-weight data gradient d(w_ca l_ca + w_cp l_cp)/d img; the per-sample importance weight enters as gscale
-            _lib.check(lib.dpi_eht_data_grad(self.op.handle, B, self.vis.data_ptr(), self.cphase_true.data_ptr(),
-                                             self.sigma_cp.data_ptr(), self.logcamp_true.data_ptr(), self.sigma_ca.data_ptr(),
-                                             self.w["cphase"], self.w["camp"], self.loss_cp.data_ptr(), self.loss_ca.data_ptr(),
-                                             self.g_img.data_ptr(), self.ws_eht.data_ptr(), self.ws_eht.numel(), st),
-                       "dpi_eht_data_grad")
-            if self.world > 1 and self.alpha != 1.0:
-                import torch.distributed as dist
-                self._objective(1, dw, st)
-                dist.all_reduce(self.stats[0:1], op=dist.ReduceOp.MAX, group=self.pg)
-                self._objective(2, dw, st)
-                dist.all_reduce(self.stats[1:2], op=dist.ReduceOp.SUM, group=self.pg)
-                self._objective(3, dw, st)
-            else:
-                self._objective(0, dw, st)
-            _lib.check(lib.dpi_crescent_backward(B, self.npix, self.ng, self.fov, self.prm.data_ptr(), self.g_img.data_ptr(),
-                                                 self.gscale.data_ptr(), self.g_prm.data_ptr(), st), "dpi_crescent_backward")
-            _lib.check(lib.dpi_sigmoid_backward(B, self.np_, self.ps.data_ptr(), self.g_prm.data_ptr(), self.g_logdet.data_ptr(),
-                                                self.g_ps.data_ptr(), st), "dpi_sigmoid_backward")
-            _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(), self.z.data_ptr(),
-                                             self.g_ps.data_ptr(), self.g_logdet.data_ptr(), None, self.ws_flow.data_ptr(),
-                                             self.ws_flow.numel(), st), "dpi_flow_backward")
+            self._enqueue_forward()
+            self._enqueue_objective(dw)
+            self._enqueue_backward()
         self.flow._bump_bn()
         return self.terms
 
-    def step(self, z=None, data_weight=None):
-        n0 = _lib.launch_count()
-        self.loss_and_grad(z, data_weight)
-        lib, st = self.lib, _lib.stream_ptr()
+    def _allreduce_grads(self):
         if self.world > 1:
             from dpi_b200.dist import allreduce_sum_
             allreduce_sum_(self.grads, self.pg)
-        b1, b2 = self.betas
+
+    def step(self, z=None, data_weight=None):
+        if z is not None:
+            self.z.copy_(z, non_blocking=True)
+        dw = self.data_weight() if data_weight is None else float(data_weight)
         with torch.cuda.device(self.device):
-            _lib.check(lib.dpi_grad_sqnorm(self.P, self.grads.data_ptr(), self.sq.data_ptr(), self.ws_opt.data_ptr(),
-                                           self.ws_opt.numel(), st), "dpi_grad_sqnorm")
-            _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
-            # under data parallel every rank's weights already sum to 1 over the GLOBAL batch: plain sum of gradients
-            _lib.check(lib.dpi_clip_adam(self.P, self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(),
-                                         self.v.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
-                                         self.step_dev.data_ptr(), 1.0, self.norm_out.data_ptr(), st), "dpi_clip_adam")
+            if self._graphs is None:
+                n0 = _lib.launch_count()
+                self._enqueue_forward()
+                self._enqueue_objective(dw)
+                self._enqueue_backward()
+                self._allreduce_grads()
+                self._enqueue_update()
+                self.launches_per_step = _lib.launch_count() - n0
+                self._warm += 1
+                if self.use_graph and self._warm >= 2:
+                    self._capture()
+            else:
+                ga, gb, gc = self._graphs
+                ga.replay()
+                self._enqueue_objective(dw)
+                gb.replay()
+                self._allreduce_grads()
+                gc.replay()
+        self.flow._bump_bn()
         self.k += 1
-        self.launches_per_step = _lib.launch_count() - n0
         return self.terms
+
+    def _capture(self):
+        """Capture the three launch sequences (they change no state while being captured: nothing executes)."""
+        torch.cuda.synchronize(self.device)
+        graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for g, fn in zip(graphs, (self._enqueue_forward, self._enqueue_backward, self._enqueue_update)):
+                with torch.cuda.graph(g, stream=s):
+                    fn()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._graphs = tuple(graphs)
+
+    def close(self):
+        if self._graphs is not None:
+            torch.cuda.synchronize(self.device)
+            self._graphs = None
+            self._warm = 0
 
     # ------------------------------------------------------------------ posterior sampling (SURVEY 8(f) n1)
     @torch.no_grad()
