@@ -232,6 +232,11 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
       int rc = upload(b, bp.tc_bwd[want_gin]);
       if (rc) return rc;
     }
+    if (h->tc_side && !h->side) {
+      DPI_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+      h->ev.resize((size_t)4 * S + 2);
+      for (auto& ev : h->ev) DPI_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     const int sm = h->n_sm;
     ftc::configure();
     bp.g_f1 = ftc::make_gemm(B, H, Da, sm);
@@ -277,6 +282,17 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     bp.oTCA = take((long long)ma);
     bp.oTCB = take((long long)mb);
     bp.oTCP = take((long long)mp);
+    ma = mb = mp = 0;
+    const ftc::Gemm* ws[3] = {&bp.g_wg3, &bp.g_wg2, &bp.g_wg1};
+    for (const ftc::Gemm* g : ws) {
+      ma = std::max(ma, ftc::a_pack_floats(*g));
+      mb = std::max(mb, ftc::b_pack_floats(*g));
+      mp = std::max(mp, ftc::part_floats(*g));
+    }
+    o = (o + 255) / 256 * 256;
+    bp.oTCA2 = take((long long)ma);
+    bp.oTCB2 = take((long long)mb);
+    bp.oTCP2 = take((long long)mp);
   }
   bp.total_floats = o;
   return DPI_OK;
@@ -352,8 +368,7 @@ struct TcBufs {
 
 int tc_gemm(const ftc::Gemm& g, const ftc::Pack& pa, const ftc::Pack& pb, const ftc::Epi& ep, const TcBufs& tb,
             cudaStream_t st) {
-  DPI_TRY(ftc::pack(pa, ftc::kM, tb.apack, st));
-  DPI_TRY(ftc::pack(pb, g.TN, tb.bpack, st));
+  DPI_TRY(ftc::pack2(pa, tb.apack, pb, g.TN, tb.bpack, st));
   return ftc::run(g, tb.apack, tb.bpack, tb.part, ep, st);
 }
 
@@ -434,6 +449,24 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
   float* GN = W + bp.oGNT;
   float* GP1 = W + bp.oGP1T;
   float* GP2 = W + bp.oGP2T;
+  // The weight-gradient GEMMs only consume what the dgrad chain has already produced: they run on a side stream
+  // (own pack / partial buffers) beside the chain. Events: A = g_pre ready, B = g_p2 ready, C = g_p1 ready (main ->
+  // side), D = side has packed the last operand of the stage (side -> main, before the chain overwrites them).
+  const bool side = h->tc_side && h->side;
+  cudaStream_t sw = side ? h->side : st;
+  const TcBufs tw = side ? TcBufs{W + bp.oTCA2, W + bp.oTCB2, W + bp.oTCP2} : tb;
+  auto fork = [&](cudaEvent_t ev) -> int {
+    if (!side) return DPI_OK;
+    DPI_CUDA(cudaEventRecord(ev, st));
+    DPI_CUDA(cudaStreamWaitEvent(sw, ev, 0));
+    return DPI_OK;
+  };
+  auto join = [&](cudaEvent_t ev) -> int {
+    if (!side) return DPI_OK;
+    DPI_CUDA(cudaEventRecord(ev, sw));
+    DPI_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    return DPI_OK;
+  };
   int pi = 0;
   DPI_TRY(launch_phase(prog, a, pi++, st));
   for (int e = S - 1; e >= 0; --e) {
@@ -444,6 +477,9 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     const float* N2 = W + bp.oN2T + (long long)e * H * LB;
     const float* gy = W + bp.oGYT + (long long)(e & 1) * D * LB;
     float* gyprev = W + bp.oGYT + (long long)((e - 1) & 1) * D * LB;
+    cudaEvent_t* ev = side ? &h->ev[(size_t)4 * e] : nullptr;
+    // B0 overwrites g_pre (and the chain then g_p2, g_p1): wait until the side stream has packed the previous stage's
+    if (side && e < S - 1) DPI_CUDA(cudaStreamWaitEvent(st, h->ev[(size_t)4 * (e + 1) + 3], 0));
     DPI_TRY(launch_phase(prog, a, pi++, st));   // B0
     const bool fused_bn = B <= ftc::kEpiMaxM;   // BatchNorm + LeakyReLU backward inside the dgrad epilogue
     auto hid_epi = [&](int which) {
@@ -465,24 +501,33 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     ftc::Epi wg{};
     wg.mode = ftc::EPI_ROWMAJOR;
     // through net.6.fc: g_n2[m][n] = sum_k g_pre[k][m] W3[k][n];  gW3[i][j] = sum_m g_pre[i][m] n2[j][m]
-    DPI_TRY(tc_gemm(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, ftc::Pack{a.P + sg.p[P_W3], H, 0, nullptr, H, Dout}, hid_epi(2), tb, st));
+    if (side) DPI_TRY(fork(ev[0]));
     wg.out = a.G + sg.p[P_W3]; wg.ldo = H;
-    DPI_TRY(tc_gemm(bp.g_wg3, ftc::Pack{GPRE, LB, 1, nullptr, Dout, B}, ftc::Pack{N2, LB, 1, nullptr, H, B}, wg, tb, st));
+    DPI_TRY(tc_gemm(bp.g_wg3, ftc::Pack{GPRE, LB, 1, nullptr, Dout, B}, ftc::Pack{N2, LB, 1, nullptr, H, B}, wg, tw, sw));
+    DPI_TRY(tc_gemm(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, ftc::Pack{a.P + sg.p[P_W3], H, 0, nullptr, H, Dout}, hid_epi(2), tb, st));
     if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // BatchNorm + LeakyReLU backward of hidden layer 2 -> GP2
     ++pi;
     // through net.3
-    DPI_TRY(tc_gemm(bp.g_dg1, ftc::Pack{GP2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 0, nullptr, H, H}, hid_epi(1), tb, st));
+    if (side) DPI_TRY(fork(ev[1]));
     wg.out = a.G + sg.p[P_W2]; wg.ldo = H;
-    DPI_TRY(tc_gemm(bp.g_wg2, ftc::Pack{GP2, LB, 1, nullptr, H, B}, ftc::Pack{N1, LB, 1, nullptr, H, B}, wg, tb, st));
+    DPI_TRY(tc_gemm(bp.g_wg2, ftc::Pack{GP2, LB, 1, nullptr, H, B}, ftc::Pack{N1, LB, 1, nullptr, H, B}, wg, tw, sw));
+    DPI_TRY(tc_gemm(bp.g_dg1, ftc::Pack{GP2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 0, nullptr, H, H}, hid_epi(1), tb, st));
     if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // hidden layer 1 -> GP1
     ++pi;
     // through net.0, written through the fused permutation, plus the ActNorm pass-through of the a-half
+    if (side) DPI_TRY(fork(ev[2]));
+    wg.out = a.G + sg.p[P_W1]; wg.ldo = Da;
+    {
+      const ftc::Pack pa{GP1, LB, 1, nullptr, H, B}, pb{yprev, LB, 1, gmap, Da, B};
+      DPI_TRY(ftc::pack2(pa, tw.apack, pb, bp.g_wg1.TN, tw.bpack, sw));
+      if (side) DPI_CUDA(cudaEventRecord(ev[3], sw));   // every operand of this stage's weight gradients is packed
+      DPI_TRY(ftc::run(bp.g_wg1, tw.apack, tw.bpack, tw.part, wg, sw));
+    }
     ftc::Epi sc{};
     sc.mode = ftc::EPI_T_SCATTER; sc.out = gyprev; sc.ldo = LB; sc.rowmap = gmap; sc.add = gy; sc.lsi = a.P + sg.lsi;
     DPI_TRY(tc_gemm(bp.g_dgin, ftc::Pack{GP1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W1], Da, 0, nullptr, Da, H}, sc, tb, st));
-    wg.out = a.G + sg.p[P_W1]; wg.ldo = Da;
-    DPI_TRY(tc_gemm(bp.g_wg1, ftc::Pack{GP1, LB, 1, nullptr, H, B}, ftc::Pack{yprev, LB, 1, gmap, Da, B}, wg, tb, st));
   }
+  if (side) DPI_TRY(join(h->ev[(size_t)4 * S]));
   return launch_phase(prog, a, pi++, st);
 }
 
@@ -517,6 +562,8 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   small_query(h.get());
   const char* tcm = getenv("DPI_B200_FLOW_TC");          // minimum batch of the tcgen05 GEMM path; 0 disables it
   if (tcm) h->tc_min_batch = std::max(0, atoi(tcm));
+  const char* tcs = getenv("DPI_B200_TC_SIDE");            // 0: weight-gradient GEMMs stay on the caller's stream
+  if (tcs) h->tc_side = atoi(tcs) ? 1 : 0;
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
   h->ctas_per_sm = cps ? std::max(1, atoi(cps)) : 1;
 
@@ -606,6 +653,8 @@ int dpi_flow_destroy(dpi_flow_t h) {
     cudaFree(kv.second->tc_bwd[0].d_phases);
     cudaFree(kv.second->tc_bwd[1].d_phases);
   }
+  for (auto& ev : h->ev) cudaEventDestroy(ev);
+  if (h->side) cudaStreamDestroy(h->side);
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
   cudaFree(h->d_tbuf);

@@ -37,6 +37,7 @@ struct BatchPlan {
   Program tc_fwd[2][2];
   Program tc_bwd[2];
   long long oTCA = 0, oTCB = 0, oTCP = 0;
+  long long oTCA2 = 0, oTCB2 = 0, oTCP2 = 0;   // second set for the weight-gradient GEMMs on the side stream
 };
 
 }  // namespace dpi
@@ -45,6 +46,9 @@ struct dpi_flow_s {
   int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
   int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   int small_mode = 1;                         // 0: never use the small-batch kernel
+  cudaStream_t side = nullptr;                // weight-gradient GEMMs of the tensor-core path run here, beside the dgrad chain
+  std::vector<cudaEvent_t> ev;                // [4 S + 2] fork / join events (main <-> side)
+  int tc_side = 1;
   int tc_min_batch = 96;                      // batches >= this run the coupling GEMMs on tcgen05 (0: never)
   int small_clusters = 0, small_cl = 1;       // CTAs without clusters; small_cl > 1: cluster launches are available
   int small_G[3] = {0, 0, 0};                 // co-resident clusters of 8, 4, 2 CTAs

@@ -32,9 +32,9 @@ __device__ __forceinline__ void tmem_dealloc_n(unsigned taddr) {
 // through shared memory, TF32 hi / lo split, float4 stores of the canonical K-major tile (position of element
 // (r, kk) in floats: (r >> 3) * 256 + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3)).
 template <int R>
-__global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, int vec, float* __restrict__ dst) {
-  __shared__ float s[kK][R + 1];
-  const int kt = blockIdx.x % k_tiles, rt = blockIdx.x / k_tiles;
+__device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, float* __restrict__ dst, int block,
+                                          float (*s)[R + 1]) {
+  const int kt = block % k_tiles, rt = block / k_tiles;
   const int r0 = rt * R, k0 = kt * kK;
   const int tid = threadIdx.x;
   constexpr int NI = R / 32;          // float4 items per thread (kK * R / 4 / 256)
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, int vec,
     }
   }
   __syncthreads();
-  float* t = dst + (size_t)blockIdx.x * (2 * R * kK);
+  float* t = dst + (size_t)block * (2 * R * kK);
 #pragma unroll
   for (int u = 0; u < NI; ++u) {
     const int within = (tid + 256 * u) * 4;
@@ -115,6 +115,18 @@ __global__ void __launch_bounds__(256) pack_kernel(Pack p, int k_tiles, int vec,
     __stcg(reinterpret_cast<float4*>(t + R * kK + within),
            make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3])));
   }
+}
+
+// Both operands of one GEMM in one launch: blocks [0, na) pack A (128-row tiles), the rest pack B (RB-row tiles).
+template <int RB>
+__global__ void __launch_bounds__(256) pack2_kernel(Pack pa, int vec_a, float* __restrict__ dst_a, int na, Pack pb, int vec_b,
+                                                    float* __restrict__ dst_b) {
+  constexpr int RM = RB > kM ? RB : kM;
+  __shared__ float s[kK * (RM + 1)];
+  if ((int)blockIdx.x < na)
+    pack_tile<kM>(pa, (pa.K + kK - 1) / kK, vec_a, dst_a, blockIdx.x, reinterpret_cast<float (*)[kM + 1]>(s));
+  else
+    pack_tile<RB>(pb, (pb.K + kK - 1) / kK, vec_b, dst_b, blockIdx.x - na, reinterpret_cast<float (*)[RB + 1]>(s));
 }
 
 // ------------------------------------------------------------------------------------------- GEMM
@@ -512,14 +524,19 @@ void configure() {
   g_force_tn = (v == 64 || v == 128 || v == 256) ? v : 0;
 }
 
-int pack(const Pack& p, int R, float* dst, cudaStream_t st) {
-  const int r_tiles = (p.rows + R - 1) / R, k_tiles = (p.K + kK - 1) / kK;
+static int pack_vec(const Pack& p) {
   // 16-byte loads need an aligned base, a row stride that keeps rows aligned, and the contiguous extent a multiple of 4
-  const int vec = ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
-  if (R == 128) pack_kernel<128><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
-  else if (R == 256) pack_kernel<256><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
-  else if (R == 64) pack_kernel<64><<<r_tiles * k_tiles, 256, 0, st>>>(p, k_tiles, vec, dst);
-  else { set_error("ftc::pack: unsupported tile rows %d", R); return DPI_ERR_INVALID; }
+  return ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
+}
+
+int pack2(const Pack& pa, float* dst_a, const Pack& pb, int RB, float* dst_b, cudaStream_t st) {
+  const int na = ((pa.rows + kM - 1) / kM) * ((pa.K + kK - 1) / kK);
+  const int nb = ((pb.rows + RB - 1) / RB) * ((pb.K + kK - 1) / kK);
+  const int va = pack_vec(pa), vb = pack_vec(pb);
+  if (RB == 64) pack2_kernel<64><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
+  else if (RB == 128) pack2_kernel<128><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
+  else if (RB == 256) pack2_kernel<256><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
+  else { set_error("ftc::pack2: unsupported tile rows %d", RB); return DPI_ERR_INVALID; }
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

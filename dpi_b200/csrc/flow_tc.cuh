@@ -46,7 +46,8 @@ struct Pack {
   const int* map;
   int rows, K;
 };
-int pack(const Pack& p, int R, float* dst, cudaStream_t st);
+// packs A (128-row tiles) and B (RB-row tiles) of one GEMM in one launch
+int pack2(const Pack& pa, float* dst_a, const Pack& pb, int RB, float* dst_b, cudaStream_t st);
 
 enum EpiMode {
   EPI_T_RAW = 0,   // out[n * ldo + m] = c
