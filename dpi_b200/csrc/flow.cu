@@ -368,7 +368,7 @@ struct TcBufs {
 
 int tc_gemm(const ftc::Gemm& g, const ftc::Pack& pa, const ftc::Pack& pb, const ftc::Epi& ep, const TcBufs& tb,
             cudaStream_t st) {
-  DPI_TRY(ftc::pack2(pa, tb.apack, pb, g.TN, tb.bpack, st));
+  DPI_TRY(ftc::pack2(g, pa, tb.apack, pb, tb.bpack, st));
   return ftc::run(g, tb.apack, tb.bpack, tb.part, ep, st);
 }
 
@@ -519,7 +519,7 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     wg.out = a.G + sg.p[P_W1]; wg.ldo = Da;
     {
       const ftc::Pack pa{GP1, LB, 1, nullptr, H, B}, pb{yprev, LB, 1, gmap, Da, B};
-      DPI_TRY(ftc::pack2(pa, tw.apack, pb, bp.g_wg1.TN, tw.bpack, sw));
+      DPI_TRY(ftc::pack2(bp.g_wg1, pa, tw.apack, pb, tw.bpack, sw));
       if (side) DPI_CUDA(cudaEventRecord(ev[3], sw));   // every operand of this stage's weight gradients is packed
       DPI_TRY(ftc::run(bp.g_wg1, tw.apack, tw.bpack, tw.part, wg, sw));
     }

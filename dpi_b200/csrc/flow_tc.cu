@@ -28,23 +28,24 @@ __device__ __forceinline__ void tmem_dealloc_n(unsigned taddr) {
 }
 
 // ------------------------------------------------------------------------------------------- pack
-// One CTA per R x 32 operand tile: coalesced reads in whichever direction the source is contiguous, transposed
+// One CTA per R x KT operand tile: coalesced reads in whichever direction the source is contiguous, transposed
 // through shared memory, TF32 hi / lo split, float4 stores of the canonical K-major tile (position of element
-// (r, kk) in floats: (r >> 3) * 256 + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3)).
-template <int R>
+// (r, kk) in floats: (r >> 3) * 8 KT + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3)).
+template <int R, int KT>
 __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, float* __restrict__ dst, int block,
                                           float (*s)[R + 1]) {
   const int kt = block % k_tiles, rt = block / k_tiles;
-  const int r0 = rt * R, k0 = kt * kK;
+  const int r0 = rt * R, k0 = kt * KT;
   const int tid = threadIdx.x;
-  constexpr int NI = R / 32;          // float4 items per thread (kK * R / 4 / 256)
+  constexpr int NI = R * KT / 1024;   // float4 items per thread
+  static_assert(NI >= 1, "tile too small for 256 threads");
   if (vec) {
     // every load of the tile is issued before the first shared-memory store: the CTA is one latency, not NI of them
     float4 v[NI];
     if (p.k_contig) {
 #pragma unroll
       for (int u = 0; u < NI; ++u) {
-        const int i = tid + 256 * u, r = i >> 3, k4 = (i & 7) * 4;
+        const int i = tid + 256 * u, r = i / (KT / 4), k4 = (i % (KT / 4)) * 4;
         const int row = r0 + r, k = k0 + k4;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < p.rows && k < p.K) {
@@ -54,7 +55,7 @@ __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, f
       }
 #pragma unroll
       for (int u = 0; u < NI; ++u) {
-        const int i = tid + 256 * u, r = i >> 3, k4 = (i & 7) * 4;
+        const int i = tid + 256 * u, r = i / (KT / 4), k4 = (i % (KT / 4)) * 4;
         s[k4][r] = v[u].x; s[k4 + 1][r] = v[u].y; s[k4 + 2][r] = v[u].z; s[k4 + 3][r] = v[u].w;
       }
     } else {
@@ -75,21 +76,20 @@ __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, f
       }
     }
   } else if (p.k_contig) {
-    const int lane = tid & 31, w = tid >> 5;
-    const int k = k0 + lane;
 #pragma unroll 8
-    for (int r = w; r < R; r += 8) {
-      const int row = r0 + r;
+    for (int i = tid; i < KT * R; i += 256) {
+      const int r = i / KT, kk = i % KT;
+      const int row = r0 + r, k = k0 + kk;
       float v = 0.f;
       if (row < p.rows && k < p.K) {
         const int rr = p.map ? __ldg(p.map + row) : row;
         v = __ldg(p.src + (long long)rr * p.ld + k);
       }
-      s[lane][r] = v;
+      s[kk][r] = v;
     }
   } else {
 #pragma unroll 8
-    for (int i = tid; i < kK * R; i += 256) {
+    for (int i = tid; i < KT * R; i += 256) {
       const int kk = i / R, r = i % R;
       const int row = r0 + r, k = k0 + kk;
       float v = 0.f;
@@ -101,43 +101,47 @@ __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, f
     }
   }
   __syncthreads();
-  float* t = dst + (size_t)block * (2 * R * kK);
+  float* t = dst + (size_t)block * (2 * R * KT);
 #pragma unroll
   for (int u = 0; u < NI; ++u) {
     const int within = (tid + 256 * u) * 4;
-    const int rg = within >> 8, rem = within & 255, kc = rem >> 5, rr = (rem & 31) >> 2;
+    const int rg = within / (8 * KT), rem = within % (8 * KT), kc = rem >> 5, rr = (rem & 31) >> 2;
     const int r = rg * 8 + rr, kk = kc * 4;
     unsigned h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) split_tf32(s[kk + q][r], h[q], l[q]);
     __stcg(reinterpret_cast<float4*>(t + within),
            make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3])));
-    __stcg(reinterpret_cast<float4*>(t + R * kK + within),
+    __stcg(reinterpret_cast<float4*>(t + R * KT + within),
            make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3])));
   }
 }
 
-// Both operands of one GEMM in one launch: blocks [0, na) pack A (128-row tiles), the rest pack B (RB-row tiles).
-template <int RB>
+// Both operands of one GEMM in one launch: blocks [0, na) pack A (RA-row tiles), the rest pack B (RB-row tiles).
+template <int RA, int RB, int KT>
 __global__ void __launch_bounds__(256) pack2_kernel(Pack pa, int vec_a, float* __restrict__ dst_a, int na, Pack pb, int vec_b,
                                                     float* __restrict__ dst_b) {
-  constexpr int RM = RB > kM ? RB : kM;
-  __shared__ float s[kK * (RM + 1)];
+  constexpr int RM = RB > RA ? RB : RA;
+  __shared__ float s[KT * (RM + 1)];
   if ((int)blockIdx.x < na)
-    pack_tile<kM>(pa, (pa.K + kK - 1) / kK, vec_a, dst_a, blockIdx.x, reinterpret_cast<float (*)[kM + 1]>(s));
+    pack_tile<RA, KT>(pa, (pa.K + KT - 1) / KT, vec_a, dst_a, blockIdx.x, reinterpret_cast<float (*)[RA + 1]>(s));
   else
-    pack_tile<RB>(pb, (pb.K + kK - 1) / kK, vec_b, dst_b, blockIdx.x - na, reinterpret_cast<float (*)[RB + 1]>(s));
+    pack_tile<RB, KT>(pb, (pb.K + KT - 1) / KT, vec_b, dst_b, blockIdx.x - na, reinterpret_cast<float (*)[RB + 1]>(s));
 }
 
 // ------------------------------------------------------------------------------------------- GEMM
 // 128 threads. Lane 0 of warp 0: producer (two bulk copies per stage); lane 0 of warp 1: MMA issuer; all four
-// warps: TMEM -> partial tile. transposed != 0 stores the tile as [n][m] (feature-major consumers read it
+// warps: TMEM -> partial tile. The CTA tile is (MH x 128) x TN: MH accumulators of 128 lanes x TN columns side by
+// side in TMEM share every B tile (MH = 2, TN = 256: 256 x 256 per CTA, the whole TMEM, 2/3 of the operand bytes
+// per MAC of a 128 x 256 tile). transposed != 0 stores partial tiles as [n][m] (feature-major consumers read them
 // coalesced along samples), else as [m][n].
-template <int TN>
+template <int TN, int KT, int MH>
 __global__ void __launch_bounds__(128) gemm_kernel(Gemm g, const float* __restrict__ Apack, const float* __restrict__ Bpack,
                                                    float* __restrict__ part, int transposed) {
-  constexpr int kATile = kM * kK, kBTile = TN * kK;
+  constexpr int kATile = MH * kM * KT, kBTile = TN * KT;
   constexpr unsigned kStageBytes = (2 * kATile + 2 * kBTile) * 4;
+  constexpr unsigned kSbo = 32 * KT;           // bytes between 8-row groups of a canonical tile
+  constexpr int kCols = MH * TN;
   extern __shared__ unsigned char raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bars[2 * kMaxStages + 1];
@@ -149,14 +153,14 @@ __global__ void __launch_bounds__(128) gemm_kernel(Gemm g, const float* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t = blockIdx.x;
   const int sp = t % g.splits; t /= g.splits;
-  const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+  const int nt = t % g.n_tiles, mt = t / g.n_tiles;          // mt counts MH x 128-row tiles
   const int kt0 = sp * g.kt_per_split, kt1 = min(g.k_tiles, kt0 + g.kt_per_split), nk = max(0, kt1 - kt0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc_n<TN>(&tmem_slot);
+  if (warp == 0) tmem_alloc_n<kCols>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -179,13 +183,17 @@ __global__ void __launch_bounds__(128) gemm_kernel(Gemm g, const float* __restri
       const unsigned a_hi = smem_u32(sm + (size_t)s * kStageBytes), a_lo = a_hi + kATile * 4;
       const unsigned b_hi = a_hi + 2 * kATile * 4, b_lo = b_hi + kBTile * 4;
 #pragma unroll
-      for (int ks = 0; ks < kK / 8; ++ks) {
+      for (int ks = 0; ks < KT / 8; ++ks) {
         const unsigned off = ks * 256;      // 8 k = two 16-byte chunks
-        const unsigned long long dah = umma_desc(a_hi + off, 128, 1024), dal = umma_desc(a_lo + off, 128, 1024);
-        const unsigned long long dbh = umma_desc(b_hi + off, 128, 1024), dbl = umma_desc(b_lo + off, 128, 1024);
-        umma_tf32(tmem, dal, dbh, idesc, (i | ks) ? 1u : 0u);   // small terms first
-        umma_tf32(tmem, dah, dbl, idesc, 1u);
-        umma_tf32(tmem, dah, dbh, idesc, 1u);
+        const unsigned long long dbh = umma_desc(b_hi + off, 128, kSbo), dbl = umma_desc(b_lo + off, 128, kSbo);
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const unsigned ah = h * (kM * KT * 4);   // 128 rows further down the A tile
+          const unsigned long long dah = umma_desc(a_hi + ah + off, 128, kSbo), dal = umma_desc(a_lo + ah + off, 128, kSbo);
+          umma_tf32(tmem + h * TN, dal, dbh, idesc, (i | ks) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem + h * TN, dah, dbl, idesc, 1u);
+          umma_tf32(tmem + h * TN, dah, dbh, idesc, 1u);
+        }
       }
       umma_commit(empty + s);
     }
@@ -197,34 +205,37 @@ __global__ void __launch_bounds__(128) gemm_kernel(Gemm g, const float* __restri
   }
   __syncwarp();
   const int row = warp * 32 + lane;
-  float* dst = part + (((size_t)sp * g.m_tiles + mt) * g.n_tiles + nt) * (size_t)(kM * TN);
+#pragma unroll 1
+  for (int h = 0; h < MH; ++h) {
+    float* dst = part + (((size_t)sp * g.m_tiles + mt * MH + h) * g.n_tiles + nt) * (size_t)(kM * TN);
+#pragma unroll 2
+    for (int c0 = 0; c0 < TN; c0 += 16) {
+      unsigned v[16];
 #pragma unroll
-  for (int c0 = 0; c0 < TN; c0 += 16) {
-    unsigned v[16];
+      for (int u = 0; u < 16; ++u) v[u] = 0u;
+      if (nk > 0) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(h * TN + c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      if (transposed) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = 0u;
-    if (nk > 0) {
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    }
-    if (transposed) {
+        for (int u = 0; u < 16; ++u) __stcg(dst + (size_t)(c0 + u) * kM + row, __uint_as_float(v[u]));
+      } else {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) __stcg(dst + (size_t)(c0 + u) * kM + row, __uint_as_float(v[u]));
-    } else {
-#pragma unroll
-      for (int u = 0; u < 16; u += 4)
-        __stcg(reinterpret_cast<float4*>(dst + (size_t)row * TN + c0 + u),
-               make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]), __uint_as_float(v[u + 2]),
-                           __uint_as_float(v[u + 3])));
+        for (int u = 0; u < 16; u += 4)
+          __stcg(reinterpret_cast<float4*>(dst + (size_t)row * TN + c0 + u),
+                 make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]), __uint_as_float(v[u + 2]),
+                             __uint_as_float(v[u + 3])));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc_n<TN>(tmem);
+  if (warp == 0) tmem_dealloc_n<kCols>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------- epilogue
@@ -470,58 +481,79 @@ __global__ void __launch_bounds__(256) epi_tail_kernel(Gemm g, const float* __re
   }
 }
 
-int g_force_tn = 0;
+int g_force_tn = 0, g_force_kt = 0, g_force_mh = 0;
 
-template <int TN>
-constexpr int stages_for() { return TN == 64 ? 4 : TN == 128 ? 3 : 2; }
-template <int TN>
-constexpr int smem_for() { return stages_for<TN>() * (2 * kM * kK + 2 * TN * kK) * 4 + 1024; }
+constexpr int kSmemBudget = 200 * 1024;
+inline int stage_bytes(int TN, int KT, int MH) { return (2 * MH * kM * KT + 2 * TN * KT) * 4; }
+inline int stages_of(int TN, int KT, int MH) { return std::max(2, std::min(kMaxStages, kSmemBudget / stage_bytes(TN, KT, MH))); }
+inline int smem_of(const Gemm& g) { return g.stages * stage_bytes(g.TN, g.KT, g.MH) + 1024; }
 
-}  // namespace
+// the instantiated (TN, KT, MH) configurations
+#define DPI_TC_CONFIGS(X) X(64, 32, 1) X(128, 32, 1) X(256, 32, 1) X(256, 16, 1) X(256, 16, 2)
 
-// Column tile: the GEMM is fed from L2 (hi + lo copies of both operands), so the widest tile that still fills the
-// GPU (with split-K over at least 4 k-tiles per split) wins; DPI_B200_TC_TN forces 64 / 128 / 256.
-Gemm make_gemm(int M, int N, int K, int n_sm) {
-  Gemm g{};
-  g.M = M; g.N = N; g.K = K;
-  g.m_tiles = (M + kM - 1) / kM;
-  g.k_tiles = (K + kK - 1) / kK;
-  const int max_splits = std::min(16, std::max(1, g.k_tiles / 4));
-  const int cands[3] = {256, 128, 64};
-  g.TN = 64;
-  for (int c = 0; c < 3; ++c) {
-    const int tn = cands[c];
-    if (g_force_tn) { g.TN = g_force_tn; break; }
-    if (tn > 64 && N < tn) continue;
-    g.TN = tn;
-    if ((long long)g.m_tiles * ((N + tn - 1) / tn) * max_splits >= (3LL * n_sm) / 4) break;
-  }
-  g.n_tiles = (N + g.TN - 1) / g.TN;
+void finish_plan(Gemm& g, int n_sm) {
+  g.k_tiles = (g.K + g.KT - 1) / g.KT;
+  g.m_tiles = ((g.M + kM - 1) / kM + g.MH - 1) / g.MH * g.MH;      // 128-row tiles, a multiple of MH
+  g.n_tiles = (g.N + g.TN - 1) / g.TN;
   // one CTA per SM (the stage ring takes the whole shared memory): split K so the grid is as close to one full
-  // wave as possible without spilling into a second, nearly empty one
-  const int mn = g.m_tiles * g.n_tiles;
+  // wave as possible without spilling into a second, nearly empty one; at least 128 k per split
+  const int max_splits = std::min(16, std::max(1, g.k_tiles * g.KT / 128));
+  const int mn = (g.m_tiles / g.MH) * g.n_tiles;
   int want = std::max(1, n_sm / std::max(1, mn));
   want = std::min(want, max_splits);
   g.kt_per_split = (g.k_tiles + want - 1) / want;
   g.splits = (g.k_tiles + g.kt_per_split - 1) / g.kt_per_split;
-  g.stages = g.TN == 64 ? stages_for<64>() : g.TN == 128 ? stages_for<128>() : stages_for<256>();
+  g.stages = stages_of(g.TN, g.KT, g.MH);
+}
+
+}  // namespace
+
+// Tile choice: the GEMM is fed from L2 (hi + lo copies of both operands), so the widest column tile that still
+// fills the GPU (with split-K) wins: 128 x 256 with k-tile 16 (4 stages; measured faster than k-tile 32 x 2 stages),
+// else 128 x 128, else 128 x 64. The 256 x 256 CTA tile (two accumulators = the whole TMEM, 2/3 of the operand
+// bytes per MAC) measured slower on the C4 shapes - fewer CTAs, more K splits, a 256 KB unoverlapped drain per CTA -
+// and is only selectable: DPI_B200_TC_TN / _KT / _MH force a configuration.
+Gemm make_gemm(int M, int N, int K, int n_sm) {
+  Gemm g{};
+  g.M = M; g.N = N; g.K = K;
+  const int cand[3][3] = {{256, 16, 1}, {128, 32, 1}, {64, 32, 1}};
+  for (int c = 0; c < 3; ++c) {
+    g.TN = cand[c][0]; g.KT = cand[c][1]; g.MH = cand[c][2];
+    if (g_force_tn) {
+      g.TN = g_force_tn;
+      g.KT = g_force_kt ? g_force_kt : 32;
+      g.MH = g_force_mh ? g_force_mh : 1;
+      if (g.TN != 256 && (g.KT != 32 || g.MH != 1)) { g.KT = 32; g.MH = 1; }
+      if (g.MH == 2) g.KT = 16;
+      finish_plan(g, n_sm);
+      return g;
+    }
+    if (g.TN > 64 && N < g.TN) continue;
+    if (g.MH == 2 && M < 256) continue;
+    finish_plan(g, n_sm);
+    if ((long long)(g.m_tiles / g.MH) * g.n_tiles * g.splits >= (3LL * n_sm) / 4) break;
+  }
   return g;
 }
 
 int init() {
   static int done = 0;
   if (done) return DPI_OK;
-  DPI_CUDA(cudaFuncSetAttribute((const void*)gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for<64>()));
-  DPI_CUDA(cudaFuncSetAttribute((const void*)gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for<128>()));
-  DPI_CUDA(cudaFuncSetAttribute((const void*)gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for<256>()));
+#define X(tn_, kt_, mh_)                                                                                               \
+  DPI_CUDA(cudaFuncSetAttribute((const void*)gemm_kernel<tn_, kt_, mh_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                stages_of(tn_, kt_, mh_) * stage_bytes(tn_, kt_, mh_) + 1024));
+  DPI_TC_CONFIGS(X)
+#undef X
   done = 1;
   return DPI_OK;
 }
 
 void configure() {
-  const char* e = getenv("DPI_B200_TC_TN");
-  const int v = e ? atoi(e) : 0;
-  g_force_tn = (v == 64 || v == 128 || v == 256) ? v : 0;
+  auto geti = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
+  const int tn = geti("DPI_B200_TC_TN"), kt = geti("DPI_B200_TC_KT"), mh = geti("DPI_B200_TC_MH");
+  g_force_tn = (tn == 64 || tn == 128 || tn == 256) ? tn : 0;
+  g_force_kt = (kt == 16 || kt == 32) ? kt : 0;
+  g_force_mh = (mh == 1 || mh == 2) ? mh : 0;
 }
 
 static int pack_vec(const Pack& p) {
@@ -529,23 +561,36 @@ static int pack_vec(const Pack& p) {
   return ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
 }
 
-int pack2(const Pack& pa, float* dst_a, const Pack& pb, int RB, float* dst_b, cudaStream_t st) {
-  const int na = ((pa.rows + kM - 1) / kM) * ((pa.K + kK - 1) / kK);
-  const int nb = ((pb.rows + RB - 1) / RB) * ((pb.K + kK - 1) / kK);
+int pack2(const Gemm& g, const Pack& pa, float* dst_a, const Pack& pb, float* dst_b, cudaStream_t st) {
+  const int RA = g.MH * kM, RB = g.TN;
+  const int na = ((pa.rows + RA - 1) / RA) * g.k_tiles, nb = ((pb.rows + RB - 1) / RB) * g.k_tiles;
   const int va = pack_vec(pa), vb = pack_vec(pb);
-  if (RB == 64) pack2_kernel<64><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
-  else if (RB == 128) pack2_kernel<128><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
-  else if (RB == 256) pack2_kernel<256><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);
-  else { set_error("ftc::pack2: unsupported tile rows %d", RB); return DPI_ERR_INVALID; }
+  bool ok = false;
+#define X(tn_, kt_, mh_)                                                                                     \
+  if (!ok && g.TN == tn_ && g.KT == kt_ && g.MH == mh_) {                                                    \
+    pack2_kernel<mh_ * kM, tn_, kt_><<<na + nb, 256, 0, st>>>(pa, va, dst_a, na, pb, vb, dst_b);             \
+    ok = true;                                                                                               \
+  }
+  DPI_TC_CONFIGS(X)
+#undef X
+  if (!ok) { set_error("ftc::pack2: unsupported configuration TN=%d KT=%d MH=%d", g.TN, g.KT, g.MH); return DPI_ERR_INVALID; }
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }
 
 int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st) {
-  const int grid = g.m_tiles * g.n_tiles * g.splits, tr = e.mode != EPI_ROWMAJOR;
-  if (g.TN == 64) gemm_kernel<64><<<grid, 128, smem_for<64>(), st>>>(g, a_pack, b_pack, part, tr);
-  else if (g.TN == 128) gemm_kernel<128><<<grid, 128, smem_for<128>(), st>>>(g, a_pack, b_pack, part, tr);
-  else gemm_kernel<256><<<grid, 128, smem_for<256>(), st>>>(g, a_pack, b_pack, part, tr);
+  const int grid = (g.m_tiles / g.MH) * g.n_tiles * g.splits, tr = e.mode != EPI_ROWMAJOR;
+  {
+    bool ok = false;
+#define X(tn_, kt_, mh_)                                                                                     \
+    if (!ok && g.TN == tn_ && g.KT == kt_ && g.MH == mh_) {                                                  \
+      gemm_kernel<tn_, kt_, mh_><<<grid, 128, smem_of(g), st>>>(g, a_pack, b_pack, part, tr);                \
+      ok = true;                                                                                             \
+    }
+    DPI_TC_CONFIGS(X)
+#undef X
+    if (!ok) { set_error("ftc::run: unsupported configuration TN=%d KT=%d MH=%d", g.TN, g.KT, g.MH); return DPI_ERR_INVALID; }
+  }
   DPI_LAUNCH_CHECK();
   const bool fused = e.mode == EPI_T_BNBWD || (e.mode == EPI_T_HID && e.bn_mode == 1);
   if (fused && g.M > kEpiMaxM) {

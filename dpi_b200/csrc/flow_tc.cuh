@@ -26,15 +26,16 @@ namespace dpi {
 namespace ftc {
 
 constexpr int kM = 128;   // UMMA M
-constexpr int kK = 32;    // k per pipeline stage = 4 UMMA k-steps of 8
 constexpr int kMaxStages = 6;
 
+// CTA tile (MH x 128) x TN, k-tile KT per pipeline stage (KT / 8 UMMA k-steps). m_tiles counts 128-row tiles
+// (padded to a multiple of MH), k_tiles counts KT-deep tiles.
 struct Gemm {
-  int M, N, K, TN, m_tiles, n_tiles, k_tiles, splits, kt_per_split, stages;
+  int M, N, K, TN, KT, MH, m_tiles, n_tiles, k_tiles, splits, kt_per_split, stages;
 };
 Gemm make_gemm(int M, int N, int K, int n_sm);
-inline size_t a_pack_floats(const Gemm& g) { return (size_t)g.m_tiles * g.k_tiles * 2 * kM * kK; }
-inline size_t b_pack_floats(const Gemm& g) { return (size_t)g.n_tiles * g.k_tiles * 2 * g.TN * kK; }
+inline size_t a_pack_floats(const Gemm& g) { return (size_t)g.m_tiles * g.k_tiles * 2 * kM * g.KT; }
+inline size_t b_pack_floats(const Gemm& g) { return (size_t)g.n_tiles * g.k_tiles * 2 * g.TN * g.KT; }
 inline size_t part_floats(const Gemm& g) { return (size_t)g.splits * g.m_tiles * g.n_tiles * kM * g.TN; }
 
 // element(r, k) of the operand = k_contig ? src[(map ? map[r] : r) * ld + k] : src[(map ? map[k] : k) * ld + r];
@@ -46,8 +47,8 @@ struct Pack {
   const int* map;
   int rows, K;
 };
-// packs A (128-row tiles) and B (RB-row tiles) of one GEMM in one launch
-int pack2(const Pack& pa, float* dst_a, const Pack& pb, int RB, float* dst_b, cudaStream_t st);
+// packs A ((MH x 128)-row tiles) and B (TN-row tiles) of one GEMM in one launch
+int pack2(const Gemm& g, const Pack& pa, float* dst_a, const Pack& pb, float* dst_b, cudaStream_t st);
 
 enum EpiMode {
   EPI_T_RAW = 0,   // out[n * ldo + m] = c
@@ -90,7 +91,7 @@ struct Epi {
 constexpr int kTailCols = 16;   // coupling columns per logdet partial
 int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st);
 int init();
-void configure();   // reads DPI_B200_TC_TN (call before make_gemm)
+void configure();   // reads DPI_B200_TC_TN / _KT / _MH (call before make_gemm)
 
 }  // namespace ftc
 }  // namespace dpi
