@@ -249,6 +249,17 @@ def gpu_run(args):
                 kernels={k: dict(ms=round(v["ms"], 5), gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)) for k, v in prof.items()})
     roof["frac"] = roof["achieved"] / hbm_peak
     roof["step"]["frac"] = roof["step"]["achieved"] / hbm_peak
+    # tensor-pipe view of the same step: algorithmic flops = B [3 * 2 * C (Da H + H^2 + H Dout) + DFT fwd + dgrad],
+    # against the measured dense bf16 peak (3xTF32 needs 6 bf16-equivalents per useful flop, so 1/6 is the ceiling)
+    H_ = flow.hidden
+    Dn = flow.ndim
+    flops = B * (3 * 2 * 2 * nf * ((Dn - Dn // 2) * H_ + H_ * H_ + H_ * 2 * (Dn // 2)))
+    if kind in ("interferometry", "dpix"):
+        flops += B * 2 * (2 * 2 * npix * npix * wl["n_vis"])
+    tf_peak = peaks.get("bf16_tflops_sustained") or 1415.5
+    tf = flops / (total_ms / args.steps * 1e-3) / 1e12
+    roof["tensor"] = dict(algorithmic_gflop_per_step=flops / 1e9, achieved=tf, peak=tf_peak, unit="TFLOP/s", frac=tf / tf_peak,
+                          path="tcgen05 3xTF32 (flow_tc.cu)" if B >= 96 else "fp32 FFMA hops (flow_small.cu), tcgen05 DFT")
     cpu = cpu_reference_run(args.workload, steps=args.cpu_steps, warmup=2)
     out = {
         "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": "samples/s", "n_gpus": world,

@@ -222,8 +222,11 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     for (int want_gin = 0; want_gin < 2; ++want_gin) {
       Builder b;
       b.add(S - 1, strip_subop(OP_TRANSPOSE, 1, tr_tiles));
+      // narrow flows (few coupling columns): one CTA per column instead of one warp per column
+      const bool wide_b0 = Db <= 128;
+      bp.tc_red_tiles = wide_b0 ? Db : bp.red_tiles;
       for (int e = S - 1; e >= 0; --e) {
-        b.add(e, strip_subop(OP_B0, 0, bp.red_tiles));
+        b.add(e, strip_subop(OP_B0, wide_b0 ? 1 : 0, bp.tc_red_tiles));
         b.add(e, strip_subop(OP_BNBWD, 2, (H + 7) / 8));
         b.add(e, strip_subop(OP_BNBWD, 1, (H + 7) / 8));
       }
@@ -269,7 +272,7 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.oGP1T = take((long long)H * LB);
   bp.oGP2T = take((long long)H * LB);
   bp.oPART = take(std::max(32LL, max_part));
-  bp.oRED = take((long long)S * bp.red_tiles * 2);
+  bp.oRED = take((long long)S * std::max(bp.red_tiles, bp.tc_red_tiles) * 2);
   if (bp.tc_ok) {
     const ftc::Gemm* gs[9] = {&bp.g_f1, &bp.g_f2, &bp.g_f3, &bp.g_dg2, &bp.g_wg3, &bp.g_dg1, &bp.g_wg2, &bp.g_dgin, &bp.g_wg1};
     size_t ma = 0, mb = 0, mp = 0;
@@ -440,6 +443,7 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
   const int D = h->D, Da = h->Da, Dout = h->Dout, H = h->H, S = h->S, B = bp.B;
   const long long LB = bp.ldb;
   a.ldp_tiles = bp.tc_ldp_tiles;
+  a.red_tiles = bp.tc_red_tiles;
   a.use_tc = 0; a.tbuf = nullptr;
   DPI_TRY(ftc::init());
   DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), st));

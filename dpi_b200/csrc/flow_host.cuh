@@ -32,7 +32,7 @@ struct BatchPlan {
   SmallPlan small;       // backward pass (and the shared facts: ok, workspace rows)
   SmallPlan small_fwd;   // forward pass (may use a different cluster size)
   // tensor-core path (flow_tc.cu): GEMM plans, the strip-op programs that run between the GEMMs, pack / partial areas
-  int tc_ok = 0, tc_ldp_tiles = 0;
+  int tc_ok = 0, tc_ldp_tiles = 0, tc_red_tiles = 0;
   ftc::Gemm g_f1, g_f2, g_f3, g_dg2, g_wg3, g_dg1, g_wg2, g_dgin, g_wg1;
   Program tc_fwd[2][2];
   Program tc_bwd[2];

@@ -440,7 +440,11 @@ __device__ __noinline__ void op_logdet_final(const KArgs& a, int t, float* sRed)
 __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t, float* sRed) {
   Ctx c(a, e);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int col = t * 8 + w;
+  // so.which == 1 (narrow flows, few coupling columns): the whole CTA works on ONE column, samples split over all
+  // 256 threads; else one warp per column.
+  const bool wide = so.which == 1;
+  const int col = wide ? t : t * 8 + w;
+  const int m0 = wide ? (int)threadIdx.x : lane, mstep = wide ? kThreads : 32;
   const float lsi = __ldg(a.P + c.st.lsi), loc = __ldg(a.P + c.st.loc);
   const float e_lsi = expf(lsi);
   const size_t B = a.B;
@@ -480,7 +484,7 @@ __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t
       d = gbp * ei;
     };
     if (c.vec && (reinterpret_cast<uintptr_t>(gld) & 15) == 0) {   // 16-byte accesses: eight independent loads in flight per lane
-      for (int m = lane * 4; m < a.B; m += 128) {
+      for (int m = m0 * 4; m < a.B; m += mstep * 4) {
         const float4 A_ = __ldcg(reinterpret_cast<const float4*>(gya + m)), B_ = __ldcg(reinterpret_cast<const float4*>(gyb + m));
         const float4 YA = __ldcg(reinterpret_cast<const float4*>(ya + m)), YB = __ldcg(reinterpret_cast<const float4*>(yb + m));
         const float4 OL = __ldcg(reinterpret_cast<const float4*>(ols + m)), OT = __ldcg(reinterpret_cast<const float4*>(ot + m));
@@ -495,7 +499,7 @@ __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t
         __stcg(reinterpret_cast<float4*>(dst + m), dd);
       }
     } else {
-      for (int m = lane; m < a.B; m += 32) {
+      for (int m = m0; m < a.B; m += mstep) {
         float v_ls, v_t, d;
         elem(__ldcg(gya + m), __ldcg(gyb + m), __ldcg(ya + m), __ldcg(yb + m), __ldcg(ols + m), __ldcg(ot + m), __ldcg(bp + m),
              __ldcg(gld + m), v_ls, v_t, d);
@@ -504,8 +508,13 @@ __device__ __noinline__ void op_b0(const KArgs& a, int e, const SubOp& so, int t
         __stcg(dst + m, d);
       }
     }
-    sc_ls = warp_sum(sc_ls); sc_t = warp_sum(sc_t); b3_ls = warp_sum(b3_ls); b3_t = warp_sum(b3_t);
-    if (lane == 0) {
+    if (wide) {   // col < Db for every thread of the CTA (the grid is exactly Db CTAs)
+      sc_ls = block_sum(sc_ls, sRed + 128); sc_t = block_sum(sc_t, sRed + 192);
+      b3_ls = block_sum(b3_ls, sRed + 256); b3_t = block_sum(b3_t, sRed + 320);
+    } else {
+      sc_ls = warp_sum(sc_ls); sc_t = warp_sum(sc_t); b3_ls = warp_sum(b3_ls); b3_t = warp_sum(b3_t);
+    }
+    if (wide ? threadIdx.x == 0 : lane == 0) {
       c.G(P_SCALE)[col] = sc_ls; c.G(P_SCALE)[a.Db + col] = sc_t;
       c.G(P_B3)[col] = b3_ls;    c.G(P_B3)[a.Db + col] = b3_t;
     }

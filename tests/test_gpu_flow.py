@@ -192,3 +192,39 @@ def test_tensor_core_path_train_eval_nobn_odd(D, NF, B, seqfrac, bn, monkeypatch
     assert rel_err(xe, xe2) < RTOL and rel_err(lde, lde2) < RTOL
     worst = max(((rel_err(gv, grads2[k]), k) for k, gv in grads.items() if "actnorm" not in k))
     assert worst[0] < 3 * RTOL, worst
+
+
+def test_tensor_core_path_beyond_fused_batchnorm_limit():
+    """Batches above 4096 samples cannot keep a feature row in registers: the tensor-core path then runs BatchNorm
+    statistics / backward as separate strip phases. Same parity bar (training pass + gradients, eval reverse)."""
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    D, NF, B, seqfrac = 12, 1, 4100, 0.5
+    sd = O.init_state(D, NF, seqfrac=seqfrac, seed=4, randomize=True)
+    sd0 = {k: v.detach().clone() for k, v in sd.items()}
+    torch.manual_seed(9)
+    z, cx, cl = torch.randn(B, D), torch.randn(B, D), torch.randn(B)
+    m = RealNVP(D, NF, seqfrac=seqfrac)
+    m.load_state_dict({k: v.clone() for k, v in sd0.items()})
+    m = m.cuda()
+    zg = z.cuda().requires_grad_(True)
+    x, ld = m.reverse(zg)
+    ((x * cx.cuda()).sum() + (ld * cl.cuda()).sum()).backward()
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    zo = z.clone().requires_grad_(True)
+    xo, ldo = O.realnvp_reverse(sd, zo, train=True)
+    ((xo * cx).sum() + (ldo * cl).sum()).backward()
+    assert rel_err(x, xo) < RTOL and rel_err(ld, ldo) < RTOL
+    assert rel_err(zg.grad, zo.grad) < RTOL
+    worst = max(((rel_err(gv, sd[k].grad), k) for k, gv in m.named_grad_views() if "actnorm" not in k))
+    assert worst[0] < 3 * RTOL, worst
+    after = {k: v.detach() for k, v in sd.items()}
+    mine = m.state_dict()
+    for k in after:
+        if "running" in k:
+            assert rel_err(mine[k].float(), after[k].float()) < RTOL, k
+    with torch.no_grad():
+        m.eval()
+        xe, lde = m.reverse(z.cuda())
+        xoe, ldoe = O.realnvp_reverse({k: v.detach() for k, v in sd.items()}, z, train=False)
+    assert rel_err(xe, xoe) < RTOL and rel_err(lde, ldoe) < RTOL
