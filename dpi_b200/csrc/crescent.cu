@@ -95,6 +95,40 @@ __device__ __forceinline__ Pix pixel(int pix, int npix, const Feat& f, int g) { 
   return q;
 }
 
+// The transcendental part of a pixel (ring, cos / sin of the azimuth offset, erf disk, Gaussian bumps) does not change
+// between the normalising passes of one image: with CACHED the first pass stores it in dynamic shared memory
+// ([4 + g][P] floats, each thread re-reads only what it wrote) and the later passes rebuild the Pix from it with the
+// same arithmetic - bit-identical to recomputing, one evaluation of atan2 / erf / exp instead of three (five backward).
+template <bool CACHED>
+__device__ __forceinline__ Pix get_pixel(int pix, int npix, int P, const Feat& f, int g, float* cache, bool first) {
+  if (!CACHED || first) {
+    const Pix q = pixel(pix, npix, f, g);
+    if (CACHED) {
+      cache[pix] = q.ring; cache[P + pix] = q.cs; cache[2 * P + pix] = q.sn; cache[3 * P + pix] = q.dk;
+      for (int k = 0; k < kMaxG; ++k)
+        if (k < g) cache[(4 + k) * P + pix] = q.n[k];
+    }
+    return q;
+  }
+  Pix q;
+  grid_at(pix, npix, q.gx, q.gy);
+  q.rg = sqrtf(q.gx * q.gx + q.gy * q.gy);
+  q.th = 0.f;   // only enters through cs / sn
+  q.ring = cache[pix]; q.cs = cache[P + pix]; q.sn = cache[2 * P + pix]; q.dk = cache[3 * P + pix];
+  q.c = (1.0f + f.s * q.cs) * q.ring;
+  for (int k = 0; k < kMaxG; ++k) {
+    if (k < g) {
+      const float xc = q.gx - f.x0[k], yc = q.gy - f.y0[k];
+      q.xr[k] = xc * f.ct[k] + yc * f.st[k];
+      q.yr[k] = -xc * f.st[k] + yc * f.ct[k];
+      q.n[k] = cache[(4 + k) * P + pix];
+    } else {
+      q.n[k] = 0.f; q.xr[k] = q.yr[k] = 0.f;
+    }
+  }
+  return q;
+}
+
 // sums v[0..K) over the CTA in a fixed order; every thread receives the totals
 template <int K>
 __device__ __forceinline__ void block_sum_multi(float (&v)[K], float* sm /* >= 8 * K floats */) {
@@ -125,13 +159,14 @@ __device__ __forceinline__ float tot_at(const Pix& q, const Feat& f, const Norms
   return t;
 }
 
-__device__ __forceinline__ Norms compute_norms(int npix, const Feat& f, int g, float* sm) {
+template <bool CACHED>
+__device__ __forceinline__ Norms compute_norms(int npix, const Feat& f, int g, float* sm, float* cache) {
   const int P = npix * npix;
   float v[2 + kMaxG];
 #pragma unroll
   for (int k = 0; k < 2 + kMaxG; ++k) v[k] = 0.f;
   for (int pix = threadIdx.x; pix < P; pix += kCT) {
-    const Pix q = pixel(pix, npix, f, g);
+    const Pix q = get_pixel<CACHED>(pix, npix, P, f, g, cache, true);
     v[0] += q.c; v[1] += q.dk;
 #pragma unroll
     for (int k = 0; k < kMaxG; ++k) v[2 + k] += q.n[k];
@@ -142,29 +177,34 @@ __device__ __forceinline__ Norms compute_norms(int npix, const Feat& f, int g, f
 #pragma unroll
   for (int k = 0; k < kMaxG; ++k) nm.N[k] = v[2 + k] + kEpsN;
   float t[1] = {0.f};
-  for (int pix = threadIdx.x; pix < P; pix += kCT) t[0] += tot_at(pixel(pix, npix, f, g), f, nm, g);
+  for (int pix = threadIdx.x; pix < P; pix += kCT) t[0] += tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g);
   block_sum_multi<1>(t, sm);
   nm.T = t[0] + kEpsN;
   return nm;
 }
 
+template <bool CACHED>
 __global__ void __launch_bounds__(kCT) crescent_fwd_kernel(int npix, int g, float fov, const float* __restrict__ params,
                                                            float* __restrict__ img) {
+  extern __shared__ float cache[];
   __shared__ float sm[8 * (2 + kMaxG)];
   __shared__ float sp[6 + 6 * kMaxG];
   const int b = blockIdx.x, np = 6 + 6 * g, P = npix * npix;
   if (threadIdx.x < np) sp[threadIdx.x] = params[(size_t)b * np + threadIdx.x];
   __syncthreads();
   const Feat f = features(sp, g, fov);
-  const Norms nm = compute_norms(npix, f, g, sm);
+  const Norms nm = compute_norms<CACHED>(npix, f, g, sm, cache);
   float* out = img + (size_t)b * P;
-  for (int pix = threadIdx.x; pix < P; pix += kCT) out[pix] = tot_at(pixel(pix, npix, f, g), f, nm, g) / nm.T;
+  for (int pix = threadIdx.x; pix < P; pix += kCT)
+    out[pix] = tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) / nm.T;
 }
 
 // g_params[b, :] = gscale[b] * sum_p g_img[b, p] * d img[b, p] / d params[b, :]
+template <bool CACHED>
 __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, float fov, const float* __restrict__ params,
                                                            const float* __restrict__ g_img, const float* __restrict__ gscale,
                                                            float* __restrict__ g_params) {
+  extern __shared__ float cache[];
   constexpr int KS = 4 + 5 * kMaxG;
   __shared__ float sm[8 * KS];
   __shared__ float sp[6 + 6 * kMaxG];
@@ -172,12 +212,12 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
   if (threadIdx.x < np) sp[threadIdx.x] = params[(size_t)b * np + threadIdx.x];
   __syncthreads();
   const Feat f = features(sp, g, fov);
-  const Norms nm = compute_norms(npix, f, g, sm);
+  const Norms nm = compute_norms<CACHED>(npix, f, g, sm, cache);
   const float* G = g_img + (size_t)b * P;
   const float gs = gscale ? gscale[b] : 1.0f;
   // img = tot / T: u = d L / d tot = (G - sum(G * img)) / T
   float gi[1] = {0.f};
-  for (int pix = threadIdx.x; pix < P; pix += kCT) gi[0] += G[pix] * (tot_at(pixel(pix, npix, f, g), f, nm, g) / nm.T);
+  for (int pix = threadIdx.x; pix < P; pix += kCT) gi[0] += G[pix] * (tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) / nm.T);
   block_sum_multi<1>(gi, sm);
   const float GI = gi[0];
   // second-level sums: sum u c, sum u dk, sum u n_k
@@ -185,7 +225,7 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
 #pragma unroll
   for (int k = 0; k < 2 + kMaxG; ++k) u2[k] = 0.f;
   for (int pix = threadIdx.x; pix < P; pix += kCT) {
-    const Pix q = pixel(pix, npix, f, g);
+    const Pix q = get_pixel<CACHED>(pix, npix, P, f, g, cache, false);
     const float u = gs * (G[pix] - GI) / nm.T;
     u2[0] += u * q.c; u2[1] += u * q.dk;
 #pragma unroll
@@ -200,7 +240,7 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
   const float kc = f.cf * (1.0f - f.fl) / nm.C, kd = f.cf * f.fl / nm.Dk;
   const float inv_sg = 1.0f / f.sg;
   for (int pix = threadIdx.x; pix < P; pix += kCT) {
-    const Pix q = pixel(pix, npix, f, g);
+    const Pix q = get_pixel<CACHED>(pix, npix, P, f, g, cache, false);
     const float u = gs * (G[pix] - GI) / nm.T;
     const float vc = kc * (u - Uc / nm.C);         // d L / d c (unnormalised crescent)
     const float vd = kd * (u - Ud / nm.Dk);        // d L / d disk
@@ -357,6 +397,19 @@ __global__ void __launch_bounds__(1024) alpha_objective_kernel(int B, int np, co
   (void)sbc;
 }
 
+// dynamic shared memory of the cached variants: [4 + g][npix^2] floats; 0 = does not fit two CTAs per SM worth keeping
+size_t cache_bytes(int npix, int g) {
+  const size_t b = (size_t)(4 + g) * npix * npix * sizeof(float);
+  return b <= 110 * 1024 ? b : 0;
+}
+bool cache_ready() {   // opt in to > 48 KB of dynamic shared memory once per process (every device shares the attribute call)
+  static const bool ok = []() {
+    return cudaFuncSetAttribute((const void*)crescent_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess &&
+           cudaFuncSetAttribute((const void*)crescent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess;
+  }();
+  return ok;
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -368,7 +421,11 @@ int dpi_crescent_forward(int batch, int npix, int n_gaussian, float fov, const f
                          dpi_stream_t stream) {
   DPI_REQUIRE(batch >= 1 && npix >= 2 && params && img, "dpi_crescent_forward: bad argument");
   DPI_REQUIRE(n_gaussian >= 0 && n_gaussian <= kMaxG, "dpi_crescent_forward: n_gaussian must be in [0, %d]", kMaxG);
-  crescent_fwd_kernel<<<batch, kCT, 0, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, img);
+  const size_t cache = cache_bytes(npix, n_gaussian);
+  if (cache && cache_ready())
+    crescent_fwd_kernel<true><<<batch, kCT, cache, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, img);
+  else
+    crescent_fwd_kernel<false><<<batch, kCT, 0, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, img);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }
@@ -377,7 +434,11 @@ int dpi_crescent_backward(int batch, int npix, int n_gaussian, float fov, const 
                           const float* gscale, float* g_params, dpi_stream_t stream) {
   DPI_REQUIRE(batch >= 1 && npix >= 2 && params && g_img && g_params, "dpi_crescent_backward: bad argument");
   DPI_REQUIRE(n_gaussian >= 0 && n_gaussian <= kMaxG, "dpi_crescent_backward: n_gaussian must be in [0, %d]", kMaxG);
-  crescent_bwd_kernel<<<batch, kCT, 0, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, g_img, gscale, g_params);
+  const size_t cache = cache_bytes(npix, n_gaussian);
+  if (cache && cache_ready())
+    crescent_bwd_kernel<true><<<batch, kCT, cache, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, g_img, gscale, g_params);
+  else
+    crescent_bwd_kernel<false><<<batch, kCT, 0, (cudaStream_t)stream>>>(npix, n_gaussian, fov, params, g_img, gscale, g_params);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }
