@@ -402,11 +402,17 @@ size_t cache_bytes(int npix, int g) {
   const size_t b = (size_t)(4 + g) * npix * npix * sizeof(float);
   return b <= 110 * 1024 ? b : 0;
 }
-bool cache_ready() {   // opt in to > 48 KB of dynamic shared memory once per process (every device shares the attribute call)
-  static const bool ok = []() {
-    return cudaFuncSetAttribute((const void*)crescent_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess &&
-           cudaFuncSetAttribute((const void*)crescent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess;
-  }();
+bool cache_ready() {   // opt in to > 48 KB of dynamic shared memory, once per device
+  static std::atomic<unsigned long long> done{0}, bad{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return !(bad.load(std::memory_order_acquire) & bit);
+  const bool ok =
+      cudaFuncSetAttribute((const void*)crescent_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess &&
+      cudaFuncSetAttribute((const void*)crescent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); bad.fetch_or(bit, std::memory_order_release); }
+  done.fetch_or(bit, std::memory_order_release);
   return ok;
 }
 

@@ -537,14 +537,18 @@ Gemm make_gemm(int M, int N, int K, int n_sm) {
 }
 
 int init() {
-  static int done = 0;
-  if (done) return DPI_OK;
+  // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
+  static std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  DPI_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return DPI_OK;
 #define X(tn_, kt_, mh_)                                                                                               \
   DPI_CUDA(cudaFuncSetAttribute((const void*)gemm_kernel<tn_, kt_, mh_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 stages_of(tn_, kt_, mh_) * stage_bytes(tn_, kt_, mh_) + 1024));
   DPI_TC_CONFIGS(X)
 #undef X
-  done = 1;
+  done.fetch_or(bit, std::memory_order_release);
   return DPI_OK;
 }
 
