@@ -14,6 +14,7 @@ backward pass and the clip (BatchNorm statistics stay per-replica = DDP semantic
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -200,7 +201,7 @@ class _FusedTrainer:
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         single = None
-        if self.world > 1:
+        if self.world > 1 and os.environ.get("DPI_B200_GRAPH_NCCL", "1") != "0":
             # Data parallel: try to capture the gradient all-reduce inside ONE graph with both halves of the step (no
             # host round trip between backward and Adam). NCCL collectives are capturable; if this build refuses,
             # fall back to two graphs with the all-reduce issued eagerly between them.
