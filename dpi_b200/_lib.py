@@ -32,6 +32,7 @@ PROTOTYPES = {
     "dpi_flow_gather_map": (i32, [vp, i32, i32, vp]),
     "dpi_flow_workspace_bytes": (sz, [vp, i32]),
     "dpi_flow_ws_offset": (i64, [vp, i32, i32, i32]),
+    "dpi_flow_tc_plan": (i32, [i32, i32, i32, i32, vp]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_debug_timing": (i32, [vp, i32]),

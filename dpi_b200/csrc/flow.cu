@@ -717,6 +717,16 @@ int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
   return (int64_t)(kCtrlWords * sizeof(unsigned)) + o * (int64_t)sizeof(float);
 }
 
+int dpi_flow_tc_plan(int M, int N, int K, int n_sm, int32_t* out) {
+  DPI_REQUIRE(out && M >= 1 && N >= 1 && K >= 1 && n_sm >= 1, "dpi_flow_tc_plan: bad argument");
+  ftc::configure();
+  const ftc::Gemm g = ftc::make_gemm(M, N, K, n_sm);
+  out[0] = g.TN; out[1] = g.KT; out[2] = g.MH; out[3] = g.m_tiles; out[4] = g.n_tiles; out[5] = g.k_tiles;
+  out[6] = g.splits; out[7] = g.kt_per_split; out[8] = g.stages;
+  out[9] = g.stages * (2 * g.MH * ftc::kM * g.KT + 2 * g.TN * g.KT) * 4 + 1024;
+  return DPI_OK;
+}
+
 int dpi_flow_debug_timing(dpi_flow_t h, int enable) {
   DPI_REQUIRE(h, "dpi_flow_debug_timing: null handle");
   DeviceGuard g(h->device);

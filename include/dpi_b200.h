@@ -97,6 +97,12 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
                       const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                       size_t workspace_bytes, dpi_stream_t stream);
 
+/* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
+ * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
+ * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory
+ * bytes. No CUDA call is made (usable without a device; the CPU test suite checks the planner's invariants). */
+int dpi_flow_tc_plan(int M, int N, int K, int n_sm, int32_t* out);
+
 /* Debug/profiling aid (synchronises; never on the hot path): when enabled, CTA 0 stamps %globaltimer at
  * the start and at the end of its work in every phase of the next launches. dpi_flow_debug_read returns
  * the number of phases of the last launch and fills stamps[2*i], stamps[2*i+1] (ns) and ops[i]

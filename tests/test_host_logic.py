@@ -144,3 +144,31 @@ def test_product_path_has_no_cpu_fallback():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 2048), (1024, 512, 512), (1024, 4096, 512), (1024, 512, 4096),
+                                   (4096, 512, 1024), (512, 2048, 1024), (2048, 144, 9), (2048, 18, 144),
+                                   (144, 144, 2048), (200, 32, 128), (97, 4, 5), (128, 64, 32)])
+def test_tcgen05_gemm_planner_invariants(M, N, K):
+    """flow_tc.cu's host planner (no CUDA call): tiles cover the problem, the K splits cover K exactly once, the grid
+    is at most one wave of 148 CTAs whenever K is split, the stage ring fits the 227 KB of shared memory, the TMEM
+    accumulator is a legal power-of-two column count."""
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 10)()
+    n_sm = 148
+    _lib.check(lib.dpi_flow_tc_plan(M, N, K, n_sm, out), "dpi_flow_tc_plan")
+    TN, KT, MH, m_tiles, n_tiles, k_tiles, splits, kt_per_split, stages, smem = list(out)
+    assert (TN, KT, MH) in {(64, 32, 1), (128, 32, 1), (256, 32, 1), (256, 16, 1), (256, 16, 2)}
+    assert m_tiles * 128 >= M and (m_tiles - MH) * 128 < M and m_tiles % MH == 0
+    assert n_tiles * TN >= N and (n_tiles - 1) * TN < N
+    assert k_tiles * KT >= K and (k_tiles - 1) * KT < K
+    assert splits >= 1 and splits * kt_per_split >= k_tiles and (splits - 1) * kt_per_split < k_tiles
+    ctas = (m_tiles // MH) * n_tiles * splits
+    if splits > 1:
+        assert ctas <= n_sm                       # never a second, nearly empty wave
+        assert kt_per_split * KT >= 128           # at least 128 k per split
+    assert 2 <= stages <= 6 and smem <= 227 * 1024
+    cols = MH * TN
+    assert cols in (64, 128, 256, 512)
+    if N >= 256 and (M + 127) // 128 * ((N + 255) // 256) * min(16, max(1, K // 128)) >= 111:
+        assert TN == 256                          # the widest tile that still fills three quarters of the GPU
