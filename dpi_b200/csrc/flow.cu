@@ -251,6 +251,29 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     bp.g_wg2 = ftc::make_gemm(H, H, B, sm);
     bp.g_dgin = ftc::make_gemm(B, Da, H, sm);
     bp.g_wg1 = ftc::make_gemm(H, Da, B, sm);
+    bp.tc_emit = h->tc_emit;
+    auto fill = [&](ftc::WeightPack& w, const ftc::Gemm* g[3], const int rows[3], const int K[3], const int ld[3], int kc) {
+      w.S = S; w.src_off = h->d_woff;
+      long long o = 0;
+      for (int l = 0; l < 3; ++l) {
+        w.rows[l] = rows[l]; w.K[l] = K[l]; w.ld[l] = ld[l]; w.k_contig[l] = kc;
+        w.TN[l] = g[l]->TN; w.KT[l] = g[l]->KT;
+        w.tiles[l] = g[l]->n_tiles * g[l]->k_tiles;
+        w.dst_off[l] = o;
+        o += (long long)ftc::b_pack_floats(*g[l]);
+      }
+      w.stage_floats = o;
+    };
+    {   // forward orientation: B[n][k] = W[n][k]
+      const ftc::Gemm* g[3] = {&bp.g_f1, &bp.g_f2, &bp.g_f3};
+      const int rows[3] = {H, H, Dout}, K[3] = {Da, H, H}, ld[3] = {Da, H, H};
+      fill(bp.wp_fwd, g, rows, K, ld, 1);
+    }
+    {   // backward (dgrad) orientation: B[n][k] = W[k][n]; layer order W1 (dgrad 0), W2 (dgrad 3), W3 (dgrad 6)
+      const ftc::Gemm* g[3] = {&bp.g_dgin, &bp.g_dg1, &bp.g_dg2};
+      const int rows[3] = {Da, H, H}, K[3] = {H, H, Dout}, ld[3] = {Da, H, H};
+      fill(bp.wp_bwd, g, rows, K, ld, 0);
+    }
   }
 
   const long long LB = bp.small.ok ? (B + 3) / 4 * 4 : B;   // workspace row stride
@@ -296,6 +319,15 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     bp.oTCA2 = take((long long)ma);
     bp.oTCB2 = take((long long)mb);
     bp.oTCP2 = take((long long)mp);
+    if (bp.tc_emit) {
+      o = (o + 255) / 256 * 256;
+      bp.oWPF = take((long long)S * bp.wp_fwd.stage_floats);
+      bp.oWPB = take((long long)S * bp.wp_bwd.stage_floats);
+      bp.oEA2 = take((long long)ftc::a_pack_floats(bp.g_f2));
+      bp.oEA3 = take((long long)ftc::a_pack_floats(bp.g_f3));
+      bp.oED1 = take((long long)ftc::a_pack_floats(bp.g_dg1));
+      bp.oEDIN = take((long long)ftc::a_pack_floats(bp.g_dgin));
+    }
   }
   bp.total_floats = o;
   return DPI_OK;
@@ -387,9 +419,24 @@ int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
   float* W = a.W;
   const TcBufs tb{W + bp.oTCA, W + bp.oTCB, W + bp.oTCP};
   const bool bn_phase = h->has_bn && a.train;
+  // fused operand path: the weights of all stages are packed once (one launch), and each hidden-layer epilogue emits
+  // the packed A operand of the next GEMM, so only the first GEMM of a stage still has a pack launch
+  const bool emit = bp.tc_emit && (!bn_phase || B <= ftc::kEpiMaxM);
+  const ftc::Pack none{nullptr, 0, 1, nullptr, 0, 1};
+  float* WPF = W + bp.oWPF;
+  float* EA2 = W + bp.oEA2;
+  float* EA3 = W + bp.oEA3;
+  if (emit) {
+    DPI_TRY(ftc::pack_weights(bp.wp_fwd, a.P, WPF, st));
+    // the emitted tiles are only written where (sample, feature) exist: their padding must read as zero
+    DPI_CUDA(cudaMemsetAsync(EA2, 0, ftc::a_pack_floats(bp.g_f2) * sizeof(float), st));
+    DPI_CUDA(cudaMemsetAsync(EA3, 0, ftc::a_pack_floats(bp.g_f3) * sizeof(float), st));
+  }
   int pi = 0;
   DPI_TRY(launch_phase(prog, a, pi++, st));
   for (int e = 0; e < S; ++e) {
+    const int sidx = a.dir ? S - 1 - e : e;
+    const float* wpf = WPF + (long long)sidx * bp.wp_fwd.stage_floats;
     const StageTab& sg = h->stages[a.dir ? S - 1 - e : e];
     const int* gmap = h->d_gmaps + ((size_t)a.dir * S + e) * D;
     const float* yprev = e == 0 ? W + bp.oZT : W + bp.oYT + (long long)(e - 1) * D * LB;
@@ -412,7 +459,16 @@ int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
           ep.rstd = ep.mean + H;
         }
       }
-      if (which == 1)
+      if (emit) {
+        const ftc::Gemm& nx = which == 1 ? bp.g_f2 : bp.g_f3;
+        ep.tp = which == 1 ? EA2 : EA3; ep.tp_R = nx.MH * ftc::kM; ep.tp_KT = nx.KT; ep.tp_ktiles = nx.k_tiles;
+        if (which == 1) {
+          DPI_TRY(ftc::pack2(bp.g_f1, ftc::Pack{yprev, LB, 0, gmap, B, Da}, tb.apack, none, tb.bpack, st));
+          DPI_TRY(ftc::run(bp.g_f1, tb.apack, wpf + bp.wp_fwd.dst_off[0], tb.part, ep, st));
+        } else {
+          DPI_TRY(ftc::run(bp.g_f2, EA2, wpf + bp.wp_fwd.dst_off[1], tb.part, ep, st));
+        }
+      } else if (which == 1)
         DPI_TRY(tc_gemm(bp.g_f1, ftc::Pack{yprev, LB, 0, gmap, B, Da}, ftc::Pack{a.P + sg.p[P_W1], Da, 1, nullptr, H, Da}, ep, tb, st));
       else
         DPI_TRY(tc_gemm(bp.g_f2, ftc::Pack{N1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 1, nullptr, H, H}, ep, tb, st));
@@ -431,7 +487,8 @@ int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     else if (e + 1 < S) { const StageTab& nx = h->stages[S - 2 - e]; ep.post_mode = 1; ep.post_lsi = a.P + nx.lsi; ep.post_loc = a.P + nx.loc; }
     else ep.post_mode = 2;
     ep.ldp = W + bp.oLDP + (long long)e * bp.tc_ldp_tiles * LB;
-    DPI_TRY(tc_gemm(bp.g_f3, ftc::Pack{N2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W3], H, 1, nullptr, Dout, H}, ep, tb, st));
+    if (emit) DPI_TRY(ftc::run(bp.g_f3, EA3, wpf + bp.wp_fwd.dst_off[2], tb.part, ep, st));
+    else DPI_TRY(tc_gemm(bp.g_f3, ftc::Pack{N2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W3], H, 1, nullptr, Dout, H}, ep, tb, st));
     ++pi;   // the strip-op tail of the program is not needed
   }
   return launch_phase(prog, a, pi++, st);
@@ -471,10 +528,21 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     DPI_CUDA(cudaStreamWaitEvent(st, ev, 0));
     return DPI_OK;
   };
+  const bool emit = bp.tc_emit && B <= ftc::kEpiMaxM;
+  const ftc::Pack none{nullptr, 0, 1, nullptr, 0, 1};
+  float* WPB = W + bp.oWPB;
+  float* ED1 = W + bp.oED1;
+  float* EDIN = W + bp.oEDIN;
+  if (emit) {
+    DPI_TRY(ftc::pack_weights(bp.wp_bwd, a.P, WPB, st));
+    DPI_CUDA(cudaMemsetAsync(ED1, 0, ftc::a_pack_floats(bp.g_dg1) * sizeof(float), st));
+    DPI_CUDA(cudaMemsetAsync(EDIN, 0, ftc::a_pack_floats(bp.g_dgin) * sizeof(float), st));
+  }
   int pi = 0;
   DPI_TRY(launch_phase(prog, a, pi++, st));
   for (int e = S - 1; e >= 0; --e) {
     const StageTab& sg = h->stages[e];
+    const float* wpb = WPB + (long long)e * bp.wp_bwd.stage_floats;
     const int* gmap = h->d_gmaps + (size_t)e * D;
     const float* yprev = e == 0 ? W + bp.oZT : W + bp.oYT + (long long)(e - 1) * D * LB;
     const float* N1 = W + bp.oN1T + (long long)e * H * LB;
@@ -500,6 +568,10 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
         ep.g_beta = a.G + sg.p[which == 1 ? P_BE1 : P_BE2];
       }
       ep.g_bias = a.G + sg.p[which == 1 ? P_B1 : P_B2];
+      if (emit) {   // g_p2 feeds dgrad through net.3, g_p1 feeds dgrad through net.0
+        const ftc::Gemm& nx = which == 2 ? bp.g_dg1 : bp.g_dgin;
+        ep.tp = which == 2 ? ED1 : EDIN; ep.tp_R = nx.MH * ftc::kM; ep.tp_KT = nx.KT; ep.tp_ktiles = nx.k_tiles;
+      }
       return ep;
     };
     ftc::Epi wg{};
@@ -508,14 +580,19 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     if (side) DPI_TRY(fork(ev[0]));
     wg.out = a.G + sg.p[P_W3]; wg.ldo = H;
     DPI_TRY(tc_gemm(bp.g_wg3, ftc::Pack{GPRE, LB, 1, nullptr, Dout, B}, ftc::Pack{N2, LB, 1, nullptr, H, B}, wg, tw, sw));
-    DPI_TRY(tc_gemm(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, ftc::Pack{a.P + sg.p[P_W3], H, 0, nullptr, H, Dout}, hid_epi(2), tb, st));
+    if (emit) {
+      DPI_TRY(ftc::pack2(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, tb.apack, none, tb.bpack, st));
+      DPI_TRY(ftc::run(bp.g_dg2, tb.apack, wpb + bp.wp_bwd.dst_off[2], tb.part, hid_epi(2), st));
+    } else
+      DPI_TRY(tc_gemm(bp.g_dg2, ftc::Pack{GPRE, LB, 0, nullptr, B, Dout}, ftc::Pack{a.P + sg.p[P_W3], H, 0, nullptr, H, Dout}, hid_epi(2), tb, st));
     if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // BatchNorm + LeakyReLU backward of hidden layer 2 -> GP2
     ++pi;
     // through net.3
     if (side) DPI_TRY(fork(ev[1]));
     wg.out = a.G + sg.p[P_W2]; wg.ldo = H;
     DPI_TRY(tc_gemm(bp.g_wg2, ftc::Pack{GP2, LB, 1, nullptr, H, B}, ftc::Pack{N1, LB, 1, nullptr, H, B}, wg, tw, sw));
-    DPI_TRY(tc_gemm(bp.g_dg1, ftc::Pack{GP2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 0, nullptr, H, H}, hid_epi(1), tb, st));
+    if (emit) DPI_TRY(ftc::run(bp.g_dg1, ED1, wpb + bp.wp_bwd.dst_off[1], tb.part, hid_epi(1), st));
+    else DPI_TRY(tc_gemm(bp.g_dg1, ftc::Pack{GP2, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W2], H, 0, nullptr, H, H}, hid_epi(1), tb, st));
     if (!fused_bn) DPI_TRY(launch_phase(prog, a, pi, st));   // hidden layer 1 -> GP1
     ++pi;
     // through net.0, written through the fused permutation, plus the ActNorm pass-through of the a-half
@@ -529,7 +606,8 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     }
     ftc::Epi sc{};
     sc.mode = ftc::EPI_T_SCATTER; sc.out = gyprev; sc.ldo = LB; sc.rowmap = gmap; sc.add = gy; sc.lsi = a.P + sg.lsi;
-    DPI_TRY(tc_gemm(bp.g_dgin, ftc::Pack{GP1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W1], Da, 0, nullptr, Da, H}, sc, tb, st));
+    if (emit) DPI_TRY(ftc::run(bp.g_dgin, EDIN, wpb + bp.wp_bwd.dst_off[0], tb.part, sc, st));
+    else DPI_TRY(tc_gemm(bp.g_dgin, ftc::Pack{GP1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W1], Da, 0, nullptr, Da, H}, sc, tb, st));
   }
   if (side) DPI_TRY(join(h->ev[(size_t)4 * S]));
   return launch_phase(prog, a, pi++, st);
@@ -566,6 +644,8 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   small_query(h.get());
   const char* tcm = getenv("DPI_B200_FLOW_TC");          // minimum batch of the tcgen05 GEMM path; 0 disables it
   if (tcm) h->tc_min_batch = std::max(0, atoi(tcm));
+  const char* tce = getenv("DPI_B200_TC_EMIT");            // 1: fused operand emission + once-per-pass weight packs
+  if (tce) h->tc_emit = atoi(tce) ? 1 : 0;
   const char* tcs = getenv("DPI_B200_TC_SIDE");            // 0: weight-gradient GEMMs stay on the caller's stream
   if (tcs) h->tc_side = atoi(tcs) ? 1 : 0;
   const char* cps = getenv("DPI_B200_CTAS_PER_SM");
@@ -618,6 +698,16 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
     const int32_t* ord = orders + (size_t)(n_flow - 1) * D;
     for (int j = 0; j < D; ++j) gf[j] = D - 1 - ord[j];
   }
+  {
+    std::vector<long long> woff((size_t)h->S * 3);
+    for (int st = 0; st < h->S; ++st) {
+      woff[(size_t)st * 3 + 0] = h->stages[st].p[P_W1];
+      woff[(size_t)st * 3 + 1] = h->stages[st].p[P_W2];
+      woff[(size_t)st * 3 + 2] = h->stages[st].p[P_W3];
+    }
+    DPI_CUDA(cudaMalloc(&h->d_woff, sizeof(long long) * woff.size()));
+    DPI_CUDA(cudaMemcpy(h->d_woff, woff.data(), sizeof(long long) * woff.size(), cudaMemcpyHostToDevice));
+  }
   DPI_CUDA(cudaMalloc(&h->d_stages, sizeof(StageTab) * h->S));
   DPI_CUDA(cudaMemcpy(h->d_stages, h->stages.data(), sizeof(StageTab) * h->S, cudaMemcpyHostToDevice));
   DPI_CUDA(cudaMalloc(&h->d_gmaps, sizeof(int32_t) * h->h_gmaps.size()));
@@ -659,6 +749,7 @@ int dpi_flow_destroy(dpi_flow_t h) {
   }
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   if (h->side) cudaStreamDestroy(h->side);
+  cudaFree(h->d_woff);
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
   cudaFree(h->d_tbuf);

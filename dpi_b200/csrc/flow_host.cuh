@@ -38,6 +38,11 @@ struct BatchPlan {
   Program tc_bwd[2];
   long long oTCA = 0, oTCB = 0, oTCP = 0;
   long long oTCA2 = 0, oTCB2 = 0, oTCP2 = 0;   // second set for the weight-gradient GEMMs on the side stream
+  // weights of all stages packed once per pass (forward / transposed orientation) and the packed A operands that the
+  // epilogues emit for the next GEMM of the chain
+  int tc_emit = 0;
+  ftc::WeightPack wp_fwd{}, wp_bwd{};
+  long long oWPF = 0, oWPB = 0, oEA2 = 0, oEA3 = 0, oED1 = 0, oEDIN = 0;
 };
 
 }  // namespace dpi
@@ -49,6 +54,8 @@ struct dpi_flow_s {
   cudaStream_t side = nullptr;                // weight-gradient GEMMs of the tensor-core path run here, beside the dgrad chain
   std::vector<cudaEvent_t> ev;                // [4 S + 2] fork / join events (main <-> side)
   int tc_side = 1;
+  int tc_emit = 0;                            // epilogues emit the next GEMM's packed operand, weights packed once per pass
+  long long* d_woff = nullptr;                // [S * 3] parameter offsets of W1, W2, W3 by stage-table index
   int tc_min_batch = 96;                      // batches >= this run the coupling GEMMs on tcgen05 (0: never)
   int small_clusters = 0, small_cl = 1;       // CTAs without clusters; small_cl > 1: cluster launches are available
   int small_G[3] = {0, 0, 0};                 // co-resident clusters of 8, 4, 2 CTAs

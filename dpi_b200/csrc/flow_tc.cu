@@ -129,6 +129,27 @@ __global__ void __launch_bounds__(256) pack2_kernel(Pack pa, int vec_a, float* _
     pack_tile<RB, KT>(pb, (pb.K + KT - 1) / KT, vec_b, dst_b, blockIdx.x - na, reinterpret_cast<float (*)[RB + 1]>(s));
 }
 
+// Weights of all stages in one launch. Every stage has the same three layer shapes, so the stage and layer of a CTA
+// follow from its index; the tile shape of a layer is the B-tile of the GEMM that consumes it.
+__global__ void __launch_bounds__(256) packw_kernel(WeightPack w, const float* __restrict__ P, float* __restrict__ dst) {
+  __shared__ float s[32 * 257];
+  const int per_stage = w.tiles[0] + w.tiles[1] + w.tiles[2];
+  const int stage = blockIdx.x / per_stage;
+  int t = blockIdx.x - stage * per_stage, l = 0;
+  if (t >= w.tiles[0]) { t -= w.tiles[0]; l = 1; }
+  if (l == 1 && t >= w.tiles[1]) { t -= w.tiles[1]; l = 2; }
+  Pack p;
+  p.src = P + __ldg(w.src_off + stage * 3 + l);
+  p.ld = w.ld[l]; p.k_contig = w.k_contig[l]; p.map = nullptr; p.rows = w.rows[l]; p.K = w.K[l];
+  const int vec = ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
+  float* d = dst + (size_t)stage * w.stage_floats + w.dst_off[l];
+  const int TN = w.TN[l], KT = w.KT[l], kt = (p.K + KT - 1) / KT;
+  if (TN == 64 && KT == 32) pack_tile<64, 32>(p, kt, vec, d, t, reinterpret_cast<float (*)[65]>(s));
+  else if (TN == 128 && KT == 32) pack_tile<128, 32>(p, kt, vec, d, t, reinterpret_cast<float (*)[129]>(s));
+  else if (TN == 256 && KT == 32) pack_tile<256, 32>(p, kt, vec, d, t, reinterpret_cast<float (*)[257]>(s));
+  else pack_tile<256, 16>(p, kt, vec, d, t, reinterpret_cast<float (*)[257]>(s));
+}
+
 // ------------------------------------------------------------------------------------------- GEMM
 // 128 threads. Lane 0 of warp 0: producer (two bulk copies per stage); lane 0 of warp 1: MMA issuer; all four
 // warps: TMEM -> partial tile. The CTA tile is (MH x 128) x TN: MH accumulators of 128 lanes x TN columns side by
@@ -270,6 +291,22 @@ __device__ __forceinline__ void fetchv(const float* p, int splits, size_t sstrid
   }
 }
 
+// Emit V consecutive samples m.. of feature n as elements (r = m, k = n) of the packed A operand of the next GEMM.
+template <int V>
+__device__ __forceinline__ void emit_tp(const Epi& e, int n, int m, const float (&x)[V]) {
+  const int R = e.tp_R, KT = e.tp_KT;
+  float* t = e.tp + ((size_t)(m / R) * e.tp_ktiles + n / KT) * (size_t)(2 * R * KT);
+  const int base = ((m % R) >> 3) * (8 * KT) + ((n % KT) >> 2) * 32 + (n & 3);
+#pragma unroll
+  for (int q = 0; q < V; ++q) {   // V == 4: m is a multiple of 4, so the four samples stay inside one 8-row group
+    unsigned hi, lo;
+    split_tf32(x[q], hi, lo);
+    const int o = base + ((m + q) & 7) * 4;
+    t[o] = __uint_as_float(hi);
+    t[R * KT + o] = __uint_as_float(lo);
+  }
+}
+
 template <int MODE, int V, int PER>
 __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restrict__ part, Epi e) {
   __shared__ float red[32];
@@ -344,6 +381,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
           for (int q = 0; q < V; ++q) nv[q] = fmaf(v[i][q] - mean, ga, be);
           stv<V>(e.out + orow + m, v[i]);
           stv<V>(e.out2 + orow + m, nv);
+          if (e.tp) emit_tp<V>(e, n, m, nv);
         }
       }
       if (tid == 0) {
@@ -366,6 +404,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
         for (int q = 0; q < V; ++q) { c[q] = lrelu_f(c[q] + bias); nv[q] = e.bn_mode == 2 ? fmaf(c[q], ga, be) : c[q]; }
         stv<V>(e.out + orow + m, c);
         if (e.out2) stv<V>(e.out2 + orow + m, nv);
+        if (e.tp) emit_tp<V>(e, n, m, nv);
       }
     }
   } else {   // EPI_T_BNBWD
@@ -401,6 +440,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
           s3 += o[q];
         }
         stv<V>(e.out + orow + m, o);
+        if (e.tp) emit_tp<V>(e, n, m, o);
       }
     }
     s3 = block_sum(s3, red);
@@ -578,6 +618,17 @@ int pack2(const Gemm& g, const Pack& pa, float* dst_a, const Pack& pb, float* ds
   DPI_TC_CONFIGS(X)
 #undef X
   if (!ok) { set_error("ftc::pack2: unsupported configuration TN=%d KT=%d MH=%d", g.TN, g.KT, g.MH); return DPI_ERR_INVALID; }
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int pack_weights(const WeightPack& w, const float* P, float* dst, cudaStream_t st) {
+  for (int l = 0; l < 3; ++l) {
+    const bool ok = (w.TN[l] == 64 && w.KT[l] == 32) || (w.TN[l] == 128 && w.KT[l] == 32) || (w.TN[l] == 256 && (w.KT[l] == 32 || w.KT[l] == 16));
+    if (!ok) { set_error("ftc::pack_weights: unsupported tile %d x %d", w.TN[l], w.KT[l]); return DPI_ERR_INVALID; }
+  }
+  const int per_stage = w.tiles[0] + w.tiles[1] + w.tiles[2];
+  packw_kernel<<<w.S * per_stage, 256, 0, st>>>(w, P, dst);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

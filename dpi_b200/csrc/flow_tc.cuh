@@ -87,9 +87,27 @@ struct Epi {
                                 // ActNorm); 2: identity
   int dir, Da, Db;
   float* ldp;                   // logdet partials of this stage: [Db / 16 chunks][ldo]
+  // HID / BNBWD: also emit the result as the packed A operand (TF32 hi / lo, canonical K-major tiles of tp_R rows x
+  // tp_KT k, k = this epilogue's feature index) of the GEMM that consumes it next - no pack pass in between
+  float* tp;
+  int tp_R, tp_KT, tp_ktiles;
 };
 constexpr int kTailCols = 16;   // coupling columns per logdet partial
 int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st);
+
+// The weights of EVERY stage packed as B operands in one launch (once per pass instead of once per GEMM).
+// Three layers per stage; layer l of stage s reads P + src_off[s * 3 + l] (rows x K, element (r, k) as in Pack with
+// the given ld / k_contig) and writes dst + s * stage_floats + dst_off[l], tiled for GEMM cfg[l].
+struct WeightPack {
+  int S;
+  const long long* src_off;     // device: [S * 3] float offsets into the flat parameter buffer
+  long long stage_floats;
+  long long dst_off[3];
+  int rows[3], K[3], ld[3], k_contig[3];
+  int TN[3], KT[3];
+  int tiles[3];                 // tiles per layer = ceil(rows / TN) * ceil(K / KT)
+};
+int pack_weights(const WeightPack& w, const float* P, float* dst, cudaStream_t st);
 int init();
 void configure();   // reads DPI_B200_TC_TN / _KT / _MH (call before make_gemm)
 
