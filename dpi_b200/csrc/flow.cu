@@ -353,6 +353,7 @@ void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
   a.oZT = bp.oZT; a.oYT = bp.oYT; a.oL1T = bp.oL1T; a.oL2T = bp.oL2T; a.oN1T = bp.oN1T; a.oN2T = bp.oN2T;
   a.oOT = bp.oOT; a.oST = bp.oST; a.oLDP = bp.oLDP; a.oGYT = bp.oGYT; a.oGPRET = bp.oGPRET; a.oGNT = bp.oGNT;
   a.oGP1T = bp.oGP1T; a.oGP2T = bp.oGP2T; a.oPART = bp.oPART; a.oRED = bp.oRED;
+  a.fin_lo = 0; a.fin_hi = h->S;
   a.ctrl = (unsigned*)workspace;
   a.W = (float*)((char*)workspace + kCtrlWords * sizeof(unsigned));
 }
@@ -495,8 +496,10 @@ int tc_forward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
 }
 
 // Backward of RealNVP.reverse: data gradients and weight gradients of the coupling nets on tcgen05.
-int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
-  const Program& prog = bp.tc_bwd[a.g_in ? 1 : 0];
+// Stages [lo, hi) in backward order (hi - 1 first); the full pass is [0, S). A partial range that does not end at
+// stage 0 finalises only its own stages' ActNorm gradients and leaves the input gradient to the last range.
+int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st, int lo, int hi) {
+  const Program& prog = bp.tc_bwd[(a.g_in && lo == 0) ? 1 : 0];
   const int D = h->D, Da = h->Da, Dout = h->Dout, H = h->H, S = h->S, B = bp.B;
   const long long LB = bp.ldb;
   a.ldp_tiles = bp.tc_ldp_tiles;
@@ -533,14 +536,16 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
   float* WPB = W + bp.oWPB;
   float* ED1 = W + bp.oED1;
   float* EDIN = W + bp.oEDIN;
-  if (emit) {
+  a.fin_lo = lo; a.fin_hi = hi;
+  if (emit && hi == S) {
     DPI_TRY(ftc::pack_weights(bp.wp_bwd, a.P, WPB, st));
     DPI_CUDA(cudaMemsetAsync(ED1, 0, ftc::a_pack_floats(bp.g_dg1) * sizeof(float), st));
     DPI_CUDA(cudaMemsetAsync(EDIN, 0, ftc::a_pack_floats(bp.g_dgin) * sizeof(float), st));
   }
-  int pi = 0;
-  DPI_TRY(launch_phase(prog, a, pi++, st));
-  for (int e = S - 1; e >= 0; --e) {
+  // program layout: [transpose] then per stage (S - 1 first) [B0, BatchNorm backward 2, BatchNorm backward 1], [final]
+  int pi = 1 + 3 * (S - hi);
+  if (hi == S) DPI_TRY(launch_phase(prog, a, 0, st));
+  for (int e = hi - 1; e >= lo; --e) {
     const StageTab& sg = h->stages[e];
     const float* wpb = WPB + (long long)e * bp.wp_bwd.stage_floats;
     const int* gmap = h->d_gmaps + (size_t)e * D;
@@ -551,7 +556,7 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     float* gyprev = W + bp.oGYT + (long long)((e - 1) & 1) * D * LB;
     cudaEvent_t* ev = side ? &h->ev[(size_t)4 * e] : nullptr;
     // B0 overwrites g_pre (and the chain then g_p2, g_p1): wait until the side stream has packed the previous stage's
-    if (side && e < S - 1) DPI_CUDA(cudaStreamWaitEvent(st, h->ev[(size_t)4 * (e + 1) + 3], 0));
+    if (side && e < hi - 1) DPI_CUDA(cudaStreamWaitEvent(st, h->ev[(size_t)4 * (e + 1) + 3], 0));
     DPI_TRY(launch_phase(prog, a, pi++, st));   // B0
     const bool fused_bn = B <= ftc::kEpiMaxM;   // BatchNorm + LeakyReLU backward inside the dgrad epilogue
     auto hid_epi = [&](int which) {
@@ -609,8 +614,8 @@ int tc_backward(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, cudaStream_t st) {
     if (emit) DPI_TRY(ftc::run(bp.g_dgin, EDIN, wpb + bp.wp_bwd.dst_off[0], tb.part, sc, st));
     else DPI_TRY(tc_gemm(bp.g_dgin, ftc::Pack{GP1, LB, 0, nullptr, B, H}, ftc::Pack{a.P + sg.p[P_W1], Da, 0, nullptr, Da, H}, sc, tb, st));
   }
-  if (side) DPI_TRY(join(h->ev[(size_t)4 * S]));
-  return launch_phase(prog, a, pi++, st);
+  if (side && hi > lo) DPI_TRY(join(h->ev[(size_t)4 * S]));
+  return launch_phase(prog, a, 1 + 3 * S, st);
 }
 
 }  // namespace
@@ -913,8 +918,46 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
   if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
-  if (bp->tc_ok) return tc_backward(h, *bp, a, (cudaStream_t)stream);
+  if (bp->tc_ok) return tc_backward(h, *bp, a, (cudaStream_t)stream, 0, h->S);
   return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
+}
+
+int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
+                            const float* g_out, const float* g_logdet, float* g_in, void* workspace,
+                            size_t workspace_bytes, int stage_lo, int stage_hi, dpi_stream_t stream) {
+  DPI_REQUIRE(h && params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward_range: null argument");
+  DPI_REQUIRE(0 <= stage_lo && stage_lo < stage_hi && stage_hi <= h->S, "dpi_flow_backward_range: bad stage range [%d, %d) of %d",
+              stage_lo, stage_hi, h->S);
+  if (stage_lo == 0 && stage_hi == h->S)
+    return dpi_flow_backward(h, batch, params, grads, in, g_out, g_logdet, g_in, workspace, workspace_bytes, stream);
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  int rc = get_plan(h, batch, &bp);
+  if (rc) return rc;
+  if (!bp->tc_ok) {
+    set_error("dpi_flow_backward_range: partial stage ranges need the tcgen05 path (batch >= %d); batch %d runs one kernel per pass",
+              h->tc_min_batch, batch);
+    return DPI_ERR_UNSUPPORTED;
+  }
+  const size_t need = kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
+  if (workspace_bytes < need) {
+    set_error("dpi_flow_backward_range: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DPI_ERR_WORKSPACE;
+  }
+  KArgs a{};
+  fill_args(h, *bp, a, workspace);
+  a.dir = 0; a.train = 1;
+  a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
+  a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
+  return tc_backward(h, *bp, a, (cudaStream_t)stream, stage_lo, stage_hi);
+}
+
+int dpi_flow_tc_active(dpi_flow_t h, int batch) {
+  if (!h || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  return bp->tc_ok;
 }
 
 }  // extern "C"

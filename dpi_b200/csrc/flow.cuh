@@ -74,6 +74,8 @@ struct KArgs {
   unsigned long long* tbuf;   // debug: per-phase globaltimer stamps of CTA 0 (start, work done), or nullptr
   int phase_begin, phase_end, persistent;
   int use_tc;                 // 1: tcgen05/TMEM tile core, 0: mma.sync tile core
+  int fin_lo, fin_hi;         // OP_BWD_FINAL: stages whose ActNorm gradients are finalised ([0, S) unless the backward
+                              // is run in stage ranges)
   int ldb;                    // row stride (floats) of the feature-major workspace matrices: B, or round_up4(B)
                               // for the small-batch kernel (every row 16-byte aligned)
 };

@@ -754,7 +754,7 @@ __device__ __noinline__ void op_bwd_final(const KArgs& a, float* sRed) {
   for (int m = threadIdx.x; m < a.B; m += kThreads) s += ldcg(a.g_ld + m);
   const float gld = block_sum(s, sRed);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int e = w; e < a.S; e += kThreads / 32) {
+  for (int e = a.fin_lo + w; e < a.fin_hi; e += kThreads / 32) {
     const float* red = a.W + a.oRED + (size_t)e * a.red_tiles * 2;
     float s1 = 0.f, s2 = 0.f;
     for (int t = lane; t < a.red_tiles; t += 32) { s1 += ldcg(red + 2 * t); s2 += ldcg(red + 2 * t + 1); }

@@ -79,11 +79,50 @@ class _FusedTrainer:
             _lib.check(-1, "dpi_flow_workspace_bytes")
         self.ws_flow = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.ws_opt = torch.zeros(self.lib.dpi_clip_adam_workspace_bytes(P), dtype=torch.uint8, device=dev)
+        # Data parallel on the tcgen05 path: run the flow backward in stage ranges and all-reduce each range's slice of
+        # the flat gradient (the backward visits the flow blocks in parameter order) while the next range runs.
+        self._buckets = self._plan_buckets()
         self.use_graph = use_graph
         self._prof = None
         self._graphs = None
         self._warm = 0
         self.launches_per_step = None
+
+    def _plan_buckets(self):
+        nb = int(os.environ.get("DPI_B200_BUCKETS", "4" if self.world > 1 else "0"))
+        if nb < 2 or not self.lib.dpi_flow_tc_active(self.handle, self.B):
+            return None
+        nf = self.flow.n_flow
+        per = -(-nf // min(nb, nf))
+        out = []
+        for i0 in range(0, nf, per):
+            i1 = min(i0 + per, nf)
+            lo = int(self.lib.dpi_flow_param_offset(self.handle, i0, 0))
+            hi = int(self.lib.dpi_flow_param_offset(self.handle, i1, 0)) if i1 < nf else self.P + 32
+            # blocks [i0, i1) = execution stages [2 (nf - i1), 2 (nf - i0)) of RealNVP.reverse
+            out.append((2 * (nf - i1), 2 * (nf - i0), lo, hi))
+        return out if len(out) > 1 else None
+
+    def _flow_backward(self, st):
+        lib = self.lib
+        if self._buckets is None:
+            _lib.check(lib.dpi_flow_backward(self.handle, self.B, self.params.data_ptr(), self.grads.data_ptr(),
+                                             self.z.data_ptr(), self.g_x.data_ptr(), self.g_det.data_ptr(), None,
+                                             self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_backward")
+            self._reduced = False
+            return
+        works = []
+        for s_lo, s_hi, f_lo, f_hi in self._buckets:
+            _lib.check(lib.dpi_flow_backward_range(self.handle, self.B, self.params.data_ptr(), self.grads.data_ptr(),
+                                                   self.z.data_ptr(), self.g_x.data_ptr(), self.g_det.data_ptr(), None,
+                                                   self.ws_flow.data_ptr(), self.ws_flow.numel(), s_lo, s_hi, st),
+                       "dpi_flow_backward_range")
+            if self.world > 1:
+                works.append(torch.distributed.all_reduce(self.grads_all[f_lo:f_hi], op=torch.distributed.ReduceOp.SUM,
+                                                          group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        self._reduced = True
 
     # -- subclass hooks -------------------------------------------------------------------------
     def _data_forward_backward(self, st):
@@ -119,12 +158,11 @@ class _FusedTrainer:
                                                self.g_img_data.data_ptr(), self.g_det.data_ptr(), self.g_x.data_ptr(),
                                                self.g_ls_partial.data_ptr(), st), "dpi_positivity_backward")
         self._mark("positivity_bwd")
-        _lib.check(lib.dpi_flow_backward(self.handle, B, self.params.data_ptr(), self.grads.data_ptr(),
-                                         self.z.data_ptr(), self.g_x.data_ptr(), self.g_det.data_ptr(), None,
-                                         self.ws_flow.data_ptr(), self.ws_flow.numel(), st), "dpi_flow_backward")
-        self._mark("flow_reverse_bwd")
+        # the log_scale gradient rides in the tail of the gradient buffer: finish it before the last range is reduced
         _lib.check(lib.dpi_reduce_sum(B, self.g_ls_partial.data_ptr(), self.g_ls.data_ptr(), None, st),
                    "dpi_reduce_sum")
+        self._flow_backward(st)
+        self._mark("flow_reverse_bwd")
         self._terms(st)
         self._mark("loss_terms")
 
@@ -148,7 +186,7 @@ class _FusedTrainer:
         self._mark("grad_allreduce")
 
     def _allreduce_impl(self):
-        if self.world > 1:
+        if self.world > 1 and not getattr(self, "_reduced", False):
             from dpi_b200.dist import allreduce_sum_
             allreduce_sum_(self.grads_all, self.pg)
 

@@ -97,6 +97,17 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
                       const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                       size_t workspace_bytes, dpi_stream_t stream);
 
+/* The same backward restricted to the execution stages [stage_lo, stage_hi) (stage S - 1 = the flow block applied last
+ * in RealNVP.reverse runs first; S = 2 n_flow). Calling it for consecutive ranges from [.., S) down to [0, ..) equals
+ * one dpi_flow_backward; after a range returns (stream order) the gradients of its stages - contiguous in `grads`
+ * because the backward visits the flow blocks in parameter order - are final, so a data-parallel caller can
+ * all-reduce them while the next range runs. Only the tcgen05 path (dpi_flow_tc_active != 0) supports partial ranges. */
+int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
+                            const float* g_out, const float* g_logdet, float* g_in, void* workspace,
+                            size_t workspace_bytes, int stage_lo, int stage_hi, dpi_stream_t stream);
+/* 1 if a pass at this batch size runs on the tcgen05 path (one launch per operation), 0 if one kernel per pass. */
+int dpi_flow_tc_active(dpi_flow_t h, int batch);
+
 /* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
  * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
  * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory

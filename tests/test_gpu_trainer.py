@@ -141,3 +141,39 @@ def test_full_size_step_vs_oracle(kind):
         assert float((up_mine - up_ref).norm() / up_ref.norm().clamp_min(1e-30)) < 0.05, k
         assert rel_err(mine[k], sd[k].detach()) < 5 * RTOL, k
     assert abs(tr.log_scale_value() - float(ls)) < 1e-6
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_bucketed_backward_equals_single_pass(use_graph, monkeypatch):
+    """Data parallel on the tcgen05 path runs the flow backward in stage ranges (dpi_flow_backward_range) so that each
+    range's slice of the flat gradient can be all-reduced while the next range runs. With one rank the all-reduce
+    drops out and the trajectory must be bit-identical to the single-pass backward (same kernels, same order)."""
+    from dpi_b200 import _lib
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    from dpi_b200.trainer import InterferometryTrainer
+    from dpi_b200.workloads import interferometry_workload
+    npix, NF, B = 8, 5, 128
+    wl = interferometry_workload(npix=npix, seed=3, n_stations=5, n_scans=8)
+    sd = O.init_state(npix * npix, NF, seed=6, randomize=True)
+    torch.manual_seed(2)
+    zs = [torch.randn(B, npix * npix).cuda() for _ in range(4)]
+
+    def run(buckets):
+        monkeypatch.setenv("DPI_B200_BUCKETS", str(buckets))
+        flow = RealNVP(npix * npix, NF)
+        flow.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+        tr = InterferometryTrainer(flow, wl, B, lr=1e-4, clip=1e-3, device="cuda", use_graph=use_graph)
+        assert _lib.load().dpi_flow_tc_active(tr.handle, B) == 1
+        assert (tr._buckets is not None) == (buckets >= 2)
+        terms = [tr.step(z).clone() for z in zs]
+        torch.cuda.synchronize()
+        return tr, terms
+
+    t0, terms0 = run(0)
+    t3, terms3 = run(3)
+    assert len(t3._buckets) == 3 and t3._buckets[0][1] == 2 * NF and t3._buckets[-1][0] == 0
+    assert t3._buckets[-1][3] == t3.P + 32 and t3._buckets[0][2] == 0
+    for a, b in zip(terms0, terms3):
+        assert torch.equal(a, b)
+    assert torch.equal(t0.params, t3.params) and torch.equal(t0.grads_all, t3.grads_all)
+    assert torch.equal(t0.log_scale, t3.log_scale)
