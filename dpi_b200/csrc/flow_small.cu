@@ -1310,6 +1310,7 @@ void small_plan_pass_w(const dpi_flow_s* h, const BatchPlan& bp, SmallPlan& sp, 
   const int NC = sp.NC;
   const long long wg3 = ((long long)Dout + 15) / 16 * ((H + 63) / 64);
   sp.wgv = wg3 > 4LL * NC ? 1 : 0;
+  if (const char* e = getenv("DPI_B200_SMALL_WGV")) sp.wgv = atoi(e) ? 1 : 0;   // A/B switch for the tile variant
   sp.ldp_tiles = std::max(sp.f3.n_tiles, (NC + h->S - 1) / h->S);   // workspace rows: one logdet partial per CTA
   sp.red_tiles = (Db + 7) / 8;
   const ActPlan* all[6] = {&sp.f1, &sp.f2, &sp.f3, &sp.dg2, &sp.dg1, &sp.dgin};
