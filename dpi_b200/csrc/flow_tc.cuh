@@ -6,9 +6,9 @@
 //                                      accumulation in TMEM): fp32-level accuracy, ~2^-21 per product
 //
 // Both operands reach shared memory as pre-split, pre-tiled K-major tiles (canonical no-swizzle UMMA layout:
-// core matrix 8 rows x 16 B, LBO 128 B, SBO 1024 B), one cp.async.bulk per tile and stage, mbarrier expect_tx
-// ring; one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M 128, N 64, K 8); the accumulator is read
-// back with tcgen05.ld 32x32b. The flow keeps its activations FEATURE-major (X^T[feature][sample], see flow.cuh),
+// core matrix 8 rows x 16 B, LBO 128 B, SBO = 32 KT B), one cp.async.bulk per tile and stage, mbarrier expect_tx
+// ring; one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M 128, N = TN in {64, 128, 256}, K 8); the
+// accumulator(s) are read back with tcgen05.ld 32x32b. The flow keeps its activations FEATURE-major (X^T[feature][sample], see flow.cuh),
 // so the pack pre-pass is also where the layout turns K-major, where the fixed permutations of the flow are
 // applied (a row map on the feature index) and where fp32 is split into TF32 hi / lo.
 //
@@ -17,8 +17,10 @@
 //   wgrad    : gW[i][j] = sum_m G^T[i][m] X^T[j][m]: both operands are already K-major (K = batch)
 //
 // Split-K partial tiles are summed in split order by the epilogue kernel (deterministic), which also applies
-// the per-layer epilogue (bias + LeakyReLU [+ eval-mode BatchNorm], row-mapped scatter with the ActNorm
-// pass-through term, or the row-major weight-gradient store).
+// the per-layer epilogue: bias + LeakyReLU + BatchNorm (batch or running statistics), BatchNorm + LeakyReLU
+// backward with the gamma / beta / bias gradients, the coupling tail (ZeroFC scale, tanh-exp affine, ActNorm,
+// logdet partials), the row-mapped scatter with the ActNorm pass-through term, or the row-major weight-gradient
+// store. Host-side planning (make_gemm) needs no device and is exposed as dpi_flow_tc_plan for the CPU tests.
 #pragma once
 #include "common.cuh"
 
