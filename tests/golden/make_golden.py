@@ -295,6 +295,57 @@ def dpix_case(name, npix, NF, B, seed, alpha, n_stations=5, n_scans=8, steps=3):
     print(name, "ok", hist[-1])
 
 
+def glow_case(name, npix, n_flow, n_block, B, seed):
+    """the reference Glow (generative_model/glow_model.py) in reverse (training direction) with
+    gradients, forward, and eval mode. The 512 x 512 1x1-conv weights are set from a closed form shared with the
+    test (oracle.glow_oracle.formula_weight) instead of being stored."""
+    from oracle import glow_oracle as G
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    ref = R["glow"].Glow(1, n_flow, n_block, affine=True, conv_lu=True)
+    with torch.no_grad():
+        for pname, p in ref.named_parameters():
+            if ".net.6." in pname or ".prior." in pname:
+                p.normal_(0, 0.05)
+            elif pname.endswith("actnorm.loc"):
+                p.normal_(0, 0.2)
+            elif pname.endswith("actnorm.scale_inv"):
+                p.copy_(0.7 + 0.6 * torch.rand_like(p))
+        for bname, b in ref.named_buffers():
+            if bname.endswith("initialized"):
+                b.fill_(1)
+        big = G.big_weight_keys(ref.state_dict().keys())
+        params = dict(ref.named_parameters())
+        for tag, k in enumerate(big):
+            params[k].copy_(G.formula_weight(params[k].shape, tag))
+    sd0 = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    out = dict(npix=npix, n_flow=n_flow, n_block=n_block, B=B)
+    out.update({("sd." + k): v.numpy().copy() for k, v in sd0.items() if k not in big})
+    shapes = R["glow"].calc_z_shapes(1, npix, n_flow, n_block)
+    zs = [torch.randn(B, *s) for s in shapes]
+    zr = [z.clone().requires_grad_(True) for z in zs]
+    x, ld = ref.reverse(zr)
+    c = torch.randn_like(x)
+    ((x * c).sum() + ld.sum()).backward()
+    out.update(x_rev=x.detach().numpy(), ld_rev=ld.detach().numpy(), c=c.numpy())
+    for i, (z, zz) in enumerate(zip(zs, zr)):
+        out[f"z{i}"] = z.numpy()
+        out[f"g_z{i}"] = zz.grad.numpy()
+    for k, v in ref.state_dict().items():
+        if "running" in k:
+            out["after." + k] = v.numpy().copy()
+    with torch.no_grad():
+        lp, ldf, zf = ref.forward(x.detach())
+        out.update(logp_fwd=lp.numpy(), ld_fwd=ldf.numpy())
+        for i, z in enumerate(zf):
+            out[f"zf{i}"] = z.numpy()
+        ref.eval()
+        xe, lde = ref.reverse(zs)
+        out.update(x_rev_eval=xe.numpy(), ld_rev_eval=lde.numpy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", sum(v.nbytes for v in out.values() if hasattr(v, "nbytes")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     flow_case("flow_even", D=20, NF=2, B=6, seqfrac=1, seed=11)          # H=10, one row tile
@@ -308,3 +359,4 @@ if __name__ == "__main__":
     mri_case("mri_small", npix=8, NF=2, B=6, seed=5)
     dpix_case("dpix_small", npix=16, NF=2, B=12, seed=9, alpha=0.95)
     dpix_case("dpix_kl", npix=16, NF=2, B=12, seed=10, alpha=1.0)
+    glow_case("glow_small", npix=8, n_flow=1, n_block=2, B=3, seed=21)

@@ -166,3 +166,32 @@ def test_dpix_renderer_and_trajectory_match_reference_run(name):
         assert np.allclose(got, g["hist"][k], rtol=2e-4, atol=1e-6), (k, got, g["hist"][k])
     for k, v in split_sd(g, "sd_final.").items():
         assert rel_err(sd[k].detach().float(), v.float()) < 1e-4, k
+
+
+def test_glow_oracle_matches_reference_fixture():
+    """oracle/glow_oracle.py against outputs of the unmodified reference Glow (reverse with input
+    gradients and BatchNorm running statistics, forward, eval mode). Algorithm pinned; the CUDA path is not built yet."""
+    from oracle import glow_oracle as G
+    g = load_golden("glow_small")
+    sd = split_sd(g)
+    n_block = int(g["n_block"])
+    # the 512 x 512 1x1-conv weights are regenerated from the closed form the fixture script used
+    flows = sorted({k[: k.index("coupling.")] for k in sd if "coupling.net.0.weight" in k})
+    for tag, k in enumerate(G.big_weight_keys([f + "coupling.net.3.weight" for f in flows])):
+        sd[k] = G.formula_weight((G.FILTER, G.FILTER, 1, 1), tag)
+    zs = [torch.from_numpy(g[f"z{i}"]).requires_grad_(True) for i in range(n_block)]
+    x, ld = G.glow_reverse(sd, zs, train=True)
+    assert rel_err(x, g["x_rev"]) < 1e-6 and rel_err(ld, g["ld_rev"]) < 1e-6
+    ((x * torch.from_numpy(g["c"])).sum() + ld.sum()).backward()
+    for i, z in enumerate(zs):
+        assert rel_err(z.grad, g[f"g_z{i}"]) < 1e-5
+    for k, v in g.items():
+        if k.startswith("after."):
+            assert rel_err(sd[k[len("after."):]].float(), v) < 1e-6, k
+    with torch.no_grad():
+        lp, ldf, zf = G.glow_forward(sd, x.detach(), train=True)
+        assert rel_err(lp, g["logp_fwd"]) < 1e-6 and rel_err(ldf, g["ld_fwd"]) < 1e-6
+        for i, z in enumerate(zf):
+            assert rel_err(z, g[f"zf{i}"]) < 1e-5
+        xe, lde = G.glow_reverse(sd, [z.detach() for z in zs], train=False)
+        assert rel_err(xe, g["x_rev_eval"]) < 1e-6 and rel_err(lde, g["ld_rev_eval"]) < 1e-6

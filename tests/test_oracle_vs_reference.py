@@ -114,3 +114,78 @@ def test_crescent_renderer_matches_reference_class(R, npix, B, ng):
     io = O.crescent_render(po, npix, 160.0, ng)
     (io * c).sum().backward()
     assert rel_err(io, ir) < 1e-6 and rel_err(po.grad, pr.grad) < 1e-5
+
+
+def _randomised_reference_glow(R, n_flow, n_block, seed):
+    """A reference Glow whose zero-initialised pieces (ZeroConv2d, ActNorm) are made non-trivial, marked initialised."""
+    torch.manual_seed(seed)
+    np.random.seed(seed)                       # InvConv2dLU draws its matrix with numpy (:185)
+    ref = R["glow"].Glow(1, n_flow, n_block, affine=True, conv_lu=True)
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if ".net.6." in name or ".prior." in name:
+                p.normal_(0, 0.05)
+            elif name.endswith("actnorm.loc"):
+                p.normal_(0, 0.2)
+            elif name.endswith("actnorm.scale_inv"):
+                p.copy_(0.7 + 0.6 * torch.rand_like(p))
+        for name, b in ref.named_buffers():
+            if name.endswith("initialized"):
+                b.fill_(1)
+    return ref
+
+
+@pytest.mark.parametrize("npix,n_flow,n_block,B", [(8, 2, 2, 5), (16, 1, 3, 3)])
+def test_glow_oracle_bit_identical_to_reference(R, npix, n_flow, n_block, B):
+    """the restatement in oracle/glow_oracle.py against the unmodified reference class -
+    reverse (the training direction) and forward, train and eval mode, running statistics, input gradients."""
+    from oracle import glow_oracle as G
+    ref = _randomised_reference_glow(R, n_flow, n_block, seed=3)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    shapes = G.calc_z_shapes(1, npix, n_flow, n_block)
+    assert shapes == R["glow"].calc_z_shapes(1, npix, n_flow, n_block)
+    torch.manual_seed(1)
+    zs = [torch.randn(B, *s) for s in shapes]
+    zr = [z.clone().requires_grad_(True) for z in zs]
+    zo = [z.clone().requires_grad_(True) for z in zs]
+    xr, lr = ref.reverse(zr)
+    xo, lo = G.glow_reverse(sd, zo, train=True)
+    assert xr.shape == (B, 1, npix, npix)
+    assert torch.equal(xr, xo) and torch.equal(lr, lo)
+    c = torch.randn_like(xr)
+    ((xr * c).sum() + lr.sum()).backward()
+    ((xo * c).sum() + lo.sum()).backward()
+    for a, b in zip(zr, zo):
+        assert torch.equal(a.grad, b.grad)
+    for k, v in ref.state_dict().items():           # BatchNorm running statistics moved identically
+        assert torch.equal(v, sd[k]), k
+    with torch.no_grad():
+        pr, dr, zl = ref.forward(xr.detach())
+        po, do, zlo = G.glow_forward(sd, xr.detach(), train=True)
+        assert torch.equal(pr, po) and torch.equal(dr, do)
+        for a, b in zip(zl, zlo):
+            assert torch.equal(a, b)
+        ref.eval()
+        xe, le = ref.reverse(zs)
+        xeo, leo = G.glow_reverse(sd, zs, train=False)
+        assert torch.equal(xe, xeo) and torch.equal(le, leo)
+        # invertibility in eval mode (the BatchNorm statistics are then fixed): forward(reverse(z)) returns z
+        _, ldf, zb = ref.forward(xe)
+        for a, b in zip(zs, zb):
+            assert float((a - b).abs().max()) < 2e-3
+        assert float((ldf + le).abs().max()) < 1e-2 * max(1.0, float(le.abs().max()))
+
+
+def test_glow_oracle_data_dependent_actnorm_init(R):
+    """First forward call of a fresh ActNorm: loc = -mean_c, scale_inv = std_c + 1e-6 (glow_model.py:91-111)."""
+    from oracle import glow_oracle as G
+    an = R["glow"].ActNorm(6)
+    sd = {k: v.detach().clone() for k, v in an.state_dict().items()}
+    torch.manual_seed(2)
+    x = torch.randn(7, 6, 4, 4) * 1.3 + 0.4
+    yr, lr = an(x)
+    G.actnorm_initialize(sd, "", x, inv_init=False)
+    yo, lo = G.actnorm_forward(sd, "", x)
+    assert torch.equal(yr, yo) and torch.equal(lr, lo)
+    for k, v in an.state_dict().items():
+        assert torch.equal(v, sd[k]), k
