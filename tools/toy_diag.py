@@ -5,7 +5,7 @@ from conftest import rel_err
 from oracle import dpi_oracle as O
 from dpi_b200.generative_model.realnvpfc_model import RealNVP
 D, NF, B, seqfrac = int(os.environ.get("TD", 2)), int(os.environ.get("TNF", 16)), int(os.environ.get("TB", 512)), 1 / 128
-if D != 2: seqfrac = 1
+if D != 2: seqfrac = float(os.environ.get("TSEQ", 1))
 sd = O.init_state(D, NF, seqfrac=seqfrac, seed=31, randomize=True)
 torch.manual_seed(8)
 z = torch.randn(B, D)
@@ -35,6 +35,8 @@ for blk in (NF - 1, 0):
     for k, gv in views.items():
         if k.startswith(f"blocks.{blk}.") and ("coupling2" in k or "actnorm2" in k):
             print("   %.3e  %-44s |ref|max %.3e" % (rel_err(gv, sdo[k].grad), k, float(sdo[k].grad.abs().max())))
+worst = max((rel_err(gv, sdo[k].grad), k) for k, gv in views.items() if "actnorm" not in k)
+print("worst non-actnorm", worst)
 k = f"blocks.{NF-1}.coupling2.net.0.bias"
 print(k, views[k][:6].cpu().tolist(), sdo[k].grad[:6].tolist())
 k = f"blocks.{NF-1}.actnorm2.loc"
