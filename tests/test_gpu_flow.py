@@ -259,8 +259,9 @@ def test_toy_2d_script_loop_body_at_its_own_sizes():
     # Gradients: the tensor-core tolerance, stated separately (BASELINE north_star). This net is the worst case for it:
     # 128 hidden units feed ONE input feature, so the data gradient of every stage is a cancelling 128-term sum, the
     # randomised weights make the 32-stage chain ill-conditioned, and 3xTF32 carries ~2^-21 per product against 2^-24
-    # for an fp32 FMA (the mma.sync and the tcgen05 path deviate from the CPU by the same 2.0e-3: the split error is a
-    # deterministic function of the operands, identical in both kernels). The stage the
+    # for an fp32 FMA. tools/tf32_emulation.py reproduces the 2.0e-3 (which the mma.sync and the tcgen05 path share) on
+    # the CPU with an fp32 accumulator that rounds toward zero, and 2e-6 with exact accumulation: it is the truncating
+    # accumulation of the tensor cores, a bias that the cancelling sums amplify. The stage the
     # backward visits first is at fp32 level (1e-6) and the error grows with depth to ~2e-3 at the last one; the same
     # depth at ndim 8 / H 4 stays at 1e-6 on every path (tools/toy_diag.py). Batches <= 64 run plain fp32 FFMA.
     TC_GRAD_TOL = 5e-3
