@@ -46,6 +46,34 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def gradient_buckets(n_flow: int, block_offsets, total: int, n_buckets: int):
+    """Split the flat gradient [flow blocks in parameter order | tail] into `n_buckets` contiguous slices of whole flow
+    blocks, in the order the backward pass finishes them. RealNVP.reverse applies block n_flow-1 first, so its
+    backward reaches block 0 first: bucket k covers blocks [i0, i1) = execution stages [2 (n_flow - i1), 2 (n_flow - i0))
+    and the flat range [block_offsets[i0], block_offsets[i1]) (the last bucket runs to `total`, which includes the
+    log_scale tail). Returns [(stage_lo, stage_hi, flat_lo, flat_hi)], or None when fewer than two buckets result."""
+    nb = min(int(n_buckets), int(n_flow))
+    if nb < 2:
+        return None
+    per = -(-n_flow // nb)
+    out = []
+    for i0 in range(0, n_flow, per):
+        i1 = min(i0 + per, n_flow)
+        lo = int(block_offsets[i0])
+        hi = int(block_offsets[i1]) if i1 < n_flow else int(total)
+        out.append((2 * (n_flow - i1), 2 * (n_flow - i0), lo, hi))
+    return out if len(out) > 1 else None
+
+
+def allreduce_buckets_(flat: torch.Tensor, buckets, group=None):
+    """Asynchronous sum-all-reduce of each bucket's slice (issue order = bucket order); returns the work handles."""
+    works = []
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for _, _, lo, hi in buckets:
+            works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
+
+
 def replicas_max_divergence(flat: torch.Tensor, group=None) -> float:
     """max |flat - rank0's flat| over all ranks (0.0 when the replicas are in sync)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -92,16 +92,10 @@ class _FusedTrainer:
         nb = int(os.environ.get("DPI_B200_BUCKETS", "4" if self.world > 1 else "0"))
         if nb < 2 or not self.lib.dpi_flow_tc_active(self.handle, self.B):
             return None
+        from dpi_b200.dist import gradient_buckets
         nf = self.flow.n_flow
-        per = -(-nf // min(nb, nf))
-        out = []
-        for i0 in range(0, nf, per):
-            i1 = min(i0 + per, nf)
-            lo = int(self.lib.dpi_flow_param_offset(self.handle, i0, 0))
-            hi = int(self.lib.dpi_flow_param_offset(self.handle, i1, 0)) if i1 < nf else self.P + 32
-            # blocks [i0, i1) = execution stages [2 (nf - i1), 2 (nf - i0)) of RealNVP.reverse
-            out.append((2 * (nf - i1), 2 * (nf - i0), lo, hi))
-        return out if len(out) > 1 else None
+        offs = [int(self.lib.dpi_flow_param_offset(self.handle, i, 0)) for i in range(nf)]
+        return gradient_buckets(nf, offs, self.P + 32, nb)
 
     def _flow_backward(self, st):
         lib = self.lib
@@ -118,8 +112,8 @@ class _FusedTrainer:
                                                    self.ws_flow.data_ptr(), self.ws_flow.numel(), s_lo, s_hi, st),
                        "dpi_flow_backward_range")
             if self.world > 1:
-                works.append(torch.distributed.all_reduce(self.grads_all[f_lo:f_hi], op=torch.distributed.ReduceOp.SUM,
-                                                          group=self.pg, async_op=True))
+                from dpi_b200.dist import allreduce_buckets_
+                works += allreduce_buckets_(self.grads_all, [(s_lo, s_hi, f_lo, f_hi)], self.pg)
         for w in works:
             w.wait()
         self._reduced = True

@@ -51,6 +51,16 @@ def _worker(rank, world, port, out):
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     O.adam_update(p, gavg * coef, m, v, 1, 1e-4)
     assert ddist.replicas_max_divergence(p) == 0.0           # replicas stay bit-identical
+    # bucketed variant (the tcgen05 trainer path): whole flow blocks in the order the backward finishes them, each slice
+    # reduced asynchronously - must equal the single all-reduce bit for bit
+    offs = [int(model._index[f"blocks.{i}.actnorm.loc"][1]) for i in range(NF)]
+    total = flat_g.numel()
+    buckets = ddist.gradient_buckets(NF, offs, total, 2)
+    assert buckets == [(2, 4, 0, offs[1]), (0, 2, offs[1], total)]
+    flat_b = ddist.pack_named(model, _shard_grads(sd, z, cx, cl))
+    for w in ddist.allreduce_buckets_(flat_b, buckets):
+        w.wait()
+    assert torch.equal(flat_b, flat_g)
     lo, hi = ddist.shard_range(10, rank, world)
     assert (hi - lo) == 5 and lo == 5 * rank
     if rank == 0:
@@ -81,3 +91,15 @@ def test_two_rank_gradient_average_matches_single_process(tmp_path):
     named = dict(model.named_grad_views(got["gavg"]))
     assert np.isclose(float(got["norm"]), float(torch.sqrt(sum((t.double() ** 2).sum() for t in named.values()))),
                       rtol=1e-6)
+
+
+def test_gradient_buckets_cover_the_buffer_in_backward_order():
+    from dpi_b200.dist import gradient_buckets
+    offs = [0, 100, 250, 400, 900]                      # 5 flow blocks, tail up to 1000
+    b = gradient_buckets(5, offs, 1000, 4)              # ceil(5/4) = 2 blocks per bucket -> 3 buckets
+    assert b == [(6, 10, 0, 250), (2, 6, 250, 900), (0, 2, 900, 1000)]
+    assert b[0][1] == 10 and b[-1][0] == 0              # stages run from S = 10 down to 0 without gaps
+    assert all(x[0] == y[1] for x, y in zip(b[:-1], b[1:]))
+    assert all(x[3] == y[2] for x, y in zip(b[:-1], b[1:]))   # flat slices tile [0, total)
+    assert gradient_buckets(5, offs, 1000, 1) is None and gradient_buckets(1, [0], 10, 4) is None
+    assert gradient_buckets(3, [0, 10, 20], 30, 8) == [(4, 6, 0, 10), (2, 4, 10, 20), (0, 2, 20, 30)]
