@@ -33,6 +33,8 @@ PROTOTYPES = {
     "dpi_flow_workspace_bytes": (sz, [vp, i32]),
     "dpi_flow_ws_offset": (i64, [vp, i32, i32, i32]),
     "dpi_flow_tc_plan": (i32, [i32, i32, i32, i32, vp]),
+    "dpi_conv2d_fm_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "dpi_conv2d_fm_forward": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward_range": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, i32, i32, vp]),

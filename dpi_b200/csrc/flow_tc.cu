@@ -95,7 +95,15 @@ __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, f
       float v = 0.f;
       if (row < p.rows && k < p.K) {
         const int kr = p.map ? __ldg(p.map + k) : k;
-        v = __ldg(p.src + (long long)kr * p.ld + row);
+        if (p.im_h > 0) {   // 3 x 3 window gather with padding
+          const int c = k / 9, t9 = k - 9 * c, dy = t9 / 3 - 1, dx = t9 - 3 * (t9 / 3) - 1;
+          const int hw = p.im_h * p.im_w, b = row / hw, rem = row - b * hw, y = rem / p.im_w, x = rem - y * p.im_w;
+          const int yy = y + dy, xx = x + dx;
+          v = (yy >= 0 && yy < p.im_h && xx >= 0 && xx < p.im_w)
+                  ? __ldg(p.src + (long long)c * p.ld + (long long)b * hw + yy * p.im_w + xx) : p.pad;
+        } else {
+          v = __ldg(p.src + (long long)kr * p.ld + row);
+        }
       }
       s[kk][r] = v;
     }
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(256) packw_kernel(WeightPack w, const float* _
   int t = blockIdx.x - stage * per_stage, l = 0;
   if (t >= w.tiles[0]) { t -= w.tiles[0]; l = 1; }
   if (l == 1 && t >= w.tiles[1]) { t -= w.tiles[1]; l = 2; }
-  Pack p;
+  Pack p{};
   p.src = P + __ldg(w.src_off + stage * 3 + l);
   p.ld = w.ld[l]; p.k_contig = w.k_contig[l]; p.map = nullptr; p.rows = w.rows[l]; p.K = w.K[l];
   const int vec = ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
@@ -331,6 +339,16 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
     for (int m = tid * V; m < g.M; m += 256 * V) {
       float c[V];
       fetchv<V>(src(m), g.splits, sstride, c);
+      stv<V>(e.out + orow + m, c);
+    }
+  } else if constexpr (MODE == EPI_T_BIAS) {
+    const float b = e.bias ? __ldg(e.bias + n) : 0.f;
+    const float sc = e.scale ? expf(3.f * __ldg(e.scale + n)) : 1.f;
+    for (int m = tid * V; m < g.M; m += 256 * V) {
+      float c[V];
+      fetchv<V>(src(m), g.splits, sstride, c);
+#pragma unroll
+      for (int q = 0; q < V; ++q) c[q] = (c[q] + b) * sc;
       stv<V>(e.out + orow + m, c);
     }
   } else if constexpr (MODE == EPI_T_SCATTER) {
@@ -601,6 +619,7 @@ void configure() {
 }
 
 static int pack_vec(const Pack& p) {
+  if (p.im_h > 0) return 0;   // window gathers are scalar
   // 16-byte loads need an aligned base, a row stride that keeps rows aligned, and the contiguous extent a multiple of 4
   return ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0 && (p.ld & 3) == 0 && ((p.k_contig ? p.K : p.rows) & 3) == 0) ? 1 : 0;
 }
@@ -664,6 +683,7 @@ int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, co
   switch (e.mode) {
     case EPI_T_RAW: DPI_EPI(EPI_T_RAW, 1); break;
     case EPI_T_SCATTER: DPI_EPI(EPI_T_SCATTER, 1); break;
+    case EPI_T_BIAS: DPI_EPI(EPI_T_BIAS, 1); break;
     case EPI_ROWMAJOR: DPI_EPI(EPI_ROWMAJOR, 1); break;
     case EPI_T_HID:
       if (g.M <= 1024) DPI_EPI(EPI_T_HID, 1); else DPI_EPI(EPI_T_HID, 4);

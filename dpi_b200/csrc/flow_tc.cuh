@@ -48,6 +48,11 @@ struct Pack {
   int k_contig;
   const int* map;
   int rows, K;
+  // im2col (k_contig must be 0, map unused): src is a feature-major image stack [channel][b * h * w] with row stride
+  // ld; r = position (b, y, x), k = (channel, dy, dx) of a 3 x 3 window with zero-based taps: element = src[channel]
+  // [b, y + dy - 1, x + dx - 1], or `pad` outside the image (glow_model.py ZeroConv2d pads with ONES, :247)
+  int im_h, im_w;      // 0: plain operand
+  float pad;
 };
 // packs A ((MH x 128)-row tiles) and B (TN-row tiles) of one GEMM in one launch
 int pack2(const Gemm& g, const Pack& pa, float* dst_a, const Pack& pb, float* dst_b, cudaStream_t st);
@@ -60,6 +65,7 @@ enum EpiMode {
   EPI_T_BNBWD,     // out[n * ldo + m] = LeakyReLU'(l) * BatchNorm-backward(c) (bn_mode 1) or LeakyReLU'(l) * c (bn_mode 0),
                    // plus the gradients of gamma / beta / the Linear bias of that feature row
   EPI_ROWMAJOR,    // out[m * ldo + n] = c
+  EPI_T_BIAS,      // out[n * ldo + m] = (c + bias[n]) * exp(3 * scale[n])   (bias / scale may be null): conv + ZeroConv2d scale
   EPI_T_TAIL       // ZeroFC bias / exp(3 scale), tanh-exp affine coupling, ActNorm, logdet partials (AffineCoupling
                    // .reverse / .forward, realnvpfc_model.py:240-249 / :222-231) on the raw ZeroFC GEMM result
 };

@@ -108,6 +108,16 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
 /* 1 if a pass at this batch size runs on the tcgen05 path (one launch per operation), 0 if one kernel per pass. */
 int dpi_flow_tc_active(dpi_flow_t h, int batch);
 
+/* Glow building block (generative_model/glow_model.py:260-268, ZeroConv2d :238-251), forward only: a k x k
+ * convolution (k = 1, or k = 3 with one pixel of padding filled with pad_value: 0 for nn.Conv2d(padding=1), 1 for
+ * ZeroConv2d) over a FEATURE-major image stack x [c_in][ldx] (position = b * h * w + y * w + x), weight
+ * [c_out][c_in][k][k] (the nn.Conv2d layout), y[c][pos] = (conv + bias[c]) * exp(3 * scale[c]); bias and scale may be
+ * NULL. One tcgen05 GEMM (3xTF32) with the window gather in the operand pack. */
+size_t dpi_conv2d_fm_workspace_bytes(int batch, int h, int w, int c_in, int c_out, int ksize);
+int dpi_conv2d_fm_forward(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x,
+                          int64_t ldx, const float* weight, const float* bias, const float* scale, float* y, int64_t ldy,
+                          void* workspace, size_t workspace_bytes, dpi_stream_t stream);
+
 /* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
  * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
  * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory
