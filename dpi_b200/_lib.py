@@ -35,6 +35,14 @@ PROTOTYPES = {
     "dpi_flow_tc_plan": (i32, [i32, i32, i32, i32, vp]),
     "dpi_conv2d_fm_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "dpi_conv2d_fm_forward": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]),
+    "dpi_conv2d_fm_lrelu": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, vp, f32, vp, i64, vp, sz, vp]),
+    "dpi_conv2d_fm_affine": (i32, [i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]),
+    "dpi_glow_bn_rows": (i32, [i32, i64, i64, vp, vp, vp, vp, vp, i32, f32, vp, vp]),
+    "dpi_glow_lu_inverse": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dpi_glow_affine_reverse": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp]),
+    "dpi_glow_prior_sample": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp]),
+    "dpi_glow_unsqueeze": (i32, [i32, i32, i32, i32, vp, vp, vp]),
+    "dpi_glow_logdet_scalar": (i32, [i32, i32, i32, vp, f32, vp, f32, vp, vp]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward_range": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, i32, i32, vp]),

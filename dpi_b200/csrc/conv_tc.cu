@@ -20,17 +20,16 @@ size_t dpi_conv2d_fm_workspace_bytes(int batch, int h, int w, int c_in, int c_ou
   return (align256(ftc::a_pack_floats(g)) + align256(ftc::b_pack_floats(g)) + align256(ftc::part_floats(g))) * sizeof(float) + 1024;
 }
 
-int dpi_conv2d_fm_forward(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x,
-                          int64_t ldx, const float* weight, const float* bias, const float* scale, float* y, int64_t ldy,
-                          void* workspace, size_t workspace_bytes, dpi_stream_t stream) {
-  DPI_REQUIRE(x && weight && y && workspace, "dpi_conv2d_fm_forward: null argument");
-  DPI_REQUIRE(batch >= 1 && h >= 1 && w >= 1 && c_in >= 1 && c_out >= 1, "dpi_conv2d_fm_forward: bad shape");
-  DPI_REQUIRE(ksize == 1 || ksize == 3, "dpi_conv2d_fm_forward: kernel size must be 1 or 3 (got %d)", ksize);
+static int conv_run(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x, int64_t ldx,
+                    const float* weight, ftc::Epi e, void* workspace, size_t workspace_bytes, dpi_stream_t stream) {
+  DPI_REQUIRE(x && weight && e.out && workspace, "dpi_conv2d_fm: null argument");
+  DPI_REQUIRE(batch >= 1 && h >= 1 && w >= 1 && c_in >= 1 && c_out >= 1, "dpi_conv2d_fm: bad shape");
+  DPI_REQUIRE(ksize == 1 || ksize == 3, "dpi_conv2d_fm: kernel size must be 1 or 3 (got %d)", ksize);
   const long long M = (long long)batch * h * w;
-  DPI_REQUIRE(M < (1LL << 30) && ldx >= M && ldy >= M, "dpi_conv2d_fm_forward: bad row stride / too many positions");
+  DPI_REQUIRE(M < (1LL << 30) && ldx >= M && e.ldo >= M, "dpi_conv2d_fm: bad row stride / too many positions");
   const size_t need = dpi_conv2d_fm_workspace_bytes(batch, h, w, c_in, c_out, ksize);
   if (workspace_bytes < need) {
-    set_error("dpi_conv2d_fm_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+    set_error("dpi_conv2d_fm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return DPI_ERR_WORKSPACE;
   }
   int rc = ftc::init();
@@ -46,9 +45,33 @@ int dpi_conv2d_fm_forward(int batch, int h, int w, int c_in, int c_out, int ksiz
   const ftc::Pack pb{weight, (long long)K, 1, nullptr, c_out, K, 0, 0, 0.f};
   rc = ftc::pack2(g, pa, apack, pb, bpack, (cudaStream_t)stream);
   if (rc) return rc;
+  return ftc::run(g, apack, bpack, part, e, (cudaStream_t)stream);
+}
+
+int dpi_conv2d_fm_forward(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x,
+                          int64_t ldx, const float* weight, const float* bias, const float* scale, float* y, int64_t ldy,
+                          void* workspace, size_t workspace_bytes, dpi_stream_t stream) {
   ftc::Epi e{};
   e.mode = ftc::EPI_T_BIAS; e.out = y; e.ldo = ldy; e.bias = bias; e.scale = scale;
-  return ftc::run(g, apack, bpack, part, e, (cudaStream_t)stream);
+  return conv_run(batch, h, w, c_in, c_out, ksize, pad_value, x, ldx, weight, e, workspace, workspace_bytes, stream);
+}
+
+int dpi_conv2d_fm_lrelu(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x, int64_t ldx,
+                        const float* weight, const float* bias, float slope, float* y, int64_t ldy, void* workspace,
+                        size_t workspace_bytes, dpi_stream_t stream) {
+  DPI_REQUIRE(bias && slope > 0.f, "dpi_conv2d_fm_lrelu: bias and a positive slope are required");
+  ftc::Epi e{};
+  e.mode = ftc::EPI_T_HID; e.out = y; e.ldo = ldy; e.bias = bias; e.bn_mode = 0; e.slope = slope;
+  return conv_run(batch, h, w, c_in, c_out, ksize, pad_value, x, ldx, weight, e, workspace, workspace_bytes, stream);
+}
+
+int dpi_conv2d_fm_affine(int batch, int h, int w, int c_in, int c_out, const float* x, int64_t ldx, const float* weight,
+                         const float* mul, const float* sub, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                         dpi_stream_t stream) {
+  DPI_REQUIRE(mul && sub, "dpi_conv2d_fm_affine: null argument");
+  ftc::Epi e{};
+  e.mode = ftc::EPI_T_AFFINE; e.out = y; e.ldo = ldy; e.gamma = mul; e.beta = sub;
+  return conv_run(batch, h, w, c_in, c_out, 1, 0.f, x, ldx, weight, e, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -362,8 +362,19 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
       for (int q = 0; q < V; ++q) c[q] = fmaf(ad[q], sc, c[q]);
       stv<V>(e.out + (long long)r * e.ldo + m, c);
     }
+  } else if constexpr (MODE == EPI_T_AFFINE) {
+    const float mul = __ldg(e.gamma + n), sub = __ldg(e.beta + n);
+    for (int m = tid * V; m < g.M; m += 256 * V) {
+      float c[V];
+      fetchv<V>(src(m), g.splits, sstride, c);
+#pragma unroll
+      for (int q = 0; q < V; ++q) c[q] = fmaf(c[q], mul, -sub);
+      stv<V>(e.out + orow + m, c);
+    }
   } else if constexpr (MODE == EPI_T_HID) {
     const float bias = __ldg(e.bias + n);
+    const float slope = e.slope != 0.f ? e.slope : kLreluSlope, bn_eps = e.eps != 0.f ? e.eps : kBnEps;
+    auto lrelu = [slope](float v) { return v > 0.f ? v : slope * v; };
     if (e.bn_mode == 1) {   // BatchNorm1d in training mode (realnvpfc_model.py:178,185): biased batch variance, eps 1e-2
       float v[PER][V];
       float s = 0.f;
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
         if (m < g.M) {
           fetchv<V>(src(m), g.splits, sstride, v[i]);
 #pragma unroll
-          for (int q = 0; q < V; ++q) { v[i][q] = lrelu_f(v[i][q] + bias); s += v[i][q]; }
+          for (int q = 0; q < V; ++q) { v[i][q] = lrelu(v[i][q] + bias); s += v[i][q]; }
         }
       }
       const float invB = 1.0f / (float)g.M;
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
           for (int q = 0; q < V; ++q) { const float d = v[i][q] - mean; qq = fmaf(d, d, qq); }
         }
       const float var = block_sum(qq, red) * invB;
-      const float rstd = 1.0f / sqrtf(var + kBnEps);
+      const float rstd = 1.0f / sqrtf(var + bn_eps);
       const float ga = __ldg(e.gamma + n) * rstd, be = __ldg(e.beta + n);
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
     } else {
       float ga = 1.f, be = 0.f;
       if (e.bn_mode == 2) {   // eval: running statistics
-        const float rs = 1.0f / sqrtf(e.rvar[n] + kBnEps);
+        const float rs = 1.0f / sqrtf(e.rvar[n] + bn_eps);
         ga = __ldg(e.gamma + n) * rs;
         be = __ldg(e.beta + n) - e.rmean[n] * ga;
       }
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(256) epi_kernel(Gemm g, const float* __restric
         float c[V], nv[V];
         fetchv<V>(src(m), g.splits, sstride, c);
 #pragma unroll
-        for (int q = 0; q < V; ++q) { c[q] = lrelu_f(c[q] + bias); nv[q] = e.bn_mode == 2 ? fmaf(c[q], ga, be) : c[q]; }
+        for (int q = 0; q < V; ++q) { c[q] = lrelu(c[q] + bias); nv[q] = e.bn_mode == 2 ? fmaf(c[q], ga, be) : c[q]; }
         stv<V>(e.out + orow + m, c);
         if (e.out2) stv<V>(e.out2 + orow + m, nv);
         if (e.tp) emit_tp<V>(e, n, m, nv);
@@ -684,6 +695,7 @@ int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, co
     case EPI_T_RAW: DPI_EPI(EPI_T_RAW, 1); break;
     case EPI_T_SCATTER: DPI_EPI(EPI_T_SCATTER, 1); break;
     case EPI_T_BIAS: DPI_EPI(EPI_T_BIAS, 1); break;
+    case EPI_T_AFFINE: DPI_EPI(EPI_T_AFFINE, 1); break;
     case EPI_ROWMAJOR: DPI_EPI(EPI_ROWMAJOR, 1); break;
     case EPI_T_HID:
       if (g.M <= 1024) DPI_EPI(EPI_T_HID, 1); else DPI_EPI(EPI_T_HID, 4);

@@ -66,6 +66,7 @@ enum EpiMode {
                    // plus the gradients of gamma / beta / the Linear bias of that feature row
   EPI_ROWMAJOR,    // out[m * ldo + n] = c
   EPI_T_BIAS,      // out[n * ldo + m] = (c + bias[n]) * exp(3 * scale[n])   (bias / scale may be null): conv + ZeroConv2d scale
+  EPI_T_AFFINE,    // out[n * ldo + m] = c * gamma[n] - beta[n]   (Glow: 1x1 inverse conv followed by ActNorm.reverse)
   EPI_T_TAIL       // ZeroFC bias / exp(3 scale), tanh-exp affine coupling, ActNorm, logdet partials (AffineCoupling
                    // .reverse / .forward, realnvpfc_model.py:240-249 / :222-231) on the raw ZeroFC GEMM result
 };
@@ -99,6 +100,7 @@ struct Epi {
   // tp_KT k, k = this epilogue's feature index) of the GEMM that consumes it next - no pack pass in between
   float* tp;
   int tp_R, tp_KT, tp_ktiles;
+  float slope, eps;             // HID / BNBWD: LeakyReLU slope and BatchNorm eps; 0 = the RealNVP constants (0.01, 1e-2)
 };
 constexpr int kTailCols = 16;   // coupling columns per logdet partial
 int run(const Gemm& g, const float* a_pack, const float* b_pack, float* part, const Epi& e, cudaStream_t st);

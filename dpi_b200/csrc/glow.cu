@@ -1,0 +1,237 @@
+// glow.cu - the non-GEMM pieces of Glow.reverse (generative_model/glow_model.py), forward only, on feature-major
+// image stacks [channel][b * h * w] (position = b * h * w + y * w + x):
+//   * BatchNorm2d over a channel row (:263,266; batch statistics + running-statistics update, or running statistics)
+//   * InvConv2dLU.calc_weight (:217-224) and its inverse (:229), one CTA, Gauss-Jordan with partial pivoting
+//   * AffineCoupling.reverse tail (:299-311): in_b = out_b / exp(tanh(log_s0)) - t, logdet -= sum tanh
+//   * the split prior of Block.reverse (:432-443): z = mean + exp(log_sd) * eps, logdet += sum log_sd
+//   * unsqueeze (:453-459) and the scalar logdet terms of InvConv2dLU / ActNorm (:231, :141-143)
+// The convolutions are conv_tc.cu. Per-sample logdet sums have a single writer per sample and a fixed order.
+#include "common.cuh"
+
+namespace dpi {
+namespace {
+
+constexpr int kT = 256;
+constexpr int kMaxC = 64;   // channels of an invertible 1x1 convolution handled in shared memory
+
+// one CTA per channel row
+__global__ void __launch_bounds__(kT) bn_rows_kernel(int M, long long ld, const float* __restrict__ x, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ rmean,
+                                                    float* __restrict__ rvar, int train, float eps, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float* row = x + (long long)n * ld;
+  float* orow = out + (long long)n * ld;
+  float mean, var;
+  if (train) {
+    float s = 0.f;
+    for (int m = threadIdx.x; m < M; m += kT) s += __ldcg(row + m);
+    mean = block_sum(s, red) / (float)M;
+    float q = 0.f;
+    for (int m = threadIdx.x; m < M; m += kT) { const float d = __ldcg(row + m) - mean; q = fmaf(d, d, q); }
+    var = block_sum(q, red) / (float)M;
+    if (threadIdx.x == 0) {
+      rmean[n] = (1.f - kBnMomentum) * rmean[n] + kBnMomentum * mean;
+      rvar[n] = (1.f - kBnMomentum) * rvar[n] + kBnMomentum * (var * (float)M / (float)(M - 1));
+    }
+  } else {
+    mean = rmean[n];
+    var = rvar[n];
+  }
+  const float ga = __ldg(gamma + n) / sqrtf(var + eps), be = __ldg(beta + n);
+  for (int m = threadIdx.x; m < M; m += kT) __stcg(orow + m, fmaf(__ldcg(row + m) - mean, ga, be));
+}
+
+// W = P (L * l_mask + I) (U * u_mask + diag(sign * exp(w_s))), then W^-1 (row-major [C][C]); one CTA
+__global__ void __launch_bounds__(kT) lu_inverse_kernel(int C, const float* __restrict__ w_p, const float* __restrict__ w_l,
+                                                       const float* __restrict__ w_s, const float* __restrict__ w_u,
+                                                       const float* __restrict__ l_mask, const float* __restrict__ u_mask,
+                                                       const float* __restrict__ s_sign, const float* __restrict__ l_eye,
+                                                       float* __restrict__ winv) {
+  __shared__ float Wm[kMaxC][2 * kMaxC + 1];   // [W | I] -> [I | W^-1]
+  __shared__ float fac[kMaxC];
+  __shared__ int piv;
+  const int tid = threadIdx.x;
+  auto Lm = [&](int r, int c) { return w_l[r * C + c] * l_mask[r * C + c] + l_eye[r * C + c]; };
+  auto Um = [&](int r, int c) { return w_u[r * C + c] * u_mask[r * C + c] + (r == c ? s_sign[r] * expf(w_s[r]) : 0.f); };
+  for (int i = tid; i < C * C; i += kT) {      // T = P L'   (parked in the right half)
+    const int r = i / C, c = i - r * C;
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s = fmaf(w_p[r * C + k], Lm(k, c), s);
+    Wm[r][kMaxC + c] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < C * C; i += kT) {      // W = T U'
+    const int r = i / C, c = i - r * C;
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s = fmaf(Wm[r][kMaxC + k], Um(k, c), s);
+    Wm[r][c] = s;
+  }
+  __syncthreads();
+  // from here the right half starts at column C (not kMaxC): move nothing, just overwrite with the identity
+  for (int i = tid; i < C * C; i += kT) {
+    const int r = i / C, c = i - r * C;
+    Wm[r][C + c] = r == c ? 1.f : 0.f;
+  }
+  __syncthreads();
+  for (int col = 0; col < C; ++col) {
+    if (tid == 0) {
+      int best = col;
+      float bv = fabsf(Wm[col][col]);
+      for (int r = col + 1; r < C; ++r)
+        if (fabsf(Wm[r][col]) > bv) { bv = fabsf(Wm[r][col]); best = r; }
+      piv = best;
+    }
+    __syncthreads();
+    const int p = piv;
+    if (p != col)
+      for (int c = tid; c < 2 * C; c += kT) { const float t = Wm[col][c]; Wm[col][c] = Wm[p][c]; Wm[p][c] = t; }
+    __syncthreads();
+    const float inv = 1.0f / Wm[col][col];
+    __syncthreads();
+    for (int c = tid; c < 2 * C; c += kT) Wm[col][c] *= inv;
+    for (int r = tid; r < C; r += kT) fac[r] = r == col ? 0.f : Wm[r][col];   // factors read before any row changes
+    __syncthreads();
+    for (int i = tid; i < C * 2 * C; i += kT) {
+      const int r = i / (2 * C), c = i - r * 2 * C;
+      Wm[r][c] = fmaf(-fac[r], Wm[col][c], Wm[r][c]);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < C * C; i += kT) {
+    const int r = i / C, c = i - r * C;
+    winv[i] = Wm[r][C + c];
+  }
+}
+
+// one CTA per sample: x rows [C/2, C) <- out_b / exp(tanh(log_s0)) - t; logdet[b] -= sum tanh
+__global__ void __launch_bounds__(kT) affine_reverse_kernel(int hw, int C, const float* __restrict__ net, long long ldn,
+                                                           float* __restrict__ x, long long ldx, float* __restrict__ logdet) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, half = C / 2;
+  float ld = 0.f;
+  for (int p = threadIdx.x; p < hw; p += kT) {
+    const long long m = (long long)b * hw + p;
+    for (int j = 0; j < half; ++j) {
+      const float ls = tanhf(__ldcg(net + (long long)j * ldn + m));
+      const float t = __ldcg(net + (long long)(half + j) * ldn + m);
+      float* xb = x + (long long)(half + j) * ldx + m;
+      *xb = *xb / expf(ls) - t;
+      ld -= ls;
+    }
+  }
+  const float tot = block_sum(ld, red);
+  if (threadIdx.x == 0) logdet[b] += tot;
+}
+
+// one CTA per sample: z = mean + exp(log_sd) * eps; logdet[b] += sum log_sd
+__global__ void __launch_bounds__(kT) prior_sample_kernel(int hw, int C2, const float* __restrict__ ml, long long ldm,
+                                                         const float* __restrict__ eps, long long lde, float* __restrict__ z,
+                                                         long long ldz, float* __restrict__ logdet) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float ld = 0.f;
+  for (int p = threadIdx.x; p < hw; p += kT) {
+    const long long m = (long long)b * hw + p;
+    for (int j = 0; j < C2; ++j) {
+      const float mean = __ldcg(ml + (long long)j * ldm + m), lsd = __ldcg(ml + (long long)(C2 + j) * ldm + m);
+      z[(long long)j * ldz + m] = fmaf(expf(lsd), __ldcg(eps + (long long)j * lde + m), mean);
+      ld += lsd;
+    }
+  }
+  const float tot = block_sum(ld, red);
+  if (threadIdx.x == 0) logdet[b] += tot;
+}
+
+// out[c][b, 2y + dy, 2x + dx] = in[4c + 2dy + dx][b, y, x]
+__global__ void unsqueeze_kernel(int batch, int h, int w, int C, const float* __restrict__ in, float* __restrict__ out) {
+  const long long Mi = (long long)batch * h * w, Mo = 4 * Mi, total = (long long)(C / 4) * Mo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / Mo);
+    const long long r = i - (long long)c * Mo;
+    const int b = (int)(r / (4LL * h * w));
+    const int q = (int)(r - (long long)b * 4 * h * w), Y = q / (2 * w), X = q - Y * 2 * w;
+    const int y = Y >> 1, dy = Y & 1, x = X >> 1, dx = X & 1;
+    out[i] = __ldcg(in + (long long)(4 * c + 2 * dy + dx) * Mi + (long long)b * h * w + y * w + x);
+  }
+}
+
+// logdet[b] += hw * (a_ws * sum w_s + a_si * sum log|scale_inv|)
+__global__ void __launch_bounds__(kT) logdet_scalar_kernel(int batch, int hw, int C, const float* __restrict__ w_s, float a_ws,
+                                                          const float* __restrict__ scale_inv, float a_si,
+                                                          float* __restrict__ logdet) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += kT) {
+    if (w_s) s += a_ws * w_s[c];
+    if (scale_inv) s += a_si * logf(fabsf(scale_inv[c]));
+  }
+  const float tot = (float)hw * block_sum(s, red);
+  for (int b = threadIdx.x; b < batch; b += kT) logdet[b] += tot;
+}
+
+}  // namespace
+}  // namespace dpi
+
+using namespace dpi;
+
+extern "C" {
+
+int dpi_glow_bn_rows(int channels, int64_t positions, int64_t ld, const float* x, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int train, float eps, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(x && gamma && beta && running_mean && running_var && out, "dpi_glow_bn_rows: null argument");
+  DPI_REQUIRE(channels >= 1 && positions >= 1 && ld >= positions && positions < (1LL << 31), "dpi_glow_bn_rows: bad shape");
+  DPI_REQUIRE(!(train && positions < 2), "dpi_glow_bn_rows: Expected more than 1 value per channel when training");
+  bn_rows_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>((int)positions, ld, x, gamma, beta, running_mean, running_var,
+                                                           train ? 1 : 0, eps, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_lu_inverse(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u,
+                        const float* l_mask, const float* u_mask, const float* s_sign, const float* l_eye, float* winv,
+                        dpi_stream_t stream) {
+  DPI_REQUIRE(w_p && w_l && w_s && w_u && l_mask && u_mask && s_sign && l_eye && winv, "dpi_glow_lu_inverse: null argument");
+  DPI_REQUIRE(channels >= 1 && channels <= kMaxC, "dpi_glow_lu_inverse: 1 <= channels <= %d (got %d)", kMaxC, channels);
+  lu_inverse_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(channels, w_p, w_l, w_s, w_u, l_mask, u_mask, s_sign, l_eye, winv);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_affine_reverse(int batch, int hw, int channels, const float* net_out, int64_t ld_net, float* x, int64_t ldx,
+                            float* logdet, dpi_stream_t stream) {
+  DPI_REQUIRE(net_out && x && logdet, "dpi_glow_affine_reverse: null argument");
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 2 && (channels & 1) == 0, "dpi_glow_affine_reverse: bad shape");
+  affine_reverse_kernel<<<batch, kT, 0, (cudaStream_t)stream>>>(hw, channels, net_out, ld_net, x, ldx, logdet);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_prior_sample(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* eps,
+                          int64_t ld_eps, float* z, int64_t ld_z, float* logdet, dpi_stream_t stream) {
+  DPI_REQUIRE(mean_logsd && eps && z && logdet, "dpi_glow_prior_sample: null argument");
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 1, "dpi_glow_prior_sample: bad shape");
+  prior_sample_kernel<<<batch, kT, 0, (cudaStream_t)stream>>>(hw, channels, mean_logsd, ld_ml, eps, ld_eps, z, ld_z, logdet);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_unsqueeze(int batch, int h, int w, int channels, const float* x, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(x && out, "dpi_glow_unsqueeze: null argument");
+  DPI_REQUIRE(batch >= 1 && h >= 1 && w >= 1 && channels >= 4 && (channels & 3) == 0, "dpi_glow_unsqueeze: bad shape");
+  const long long total = (long long)channels * batch * h * w;
+  unsqueeze_kernel<<<(unsigned)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      batch, h, w, channels, x, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_logdet_scalar(int batch, int hw, int channels, const float* w_s, float coef_ws, const float* scale_inv,
+                           float coef_si, float* logdet, dpi_stream_t stream) {
+  DPI_REQUIRE(logdet && batch >= 1 && hw >= 1 && channels >= 1, "dpi_glow_logdet_scalar: bad argument");
+  logdet_scalar_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(batch, hw, channels, w_s, coef_ws, scale_inv, coef_si, logdet);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+"""Glow flow of DPI (`--model_form glow`), sampling direction, on the B200 kernels.
+
+Mirrors the module and state_dict surface of the reference's generative_model/glow_model.py (Glow, Block, Flow,
+ActNorm, InvConv2dLU, AffineCoupling, ZeroConv2d, calc_z_shapes; same parameter / buffer names and shapes, so
+checkpoints written by the reference load unchanged). What runs on the GPU is `Glow.reverse(z_list) -> (image,
+logdet)` (:526-539), forward only: train mode (BatchNorm batch statistics, running statistics updated) and eval mode.
+NOT built yet: gradients through it and `Glow.forward` (density direction) - both raise. SURVEY.md 8 row a20.
+
+All activations are feature-major image stacks [channel][b*h*w]; every convolution is a tcgen05 GEMM (conv_tc.cu),
+the rest are the small kernels of glow.cu. There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from dpi_b200 import _lib
+from dpi_b200.generative_model import glow_ops
+
+LRELU_SLOPE = 0.1     # glow_model.py:262,265
+BN_EPS = 1e-5         # nn.BatchNorm2d default (:263,266)
+FILTER = 512          # AffineCoupling(filter_size=512)
+
+
+def calc_z_shapes(n_channel: int, input_size: int, n_flow: int, n_block: int) -> List[Tuple[int, int, int]]:
+    """glow_model.py:541-553."""
+    shapes = []
+    for _ in range(n_block - 1):
+        input_size //= 2
+        n_channel *= 2
+        shapes.append((n_channel, input_size, input_size))
+    input_size //= 2
+    shapes.append((n_channel * 4, input_size, input_size))
+    return shapes
+
+
+class ActNorm(nn.Module):
+    """Per-channel affine (:80-148); `scale_inv` is stored directly, not as a logarithm."""
+
+    def __init__(self, in_channel: int):
+        super().__init__()
+        self.loc = nn.Parameter(torch.zeros(1, in_channel, 1, 1))
+        self.scale_inv = nn.Parameter(torch.ones(1, in_channel, 1, 1))
+        self.register_buffer("initialized", torch.tensor(0, dtype=torch.uint8))
+
+
+class InvConv2dLU(nn.Module):
+    """Invertible 1x1 convolution parametrised as P (L + I) (U + diag(sign exp(w_s))) (:183-234)."""
+
+    def __init__(self, in_channel: int):
+        super().__init__()
+        from scipy import linalg as la
+        q, _ = la.qr(np.random.randn(in_channel, in_channel))
+        p_mat, l_mat, u_mat = la.lu(q.astype(np.float32))
+        s_vec = np.diag(u_mat).copy()
+        upper = np.triu(np.ones((in_channel, in_channel), dtype=np.float32), 1)
+        self.register_buffer("w_p", torch.from_numpy(np.ascontiguousarray(p_mat)))
+        self.register_buffer("u_mask", torch.from_numpy(upper.copy()))
+        self.register_buffer("l_mask", torch.from_numpy(upper.T.copy()))
+        self.register_buffer("s_sign", torch.sign(torch.from_numpy(s_vec)))
+        self.register_buffer("l_eye", torch.eye(in_channel))
+        self.w_l = nn.Parameter(torch.from_numpy(np.ascontiguousarray(l_mat)))
+        self.w_s = nn.Parameter(torch.log(torch.abs(torch.from_numpy(s_vec))))
+        self.w_u = nn.Parameter(torch.from_numpy(np.triu(u_mat, 1).copy()))
+
+
+class ZeroConv2d(nn.Module):
+    """3x3 convolution over an input padded with ONES, times exp(3 scale); zero-initialised (:238-251)."""
+
+    def __init__(self, in_channel: int, out_channel: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channel, out_channel, 3, padding=0)
+        nn.init.zeros_(self.conv.weight)
+        nn.init.zeros_(self.conv.bias)
+        self.scale = nn.Parameter(torch.zeros(1, out_channel, 1, 1))
+
+
+class AffineCoupling(nn.Module):
+    def __init__(self, in_channel: int, filter_size: int = FILTER):
+        super().__init__()
+        # containers with the reference's indices (:260-268); their own forward() is never called
+        self.net = nn.Sequential(nn.Conv2d(in_channel // 2, filter_size, 3, padding=1), nn.LeakyReLU(LRELU_SLOPE),
+                                 nn.BatchNorm2d(filter_size), nn.Conv2d(filter_size, filter_size, 1),
+                                 nn.LeakyReLU(LRELU_SLOPE), nn.BatchNorm2d(filter_size), ZeroConv2d(filter_size, in_channel))
+        for i in (0, 3):                                                   # :270-274
+            nn.init.normal_(self.net[i].weight, 0, 0.05)
+            nn.init.zeros_(self.net[i].bias)
+
+
+class Flow(nn.Module):
+    def __init__(self, in_channel: int):
+        super().__init__()
+        self.actnorm = ActNorm(in_channel)
+        self.invconv = InvConv2dLU(in_channel)
+        self.coupling = AffineCoupling(in_channel)
+
+
+class Block(nn.Module):
+    def __init__(self, in_channel: int, n_flow: int, split: bool = True):
+        super().__init__()
+        self.flows = nn.ModuleList([Flow(in_channel * 4) for _ in range(n_flow)])
+        self.split = split
+        self.prior = ZeroConv2d(in_channel * 2, in_channel * 4) if split else ZeroConv2d(in_channel * 4, in_channel * 8)
+
+
+class Glow(nn.Module):
+    """Glow(in_channel, n_flow, n_block, affine=True, conv_lu=True) (:495-506); only the affine / LU form is built."""
+
+    def __init__(self, in_channel: int, n_flow: int, n_block: int, affine: bool = True, conv_lu: bool = True):
+        super().__init__()
+        if not affine or not conv_lu:
+            raise NotImplementedError("dpi_b200 Glow: only affine=True, conv_lu=True is built")
+        self.in_channel, self.n_flow, self.n_block = in_channel, n_flow, n_block
+        self.blocks = nn.ModuleList()
+        n_channel = in_channel
+        for _ in range(n_block - 1):
+            self.blocks.append(Block(n_channel, n_flow, split=True))
+            n_channel *= 2
+        self.blocks.append(Block(n_channel, n_flow, split=False))
+
+    def forward(self, input):
+        raise NotImplementedError("dpi_b200 Glow.forward (density direction) is not built yet; reverse() is")
+
+    # ------------------------------------------------------------------------------------------ kernels
+    def _zero_conv(self, zc: ZeroConv2d, x_fm, B, h, w):
+        return glow_ops.conv2d_fm(x_fm, zc.conv.weight.detach(), zc.conv.bias.detach(), B, h, w, pad_value=1.0,
+                                  scale=zc.scale.detach())
+
+    def _conv_lrelu_bn(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, x_fm, B, h, w):
+        lib = _lib.load()
+        wt = conv.weight.detach().contiguous()
+        c_out, c_in, k, _ = wt.shape
+        M = B * h * w
+        y = torch.empty(c_out, M, dtype=torch.float32, device=x_fm.device)
+        ws = torch.empty(lib.dpi_conv2d_fm_workspace_bytes(B, h, w, c_in, c_out, k), dtype=torch.uint8, device=x_fm.device)
+        st = _lib.stream_ptr()
+        _lib.check(lib.dpi_conv2d_fm_lrelu(B, h, w, c_in, c_out, k, 0.0, x_fm.data_ptr(), x_fm.shape[1], wt.data_ptr(),
+                                           conv.bias.detach().data_ptr(), LRELU_SLOPE, y.data_ptr(), M, ws.data_ptr(),
+                                           ws.numel(), st), "dpi_conv2d_fm_lrelu")
+        _lib.check(lib.dpi_glow_bn_rows(c_out, M, M, y.data_ptr(), bn.weight.detach().data_ptr(), bn.bias.detach().data_ptr(),
+                                        bn.running_mean.data_ptr(), bn.running_var.data_ptr(), int(self.training), BN_EPS,
+                                        y.data_ptr(), st), "dpi_glow_bn_rows")
+        if self.training:
+            bn.num_batches_tracked += 1
+        return y
+
+    def _flow_reverse(self, fl: Flow, x_fm, logdet, B, h, w):
+        lib, st = _lib.load(), _lib.stream_ptr()
+        C, M = x_fm.shape
+        net = fl.coupling.net
+        a = x_fm[: C // 2]                                           # rows of the a-half: a contiguous block
+        h1 = self._conv_lrelu_bn(net[0], net[2], a, B, h, w)
+        h2 = self._conv_lrelu_bn(net[3], net[5], h1, B, h, w)
+        out = self._zero_conv(net[6], h2, B, h, w)                   # rows [0, C/2): log_s0, rows [C/2, C): t
+        _lib.check(lib.dpi_glow_affine_reverse(B, h * w, C, out.data_ptr(), M, x_fm.data_ptr(), M, logdet.data_ptr(), st),
+                   "dpi_glow_affine_reverse")
+        ic, an = fl.invconv, fl.actnorm
+        winv = torch.empty(C, C, dtype=torch.float32, device=x_fm.device)
+        _lib.check(lib.dpi_glow_lu_inverse(C, ic.w_p.data_ptr(), ic.w_l.detach().data_ptr(), ic.w_s.detach().data_ptr(),
+                                           ic.w_u.detach().data_ptr(), ic.l_mask.data_ptr(), ic.u_mask.data_ptr(),
+                                           ic.s_sign.data_ptr(), ic.l_eye.data_ptr(), winv.data_ptr(), st), "dpi_glow_lu_inverse")
+        if int(an.initialized) == 0:                                 # first call in reverse: zeros / ones (:135-137)
+            with torch.no_grad():
+                an.loc.zero_()
+                an.scale_inv.fill_(1.0)
+            an.initialized.fill_(1)
+        y = torch.empty_like(x_fm)
+        ws = torch.empty(lib.dpi_conv2d_fm_workspace_bytes(B, h, w, C, C, 1), dtype=torch.uint8, device=x_fm.device)
+        _lib.check(lib.dpi_conv2d_fm_affine(B, h, w, C, C, x_fm.data_ptr(), M, winv.data_ptr(), an.scale_inv.detach().data_ptr(),
+                                            an.loc.detach().data_ptr(), y.data_ptr(), M, ws.data_ptr(), ws.numel(), st),
+                   "dpi_conv2d_fm_affine")
+        # InvConv2dLU.reverse: -h w sum w_s (:231); ActNorm.reverse: +h w sum log|scale_inv| (:141-143)
+        _lib.check(lib.dpi_glow_logdet_scalar(B, h * w, C, ic.w_s.detach().data_ptr(), -1.0, an.scale_inv.detach().data_ptr(), 1.0,
+                                              logdet.data_ptr(), st), "dpi_glow_logdet_scalar")
+        return y
+
+    @torch.no_grad()
+    def reverse(self, z_list):
+        """z_list[i]: [B, c_i, h_i, w_i] as calc_z_shapes gives them -> (image [B, in_channel, npix, npix], logdet [B])."""
+        z_list = [z.detach().to(torch.float32) for z in z_list]
+        if not all(z.is_cuda for z in z_list):
+            raise RuntimeError("dpi_b200 has no CPU path: Glow.reverse needs CUDA tensors")
+        lib = _lib.load()
+        dev = z_list[0].device
+        B = z_list[-1].shape[0]
+        logdet = torch.zeros(B, dtype=torch.float32, device=dev)
+        x = None
+        with torch.cuda.device(dev):
+            for i, blk in enumerate(reversed(self.blocks)):
+                eps = z_list[-(i + 1)]
+                _, c_eps, h, w = eps.shape
+                M = B * h * w
+                st = _lib.stream_ptr()
+                eps_fm = glow_ops.to_feature_major(eps)
+                if blk.split:
+                    ml = self._zero_conv(blk.prior, x, B, h, w)                     # [mean ; log_sd] of the dropped half
+                    full = torch.empty(x.shape[0] + c_eps, M, dtype=torch.float32, device=dev)
+                    full[: x.shape[0]].copy_(x)
+                    z_rows = full[x.shape[0]:]
+                else:
+                    ml = self._zero_conv(blk.prior, torch.zeros(c_eps, M, dtype=torch.float32, device=dev), B, h, w)
+                    full = torch.empty(c_eps, M, dtype=torch.float32, device=dev)
+                    z_rows = full
+                _lib.check(lib.dpi_glow_prior_sample(B, h * w, c_eps, ml.data_ptr(), M, eps_fm.data_ptr(), M, z_rows.data_ptr(), M,
+                                                     logdet.data_ptr(), st), "dpi_glow_prior_sample")
+                x = full
+                for fl in reversed(blk.flows):
+                    x = self._flow_reverse(fl, x, logdet, B, h, w)
+                C = x.shape[0]
+                up = torch.empty(C // 4, 4 * M, dtype=torch.float32, device=dev)
+                _lib.check(lib.dpi_glow_unsqueeze(B, h, w, C, x.data_ptr(), up.data_ptr(), st), "dpi_glow_unsqueeze")
+                x = up
+                h, w = 2 * h, 2 * w
+        return glow_ops.from_feature_major(x, B, h, w), logdet

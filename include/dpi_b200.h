@@ -118,6 +118,36 @@ int dpi_conv2d_fm_forward(int batch, int h, int w, int c_in, int c_out, int ksiz
                           int64_t ldx, const float* weight, const float* bias, const float* scale, float* y, int64_t ldy,
                           void* workspace, size_t workspace_bytes, dpi_stream_t stream);
 
+/* Same convolution with bias + LeakyReLU(slope) (glow_model.py:261-265), and the 1 x 1 convolution with a per-channel
+ * y = conv * mul[c] - sub[c] epilogue (InvConv2dLU.reverse followed by ActNorm.reverse, :226-234, :132-148). */
+int dpi_conv2d_fm_lrelu(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x, int64_t ldx,
+                        const float* weight, const float* bias, float slope, float* y, int64_t ldy, void* workspace,
+                        size_t workspace_bytes, dpi_stream_t stream);
+int dpi_conv2d_fm_affine(int batch, int h, int w, int c_in, int c_out, const float* x, int64_t ldx, const float* weight,
+                         const float* mul, const float* sub, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
+                         dpi_stream_t stream);
+
+/* The non-GEMM pieces of Glow.reverse on feature-major image stacks [channel][b * h * w] (glow.cu), forward only.
+ * dpi_glow_bn_rows: nn.BatchNorm2d over each channel row (train != 0: batch statistics, running statistics updated
+ *   with momentum 0.1 and the unbiased variance; else running statistics), out may alias x.
+ * dpi_glow_lu_inverse: winv [C][C] = (w_p (w_l * l_mask + l_eye) (w_u * u_mask + diag(s_sign * exp(w_s))))^-1, C <= 64.
+ * dpi_glow_affine_reverse: rows [C/2, C) of x <- x / exp(tanh(net_out[j])) - net_out[C/2 + j]; logdet[b] -= sum tanh.
+ * dpi_glow_prior_sample: z[j] = mean_logsd[j] + exp(mean_logsd[C + j]) * eps[j]; logdet[b] += sum mean_logsd[C + j].
+ * dpi_glow_unsqueeze: [C][b, h, w] -> [C/4][b, 2h, 2w], Block.reverse :453-459.
+ * dpi_glow_logdet_scalar: logdet[b] += hw * (coef_ws * sum w_s + coef_si * sum log|scale_inv|) (either array may be NULL). */
+int dpi_glow_bn_rows(int channels, int64_t positions, int64_t ld, const float* x, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int train, float eps, float* out, dpi_stream_t stream);
+int dpi_glow_lu_inverse(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u,
+                        const float* l_mask, const float* u_mask, const float* s_sign, const float* l_eye, float* winv,
+                        dpi_stream_t stream);
+int dpi_glow_affine_reverse(int batch, int hw, int channels, const float* net_out, int64_t ld_net, float* x, int64_t ldx,
+                            float* logdet, dpi_stream_t stream);
+int dpi_glow_prior_sample(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* eps,
+                          int64_t ld_eps, float* z, int64_t ld_z, float* logdet, dpi_stream_t stream);
+int dpi_glow_unsqueeze(int batch, int h, int w, int channels, const float* x, float* out, dpi_stream_t stream);
+int dpi_glow_logdet_scalar(int batch, int hw, int channels, const float* w_s, float coef_ws, const float* scale_inv,
+                           float coef_si, float* logdet, dpi_stream_t stream);
+
 /* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
  * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
  * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory

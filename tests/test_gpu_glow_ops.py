@@ -45,3 +45,85 @@ def test_zero_conv_matches_glow_oracle():
     y = G.conv2d_fm(G.to_feature_major(x.cuda()), sd["conv.weight"].cuda(), sd["conv.bias"].cuda(), B, hw, hw, pad_value=1.0,
                     scale=sd["scale"].cuda())
     assert rel_err(G.from_feature_major(y, B, hw, hw).cpu(), ref) < RTOL
+
+
+def _glow_from_fixture():
+    from conftest import load_golden, split_sd
+    from dpi_b200.generative_model.glow_model import Glow
+    from oracle import glow_oracle as GO
+    g = load_golden("glow_small")
+    sd = split_sd(g)
+    flows = sorted({k[: k.index("coupling.")] for k in sd if "coupling.net.0.weight" in k})
+    for tag, k in enumerate(GO.big_weight_keys([f + "coupling.net.3.weight" for f in flows])):
+        sd[k] = GO.formula_weight((GO.FILTER, GO.FILTER, 1, 1), tag)
+    m = Glow(1, int(g["n_flow"]), int(g["n_block"]))
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return g, sd, m.cuda()
+
+
+def test_glow_reverse_matches_reference_fixture():
+    """SURVEY 8 a20, sampling direction: a state dict WRITTEN BY THE REFERENCE loads into the drop-in Glow and
+    Glow.reverse reproduces the reference's image and log-determinant (train mode incl. the BatchNorm running
+    statistics, then eval mode)."""
+    g, sd, m = _glow_from_fixture()
+    zs = [torch.from_numpy(g[f"z{i}"]).cuda() for i in range(int(g["n_block"]))]
+    m.train()
+    x, ld = m.reverse(zs)
+    assert rel_err(x, g["x_rev"]) < RTOL, rel_err(x, g["x_rev"])
+    assert rel_err(ld, g["ld_rev"]) < RTOL, rel_err(ld, g["ld_rev"])
+    mine = m.state_dict()
+    for k, v in g.items():
+        if k.startswith("after."):
+            assert rel_err(mine[k[len("after."):]].float(), v) < RTOL, k
+    # the fixture script ran the reference's forward() in train mode before switching to eval(): advance the running
+    # statistics the same way with the oracle's forward (that direction is not built on the GPU yet), then compare
+    from oracle import glow_oracle as GO
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        GO.glow_forward(sd_cpu, torch.from_numpy(g["x_rev"]), train=True)
+    m.load_state_dict(sd_cpu)
+    m.eval()
+    xe, lde = m.reverse(zs)
+    assert rel_err(xe, g["x_rev_eval"]) < RTOL and rel_err(lde, g["ld_rev_eval"]) < RTOL
+
+
+@pytest.mark.parametrize("npix,n_flow,n_block,B", [(16, 2, 3, 4), (8, 1, 2, 20)])
+def test_glow_reverse_matches_oracle(npix, n_flow, n_block, B):
+    """A fresh drop-in Glow with its zero-initialised pieces randomised, against the Glow oracle on its state dict."""
+    from dpi_b200.generative_model.glow_model import Glow, calc_z_shapes
+    from oracle import glow_oracle as GO
+    torch.manual_seed(npix + B)
+    import numpy as np
+    np.random.seed(npix + B)
+    m = Glow(1, n_flow, n_block)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if ".net.6." in name or ".prior." in name:
+                p.normal_(0, 0.05)
+            elif name.endswith("actnorm.loc"):
+                p.normal_(0, 0.2)
+            elif name.endswith("actnorm.scale_inv"):
+                p.copy_(0.7 + 0.6 * torch.rand_like(p))
+        for name, b in m.named_buffers():
+            if name.endswith("initialized"):
+                b.fill_(1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    shapes = calc_z_shapes(1, npix, n_flow, n_block)
+    assert shapes == GO.calc_z_shapes(1, npix, n_flow, n_block)
+    zs = [torch.randn(B, *s) for s in shapes]
+    xo, lo = GO.glow_reverse(sd, zs, train=True)
+    m = m.cuda().train()
+    x, ld = m.reverse([z.cuda() for z in zs])
+    assert x.shape == (B, 1, npix, npix)
+    assert rel_err(x, xo) < RTOL, rel_err(x, xo)
+    assert rel_err(ld, lo) < RTOL, rel_err(ld, lo)
+    mine = m.state_dict()
+    for k, v in sd.items():
+        if "running" in k:
+            assert rel_err(mine[k].float(), v.float()) < RTOL, k
+    xoe, loe = GO.glow_reverse(sd, zs, train=False)
+    m.eval()
+    xe, lde = m.reverse([z.cuda() for z in zs])
+    assert rel_err(xe, xoe) < RTOL and rel_err(lde, loe) < RTOL
+    with pytest.raises(NotImplementedError):
+        m.forward(x)
