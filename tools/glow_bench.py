@@ -1,0 +1,33 @@
+"""Throughput of Glow.reverse (sampling direction) at the reference's `--model_form glow` shape: Glow(1, 16, 4), npix 32."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from dpi_b200 import _lib  # noqa: E402
+from dpi_b200.generative_model.glow_model import Glow, calc_z_shapes  # noqa: E402
+
+npix, n_flow, n_block = 32, int(os.environ.get("GLOW_NFLOW", 16)), 4
+torch.manual_seed(0)
+np.random.seed(0)
+m = Glow(1, n_flow, n_block).cuda()
+print("parameters:", sum(p.numel() for p in m.parameters()))
+for B in (32, 64):
+    zs = [torch.randn(B, *s, device="cuda") for s in calc_z_shapes(1, npix, n_flow, n_block)]
+    for mode in ("train", "eval"):
+        m.train(mode == "train")
+        for _ in range(2):
+            x, ld = m.reverse(zs)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            x, ld = m.reverse(zs)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        print(f"B={B} {mode}: {1e3 * dt:.2f} ms per reverse pass, {B / dt:.0f} samples/s, "
+              f"{(_lib.launch_count() - n0) // reps} library launches, finite={bool(torch.isfinite(x).all())}")
