@@ -162,11 +162,13 @@ class Glow(nn.Module):
         _lib.check(lib.dpi_glow_lu_inverse(C, ic.w_p.data_ptr(), ic.w_l.detach().data_ptr(), ic.w_s.detach().data_ptr(),
                                            ic.w_u.detach().data_ptr(), ic.l_mask.data_ptr(), ic.u_mask.data_ptr(),
                                            ic.s_sign.data_ptr(), ic.l_eye.data_ptr(), winv.data_ptr(), st), "dpi_glow_lu_inverse")
-        if int(an.initialized) == 0:                                 # first call in reverse: zeros / ones (:135-137)
-            with torch.no_grad():
-                an.loc.zero_()
-                an.scale_inv.fill_(1.0)
-            an.initialized.fill_(1)
+        if not getattr(an, "_checked", False):                       # one host read per layer, not one per call
+            if int(an.initialized) == 0:                             # first call in reverse: zeros / ones (:135-137)
+                with torch.no_grad():
+                    an.loc.zero_()
+                    an.scale_inv.fill_(1.0)
+                an.initialized.fill_(1)
+            an._checked = True
         y = torch.empty_like(x_fm)
         ws = torch.empty(lib.dpi_conv2d_fm_workspace_bytes(B, h, w, C, C, 1), dtype=torch.uint8, device=x_fm.device)
         _lib.check(lib.dpi_conv2d_fm_affine(B, h, w, C, C, x_fm.data_ptr(), M, winv.data_ptr(), an.scale_inv.detach().data_ptr(),
