@@ -37,6 +37,8 @@ PROTOTYPES = {
     "dpi_conv2d_fm_forward": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]),
     "dpi_conv2d_fm_lrelu": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, vp, f32, vp, i64, vp, sz, vp]),
     "dpi_conv2d_fm_affine": (i32, [i32, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]),
+    "dpi_conv2d_fm_wgrad_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "dpi_conv2d_fm_wgrad": (i32, [i32, i32, i32, i32, i32, i32, f32, vp, i64, vp, i64, vp, vp, sz, vp]),
     "dpi_glow_bn_rows": (i32, [i32, i64, i64, vp, vp, vp, vp, vp, i32, f32, vp, vp]),
     "dpi_glow_lu_inverse": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "dpi_glow_affine_reverse": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp]),

@@ -82,8 +82,16 @@ __device__ __forceinline__ void pack_tile(const Pack& p, int k_tiles, int vec, f
       const int row = r0 + r, k = k0 + kk;
       float v = 0.f;
       if (row < p.rows && k < p.K) {
-        const int rr = p.map ? __ldg(p.map + row) : row;
-        v = __ldg(p.src + (long long)rr * p.ld + k);
+        if (p.im_h > 0) {   // weight-gradient operand: row = (channel, tap) of the 3 x 3 window, k = position
+          const int c = row / 9, t9 = row - 9 * c, dy = t9 / 3 - 1, dx = t9 - 3 * (t9 / 3) - 1;
+          const int hw = p.im_h * p.im_w, b = k / hw, rem = k - b * hw, y = rem / p.im_w, x = rem - y * p.im_w;
+          const int yy = y + dy, xx = x + dx;
+          v = (yy >= 0 && yy < p.im_h && xx >= 0 && xx < p.im_w)
+                  ? __ldg(p.src + (long long)c * p.ld + (long long)b * hw + yy * p.im_w + xx) : p.pad;
+        } else {
+          const int rr = p.map ? __ldg(p.map + row) : row;
+          v = __ldg(p.src + (long long)rr * p.ld + k);
+        }
       }
       s[kk][r] = v;
     }

@@ -48,9 +48,10 @@ struct Pack {
   int k_contig;
   const int* map;
   int rows, K;
-  // im2col (k_contig must be 0, map unused): src is a feature-major image stack [channel][b * h * w] with row stride
-  // ld; r = position (b, y, x), k = (channel, dy, dx) of a 3 x 3 window with zero-based taps: element = src[channel]
-  // [b, y + dy - 1, x + dx - 1], or `pad` outside the image (glow_model.py ZeroConv2d pads with ONES, :247)
+  // im2col (map unused): src is a feature-major image stack [channel][b * h * w] with row stride ld. k_contig = 0:
+  // r = position (b, y, x), k = (channel, dy, dx) of a 3 x 3 window; k_contig = 1 (weight-gradient operand): r =
+  // (channel, dy, dx), k = position. element = src[channel][b, y + dy - 1, x + dx - 1], or `pad` outside the image
+  // (glow_model.py ZeroConv2d pads with ONES, :247)
   int im_h, im_w;      // 0: plain operand
   float pad;
 };

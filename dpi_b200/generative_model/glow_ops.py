@@ -46,3 +46,29 @@ def conv2d_fm(x_fm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
                                              y.data_ptr(), y.shape[1], ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
                    "dpi_conv2d_fm_forward")
     return y
+
+
+def conv2d_fm_dgrad(g_fm: torch.Tensor, weight: torch.Tensor, batch: int, h: int, w: int) -> torch.Tensor:
+    """Gradient of conv2d_fm with respect to its input stack: the same convolution applied to the output gradient with
+    the spatially flipped, channel-transposed weight (padding contributes nothing: it is a constant)."""
+    wt = weight.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    return conv2d_fm(g_fm, wt, None, batch, h, w, pad_value=0.0)
+
+
+def conv2d_fm_wgrad(x_fm: torch.Tensor, g_fm: torch.Tensor, ksize: int, batch: int, h: int, w: int,
+                    pad_value: float = 0.0) -> torch.Tensor:
+    """Gradient with respect to the weight [c_out, c_in, k, k] (for ZeroConv2d pass pad_value=1 and the gradient of the
+    un-scaled convolution output)."""
+    if not x_fm.is_cuda:
+        raise RuntimeError("dpi_b200 has no CPU path: conv2d_fm_wgrad needs CUDA tensors")
+    lib = _lib.load()
+    c_in, c_out = x_fm.shape[0], g_fm.shape[0]
+    x_fm, g_fm = x_fm.contiguous(), g_fm.contiguous()
+    gw = torch.empty(c_out, c_in, ksize, ksize, dtype=torch.float32, device=x_fm.device)
+    ws = torch.empty(lib.dpi_conv2d_fm_wgrad_workspace_bytes(batch, h, w, c_in, c_out, ksize), dtype=torch.uint8,
+                     device=x_fm.device)
+    with torch.cuda.device(x_fm.device):
+        _lib.check(lib.dpi_conv2d_fm_wgrad(batch, h, w, c_in, c_out, ksize, float(pad_value), x_fm.data_ptr(), x_fm.shape[1],
+                                           g_fm.data_ptr(), g_fm.shape[1], gw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr()), "dpi_conv2d_fm_wgrad")
+    return gw

@@ -127,6 +127,14 @@ int dpi_conv2d_fm_affine(int batch, int h, int w, int c_in, int c_out, const flo
                          const float* mul, const float* sub, float* y, int64_t ldy, void* workspace, size_t workspace_bytes,
                          dpi_stream_t stream);
 
+/* Weight gradient of the same convolution: g_weight [c_out][c_in][k][k] = sum over positions of g_out[c_out][pos] times the
+ * (padded) input window - one tcgen05 GEMM with K = positions and the window gather in the B-operand pack. The data
+ * gradient is the forward entry point applied to g_out with the flipped, transposed weight. */
+size_t dpi_conv2d_fm_wgrad_workspace_bytes(int batch, int h, int w, int c_in, int c_out, int ksize);
+int dpi_conv2d_fm_wgrad(int batch, int h, int w, int c_in, int c_out, int ksize, float pad_value, const float* x, int64_t ldx,
+                        const float* g_out, int64_t ldg, float* g_weight, void* workspace, size_t workspace_bytes,
+                        dpi_stream_t stream);
+
 /* The non-GEMM pieces of Glow.reverse on feature-major image stacks [channel][b * h * w] (glow.cu), forward only.
  * dpi_glow_bn_rows: nn.BatchNorm2d over each channel row (train != 0: batch statistics, running statistics updated
  *   with momentum 0.1 and the unbiased variance; else running statistics), out may alias x.

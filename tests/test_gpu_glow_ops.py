@@ -127,3 +127,22 @@ def test_glow_reverse_matches_oracle(npix, n_flow, n_block, B):
     assert rel_err(xe, xoe) < RTOL and rel_err(lde, loe) < RTOL
     with pytest.raises(NotImplementedError):
         m.forward(x)
+
+
+@pytest.mark.parametrize("B,cin,cout,hw,k,pad", [(3, 6, 20, 8, 3, 1.0), (4, 2, 512, 4, 3, 0.0), (4, 512, 512, 4, 1, 0.0),
+                                                   (5, 512, 8, 6, 3, 1.0)])
+def test_conv2d_gradients_match_torch_autograd(B, cin, cout, hw, k, pad):
+    """Building blocks of the Glow backward (not assembled yet): data and weight gradient of the coupling-net
+    convolutions on tcgen05, against torch autograd on the CPU."""
+    from dpi_b200.generative_model import glow_ops as G
+    torch.manual_seed(B + cout)
+    x = torch.randn(B, cin, hw, hw, requires_grad=True)
+    wt = (torch.randn(cout, cin, k, k) * 0.1).requires_grad_(True)
+    c = torch.randn(B, cout, hw, hw)
+    y = F.conv2d(F.pad(x, [1, 1, 1, 1], value=pad), wt) if k == 3 else F.conv2d(x, wt)
+    (y * c).sum().backward()
+    g_fm = G.to_feature_major(c.cuda())
+    gx = G.from_feature_major(G.conv2d_fm_dgrad(g_fm, wt.detach().cuda(), B, hw, hw), B, hw, hw).cpu()
+    gw = G.conv2d_fm_wgrad(G.to_feature_major(x.detach().cuda()), g_fm, k, B, hw, hw, pad_value=pad).cpu()
+    assert rel_err(gx, x.grad) < RTOL, rel_err(gx, x.grad)
+    assert rel_err(gw, wt.grad) < RTOL, rel_err(gw, wt.grad)
