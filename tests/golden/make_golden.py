@@ -331,6 +331,11 @@ def glow_case(name, npix, n_flow, n_block, B, seed):
     for i, (z, zz) in enumerate(zip(zs, zr)):
         out[f"z{i}"] = z.numpy()
         out[f"g_z{i}"] = zz.grad.numpy()
+    # parameter gradients of the same objective (for the backward pass of the CUDA path): small tensors verbatim, the
+    # 512 x 512 ones as every 1021st entry of the flattened gradient
+    for k, p in ref.named_parameters():
+        gflat = p.grad.detach().reshape(-1)
+        out["grad." + k] = gflat[::1021].numpy().copy() if k in big else p.grad.detach().numpy().copy()
     for k, v in ref.state_dict().items():
         if "running" in k:
             out["after." + k] = v.numpy().copy()

@@ -180,9 +180,16 @@ def test_glow_oracle_matches_reference_fixture():
     for tag, k in enumerate(G.big_weight_keys([f + "coupling.net.3.weight" for f in flows])):
         sd[k] = G.formula_weight((G.FILTER, G.FILTER, 1, 1), tag)
     zs = [torch.from_numpy(g[f"z{i}"]).requires_grad_(True) for i in range(n_block)]
+    pkeys = [k[len("grad."):] for k in g if k.startswith("grad.")]
+    for k in pkeys:
+        sd[k] = sd[k].clone().requires_grad_(True)
     x, ld = G.glow_reverse(sd, zs, train=True)
     assert rel_err(x, g["x_rev"]) < 1e-6 and rel_err(ld, g["ld_rev"]) < 1e-6
     ((x * torch.from_numpy(g["c"])).sum() + ld.sum()).backward()
+    big = set(G.big_weight_keys(pkeys))
+    for k in pkeys:                              # parameter gradients (the 512 x 512 ones are stored subsampled)
+        mine = sd[k].grad.reshape(-1)[::1021] if k in big else sd[k].grad
+        assert rel_err(mine, g["grad." + k]) < 1e-4, k
     for i, z in enumerate(zs):
         assert rel_err(z.grad, g[f"g_z{i}"]) < 1e-5
     for k, v in g.items():
