@@ -44,6 +44,11 @@ PROTOTYPES = {
     "dpi_glow_affine_reverse": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp]),
     "dpi_glow_prior_sample": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp]),
     "dpi_glow_unsqueeze": (i32, [i32, i32, i32, i32, vp, vp, vp]),
+    "dpi_glow_lu_weight": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dpi_glow_affine_forward": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp]),
+    "dpi_glow_prior_forward": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp]),
+    "dpi_glow_squeeze": (i32, [i32, i32, i32, i32, vp, vp, vp]),
+    "dpi_glow_row_affine": (i32, [i32, i64, vp, vp, vp, vp, vp]),
     "dpi_glow_logdet_scalar": (i32, [i32, i32, i32, vp, f32, vp, f32, vp, vp]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kT) lu_inverse_kernel(int C, const float* __re
                                                        const float* __restrict__ w_s, const float* __restrict__ w_u,
                                                        const float* __restrict__ l_mask, const float* __restrict__ u_mask,
                                                        const float* __restrict__ s_sign, const float* __restrict__ l_eye,
-                                                       float* __restrict__ winv) {
+                                                       float* __restrict__ winv, int invert) {
   __shared__ float Wm[kMaxC][2 * kMaxC + 1];   // [W | I] -> [I | W^-1]
   __shared__ float fac[kMaxC];
   __shared__ int piv;
@@ -68,6 +68,10 @@ __global__ void __launch_bounds__(kT) lu_inverse_kernel(int C, const float* __re
     Wm[r][c] = s;
   }
   __syncthreads();
+  if (!invert) {                               // InvConv2dLU.forward uses W itself
+    for (int i = tid; i < C * C; i += kT) winv[i] = Wm[i / C][i % C];
+    return;
+  }
   // from here the right half starts at column C (not kMaxC): move nothing, just overwrite with the identity
   for (int i = tid; i < C * C; i += kT) {
     const int r = i / C, c = i - r * C;
@@ -170,6 +174,70 @@ __global__ void __launch_bounds__(kT) logdet_scalar_kernel(int batch, int hw, in
   for (int b = threadIdx.x; b < batch; b += kT) logdet[b] += tot;
 }
 
+// one CTA per sample: x rows [C/2, C) <- (in_b + t) * exp(tanh(log_s0)); logdet[b] += sum tanh   (:277-297)
+__global__ void __launch_bounds__(kT) affine_forward_kernel(int hw, int C, const float* __restrict__ net, long long ldn,
+                                                           float* __restrict__ x, long long ldx, float* __restrict__ logdet) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, half = C / 2;
+  float ld = 0.f;
+  for (int p = threadIdx.x; p < hw; p += kT) {
+    const long long m = (long long)b * hw + p;
+    for (int j = 0; j < half; ++j) {
+      const float ls = tanhf(__ldcg(net + (long long)j * ldn + m));
+      const float t = __ldcg(net + (long long)(half + j) * ldn + m);
+      float* xb = x + (long long)(half + j) * ldx + m;
+      *xb = (*xb + t) * expf(ls);
+      ld += ls;
+    }
+  }
+  const float tot = block_sum(ld, red);
+  if (threadIdx.x == 0) logdet[b] += tot;
+}
+
+// one CTA per sample: z_eps = (z - mean) * exp(-log_sd); logdet[b] -= sum log_sd; log_p[b] += sum(-0.5 log 2 pi - 0.5 z_eps^2)
+__global__ void __launch_bounds__(kT) prior_forward_kernel(int hw, int C2, const float* __restrict__ ml, long long ldm,
+                                                          const float* __restrict__ z, long long ldz, float* __restrict__ z_eps,
+                                                          long long lde, float* __restrict__ logdet, float* __restrict__ log_p) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float ld = 0.f, lp = 0.f;
+  for (int p = threadIdx.x; p < hw; p += kT) {
+    const long long m = (long long)b * hw + p;
+    for (int j = 0; j < C2; ++j) {
+      const float mean = __ldcg(ml + (long long)j * ldm + m), lsd = __ldcg(ml + (long long)(C2 + j) * ldm + m);
+      const float e = (__ldcg(z + (long long)j * ldz + m) - mean) * expf(-lsd);
+      z_eps[(long long)j * lde + m] = e;
+      ld += lsd;
+      lp += -0.918938533204672742f - 0.5f * e * e;
+    }
+  }
+  const float t1 = block_sum(ld, red);
+  const float t2 = block_sum(lp, red);
+  if (threadIdx.x == 0) { logdet[b] -= t1; log_p[b] += t2; }
+}
+
+// out[4c + 2dy + dx][b, y, x] = in[c][b, 2y + dy, 2x + dx]   (h, w: OUTPUT height / width)
+__global__ void squeeze_kernel(int batch, int h, int w, int C, const float* __restrict__ in, float* __restrict__ out) {
+  const long long Mo = (long long)batch * h * w, total = (long long)4 * C * Mo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / Mo);
+    const long long r = i - (long long)co * Mo;
+    const int b = (int)(r / (h * w)), q = (int)(r - (long long)b * h * w), y = q / w, x = q - y * w;
+    const int c = co >> 2, dy = (co >> 1) & 1, dx = co & 1;
+    out[i] = __ldcg(in + (long long)c * 4 * Mo + (long long)b * 4 * h * w + (2 * y + dy) * (2 * w) + 2 * x + dx);
+  }
+}
+
+// out[c][m] = (x[c][m] + add[c]) / div[c]   (ActNorm.forward :113-130)
+__global__ void row_affine_kernel(int C, long long M, const float* __restrict__ x, const float* __restrict__ add,
+                                  const float* __restrict__ div, float* __restrict__ out) {
+  const long long total = (long long)C * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / M);
+    out[i] = (1.0f / __ldg(div + c)) * (__ldcg(x + i) + __ldg(add + c));
+  }
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -193,7 +261,7 @@ int dpi_glow_lu_inverse(int channels, const float* w_p, const float* w_l, const 
                         dpi_stream_t stream) {
   DPI_REQUIRE(w_p && w_l && w_s && w_u && l_mask && u_mask && s_sign && l_eye && winv, "dpi_glow_lu_inverse: null argument");
   DPI_REQUIRE(channels >= 1 && channels <= kMaxC, "dpi_glow_lu_inverse: 1 <= channels <= %d (got %d)", kMaxC, channels);
-  lu_inverse_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(channels, w_p, w_l, w_s, w_u, l_mask, u_mask, s_sign, l_eye, winv);
+  lu_inverse_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(channels, w_p, w_l, w_s, w_u, l_mask, u_mask, s_sign, l_eye, winv, 1);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }
@@ -230,6 +298,55 @@ int dpi_glow_logdet_scalar(int batch, int hw, int channels, const float* w_s, fl
                            float coef_si, float* logdet, dpi_stream_t stream) {
   DPI_REQUIRE(logdet && batch >= 1 && hw >= 1 && channels >= 1, "dpi_glow_logdet_scalar: bad argument");
   logdet_scalar_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(batch, hw, channels, w_s, coef_ws, scale_inv, coef_si, logdet);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_lu_weight(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u,
+                       const float* l_mask, const float* u_mask, const float* s_sign, const float* l_eye, float* weight,
+                       dpi_stream_t stream) {
+  DPI_REQUIRE(w_p && w_l && w_s && w_u && l_mask && u_mask && s_sign && l_eye && weight, "dpi_glow_lu_weight: null argument");
+  DPI_REQUIRE(channels >= 1 && channels <= kMaxC, "dpi_glow_lu_weight: 1 <= channels <= %d (got %d)", kMaxC, channels);
+  lu_inverse_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(channels, w_p, w_l, w_s, w_u, l_mask, u_mask, s_sign, l_eye, weight, 0);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_affine_forward(int batch, int hw, int channels, const float* net_out, int64_t ld_net, float* x, int64_t ldx,
+                            float* logdet, dpi_stream_t stream) {
+  DPI_REQUIRE(net_out && x && logdet, "dpi_glow_affine_forward: null argument");
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 2 && (channels & 1) == 0, "dpi_glow_affine_forward: bad shape");
+  affine_forward_kernel<<<batch, kT, 0, (cudaStream_t)stream>>>(hw, channels, net_out, ld_net, x, ldx, logdet);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_prior_forward(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* z,
+                           int64_t ld_z, float* z_eps, int64_t ld_eps, float* logdet, float* log_p, dpi_stream_t stream) {
+  DPI_REQUIRE(mean_logsd && z && z_eps && logdet && log_p, "dpi_glow_prior_forward: null argument");
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 1, "dpi_glow_prior_forward: bad shape");
+  prior_forward_kernel<<<batch, kT, 0, (cudaStream_t)stream>>>(hw, channels, mean_logsd, ld_ml, z, ld_z, z_eps, ld_eps, logdet,
+                                                              log_p);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_squeeze(int batch, int h_out, int w_out, int channels_in, const float* x, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(x && out, "dpi_glow_squeeze: null argument");
+  DPI_REQUIRE(batch >= 1 && h_out >= 1 && w_out >= 1 && channels_in >= 1, "dpi_glow_squeeze: bad shape");
+  const long long total = (long long)4 * channels_in * batch * h_out * w_out;
+  squeeze_kernel<<<(unsigned)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      batch, h_out, w_out, channels_in, x, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_row_affine(int channels, int64_t positions, const float* x, const float* add, const float* div, float* out,
+                        dpi_stream_t stream) {
+  DPI_REQUIRE(x && add && div && out && channels >= 1 && positions >= 1, "dpi_glow_row_affine: bad argument");
+  const long long total = (long long)channels * positions;
+  row_affine_kernel<<<(unsigned)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      channels, positions, x, add, div, out);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

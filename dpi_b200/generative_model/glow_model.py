@@ -3,8 +3,9 @@
 Mirrors the module and state_dict surface of the reference's generative_model/glow_model.py (Glow, Block, Flow,
 ActNorm, InvConv2dLU, AffineCoupling, ZeroConv2d, calc_z_shapes; same parameter / buffer names and shapes, so
 checkpoints written by the reference load unchanged). What runs on the GPU is `Glow.reverse(z_list) -> (image,
-logdet)` (:526-539), forward only: train mode (BatchNorm batch statistics, running statistics updated) and eval mode.
-NOT built yet: gradients through it and `Glow.forward` (density direction) - both raise. SURVEY.md 8 row a20.
+logdet)` (:526-539) and `Glow.forward(image) -> (log_p, logdet, z_outs)` (:508-524), forward only: train mode
+(BatchNorm batch statistics, running statistics updated) and eval mode. NOT built yet: gradients through them (the
+calls run under no_grad and return tensors without history). SURVEY.md 8 row a20.
 
 All activations are feature-major image stacks [channel][b*h*w]; every convolution is a tcgen05 GEMM (conv_tc.cu),
 the rest are the small kernels of glow.cu. There is no CPU path.
@@ -121,8 +122,76 @@ class Glow(nn.Module):
             n_channel *= 2
         self.blocks.append(Block(n_channel, n_flow, split=False))
 
+    @torch.no_grad()
     def forward(self, input):
-        raise NotImplementedError("dpi_b200 Glow.forward (density direction) is not built yet; reverse() is")
+        """Density direction (:508-524): image [B, in_channel, npix, npix] -> (log_p_sum [B], logdet [B], z_outs)."""
+        x_in = input.detach().to(torch.float32)
+        if not x_in.is_cuda:
+            raise RuntimeError("dpi_b200 has no CPU path: Glow.forward needs CUDA tensors")
+        lib = _lib.load()
+        dev = x_in.device
+        B, _, h, w = x_in.shape
+        logdet = torch.zeros(B, dtype=torch.float32, device=dev)
+        log_p = torch.zeros(B, dtype=torch.float32, device=dev)
+        z_outs = []
+        with torch.cuda.device(dev):
+            x = glow_ops.to_feature_major(x_in)
+            for blk in self.blocks:
+                st = _lib.stream_ptr()
+                C_in = x.shape[0]
+                h, w = h // 2, w // 2
+                M = B * h * w
+                sq = torch.empty(4 * C_in, M, dtype=torch.float32, device=dev)
+                _lib.check(lib.dpi_glow_squeeze(B, h, w, C_in, x.data_ptr(), sq.data_ptr(), st), "dpi_glow_squeeze")
+                x = sq
+                for fl in blk.flows:
+                    x = self._flow_forward(fl, x, logdet, B, h, w)
+                C = x.shape[0]
+                if blk.split:
+                    keep, z_new = x[: C // 2], x[C // 2:]
+                    ml = self._zero_conv(blk.prior, keep, B, h, w)
+                else:
+                    keep, z_new = x, x
+                    ml = self._zero_conv(blk.prior, torch.zeros(C, M, dtype=torch.float32, device=dev), B, h, w)
+                c2 = z_new.shape[0]
+                z_eps = torch.empty(c2, M, dtype=torch.float32, device=dev)
+                _lib.check(lib.dpi_glow_prior_forward(B, h * w, c2, ml.data_ptr(), M, z_new.data_ptr(), M, z_eps.data_ptr(), M,
+                                                      logdet.data_ptr(), log_p.data_ptr(), st), "dpi_glow_prior_forward")
+                z_outs.append(glow_ops.from_feature_major(z_eps, B, h, w))
+                x = keep.contiguous() if blk.split else keep
+        return log_p, logdet, z_outs
+
+    def _flow_forward(self, fl: "Flow", x_fm, logdet, B, h, w):
+        """Flow.forward :338-347: actnorm -> invconv -> coupling."""
+        lib, st = _lib.load(), _lib.stream_ptr()
+        C, M = x_fm.shape
+        ic, an = fl.invconv, fl.actnorm
+        if not getattr(an, "_checked", False):
+            if int(an.initialized) == 0:          # data-dependent init (:91-111): loc = -mean_c, scale_inv = std_c + 1e-6
+                with torch.no_grad():
+                    an.loc.copy_(-x_fm.mean(1).view(1, C, 1, 1))
+                    an.scale_inv.copy_((x_fm.std(1) + 1e-6).view(1, C, 1, 1))
+                an.initialized.fill_(1)
+            an._checked = True
+        y = torch.empty_like(x_fm)
+        _lib.check(lib.dpi_glow_row_affine(C, M, x_fm.data_ptr(), an.loc.detach().data_ptr(), an.scale_inv.detach().data_ptr(),
+                                           y.data_ptr(), st), "dpi_glow_row_affine")
+        wmat = torch.empty(C, C, 1, 1, dtype=torch.float32, device=x_fm.device)
+        _lib.check(lib.dpi_glow_lu_weight(C, ic.w_p.data_ptr(), ic.w_l.detach().data_ptr(), ic.w_s.detach().data_ptr(),
+                                          ic.w_u.detach().data_ptr(), ic.l_mask.data_ptr(), ic.u_mask.data_ptr(),
+                                          ic.s_sign.data_ptr(), ic.l_eye.data_ptr(), wmat.data_ptr(), st), "dpi_glow_lu_weight")
+        x2 = glow_ops.conv2d_fm(y, wmat, None, B, h, w)
+        # ActNorm.forward: -h w sum log|scale_inv| (:123-125); InvConv2dLU.forward: +h w sum w_s (:213)
+        _lib.check(lib.dpi_glow_logdet_scalar(B, h * w, C, ic.w_s.detach().data_ptr(), 1.0, an.scale_inv.detach().data_ptr(), -1.0,
+                                              logdet.data_ptr(), st), "dpi_glow_logdet_scalar")
+        net = fl.coupling.net
+        a = x2[: C // 2]
+        h1 = self._conv_lrelu_bn(net[0], net[2], a, B, h, w)
+        h2 = self._conv_lrelu_bn(net[3], net[5], h1, B, h, w)
+        out = self._zero_conv(net[6], h2, B, h, w)
+        _lib.check(lib.dpi_glow_affine_forward(B, h * w, C, out.data_ptr(), M, x2.data_ptr(), M, logdet.data_ptr(), st),
+                   "dpi_glow_affine_forward")
+        return x2
 
     # ------------------------------------------------------------------------------------------ kernels
     def _zero_conv(self, zc: ZeroConv2d, x_fm, B, h, w):

@@ -156,6 +156,21 @@ int dpi_glow_unsqueeze(int batch, int h, int w, int channels, const float* x, fl
 int dpi_glow_logdet_scalar(int batch, int hw, int channels, const float* w_s, float coef_ws, const float* scale_inv,
                            float coef_si, float* logdet, dpi_stream_t stream);
 
+/* The density direction (Glow.forward, :508-524), forward only. dpi_glow_lu_weight: the 1x1 convolution matrix itself;
+ * dpi_glow_affine_forward: rows [C/2, C) of x <- (x + t) * exp(tanh(log_s0)), logdet[b] += sum tanh; dpi_glow_prior_forward:
+ * z_eps = (z - mean) * exp(-log_sd), logdet[b] -= sum log_sd, log_p[b] += sum(-0.5 log 2 pi - 0.5 z_eps^2);
+ * dpi_glow_squeeze: [C][b, 2h, 2w] -> [4C][b, h, w] (:395-398); dpi_glow_row_affine: out = (x + add[c]) / div[c]. */
+int dpi_glow_lu_weight(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u,
+                       const float* l_mask, const float* u_mask, const float* s_sign, const float* l_eye, float* weight,
+                       dpi_stream_t stream);
+int dpi_glow_affine_forward(int batch, int hw, int channels, const float* net_out, int64_t ld_net, float* x, int64_t ldx,
+                            float* logdet, dpi_stream_t stream);
+int dpi_glow_prior_forward(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* z,
+                           int64_t ld_z, float* z_eps, int64_t ld_eps, float* logdet, float* log_p, dpi_stream_t stream);
+int dpi_glow_squeeze(int batch, int h_out, int w_out, int channels_in, const float* x, float* out, dpi_stream_t stream);
+int dpi_glow_row_affine(int channels, int64_t positions, const float* x, const float* add, const float* div, float* out,
+                        dpi_stream_t stream);
+
 /* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
  * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
  * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory
