@@ -202,3 +202,45 @@ def test_glow_oracle_matches_reference_fixture():
             assert rel_err(z, g[f"zf{i}"]) < 1e-5
         xe, lde = G.glow_reverse(sd, [z.detach() for z in zs], train=False)
         assert rel_err(xe, g["x_rev_eval"]) < 1e-6 and rel_err(lde, g["ld_rev_eval"]) < 1e-6
+
+
+def test_glow_manual_backward_formulas_match_autograd():
+    """oracle/glow_backward_spec.py: the op-by-op backward the Glow CUDA path will implement (flow step in the sampling
+    direction and the split prior), against torch autograd through the Glow oracle."""
+    from oracle import glow_backward_spec as S
+    from oracle import glow_oracle as G
+    g = load_golden("glow_small")
+    sd = split_sd(g)
+    flows = sorted({k[: k.index("coupling.")] for k in sd if "coupling.net.0.weight" in k})
+    for tag, k in enumerate(G.big_weight_keys([f + "coupling.net.3.weight" for f in flows])):
+        sd[k] = G.formula_weight((G.FILTER, G.FILTER, 1, 1), tag)
+    torch.manual_seed(3)
+    p = "blocks.0.flows.0."
+    B, C, h = 4, 4, 4
+    y = torch.randn(B, C, h, h, requires_grad=True)
+    pk = [k for k in sd if k.startswith(p) and sd[k].is_floating_point() and "running" not in k and "mask" not in k
+          and not k.endswith(("w_p", "s_sign", "l_eye"))]
+    sda = {k: (v.clone().requires_grad_(True) if k in pk else v.clone()) for k, v in sd.items()}
+    x, ld = G.flow_reverse(sda, p, y, train=True)
+    cx, cl = torch.randn_like(x), torch.randn(B)
+    ((x * cx).sum() + (ld * cl).sum()).backward()
+    g_y, grads = S.flow_reverse_backward({k: v.detach() for k, v in sd.items()}, p, y.detach(), cx, cl)
+    assert rel_err(g_y, y.grad) < 1e-4, rel_err(g_y, y.grad)
+    assert sorted(grads) == sorted(pk)
+    for k in pk:
+        assert rel_err(grads[k], sda[k].grad) < 2e-4, (k, rel_err(grads[k], sda[k].grad))
+    # split prior of block 0: full = cat[y, mean + exp(log_sd) eps]
+    pp = "blocks.0.prior."
+    yk = torch.randn(B, 2, h, h, requires_grad=True)
+    eps = torch.randn(B, 2, h, h, requires_grad=True)
+    ppk = [pp + "conv.weight", pp + "conv.bias", pp + "scale"]
+    sdb = {k: (v.clone().requires_grad_(True) if k in ppk else v.clone()) for k, v in sd.items()}
+    mean, lsd = G.zero_conv(sdb, pp, yk).chunk(2, 1)
+    full = torch.cat([yk, mean + torch.exp(lsd) * eps], 1)
+    ldp = lsd.reshape(B, -1).sum(1)
+    cf = torch.randn_like(full)
+    ((full * cf).sum() + (ldp * cl).sum()).backward()
+    g_yk, g_eps, gp = S.prior_sample_backward({k: v.detach() for k, v in sd.items()}, pp, yk.detach(), eps.detach(), cf, cl)
+    assert rel_err(g_yk, yk.grad) < 1e-4 and rel_err(g_eps, eps.grad) < 1e-4
+    for k in ppk:
+        assert rel_err(gp[k], sdb[k].grad) < 2e-4, k
