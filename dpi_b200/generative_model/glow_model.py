@@ -122,9 +122,24 @@ class Glow(nn.Module):
             n_channel *= 2
         self.blocks.append(Block(n_channel, n_flow, split=False))
 
-    @torch.no_grad()
+    def _no_gradients_yet(self, inputs, what):
+        """The backward of the Glow path is not built: say so instead of returning history-free tensors silently."""
+        if any(t.requires_grad for t in inputs):
+            raise NotImplementedError(f"dpi_b200 Glow.{what}: gradients are not built yet (input requires grad); "
+                                      "use the RealNVP flow for training or call under torch.no_grad() for sampling")
+        if torch.is_grad_enabled() and not getattr(self, "_warned", False):
+            import warnings
+            warnings.warn(f"dpi_b200 Glow.{what} runs as an inference pass: its outputs carry no autograd history "
+                          "(the training backward of Glow is not built yet)", stacklevel=3)
+            self._warned = True
+
     def forward(self, input):
         """Density direction (:508-524): image [B, in_channel, npix, npix] -> (log_p_sum [B], logdet [B], z_outs)."""
+        self._no_gradients_yet([input], "forward")
+        with torch.no_grad():
+            return self._forward(input)
+
+    def _forward(self, input):
         x_in = input.detach().to(torch.float32)
         if not x_in.is_cuda:
             raise RuntimeError("dpi_b200 has no CPU path: Glow.forward needs CUDA tensors")
@@ -248,9 +263,13 @@ class Glow(nn.Module):
                                               logdet.data_ptr(), st), "dpi_glow_logdet_scalar")
         return y
 
-    @torch.no_grad()
     def reverse(self, z_list):
         """z_list[i]: [B, c_i, h_i, w_i] as calc_z_shapes gives them -> (image [B, in_channel, npix, npix], logdet [B])."""
+        self._no_gradients_yet(list(z_list), "reverse")
+        with torch.no_grad():
+            return self._reverse(z_list)
+
+    def _reverse(self, z_list):
         z_list = [z.detach().to(torch.float32) for z in z_list]
         if not all(z.is_cuda for z in z_list):
             raise RuntimeError("dpi_b200 has no CPU path: Glow.reverse needs CUDA tensors")
