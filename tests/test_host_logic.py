@@ -172,3 +172,38 @@ def test_tcgen05_gemm_planner_invariants(M, N, K):
     assert cols in (64, 128, 256, 512)
     if N >= 256 and (M + 127) // 128 * ((N + 255) // 256) * min(16, max(1, K // 128)) >= 111:
         assert TN == 256                          # the widest tile that still fills three quarters of the GPU
+
+
+def test_glow_module_surface_and_reference_state_dict():
+    """the drop-in glow_model has the reference's constructor, calc_z_shapes and state_dict keys / shapes -
+    a state dict written by the unmodified reference (tests/golden/glow_small.npz) loads with strict=True - and it
+    refuses CPU tensors and gradient requests instead of falling back (no CUDA call is made here)."""
+    import warnings
+    from dpi_b200.generative_model.glow_model import Glow, calc_z_shapes
+    from oracle import glow_oracle as GO
+    g = load_golden("glow_small")
+    sd = split_sd(g)
+    flows = sorted({k[: k.index("coupling.")] for k in sd if "coupling.net.0.weight" in k})
+    for tag, k in enumerate(GO.big_weight_keys([f + "coupling.net.3.weight" for f in flows])):
+        sd[k] = GO.formula_weight((GO.FILTER, GO.FILTER, 1, 1), tag)
+    m = Glow(1, int(g["n_flow"]), int(g["n_block"]))
+    mine = m.state_dict()
+    assert sorted(mine) == sorted(sd)
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape) and mine[k].dtype == sd[k].dtype, k
+    m.load_state_dict(sd, strict=True)
+    for npix, nf, nb in [(32, 16, 4), (8, 1, 2), (64, 4, 5)]:
+        assert calc_z_shapes(1, npix, nf, nb) == GO.calc_z_shapes(1, npix, nf, nb)
+    assert calc_z_shapes(1, 32, 16, 4) == [(2, 16, 16), (4, 8, 8), (8, 4, 4), (32, 2, 2)]     # SURVEY 8 a20
+    assert sum(p.numel() for p in Glow(1, 16, 4).parameters()) == 23677792                      # SURVEY Appendix C
+    zs = [torch.randn(2, *s) for s in calc_z_shapes(1, 8, 1, 2)]
+    with pytest.raises(NotImplementedError):
+        m.reverse([z.clone().requires_grad_(True) for z in zs])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.reverse(zs)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.forward(torch.randn(2, 1, 8, 8))
+    with pytest.raises(NotImplementedError):
+        Glow(1, 1, 2, affine=False)
