@@ -296,6 +296,13 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.oGP2T = take((long long)H * LB);
   bp.oPART = take(std::max(32LL, max_part));
   bp.oRED = take((long long)S * std::max(bp.red_tiles, bp.tc_red_tiles) * 2);
+  bp.cl.ok = (h->cl_avail && bp.small.ok && fcl::shape_ok(D, H, B)) ? 1 : 0;
+  if (bp.cl.ok) {
+    o = (o + 255) / 256 * 256;                  // packed tiles are fetched with cp.async.bulk
+    bp.cl.oPackF = take((long long)S * fcl::kCL * fcl::kPackFloats);
+    bp.cl.oPackB = take((long long)S * fcl::kCL * fcl::kPackFloats);
+    bp.cl.oScratch = take(fcl::kScratchFloats);
+  }
   if (bp.tc_ok) {
     const ftc::Gemm* gs[9] = {&bp.g_f1, &bp.g_f2, &bp.g_f3, &bp.g_dg2, &bp.g_wg3, &bp.g_dg1, &bp.g_wg2, &bp.g_dgin, &bp.g_wg1};
     size_t ma = 0, mb = 0, mp = 0;
@@ -647,6 +654,10 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   const char* tile = getenv("DPI_B200_TILE");
   h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
   small_query(h.get());
+  {
+    const char* cle = getenv("DPI_B200_CL");               // 0: never use the cluster-resident tcgen05 pass
+    h->cl_avail = (cle && cle[0] == '0') ? 0 : fcl::query(device);
+  }
   const char* tcm = getenv("DPI_B200_FLOW_TC");          // minimum batch of the tcgen05 GEMM path; 0 disables it
   if (tcm) h->tc_min_batch = std::max(0, atoi(tcm));
   const char* tce = getenv("DPI_B200_TC_EMIT");            // 1: fused operand emission + once-per-pass weight packs
@@ -894,6 +905,10 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
   a.dir = direction; a.train = train ? 1 : 0;
   a.P = params; a.G = nullptr; a.R = bn_running; a.in = in; a.out = out; a.logdet = logdet;
   a.g_out = nullptr; a.g_ld = nullptr; a.g_in = nullptr;
+  if (bp->cl.ok && direction == 0) {
+    a.tbuf = h->d_tbuf;
+    return fcl::forward(a, bp->cl, h->S, (cudaStream_t)stream);
+  }
   if (bp->small.ok) return small_launch(h, *bp, a, 0, (cudaStream_t)stream);
   if (bp->tc_ok) return tc_forward(h, *bp, a, (cudaStream_t)stream);
   return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
@@ -917,6 +932,10 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   a.dir = 0; a.train = 1;
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
+  if (bp->cl.ok && fcl::has_backward()) {
+    a.tbuf = h->d_tbuf;
+    return fcl::backward(a, bp->cl, h->S, (cudaStream_t)stream);
+  }
   if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
   if (bp->tc_ok) return tc_backward(h, *bp, a, (cudaStream_t)stream, 0, h->S);
   return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
@@ -950,6 +969,14 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
   return tc_backward(h, *bp, a, (cudaStream_t)stream, stage_lo, stage_hi);
+}
+
+int dpi_flow_cl_active(dpi_flow_t h, int batch) {
+  if (!h || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  return bp->cl.ok ? (1 | (fcl::has_backward() ? 2 : 0)) : 0;
 }
 
 int dpi_flow_tc_active(dpi_flow_t h, int batch) {

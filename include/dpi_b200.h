@@ -107,6 +107,10 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
                             size_t workspace_bytes, int stage_lo, int stage_hi, dpi_stream_t stream);
 /* 1 if a pass at this batch size runs on the tcgen05 path (one launch per operation), 0 if one kernel per pass. */
 int dpi_flow_tc_active(dpi_flow_t h, int batch);
+/* 1 when `batch` runs RealNVP.reverse (realnvpfc_model.py:594-603) as the cluster-resident tcgen05 pass (flow_cl.cu:
+ * ndim 1024, hidden 128, batch a multiple of 4 up to 64 - the reference's default interferometry flow,
+ * DPI_interferometry.py:127); bit 1 is set when the backward pass runs there too. DPI_B200_CL=0 disables it. */
+int dpi_flow_cl_active(dpi_flow_t h, int batch);
 
 /* Glow building block (generative_model/glow_model.py:260-268, ZeroConv2d :238-251), forward only: a k x k
  * convolution (k = 1, or k = 3 with one pixel of padding filled with pad_value: 0 for nn.Conv2d(padding=1), 1 for
