@@ -354,7 +354,7 @@ int get_plan(dpi_flow_s* h, int B, BatchPlan** out) {
 }
 
 void fill_args(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, void* workspace) {
-  a.st = h->d_stages; a.gmaps = h->d_gmaps;
+  a.st = h->d_stages; a.gmaps = h->d_gmaps; a.pmaps = h->d_pmaps;
   a.D = h->D; a.Da = h->Da; a.Db = h->Db; a.Dout = h->Dout; a.H = h->H; a.S = h->S; a.has_bn = h->has_bn;
   a.B = bp.B; a.ldb = bp.ldb; a.tiles_m = bp.tiles_m; a.ldp_tiles = bp.ldp_tiles; a.red_tiles = bp.red_tiles;
   a.oZT = bp.oZT; a.oYT = bp.oYT; a.oL1T = bp.oL1T; a.oL2T = bp.oL2T; a.oN1T = bp.oN1T; a.oN2T = bp.oN2T;
@@ -655,8 +655,10 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
   small_query(h.get());
   {
-    const char* cle = getenv("DPI_B200_CL");               // 0: never use the cluster-resident tcgen05 pass
-    h->cl_avail = (cle && cle[0] == '0') ? 0 : fcl::query(device);
+    // The cluster-resident tcgen05 pass (flow_cl.cu) is opt-in (DPI_B200_CL=1): parity-green, but measured at 585 us
+    // per RealNVP(1024, 16) reverse pass against 501 us for the fp32 small-batch kernel (profiles/cl_fwd_r02.md)
+    const char* cle = getenv("DPI_B200_CL");
+    h->cl_avail = (cle && cle[0] == '1') ? fcl::query(device) : 0;
   }
   const char* tcm = getenv("DPI_B200_FLOW_TC");          // minimum batch of the tcgen05 GEMM path; 0 disables it
   if (tcm) h->tc_min_batch = std::max(0, atoi(tcm));
@@ -724,6 +726,20 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
     DPI_CUDA(cudaMalloc(&h->d_woff, sizeof(long long) * woff.size()));
     DPI_CUDA(cudaMemcpy(h->d_woff, woff.data(), sizeof(long long) * woff.size(), cudaMemcpyHostToDevice));
   }
+  if (h->cl_avail && D == fcl::kDc && H == fcl::kHc) {
+    // flow_cl.cu pushes every output row of stage e straight into the shared memory of the CTA that consumes it in
+    // stage e + 1: CTA = (j' mod Da) / 32, slot = (a-half ? 0 : 32) + j' mod 32 for the consumer's feature j'
+    std::vector<int32_t> pm((size_t)h->S * D, 0);
+    for (int e = 0; e + 1 < h->S; ++e) {
+      const int32_t* g = &h->h_gmaps[(size_t)(e + 1) * D];      // reverse direction, stage e + 1
+      for (int jp = 0; jp < D; ++jp) {
+        const int half = jp >= Da ? 1 : 0, jl = jp - half * Da;
+        pm[(size_t)e * D + g[jp]] = (jl / fcl::kKS1) * 64 + half * 32 + jl % fcl::kKS1;
+      }
+    }
+    DPI_CUDA(cudaMalloc(&h->d_pmaps, sizeof(int32_t) * pm.size()));
+    DPI_CUDA(cudaMemcpy(h->d_pmaps, pm.data(), sizeof(int32_t) * pm.size(), cudaMemcpyHostToDevice));
+  }
   DPI_CUDA(cudaMalloc(&h->d_stages, sizeof(StageTab) * h->S));
   DPI_CUDA(cudaMemcpy(h->d_stages, h->stages.data(), sizeof(StageTab) * h->S, cudaMemcpyHostToDevice));
   DPI_CUDA(cudaMalloc(&h->d_gmaps, sizeof(int32_t) * h->h_gmaps.size()));
@@ -768,6 +784,7 @@ int dpi_flow_destroy(dpi_flow_t h) {
   cudaFree(h->d_woff);
   cudaFree(h->d_stages);
   cudaFree(h->d_gmaps);
+  cudaFree(h->d_pmaps);
   cudaFree(h->d_tbuf);
   delete h;
   return DPI_OK;

@@ -10,7 +10,7 @@ namespace dpi {
 namespace fcl {
 
 constexpr int kCL = 16;                 // CTAs of the cluster
-constexpr int kThreadsCl = 256;
+constexpr int kThreadsCl = 544;
 constexpr int kHc = 128;                // hidden width == UMMA M
 constexpr int kNS = 64;                 // sample columns of every accumulator (batch zero-padded to 64)
 constexpr int kKS1 = 32;                // a-half features per CTA (K slice of net.0)
@@ -24,8 +24,9 @@ constexpr int kW1Floats = 2 * kHc * kKS1;            // 8192
 constexpr int kW2Floats = 2 * kHc * kHS;             // 2048
 constexpr int kW3Floats = 2 * (2 * kJB) * kHc;       // 16384
 constexpr int kPackFloats = kW1Floats + kW2Floats + kW3Floats;   // 26624 per (stage, CTA), forward and backward alike
-constexpr int kPartFloats = 2 * kCL * kHc * kNS;     // two reduce-scatter partial areas
-constexpr int kScratchFloats = kPartFloats + kCL * kNS + 2 * kCL * 64;   // + logdet rows + ActNorm partial sums
+constexpr int kPartFloats = 2 * kCL * kHc * kNS;     // two reduce-scatter partial areas [16 sources][128][64]
+constexpr int kAgFloats = kCL * 2 * kNS * kHS;       // all-gather staging: per CTA one [64 x 8] operand tile, hi | lo
+constexpr int kScratchFloats = kPartFloats + kAgFloats + kCL * kNS + 4096;   // + logdet rows + ActNorm partial sums
 
 struct Plan {
   int ok = 0;

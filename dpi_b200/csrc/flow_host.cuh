@@ -72,6 +72,7 @@ struct dpi_flow_s {
   std::vector<int32_t> h_gmaps;               // [2][S][D] + trailing [D]
   dpi::StageTab* d_stages = nullptr;
   int* d_gmaps = nullptr;
+  int* d_pmaps = nullptr;                     // flow_cl push maps [S][D] (nullptr unless the shape qualifies)
   std::mutex mu;
   std::map<int, std::unique_ptr<dpi::BatchPlan>> plans;
   unsigned long long* d_tbuf = nullptr;       // debug timing stamps (2 per phase)

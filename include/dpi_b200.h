@@ -109,7 +109,8 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
 int dpi_flow_tc_active(dpi_flow_t h, int batch);
 /* 1 when `batch` runs RealNVP.reverse (realnvpfc_model.py:594-603) as the cluster-resident tcgen05 pass (flow_cl.cu:
  * ndim 1024, hidden 128, batch a multiple of 4 up to 64 - the reference's default interferometry flow,
- * DPI_interferometry.py:127); bit 1 is set when the backward pass runs there too. DPI_B200_CL=0 disables it. */
+ * DPI_interferometry.py:127); bit 1 is set when the backward pass runs there too. Opt-in: DPI_B200_CL=1 (it is
+ * parity-green but not yet faster than the fp32 small-batch kernel). */
 int dpi_flow_cl_active(dpi_flow_t h, int batch);
 
 /* Glow building block (generative_model/glow_model.py:260-268, ZeroConv2d :238-251), forward only: a k x k
