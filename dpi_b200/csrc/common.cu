@@ -3,6 +3,9 @@
 
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace dpi {
 
 static thread_local char t_error[1024] = "";
@@ -13,6 +16,31 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_error, sizeof(t_error), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+std::mutex g_handle_mu;
+std::unordered_map<const void*, int>& handle_table() {
+  static std::unordered_map<const void*, int> t;
+  return t;
+}
+}  // namespace
+void handle_register(const void* h, int kind) {
+  std::lock_guard<std::mutex> lk(g_handle_mu);
+  handle_table()[h] = kind;
+}
+bool handle_unregister(const void* h, int kind) {
+  std::lock_guard<std::mutex> lk(g_handle_mu);
+  auto it = handle_table().find(h);
+  if (it == handle_table().end() || it->second != kind) return false;
+  handle_table().erase(it);
+  return true;
+}
+bool handle_live(const void* h, int kind) {
+  if (!h) return false;
+  std::lock_guard<std::mutex> lk(g_handle_mu);
+  auto it = handle_table().find(h);
+  return it != handle_table().end() && it->second == kind;
 }
 
 int sm_count(int device) {

@@ -67,6 +67,13 @@ inline int device_of_pointer(const void* p) {
   return a.device;
 }
 
+// Live-handle registry: every entry point that takes a dpi_flow_t / dpi_eht_t rejects a pointer that was never returned by
+// its create function or has already been destroyed (a handle duplicated by copy.deepcopy / pickle must not be freed twice
+// or used after its owner is gone).
+void handle_register(const void* h, int kind);     // kind: 1 flow, 2 eht
+bool handle_unregister(const void* h, int kind);   // false: not live (double destroy)
+bool handle_live(const void* h, int kind);
+
 int sm_count(int device);
 int current_sm_count();  // SM count of the calling thread's current device (cached)
 

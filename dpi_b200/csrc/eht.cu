@@ -421,12 +421,14 @@ int dpi_eht_create(dpi_eht_t* out, int device, int npix, int n_vis, const float*
       (rc = upload(&h->d_cp_adj_sign, cp_adj_sign)) || (rc = upload(&h->d_ca_ptr, ca_ptr)) ||
       (rc = upload(&h->d_ca_adj, ca_adj)) || (rc = upload(&h->d_ca_adj_sign, ca_adj_sign)))
     return rc;
+  handle_register(h.get(), 2);
   *out = h.release();
   return DPI_OK;
 }
 
 int dpi_eht_destroy(dpi_eht_t h) {
   if (!h) return DPI_OK;
+  DPI_REQUIRE(handle_unregister(h, 2), "dpi_eht_destroy: unknown or already destroyed handle %p", (void*)h);
   DeviceGuard g(h->device);
   cudaFree(h->d_F);
   cudaFree(h->d_Bf);
@@ -438,13 +440,14 @@ int dpi_eht_destroy(dpi_eht_t h) {
 }
 
 size_t dpi_eht_workspace_bytes(dpi_eht_t h, int batch) {
-  if (!h || batch < 1) return 0;
+  if (!handle_live(h, 2) || batch < 1) return 0;
   return kCtrl * sizeof(unsigned) + (eht_ws_floats(h, batch, nullptr, nullptr) + eht_tc_floats(h, batch)) * sizeof(float) + 1024;
 }
 
 int dpi_eht_forward(dpi_eht_t h, int batch, const float* img, float* vis, float* visamp, double* cphase,
                     float* logcamp, void* workspace, size_t workspace_bytes, dpi_stream_t stream) {
-  DPI_REQUIRE(h && img && vis && workspace && batch >= 1, "dpi_eht_forward: bad argument");
+  DPI_REQUIRE(handle_live(h, 2), "dpi_eht_forward: null, unknown or destroyed operator handle");
+  DPI_REQUIRE(img && vis && workspace && batch >= 1, "dpi_eht_forward: bad argument");
   DPI_REQUIRE(workspace_bytes >= dpi_eht_workspace_bytes(h, batch), "dpi_eht_forward: workspace too small");
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -461,7 +464,8 @@ int dpi_eht_forward(dpi_eht_t h, int batch, const float* img, float* vis, float*
 int dpi_eht_backward(dpi_eht_t h, int batch, const float* vis, const float* g_vis, const float* g_visamp,
                      const double* g_cphase, const float* g_logcamp, float* g_img, void* workspace,
                      size_t workspace_bytes, dpi_stream_t stream) {
-  DPI_REQUIRE(h && vis && g_img && workspace && batch >= 1, "dpi_eht_backward: bad argument");
+  DPI_REQUIRE(handle_live(h, 2), "dpi_eht_backward: null, unknown or destroyed operator handle");
+  DPI_REQUIRE(vis && g_img && workspace && batch >= 1, "dpi_eht_backward: bad argument");
   DPI_REQUIRE(workspace_bytes >= dpi_eht_workspace_bytes(h, batch), "dpi_eht_backward: workspace too small");
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -483,6 +487,7 @@ int dpi_eht_backward(dpi_eht_t h, int batch, const float* vis, const float* g_vi
 int dpi_eht_data_grad(dpi_eht_t h, int batch, const float* vis, const float* cphase_true, const float* sigma_cp,
                       const float* logcamp_true, const float* sigma_ca, float w_cp, float w_ca, double* loss_cp,
                       float* loss_ca, float* g_img, void* workspace, size_t workspace_bytes, dpi_stream_t stream) {
+  DPI_REQUIRE(handle_live(h, 2), "dpi_eht_data_grad: null, unknown or destroyed operator handle");
   DPI_REQUIRE(h && vis && cphase_true && sigma_cp && logcamp_true && sigma_ca && loss_cp && loss_ca && g_img &&
                   workspace && batch >= 1, "dpi_eht_data_grad: bad argument");
   DPI_REQUIRE(workspace_bytes >= dpi_eht_workspace_bytes(h, batch), "dpi_eht_data_grad: workspace too small");

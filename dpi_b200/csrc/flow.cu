@@ -744,6 +744,7 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   DPI_CUDA(cudaMemcpy(h->d_stages, h->stages.data(), sizeof(StageTab) * h->S, cudaMemcpyHostToDevice));
   DPI_CUDA(cudaMalloc(&h->d_gmaps, sizeof(int32_t) * h->h_gmaps.size()));
   DPI_CUDA(cudaMemcpy(h->d_gmaps, h->h_gmaps.data(), sizeof(int32_t) * h->h_gmaps.size(), cudaMemcpyHostToDevice));
+  handle_register(h.get(), 1);
   *out = h.release();
   return DPI_OK;
 }
@@ -768,6 +769,7 @@ int dpi_flow_layout(int ndim, int n_flow, int hidden, int batch_norm, int64_t* p
 
 int dpi_flow_destroy(dpi_flow_t h) {
   if (!h) return DPI_OK;
+  DPI_REQUIRE(handle_unregister(h, 1), "dpi_flow_destroy: unknown or already destroyed handle %p", (void*)h);
   DeviceGuard g(h->device);
   for (auto& kv : h->plans) {
     for (int d = 0; d < 2; ++d)
@@ -790,23 +792,23 @@ int dpi_flow_destroy(dpi_flow_t h) {
   return DPI_OK;
 }
 
-int64_t dpi_flow_param_count(dpi_flow_t h) { return h ? h->n_params : -1; }
-int64_t dpi_flow_bn_count(dpi_flow_t h) { return h ? h->n_bn : -1; }
+int64_t dpi_flow_param_count(dpi_flow_t h) { return handle_live(h, 1) ? h->n_params : -1; }
+int64_t dpi_flow_bn_count(dpi_flow_t h) { return handle_live(h, 1) ? h->n_bn : -1; }
 
 int64_t dpi_flow_param_offset(dpi_flow_t h, int flow, int tensor_id) {
-  if (!h || flow < 0 || flow >= h->n_flow || tensor_id < 0 || tensor_id >= 4 + 2 * P_COUNT) return -1;
+  if (!handle_live(h, 1) || flow < 0 || flow >= h->n_flow || tensor_id < 0 || tensor_id >= 4 + 2 * P_COUNT) return -1;
   if (tensor_id < 4) return h->act_off[(size_t)flow * 4 + tensor_id];
   const int c = (tensor_id - 4) / P_COUNT, k = (tensor_id - 4) % P_COUNT;
   return h->cpl_off[((size_t)flow * 2 + c) * P_COUNT + k];
 }
 
 int64_t dpi_flow_bn_offset(dpi_flow_t h, int flow, int coupling, int stat_id) {
-  if (!h || flow < 0 || flow >= h->n_flow || coupling < 0 || coupling > 1 || stat_id < 0 || stat_id > 3) return -1;
+  if (!handle_live(h, 1) || flow < 0 || flow >= h->n_flow || coupling < 0 || coupling > 1 || stat_id < 0 || stat_id > 3) return -1;
   return h->bn_off[((size_t)flow * 2 + coupling) * 4 + stat_id];
 }
 
 int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out) {
-  DPI_REQUIRE(h && out, "dpi_flow_gather_map: null argument");
+  DPI_REQUIRE(handle_live(h, 1) && out, "dpi_flow_gather_map: null argument or dead handle");
   DPI_REQUIRE(direction >= 0 && direction <= 2 && stage >= 0 && (direction == 2 ? stage == 0 : stage < h->S),
               "dpi_flow_gather_map: bad direction/stage");
   const int32_t* src = &h->h_gmaps[((size_t)direction * h->S + stage) * h->D];
@@ -815,7 +817,7 @@ int dpi_flow_gather_map(dpi_flow_t h, int direction, int stage, int32_t* out) {
 }
 
 size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch) {
-  if (!h || batch < 1) return 0;
+  if (!handle_live(h, 1) || batch < 1) return 0;
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
@@ -823,7 +825,7 @@ size_t dpi_flow_workspace_bytes(dpi_flow_t h, int batch) {
 }
 
 int64_t dpi_flow_ws_offset(dpi_flow_t h, int batch, int what, int stage) {
-  if (!h || batch < 1 || stage < 0 || stage >= h->S) return -1;
+  if (!handle_live(h, 1) || batch < 1 || stage < 0 || stage >= h->S) return -1;
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return -1;
@@ -852,7 +854,7 @@ int dpi_flow_tc_plan(int M, int N, int K, int n_sm, int32_t* out) {
 }
 
 int dpi_flow_debug_timing(dpi_flow_t h, int enable) {
-  DPI_REQUIRE(h, "dpi_flow_debug_timing: null handle");
+  DPI_REQUIRE(handle_live(h, 1), "dpi_flow_debug_timing: null or dead handle");
   DeviceGuard g(h->device);
   std::lock_guard<std::mutex> lk(h->mu);
   if (enable && !h->d_tbuf) {
@@ -867,7 +869,7 @@ int dpi_flow_debug_timing(dpi_flow_t h, int enable) {
 }
 
 int dpi_flow_debug_read(dpi_flow_t h, uint64_t* stamps, int32_t* ops, int max_phases) {
-  DPI_REQUIRE(h && stamps && ops, "dpi_flow_debug_read: null argument");
+  DPI_REQUIRE(handle_live(h, 1) && stamps && ops, "dpi_flow_debug_read: null argument or dead handle");
   DPI_REQUIRE(h->d_tbuf, "dpi_flow_debug_read: timing not enabled");
   DeviceGuard g(h->device);
   DPI_CUDA(cudaDeviceSynchronize());
@@ -880,7 +882,7 @@ int dpi_flow_debug_read(dpi_flow_t h, uint64_t* stamps, int32_t* ops, int max_ph
 }
 
 int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {
-  DPI_REQUIRE(h, "dpi_flow_set_mode: null handle");
+  DPI_REQUIRE(handle_live(h, 1), "dpi_flow_set_mode: null or dead handle");
   std::lock_guard<std::mutex> lk(h->mu);
   h->persistent = persistent ? 1 : 0;
   if (ctas_per_sm > 0 && ctas_per_sm != h->ctas_per_sm) {
@@ -902,7 +904,8 @@ int dpi_flow_set_mode(dpi_flow_t h, int persistent, int ctas_per_sm) {
 int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float* params, float* bn_running,
                  const float* in, float* out, float* logdet, void* workspace, size_t workspace_bytes,
                  dpi_stream_t stream) {
-  DPI_REQUIRE(h && params && in && out && logdet && workspace, "dpi_flow_run: null argument");
+  DPI_REQUIRE(handle_live(h, 1), "dpi_flow_run: null, unknown or destroyed flow handle");
+  DPI_REQUIRE(params && in && out && logdet && workspace, "dpi_flow_run: null argument");
   DPI_REQUIRE(direction == 0 || direction == 1, "dpi_flow_run: direction must be 0 (reverse) or 1 (forward)");
   DPI_REQUIRE(batch >= 1, "dpi_flow_run: batch must be >= 1");
   DPI_REQUIRE(!(h->has_bn && !bn_running), "dpi_flow_run: bn_running required for a BatchNorm flow");
@@ -934,7 +937,8 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
 int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
                       const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                       size_t workspace_bytes, dpi_stream_t stream) {
-  DPI_REQUIRE(h && params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward: null argument");
+  DPI_REQUIRE(handle_live(h, 1), "dpi_flow_backward: null, unknown or destroyed flow handle");
+  DPI_REQUIRE(params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward: null argument");
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   int rc = get_plan(h, batch, &bp);
@@ -961,7 +965,8 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
 int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
                             const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                             size_t workspace_bytes, int stage_lo, int stage_hi, dpi_stream_t stream) {
-  DPI_REQUIRE(h && params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward_range: null argument");
+  DPI_REQUIRE(handle_live(h, 1), "dpi_flow_backward_range: null, unknown or destroyed flow handle");
+  DPI_REQUIRE(params && grads && in && g_out && g_logdet && workspace, "dpi_flow_backward_range: null argument");
   DPI_REQUIRE(0 <= stage_lo && stage_lo < stage_hi && stage_hi <= h->S, "dpi_flow_backward_range: bad stage range [%d, %d) of %d",
               stage_lo, stage_hi, h->S);
   if (stage_lo == 0 && stage_hi == h->S)
@@ -989,7 +994,7 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
 }
 
 int dpi_flow_cl_active(dpi_flow_t h, int batch) {
-  if (!h || batch < 1) return 0;
+  if (!handle_live(h, 1) || batch < 1) return 0;
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
@@ -997,7 +1002,7 @@ int dpi_flow_cl_active(dpi_flow_t h, int batch) {
 }
 
 int dpi_flow_tc_active(dpi_flow_t h, int batch) {
-  if (!h || batch < 1) return 0;
+  if (!handle_live(h, 1) || batch < 1) return 0;
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;

@@ -18,8 +18,8 @@ namespace dpi {
 // Monotonic-counter barrier over all CTAs of a cooperative launch: ctrl[0] counts arrivals over the
 // whole launch (zeroed by the host before the launch), barrier number `idx` completes when it reaches
 // (idx + 1) * nblocks. Thread 0 publishes the CTA's writes with a release-add (cumulative over the
-// preceding bar.sync) and polls with acquire loads. The spin is bounded (about 2 s) so a protocol bug
-// cannot hang the GPU; ctrl[2] is the error flag.
+// preceding bar.sync) and polls with acquire loads. The spin is bounded (4e9 cycles, about 2 s) so a protocol
+// bug cannot hang the GPU; ctrl[2] is the sticky error flag, which the final phases turn into NaN outputs.
 __device__ __forceinline__ void grid_sync(unsigned* ctrl, unsigned nblocks, unsigned idx) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -428,7 +428,8 @@ __device__ __noinline__ void op_logdet_final(const KArgs& a, int t, float* sRed)
     for (int r = 0; r < 8; ++r) s += sRed[r * 32 + lane];
     float lsum = 0.f;
     for (int e = 0; e < a.S; ++e) lsum += __ldg(a.P + a.st[e].lsi);
-    a.logdet[m] = s + (a.dir == 0 ? (float)a.D * lsum : -(float)a.D * lsum);
+    // a grid barrier that timed out (sticky flag ctrl[2]) must not pass silently: the outputs become NaN
+    a.logdet[m] = s + (a.dir == 0 ? (float)a.D * lsum : -(float)a.D * lsum) + (__ldcg(a.ctrl + 2) ? __int_as_float(0x7fc00000) : 0.f);
   }
 }
 
@@ -762,8 +763,9 @@ __device__ __noinline__ void op_bwd_final(const KArgs& a, float* sRed) {
     s2 = warp_sum(s2);
     if (lane == 0) {
       const StageTab& st = a.st[e];
-      a.G[st.loc] = -s1;
-      a.G[st.lsi] = s2 + (float)a.D * gld;
+      const float bad = (__ldcg(a.ctrl + 2) ? __int_as_float(0x7fc00000) : 0.f);   // timed-out grid barrier -> NaN gradients
+      a.G[st.loc] = -s1 + bad;
+      a.G[st.lsi] = s2 + (float)a.D * gld + bad;
     }
   }
 }

@@ -71,7 +71,8 @@ __device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
 }
 // Split grid barrier on a monotonic counter (zeroed by the host before the launch). arrive publishes
 // every global write of the CTA (bar.sync, then a gpu-scope release by thread 0); wait spins with acquire
-// loads, bounded (~2 s) so a protocol bug sets the error flag ctrl[2] instead of hanging the GPU.
+// loads, bounded (4e9 cycles, about 2 s) so a protocol bug sets the sticky error flag ctrl[2] instead of hanging the
+// GPU; the final phase of the pass turns the flag into NaN outputs (logdet / ActNorm gradients) so it cannot be missed.
 __device__ __forceinline__ void grid_arrive(unsigned* ctrl) {
   __syncthreads();
   if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctrl), "r"(1u) : "memory");
@@ -85,7 +86,7 @@ __device__ __forceinline__ void grid_wait(unsigned* ctrl, unsigned target) {
       const long long t0 = clock64();
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(ctrl) : "memory");
-        if (cur < target && (clock64() - t0 > 400000000LL || ld_flag(ctrl + 2))) {
+        if (cur < target && (clock64() - t0 > 4000000000LL || ld_flag(ctrl + 2))) {
           atomicExch(ctrl + 2, 1u);   // sticky: every later wait of every CTA gives up at once
           break;
         }
@@ -814,7 +815,8 @@ __device__ __noinline__ void run_logdet_final(const SArgs& A, const Sm& s) {
       float t = 0.f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) t += s.red[r * 32 + lane];
-      a.logdet[m] = t + (a.dir == 0 ? (float)a.D * lsum : -(float)a.D * lsum);
+      // a grid barrier that timed out (sticky flag ctrl[2]) must not pass silently: the outputs become NaN
+      a.logdet[m] = t + (a.dir == 0 ? (float)a.D * lsum : -(float)a.D * lsum) + (__ldcg(a.ctrl + 2) ? __int_as_float(0x7fc00000) : 0.f);
     }
   }
 }
@@ -1022,8 +1024,9 @@ __device__ __noinline__ void run_bwd_final(const SArgs& A, const Sm& s) {
     s2 = warp_sum(s2);
     if (lane == 0) {
       const StageTab& st = s.st[e];
-      a.G[st.loc] = -s1;
-      a.G[st.lsi] = s2 + (float)a.D * gld;
+      const float bad = (__ldcg(a.ctrl + 2) ? __int_as_float(0x7fc00000) : 0.f);   // timed-out grid barrier -> NaN gradients
+      a.G[st.loc] = -s1 + bad;
+      a.G[st.lsi] = s2 + (float)a.D * gld + bad;
     }
   }
 }

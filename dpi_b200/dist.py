@@ -74,6 +74,47 @@ def allreduce_buckets_(flat: torch.Tensor, buckets, group=None):
     return works
 
 
+def shard_layout(n: int, world: int, align: int = 32):
+    """Equal contiguous shards of a flat buffer of `n` floats: (floats per rank - a multiple of `align` -, padded total).
+    SURVEY 8(e): reduce-scatter -> per-shard ||g||^2 -> scalar all-reduce -> clip + Adam on the shard -> all-gather."""
+    per = -(-int(n) // (int(world) * align)) * align
+    return per, per * int(world)
+
+
+def reduce_scatter_sum_(shard: torch.Tensor, full: torch.Tensor, group=None) -> torch.Tensor:
+    """shard <- this rank's slice of the element-wise sum of `full` over all ranks (NCCL reduce-scatter; gloo, which has
+    no reduce-scatter, falls back to all-reduce + slice so the host logic can be tested on CPU)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert full.numel() == shard.numel() * world
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(shard, full, op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        shard.copy_(tmp[rank * shard.numel():(rank + 1) * shard.numel()])
+    return shard
+
+
+def all_gather_shards_(full: torch.Tensor, shard: torch.Tensor, group=None) -> torch.Tensor:
+    """full <- concatenation of every rank's shard (in place when `shard` is this rank's slice of `full`)."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(full, shard, group=group)
+    else:
+        parts = [torch.empty_like(shard) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, shard.clone(), group=group)
+        full.copy_(torch.cat(parts))
+    return full
+
+
+def broadcast_state_(tensors, src: int = 0, group=None):
+    """Make every replica start from rank `src`'s tensors (parameters, BatchNorm running statistics, log_scale): the
+    data-parallel step keeps replicas identical only if they start identical."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+
+
 def replicas_max_divergence(flat: torch.Tensor, group=None) -> float:
     """max |flat - rank0's flat| over all ranks (0.0 when the replicas are in sync)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -123,15 +123,18 @@ class Glow(nn.Module):
         self.blocks.append(Block(n_channel, n_flow, split=False))
 
     def _no_gradients_yet(self, inputs, what):
-        """The backward of the Glow path is not built: say so instead of returning history-free tensors silently."""
+        """The backward of the Glow path is not built. A training loop (gradients enabled, trainable parameters) must
+        not receive history-free tensors silently - loss.backward() would then reach only `logscale_factor`, Adam would
+        never move the flow and the BatchNorm running statistics would still drift: raise. Sampling / density
+        evaluation is opt-in through torch.no_grad() (or a model whose parameters do not require grad)."""
         if any(t.requires_grad for t in inputs):
             raise NotImplementedError(f"dpi_b200 Glow.{what}: gradients are not built yet (input requires grad); "
                                       "use the RealNVP flow for training or call under torch.no_grad() for sampling")
-        if torch.is_grad_enabled() and not getattr(self, "_warned", False):
-            import warnings
-            warnings.warn(f"dpi_b200 Glow.{what} runs as an inference pass: its outputs carry no autograd history "
-                          "(the training backward of Glow is not built yet)", stacklevel=3)
-            self._warned = True
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                f"dpi_b200 Glow.{what}: the training backward of Glow is not built yet, so this call cannot record "
+                "autograd history for its parameters. Wrap inference in torch.no_grad() (or freeze the parameters); "
+                "train with generative_model.realnvpfc_model.RealNVP.")
 
     def forward(self, input):
         """Density direction (:508-524): image [B, in_channel, npix, npix] -> (log_p_sum [B], logdet [B], z_outs)."""

@@ -328,10 +328,31 @@ class RealNVP(nn.Module):
     def __del__(self):
         try:
             lib = _lib.load()
-            for h in self._handles.values():
+            for h in self.__dict__.get("_handles", {}).values():
                 lib.dpi_flow_destroy(h)
         except Exception:
             pass
+
+    # A native handle is a raw pointer owned by exactly one Python object: copies (copy.deepcopy for an EMA / best-model
+    # snapshot) and pickles (torch.save(model)) drop it and re-create their own lazily on first use.
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_handles"] = {}
+        state["_last_ws"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_handles", "_last_ws", "blocks"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__["_handles"] = {}
+        new.__dict__["_last_ws"] = None
+        object.__setattr__(new, "blocks", [Flow(new, f"blocks.{i}.") for i in range(self.n_flow)])
+        return new
 
     def gather_map(self, direction: int, stage: int) -> np.ndarray:
         """The fused permutation map the kernels use for execution stage `stage` (direction 0 = reverse,

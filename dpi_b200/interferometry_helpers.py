@@ -171,12 +171,28 @@ class _EhtOp:
         cai = np.ascontiguousarray(np.stack([np.asarray(t.cpu()) for t in ca_ind]).astype(np.int64)) \
             if len(ca_ind) and len(ca_ind[0]) else np.zeros((4, 0), np.int64)
         self.n_cp, self.n_ca = cpi.shape[1], cai.shape[1]
-        out = C.c_void_p()
-        _lib.check(lib.dpi_eht_create(C.byref(out), self.device.index, self.npix, self.n_vis, F.ctypes.data,
-                                      self.n_cp, cpi.ctypes.data, cps.ctypes.data, self.n_ca, cai.ctypes.data),
-                   "dpi_eht_create")
-        self.handle = out.value
+        self._tables = (F, cpi, cps, cai)     # kept so that a copy / unpickled instance can build its own native handle
+        self._handle = None
         self._ws = {}
+        _ = self.handle
+
+    @property
+    def handle(self):
+        """The native operator handle (a raw pointer owned by exactly this object; created on first use)."""
+        if self._handle is None:
+            F, cpi, cps, cai = self._tables
+            out = C.c_void_p()
+            _lib.check(_lib.load().dpi_eht_create(C.byref(out), self.device.index, self.npix, self.n_vis, F.ctypes.data,
+                                                  self.n_cp, cpi.ctypes.data, cps.ctypes.data, self.n_ca,
+                                                  cai.ctypes.data), "dpi_eht_create")
+            self._handle = out.value
+        return self._handle
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_handle"] = None     # copies and pickles never share (and never double-free) the pointer
+        state["_ws"] = {}
+        return state
 
     def workspace(self, B):
         ws = self._ws.get(B)
@@ -188,7 +204,8 @@ class _EhtOp:
 
     def __del__(self):
         try:
-            _lib.load().dpi_eht_destroy(self.handle)
+            if self.__dict__.get("_handle") is not None:
+                _lib.load().dpi_eht_destroy(self._handle)
         except Exception:
             pass
 

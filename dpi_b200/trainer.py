@@ -47,15 +47,36 @@ class _FusedTrainer:
         dev, f32 = self.device, torch.float32
         P = self.flow.flat.numel()
         self.P = P
-        # parameters: [flow flat | log_scale | pad]; gradients share the layout so ONE all-reduce covers both
-        self.params = self.flow.flat.data
-        self.log_scale = torch.full((32,), 0.0, dtype=f32, device=dev)
-        self.log_scale[0] = float(log_scale_init)
-        self.grads_all = torch.zeros(P + 32, dtype=f32, device=dev)
+        # Data parallel, SURVEY 8(e): reduce-scatter the flat gradient -> per-shard ||g||^2 -> scalar all-reduce ->
+        # clip + Adam on this rank's 1/world shard (optimizer state and traffic / world) -> all-gather the parameters.
+        # DPI_B200_ZERO=0 keeps the plain all-reduce + replicated Adam.
+        self.zero = self.world > 1 and os.environ.get("DPI_B200_ZERO", "1") != "0"
+        if self.zero:
+            from dpi_b200.dist import shard_layout
+            self.rank = torch.distributed.get_rank(process_group)
+            self.shard_n, n_all = shard_layout(P + 32, self.world)
+            # ONE buffer [flow flat | log_scale (32) | pad]: the flow's parameter becomes a view of it
+            self.pall = torch.zeros(n_all, dtype=f32, device=dev)
+            self.pall[:P].copy_(self.flow.flat.data)
+            self.flow.flat.data = self.pall[:P]
+            self.params = self.flow.flat.data
+            self.log_scale = self.pall[P:P + 32]
+            self.log_scale[0] = float(log_scale_init)
+            self.grads_all = torch.zeros(n_all, dtype=f32, device=dev)
+            self.p_shard = self.pall[self.rank * self.shard_n:(self.rank + 1) * self.shard_n]
+            self.g_shard = torch.zeros(self.shard_n, dtype=f32, device=dev)
+            self.m = torch.zeros(self.shard_n, dtype=f32, device=dev)     # Adam state of this rank's shard only
+            self.v = torch.zeros(self.shard_n, dtype=f32, device=dev)
+        else:
+            # parameters: [flow flat | log_scale | pad]; gradients share the layout so ONE all-reduce covers both
+            self.params = self.flow.flat.data
+            self.log_scale = torch.full((32,), 0.0, dtype=f32, device=dev)
+            self.log_scale[0] = float(log_scale_init)
+            self.grads_all = torch.zeros(P + 32, dtype=f32, device=dev)
+            self.m = torch.zeros(P, dtype=f32, device=dev)
+            self.v = torch.zeros(P, dtype=f32, device=dev)
         self.grads = self.grads_all[:P]
         self.g_ls = self.grads_all[P:P + 1]
-        self.m = torch.zeros(P, dtype=f32, device=dev)
-        self.v = torch.zeros(P, dtype=f32, device=dev)
         self.m_ls = torch.zeros(32, dtype=f32, device=dev)
         self.v_ls = torch.zeros(32, dtype=f32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -82,6 +103,11 @@ class _FusedTrainer:
         # Data parallel on the tcgen05 path: run the flow backward in stage ranges and all-reduce each range's slice of
         # the flat gradient (the backward visits the flow blocks in parameter order) while the next range runs.
         self._buckets = self._plan_buckets()
+        if self.world > 1:
+            # replicas must START identical: every rank takes rank 0's parameters, running statistics, scale
+            from dpi_b200.dist import broadcast_state_
+            broadcast_state_([self.pall] if self.zero else [self.params, self.log_scale], 0, self.pg)
+            broadcast_state_([self.flow.bn_running], 0, self.pg)
         self.use_graph = use_graph
         self._prof = None
         self._graphs = None
@@ -163,6 +189,21 @@ class _FusedTrainer:
     def _enqueue_update(self):
         lib, st = self.lib, _lib.stream_ptr()
         gs = 1.0 / self.world
+        if self.zero:
+            from dpi_b200.dist import all_gather_shards_
+            b1, b2 = self.betas
+            # g_shard holds this rank's slice of the summed gradient (reduce-scatter, or a slice of the bucket-reduced buffer)
+            g = self.g_shard if not self._reduced else self.grads_all[self.rank * self.shard_n:(self.rank + 1) * self.shard_n]
+            _lib.check(lib.dpi_grad_sqnorm(self.shard_n, g.data_ptr(), self.sq.data_ptr(), self.ws_opt.data_ptr(),
+                                           self.ws_opt.numel(), st), "dpi_grad_sqnorm")
+            torch.distributed.all_reduce(self.sq[:1], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
+            _lib.check(lib.dpi_clip_adam(self.shard_n, self.p_shard.data_ptr(), g.data_ptr(), self.m.data_ptr(),
+                                         self.v.data_ptr(), self.sq.data_ptr(), 1, self.clip, self.lr, b1, b2, self.eps,
+                                         self.step_dev.data_ptr(), gs, self.norm_out.data_ptr(), st), "dpi_clip_adam")
+            all_gather_shards_(self.pall, self.p_shard, self.pg)
+            self._mark("clip_adam")
+            return
         _lib.check(lib.dpi_grad_sqnorm(self.P + 1, self.grads_all.data_ptr(), self.sq.data_ptr(),
                                        self.ws_opt.data_ptr(), self.ws_opt.numel(), st), "dpi_grad_sqnorm")
         _lib.check(lib.dpi_step_increment(self.step_dev.data_ptr(), st), "dpi_step_increment")
@@ -181,8 +222,12 @@ class _FusedTrainer:
 
     def _allreduce_impl(self):
         if self.world > 1 and not getattr(self, "_reduced", False):
-            from dpi_b200.dist import allreduce_sum_
-            allreduce_sum_(self.grads_all, self.pg)
+            if self.zero:
+                from dpi_b200.dist import reduce_scatter_sum_
+                reduce_scatter_sum_(self.g_shard, self.grads_all, self.pg)
+            else:
+                from dpi_b200.dist import allreduce_sum_
+                allreduce_sum_(self.grads_all, self.pg)
 
     def loss_and_grad(self, z: Optional[torch.Tensor] = None):
         """Forward + backward only (no update): fills self.grads / self.g_ls / self.terms."""
@@ -483,6 +528,9 @@ class DPIxTrainer:
         self.ws_eht = self.op.workspace(B)
         self.ws_opt = torch.zeros(self.lib.dpi_clip_adam_workspace_bytes(P), dtype=torch.uint8, device=dev)
         self.launches_per_step = None
+        if self.world > 1:      # replicas must start identical
+            from dpi_b200.dist import broadcast_state_
+            broadcast_state_([self.params, self.flow.bn_running], 0, self.pg)
 
     def data_weight(self):
         return min(10.0 ** (-self.start_order + self.k / self.decay_rate), 1.0)      # DPIx_interferometry.py:331

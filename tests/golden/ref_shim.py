@@ -1,8 +1,9 @@
 """Import the *unmodified* reference modules from /root/reference (build container only).
 
-Used by `make_golden.py` (fixture generation) and by the `needs_reference` tests that pin the
-oracle against the live reference. Never imported by the product path, `bench.py` or any
-`-m gpu` test: /root/reference does not exist on the GPU box.
+Used by `make_golden.py` (fixture generation), by the `needs_reference` tests that pin the oracle
+against the live reference, and by `baseline/ref_step.py` (the reference arm of bench.py, which
+points REF_ROOT at the git-ignored reference install `baseline/_ref/DPItorch` on the GPU box).
+Never imported by the product path or any `-m gpu` test.
 
 Third-party imports the reference makes at module scope (matplotlib, torchkbnufft, ehtim,
 astropy, pynfft - none installed here) are replaced by stub modules; the two ehtim helpers the

@@ -61,6 +61,35 @@ def _worker(rank, world, port, out):
     for w in ddist.allreduce_buckets_(flat_b, buckets):
         w.wait()
     assert torch.equal(flat_b, flat_g)
+    # SURVEY 8(e) sharded optimiser: reduce-scatter -> per-shard ||g||^2 -> scalar all-reduce -> clip + Adam on the shard ->
+    # all-gather. Must reproduce the replicated update bit for bit (same element-wise arithmetic, the norm is a sum of the
+    # per-shard sums) and leave every replica with identical parameters.
+    n = flat_g.numel() - 7                                # a length that does not divide evenly: the tail is padding
+    per, n_all = ddist.shard_layout(n, world)
+    assert per % 32 == 0 and n_all == per * world and n_all >= n and n_all - n < world * 32
+    g_full = torch.zeros(n_all)
+    g_full[:n] = ddist.pack_named(model, _shard_grads(sd, z, cx, cl))[:n]
+    p_full = torch.zeros(n_all)
+    p_full[:n] = model.flat.detach()[:n]
+    if rank == 1:
+        p_full[:n] += 1.0                                   # a replica that starts different ...
+    ddist.broadcast_state_([p_full], 0)                     # ... is overwritten with rank 0's state
+    g_sh = torch.empty(per)
+    ddist.reduce_scatter_sum_(g_sh, g_full)
+    kk = max(0, min(per, n - rank * per))
+    assert torch.equal(g_sh[:kk], flat_g[rank * per:rank * per + kk]) and float(g_sh[kk:].abs().sum()) == 0.0
+    sq = (g_sh.double() ** 2).sum().reshape(1)
+    dist.all_reduce(sq)
+    norm_z = float(torch.sqrt(sq)) / world
+    assert abs(norm_z - float(norm)) <= 1e-6 * float(norm)
+    coef_z = min(1.0, 1e-3 / (norm_z + 1e-6))
+    p_sh = p_full[rank * per:(rank + 1) * per]
+    m_sh, v_sh = torch.zeros(per), torch.zeros(per)
+    O.adam_update(p_sh, g_sh / world * coef_z, m_sh, v_sh, 1, 1e-4)
+    ddist.all_gather_shards_(p_full, p_sh)
+    assert ddist.replicas_max_divergence(p_full) == 0.0
+    assert float((p_full[:n] - p[:n]).abs().max()) <= 2e-7 * float(p.abs().max())
+    assert float(p_full[n:].abs().max()) == 0.0             # padding never moves
     lo, hi = ddist.shard_range(10, rank, world)
     assert (hi - lo) == 5 and lo == 5 * rank
     if rank == 0:

@@ -68,6 +68,9 @@ def test_glow_reverse_matches_reference_fixture():
     g, sd, m = _glow_from_fixture()
     zs = [torch.from_numpy(g[f"z{i}"]).cuda() for i in range(int(g["n_block"]))]
     m.train()
+    with pytest.raises(NotImplementedError):        # a training loop must not get history-free tensors silently
+        m.reverse(zs)
+    torch.set_grad_enabled(False)                   # inference is opt-in (the whole test runs under no_grad)
     x, ld = m.reverse(zs)
     assert rel_err(x, g["x_rev"]) < RTOL, rel_err(x, g["x_rev"])
     assert rel_err(ld, g["ld_rev"]) < RTOL, rel_err(ld, g["ld_rev"])
@@ -83,6 +86,7 @@ def test_glow_reverse_matches_reference_fixture():
         assert rel_err(z, g[f"zf{i}"]) < RTOL, (i, rel_err(z, g[f"zf{i}"]))
     m.eval()
     xe, lde = m.reverse(zs)
+    torch.set_grad_enabled(True)
     assert rel_err(xe, g["x_rev_eval"]) < RTOL and rel_err(lde, g["ld_rev_eval"]) < RTOL
 
 
@@ -112,6 +116,8 @@ def test_glow_reverse_matches_oracle(npix, n_flow, n_block, B):
     zs = [torch.randn(B, *s) for s in shapes]
     xo, lo = GO.glow_reverse(sd, zs, train=True)
     m = m.cuda().train()
+    for p_ in m.parameters():                                # frozen parameters: the other way to opt in to inference
+        p_.requires_grad_(False)
     x, ld = m.reverse([z.cuda() for z in zs])
     assert x.shape == (B, 1, npix, npix)
     assert rel_err(x, xo) < RTOL, rel_err(x, xo)

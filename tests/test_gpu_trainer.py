@@ -103,22 +103,28 @@ def test_mri_trainer_matches_reference_run():
         assert rel_err(mine[k].float(), v.float()) < RTOL, k
 
 
-@pytest.mark.parametrize("kind", ["interferometry", "mri"])
+@pytest.mark.parametrize("kind", ["interferometry", "mri", "scaleup"])
 def test_full_size_step_vs_oracle(kind):
-    """BASELINE configs C1 (npix=32, n_flow=16, B=64) / C2 shape class (npix=64, B=64; n_flow reduced to 4 so
-    the CPU oracle finishes in seconds): two optimisation steps, non-trivial weights."""
+    """BASELINE configs at their own sizes: C1 (npix=32, n_flow=16, B=64), C2 (MRI npix=64, n_flow=16, B=64) and the
+    layer shapes of C4 on the tcgen05 path (npix=64: D=4096, H=512, batch 1024; 4 of its 32 flows, the per-flow work
+    is identical): two optimisation steps from non-trivial weights against the CPU oracle trainer."""
+    from dpi_b200 import _lib
     from dpi_b200.trainer import InterferometryTrainer, MRITrainer
     from dpi_b200.workloads import interferometry_workload, mri_workload
     if kind == "interferometry":
         wl, NF, B, lr, clip = interferometry_workload(npix=32), 16, 64, 1e-4, 1e-3
         T, loss_fn = InterferometryTrainer, O.interferometry_loss
-    else:
-        wl, NF, B, lr, clip = mri_workload(npix=64), 4, 64, 1e-5, 1e-2
+    elif kind == "mri":
+        wl, NF, B, lr, clip = mri_workload(npix=64), 16, 64, 1e-5, 1e-2
         T, loss_fn = MRITrainer, O.mri_loss
+    else:
+        wl, NF, B, lr, clip = interferometry_workload(npix=64), 4, 1024, 1e-4, 1e-3
+        T, loss_fn = InterferometryTrainer, O.interferometry_loss
     D = wl["npix"] ** 2
     sd = O.init_state(D, NF, seed=21, randomize=True)
     sd0 = {k: v.clone() for k, v in sd.items()}
     tr = T(_flow(D, NF, {k: v.clone() for k, v in sd.items()}), wl, B, lr=lr, clip=clip, use_graph=False)
+    assert _lib.load().dpi_flow_tc_active(tr.handle, B) == (1 if kind == "scaleup" else 0)
     ls = torch.tensor([wl["log_scale_init"]], dtype=torch.float32)
     ot = O.OracleTrainer(sd, ls, loss_fn, _consts(wl), lr=lr, clip=clip)
     torch.manual_seed(9)
@@ -128,7 +134,11 @@ def test_full_size_step_vs_oracle(kind):
         terms = tr.step(z.cuda()).cpu()
         assert rel_err(terms[0], lo) < RTOL, (k, float(terms[0]), float(lo))
         assert rel_err(terms[4], to["logdet"]) < RTOL
-        assert rel_err(tr.norm_out[0], to["grad_norm"]) < RTOL
+        # Step 0 is the parity statement (same weights, same z): 1e-4. Step 1 starts from weights that already differ:
+        # Adam's first update is lr * sign(g), so every element whose gradient is at round-off level moves by +-lr on one
+        # side and -+lr on the other (measured at C2's size: step 0 loss 1.2e-7 / ||g|| 6.7e-5, step 1 loss 8e-5 /
+        # ||g|| 3.6e-4 with a 1/sigma^2 = 4e12 objective) - the second step only has to stay on the same trajectory.
+        assert rel_err(tr.norm_out[0], to["grad_norm"]) < (RTOL if k == 0 else 10 * RTOL), (k, kind)
         if k == 0:
             assert rel_err(tr.x, to["x"]) < RTOL and rel_err(tr.img.view_as(to["img"]), to["img"]) < RTOL
     # Adam normalises every element by its own |g| (update ~ +-lr even where the gradient is at noise

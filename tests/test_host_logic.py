@@ -199,11 +199,36 @@ def test_glow_module_surface_and_reference_state_dict():
     zs = [torch.randn(2, *s) for s in calc_z_shapes(1, 8, 1, 2)]
     with pytest.raises(NotImplementedError):
         m.reverse([z.clone().requires_grad_(True) for z in zs])
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
+    with pytest.raises(NotImplementedError, match="training backward"):    # grad enabled + trainable parameters
+        m.reverse(zs)
+    with torch.no_grad():
         with pytest.raises(RuntimeError, match="no CPU path"):
             m.reverse(zs)
         with pytest.raises(RuntimeError, match="no CPU path"):
             m.forward(torch.randn(2, 1, 8, 8))
     with pytest.raises(NotImplementedError):
         Glow(1, 1, 2, affine=False)
+
+
+def test_native_handles_are_validated_and_never_shared_by_copies():
+    """a raw handle duplicated by copy.deepcopy / pickle must not be double-freed, and an unknown pointer is
+    rejected by the C ABI instead of being dereferenced (no CUDA call is made here)."""
+    import copy
+    import ctypes as C
+    import pickle
+    from dpi_b200 import _lib
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    lib = _lib.load()
+    bogus = C.c_void_p(0xDEADBEE0)
+    assert lib.dpi_flow_destroy(bogus) != 0 and b"destroyed" in lib.dpi_last_error()
+    assert lib.dpi_eht_destroy(bogus) != 0
+    assert lib.dpi_flow_param_count(bogus) == -1 and lib.dpi_flow_workspace_bytes(bogus, 8) == 0
+    assert lib.dpi_flow_cl_active(bogus, 8) == 0 and lib.dpi_eht_workspace_bytes(bogus, 8) == 0
+    assert lib.dpi_flow_run(bogus, 0, 1, 8, None, None, None, None, None, None, 0, None) != 0
+    m = RealNVP(8, 2, seqfrac=1)
+    m._handles[0] = 0xDEADBEE0                      # stands for a live native handle
+    for other in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert other._handles == {} and other._last_ws is None
+        assert torch.equal(other.flat.detach(), m.flat.detach())
+        assert other.blocks[1].coupling2 is not None and other.blocks[0]._m is other
+    m._handles.clear()
