@@ -65,6 +65,18 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, unsigned
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"((unsigned short)mask)
       : "memory");
 }
+__device__ __forceinline__ unsigned mapa_u32(unsigned laddr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
+  return r;
+}
+// 16 bytes from registers straight into a peer CTA's shared memory; the peer's mbarrier counts them (complete_tx):
+// no staging, no proxy fence, no bulk-copy issue slot (each cp.async.bulk costs ~65 cycles of a per-SM serial resource)
+__device__ __forceinline__ void st_async4(unsigned raddr, float4 v, unsigned rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rbar)
+               : "memory");
+}
 // generic-proxy global writes -> visible to the bulk-copy engine
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
@@ -198,7 +210,7 @@ struct SmemFwd {
   static constexpr int oW1 = 0;                                  // 32 KB   W1 slice (hi | lo)
   static constexpr int oW2 = oW1 + kW1Floats * 4;                // 8 KB    W2 slice
   static constexpr int oW3 = oW2 + kW2Floats * 4;                // 64 KB   W3 slice: 16 hi k-tiles | 16 lo k-tiles (a descriptor
-                                                                 //         spans 128 rows: it reads 2 KB past its tile)
+                                                                 //         is an M = 64 operand)
   static constexpr int oN2 = oW3 + kW3Floats * 4;                // 64 KB   n2 operand: 16 slices x [64 x 8] (hi | lo), pushed by
                                                                  //         their owners; its first 32 KB double as the
                                                                  //         reduce-scatter buffer of net.0
@@ -212,9 +224,15 @@ struct SmemFwd {
 static_assert(64 * kTilePitch * 4 <= kCL * kHS * kNS * 4, "tail tile must fit the region it aliases");
 static_assert(SmemFwd::bytes <= 222 * 1024, "dynamic shared memory budget");
 
+// debug stamps: every CTA records %globaltimer (ns, common to all SMs) at 16 points per stage: tbuf[(cta * 32 + e) * 16 + slot]
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define CL_STAMP(slot)                                                                      \
   do {                                                                                      \
-    if (a.tbuf && blockIdx.x == 0 && threadIdx.x == 0) a.tbuf[(size_t)e * 16 + (slot)] = (unsigned long long)clock64(); \
+    if (a.tbuf && threadIdx.x == 0 && e < 32) a.tbuf[((size_t)c * 32 + e) * 16 + (slot)] = gtime(); \
   } while (0)
 
 // mbarrier slots of the forward kernel
@@ -232,7 +250,7 @@ struct StageRegs {
   float b1, g1, be1, rm1, rv1;         // hidden feature 8c + warp (warps 0..7): net.0 bias, BatchNorm 1
   float b2, g2, be2, rm2, rv2;
   float b3, sc3;                       // ZeroFC row of this thread's TMEM lane (lanes 0..63)
-  int push;                            // consumer slot of output row t (t < 64)
+  int push_a, push_b;                  // consumer (cta * 64 + slot) of output rows 32c + p and Da + 32c + p, p = t >> 4
 };
 __device__ __forceinline__ void load_stage_regs(StageRegs& r, const KArgs& a, int e, int c, int t) {
   constexpr int Da = kDc / 2, Db = kDc / 2;
@@ -251,14 +269,17 @@ __device__ __forceinline__ void load_stage_regs(StageRegs& r, const KArgs& a, in
     }
   }
   r.b3 = 0.f; r.sc3 = 0.f;
-  const int trow = (warp & 3) * 32 + lane;
+  const int trow = lane < 16 ? (warp & 3) * 16 + lane : 2 * kJB;      // M = 64 accumulator: row r in TMEM lane r % 16 + 32 (r / 16)
   if (trow < 2 * kJB) {
     const int j3 = trow < kJB ? c * kJB + trow : Db + c * kJB + trow - kJB;
     r.b3 = __ldg(a.P + st.p[P_B3] + j3);
     r.sc3 = __ldg(a.P + st.p[P_SCALE] + j3);
   }
-  r.push = 0;
-  if (t < 64 && e + 1 < a.S) r.push = __ldg(a.pmaps + (size_t)e * kDc + (t < 32 ? c * kKS1 + t : Da + c * kJB + (t - 32)));
+  r.push_a = r.push_b = 0;
+  if (e + 1 < a.S) {
+    r.push_a = __ldg(a.pmaps + (size_t)e * kDc + c * kKS1 + (t >> 4));
+    r.push_b = __ldg(a.pmaps + (size_t)e * kDc + Da + c * kJB + (t >> 4));
+  }
 }
 
 // Reduce-scatter epilogue of a hidden layer (warps 0..7: warp = hidden feature 8c + fl, lane = sample quad q + 16 x
@@ -314,23 +335,51 @@ __device__ __forceinline__ float4 hidden_epilogue(const KArgs& a, const StageTab
   return nrm;
 }
 
-// this CTA's K-split partial accumulator (TMEM lane = hidden feature, column = sample) -> part[c][feature][sample] in
-// global memory, then one bulk copy per destination CTA d: rows 8d..8d+7 -> slot c of d's reduce-scatter buffer
-__device__ __forceinline__ void send_partial(unsigned tmem_d, float* part, int c, float* rsbuf, unsigned long long* bar) {
+// this CTA's K-split partial accumulator (TMEM lane = hidden feature, column = sample): rows 8d..8d+7 go straight from
+// registers into slot c of CTA d's reduce-scatter buffer (st.async through distributed shared memory)
+__device__ __forceinline__ void send_partial(unsigned tmem_d, int c, float* rsbuf, unsigned long long* bar,
+                                             unsigned long long* stamp = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 16;
   float v[16];
   tmem_ld16(tmem_d + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)c0, v);
-  float* dst = part + ((size_t)c * kHc + m) * kNS + c0;
+  if (stamp) stamp[0] = gtime();
+  // 4 x 4 transpose of 16-byte chunks inside every group of four lanes (rows 4g..4g+3): afterwards lane k of a group
+  // holds chunk k of each of the group's rows, so that one st.async writes 64 contiguous bytes of ONE row per group
+  // instead of 32 scattered 16-byte pieces (measured: 2.4 k cycles to issue the scattered form, DSMEM request-bound)
+  float4 ch[4];
 #pragma unroll
-  for (int i = 0; i < 16; i += 4) stcg4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-  fence_async_global();
-  tc_fence_before();
-  bar_workers();
-  if (threadIdx.x < kCL) {
-    const int d = threadIdx.x;
-    bulk_g2s_mc(rsbuf + (size_t)c * (kHS * kNS), part + ((size_t)c * kHc + d * kHS) * kNS, kHS * kNS * 4, bar, 1u << d);
+  for (int j = 0; j < 4; ++j) ch[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  auto xchg = [](float4 x, int mask) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, x.x, mask), __shfl_xor_sync(0xffffffffu, x.y, mask),
+                       __shfl_xor_sync(0xffffffffu, x.z, mask), __shfl_xor_sync(0xffffffffu, x.w, mask));
+  };
+  {   // bit 0: lanes with b0 = 0 keep even chunks; slot j holds (row r ^ (j & 1), chunk (j & ~1) | b0)
+    const int b0 = lane & 1;
+    const float4 s0 = b0 ? ch[0] : ch[1], s1 = b0 ? ch[2] : ch[3];
+    const float4 r0 = xchg(s0, 1), r1 = xchg(s1, 1);
+    if (b0) { ch[0] = r0; ch[2] = r1; } else { ch[1] = r0; ch[3] = r1; }
+    // now: b0 = 0: ch[0] = (own, c0), ch[1] = (peer, c0), ch[2] = (own, c2), ch[3] = (peer, c2)
+    //      b0 = 1: ch[0] = (peer, c1), ch[1] = (own, c1), ch[2] = (peer, c3), ch[3] = (own, c3)
   }
+  {   // bit 1: lanes with b1 = 0 keep the low chunk pair
+    const int b1 = (lane >> 1) & 1;
+    const float4 s0 = b1 ? ch[0] : ch[2], s1 = b1 ? ch[1] : ch[3];
+    const float4 r0 = xchg(s0, 2), r1 = xchg(s1, 2);
+    if (b1) { ch[0] = r0; ch[1] = r1; } else { ch[2] = r0; ch[3] = r1; }
+  }
+  // lane L = (b1, b0) of a group now holds chunk k = L of all four rows, and slot j is row j of the group (step 1 moved
+  // the slots whose low bit differs from b0, step 2 those whose high bit differs from b1: row = L ^ (j ^ L) = j)
+  const int k = lane & 3, g4 = m & ~3;
+  const unsigned d = (unsigned)m >> 3;
+  const unsigned rbar = mapa_u32(smem_u32(bar), d);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = g4 + j;
+    const unsigned dst = mapa_u32(smem_u32(rsbuf + (size_t)c * (kHS * kNS) + (row & 7) * kNS + c0 + 4 * k), d);
+    st_async4(dst, ch[j], rbar);
+  }
+  if (stamp) stamp[1] = gtime();
 }
 
 // inline bounded wait of the control thread (its loop must stay tight: it is the only serial instruction stream)
@@ -342,6 +391,10 @@ __device__ __forceinline__ void ctl_wait(unsigned long long* bar, unsigned parit
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(ad), "r"(parity) : "memory");
   if (!done) atomicExch(ctrl + 2, 1u);
+}
+// instruction descriptor: D fp32, A / B tf32 K-major, M x N (tile_cp.cuh's umma_idesc fixes M = 128)
+__device__ __forceinline__ unsigned idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 __device__ __forceinline__ void mma3(unsigned tmem_d, unsigned long long ah, unsigned long long al, unsigned long long bh,
                                      unsigned long long bl, unsigned idesc, unsigned accumulate) {
@@ -366,8 +419,6 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
   const int c = (int)cta_rank();
   const int LB = a.ldb, B = a.B, S = a.S;
   constexpr int D = kDc, Da = kDc / 2, Db = kDc / 2;
-  float* part1 = scratch;
-  float* part2 = scratch + (size_t)kCL * kHc * kNS;
   float* agbuf = scratch + kPartFloats;
   float* ldrows = agbuf + kAgFloats;
 
@@ -413,7 +464,10 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
     if (lane == 0) {
       const unsigned sW1 = smem_u32(sm + SmemFwd::oW1), sW2 = smem_u32(sm + SmemFwd::oW2), sW3 = smem_u32(sm + SmemFwd::oW3);
       const unsigned sN2 = smem_u32(N2C), sAC = smem_u32(AC), sN1 = smem_u32(N1C);
-      const unsigned idesc = umma_idesc(kNS, 0, 0);
+      const unsigned idesc = idesc_tf32(128, kNS);
+      // net.6 has 64 output rows per CTA: M = 64 halves the A-operand fetch (these K = 8 MMAs are bound by the tensor core's
+      // shared-memory operand bandwidth, ~64 B/clk measured: (M + N) * 32 B per instruction)
+      const unsigned idesc64 = idesc_tf32(64, kNS);
       // operand descriptors (canonical K-major, LBO 128 B); a K = 8 step is 256 B = 16 descriptor units further on
       const unsigned long long dW1h = umma_desc(sW1, 128, kKS1 * 32), dW1l = umma_desc(sW1 + kW1Floats * 2, 128, kKS1 * 32);
       const unsigned long long dACh = umma_desc(sAC, 128, kKS1 * 32), dACl = umma_desc(sAC + kNS * kKS1 * 4, 128, kKS1 * 32);
@@ -455,7 +509,7 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
           ctl_wait(bars + B_AG + s, par, a.ctrl);
           tc_fence_after();
           // W3 k-tile s: 64 x 8 floats = 2 KB = 128 units; n2 slice s: (hi | lo) = 4 KB = 256 units
-          mma3(tD3, dW3h + 128ull * s, dW3l + 128ull * s, dN2h + 256ull * s, dN2l + 256ull * s, idesc, s ? 1u : 0u);
+          mma3(tD3, dW3h + 128ull * s, dW3l + 128ull * s, dN2h + 256ull * s, dN2l + 256ull * s, idesc64, s ? 1u : 0u);
         }
         umma_commit(bars + B_M3);
         ctl_wait(bars + B_M3, par, a.ctrl);
@@ -469,7 +523,7 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
     // ================================================================ worker warps
     StageRegs cur, nx;
     load_stage_regs(nx, a, 0, c, t);
-    const int trow = (warp & 3) * 32 + lane;               // TMEM lane of this thread; rows 0..63 of D3 are real
+    const int trow = lane < 16 ? (warp & 3) * 16 + lane : 2 * kJB;   // output row of net.6 held by this thread's TMEM lane
 #pragma unroll 1
     for (int e = 0; e < S; ++e) {
       const StageTab& st = a.st[e];
@@ -487,21 +541,22 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
       // ---- input rows (pushed by the previous stage's owners) -> canonical B operand of net.0 (hi / lo) + the
       //      pass-through rows of y; this thread's four b values -> registers
       if (e > 0) warp_wait(bars + B_X, (e - 1) & 1, a.ctrl);
-      float4 bv;
+      CL_STAMP(10);
+      float4 bv, ya;
       {
         const int p = t >> 4, s0 = (t & 15) * 4;
         bv = *reinterpret_cast<const float4*>(XR + (32 + p) * kNS + s0);
+        const float4 av = *reinterpret_cast<const float4*>(XR + p * kNS + s0);
+        // pass-through half: ActNorm.reverse only (:66); stored now, pushed to its consumer with the b rows at the tail
+        ya = make_float4(fmaf(av.x, qa, qc), fmaf(av.y, qa, qc), fmaf(av.z, qa, qc), fmaf(av.w, qa, qc));
+        if (s0 < B) stcg4(y + (size_t)(c * kKS1 + p) * LB + s0, ya);
+        else ya = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       {
         const int n = t & 63, kc = t >> 6;                 // one 16-byte chunk (sample n, features 4kc..4kc+3) per thread
         float v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = XR[(4 * kc + u) * kNS + n];
-        if (n < B) {
-          float* yr = y + (size_t)(c * kKS1 + 4 * kc) * LB + n;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) __stcg(yr + u * LB, fmaf(v[u], qa, qc));
-        }
         float4 hi, lo;
         split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
         const int off = (n >> 3) * 256 + kc * 32 + (n & 7) * 4;      // [64 x 32] tile: SBO 1024 B, LBO 128 B
@@ -518,14 +573,14 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
       warp_wait(bars + B_M1, par, a.ctrl);
       tc_fence_after();
       CL_STAMP(2);
-      send_partial(tD1, part1, c, RS1, bars + B_R1);
-      // XR is consumed by every worker (bar_workers inside send_partial): the next stage's rows may land
-      if (t == 0 && e + 1 < S) mbar_expect_tx(bars + B_X, 64 * LB * 4);
+      send_partial(tD1, c, RS1, bars + B_R1);
+      if (t == 0 && e + 1 < S) mbar_expect_tx(bars + B_X, 64 * kNS * 4);     // the next stage's rows (full 64-sample rows)
       warp_wait(bars + B_R1, par, a.ctrl);
       CL_STAMP(3);
       if (warp < 8) {
         bool valid;
         const float4 nr = hidden_epilogue(a, st, e, 1, c, RS1, cur.b1, cur.g1, cur.be1, cur.rm1, cur.rv1, valid);
+        CL_STAMP(15);
         // canonical B operand of net.3: [64 samples x 8 k], k = this CTA's hidden features (SBO 256 B, LBO 128 B)
         if (lane < 16) {
           const int fl = warp, q = lane;
@@ -549,12 +604,13 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
       //      net.3 partial can only arrive after it received this CTA's net.0 partial, sent after them
       warp_wait(bars + B_M2, par, a.ctrl);
       tc_fence_after();
-      send_partial(tD2, part2, c, RS2, bars + B_R2);
+      send_partial(tD2, c, RS2, bars + B_R2);
       warp_wait(bars + B_R2, par, a.ctrl);
       CL_STAMP(5);
       if (warp < 8) {
         bool valid;
         const float4 nr = hidden_epilogue(a, st, e, 2, c, RS2, cur.b2, cur.g2, cur.be2, cur.rm2, cur.rv2, valid);
+        CL_STAMP(11);
         // n2 rows 8c..8c+7 -> one [64 x 8] operand tile (hi | lo) in L2: slice c of net.6's K loop on every CTA
         if (lane < 16) {
           const int fl = warp, q = lane;
@@ -569,10 +625,12 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
             __stcg(dst + off, __uint_as_float(hi));
             __stcg(dst + kNS * kHS + off, __uint_as_float(lo));
           }
+          CL_STAMP(12);
           fence_async_global();
         }
       }
       bar_workers();
+      CL_STAMP(13);
       if (t == 0) bulk_g2s_mc(N2C + (size_t)c * (2 * kNS * kHS), agbuf + (size_t)c * (2 * kNS * kHS), 2 * kNS * kHS * 4, bars + B_AG + c, 0xffffu);
       CL_STAMP(6);
       // ---- net.6 accumulator -> tail
@@ -580,14 +638,16 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
       tc_fence_after();
       CL_STAMP(7);
       // step 1: ZeroFC bias + exp(3 scale) (:137-141) on this thread's output row -> exchange tile (aliases RS2: consumed)
-      if (trow < 2 * kJB) {
+      {
         const int c0 = (warp >> 2) * 16;
         float v[16];
-        tmem_ld16(tD3 + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)c0, v);
+        tmem_ld16(tD3 + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)c0, v);     // warp-collective: lanes >= 16 idle
+        if (trow < 2 * kJB) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(TT + trow * kTilePitch + c0 + i) =
-              make_float4((v[i] + cur.b3) * e3v, (v[i + 1] + cur.b3) * e3v, (v[i + 2] + cur.b3) * e3v, (v[i + 3] + cur.b3) * e3v);
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(TT + trow * kTilePitch + c0 + i) =
+                make_float4((v[i] + cur.b3) * e3v, (v[i + 1] + cur.b3) * e3v, (v[i + 2] + cur.b3) * e3v, (v[i + 3] + cur.b3) * e3v);
+        }
       }
       tc_fence_before();
       bar_workers();
@@ -607,25 +667,28 @@ __global__ void __launch_bounds__(kT, 1) flow_cl_fwd_kernel(const __grid_constan
           yb[i] = fmaf(bp, qa, qc);
           dl[i] = s0 + i < B ? -ls : 0.f;
         }
+        float4 yb4 = make_float4(yb[0], yb[1], yb[2], yb[3]);
         if (s0 < B) {
           float* O = a.W + a.oOT + (size_t)e * (2 * Db) * LB;
           stcg4(O + (size_t)col * LB + s0, ol);
           stcg4(O + (size_t)(Db + col) * LB + s0, ot);
-          stcg4(y + (size_t)(Da + col) * LB + s0, make_float4(yb[0], yb[1], yb[2], yb[3]));
+          stcg4(y + (size_t)(Da + col) * LB + s0, yb4);
+        } else {
+          yb4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        fence_async_global();
+        // push this thread's quads of output rows 32c + p (pass-through) and Da + 32c + p (coupled) to the CTAs that
+        // consume them in the next stage: the inter-stage permutation (:599, :459) is this routing
+        if (e + 1 < S) {
+          const unsigned da = (unsigned)cur.push_a >> 6, db = (unsigned)cur.push_b >> 6;
+          st_async4(mapa_u32(smem_u32(XR + (cur.push_a & 63) * kNS + s0), da), ya, mapa_u32(smem_u32(bars + B_X), da));
+          st_async4(mapa_u32(smem_u32(XR + (cur.push_b & 63) * kNS + s0), db), yb4, mapa_u32(smem_u32(bars + B_X), db));
+        }
         // per-sample sum over this CTA's 32 columns: 2 columns per warp (lanes 16 apart), then the 16 warps in order
 #pragma unroll
         for (int i = 0; i < 4; ++i) dl[i] += __shfl_xor_sync(0xffffffffu, dl[i], 16);
         if (lane < 16) *reinterpret_cast<float4*>(sRed + warp * 64 + lane * 4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
       }
       bar_workers();
-      // ---- push this CTA's 64 output rows (a pass-through rows written at the top of the stage, b rows just now) to the
-      //      CTAs that consume them in the next stage: the inter-stage permutation (:599, :459) is this routing
-      if (t < 64 && e + 1 < S) {
-        const int j = t < 32 ? c * kKS1 + t : Da + c * kJB + (t - 32);
-        bulk_g2s_mc(XR + (size_t)(cur.push & 63) * kNS, y + (size_t)j * LB, LB * 4, bars + B_X, 1u << (cur.push >> 6));
-      }
       if (t < 64) {
         float sum = 0.f;
 #pragma unroll

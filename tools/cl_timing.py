@@ -60,13 +60,24 @@ def main():
             ops = np.zeros(4096, dtype=np.int32)
             lib.dpi_flow_debug_read(h, st.ctypes.data, ops.ctypes.data, 4096)
             S = 2 * NF
-            s = st[:16 * S].astype(np.int64).reshape(S, 16)
-            names = ["gather", "L1 mma", "part1 store + CB1", "epilogue 1", "L2 mma + part2 + CB2", "epilogue 2 + CB3", "n2 gather", "L3 mma", "tail", "CB4", ""]
-            d = np.diff(np.concatenate([s[:, :10], np.roll(s[:, 0], -1)[:, None]], axis=1), axis=1)[1:-1]
-            print("per-stage cycles (median over stages, CTA 0):")
-            for i, nme in enumerate(names[:10]):
-                print(f"   {nme:18s} {np.median(d[:, i]):8.0f}")
-            print(f"   stage total        {np.median(d.sum(1)):8.0f}")
+            T = st[:16 * 32 * 16].astype(np.int64).reshape(16, 32, 16)[:, :S, :]      # [cta][stage][slot], ns
+            names = ["rows landed -> net.0 operand", "net.0 MMA", "net.0 partial push + wait", "BatchNorm 1 epilogue",
+                     "net.3 MMA + partial push + wait", "BatchNorm 2 epilogue + slice push", "net.6 (wait slices + MMA)",
+                     "TMEM -> tile", "coupling tail + row push", "(to next stage)"]
+            nxt = np.roll(T[:, :, 0], -1, axis=1)
+            seq = np.concatenate([T[:, :, :10], nxt[:, :, None]], axis=2)[:, 1:-1, :]
+            d = np.diff(seq, axis=2)                                                    # [cta][stage][phase]
+            print("per-stage ns (median over stages), CTA 0 / min / max over CTAs; and skew = spread over CTAs of the phase END time:")
+            for i, nme in enumerate(names):
+                per_cta = np.median(d[:, :, i], axis=1)
+                skew = np.median(seq[:, :, i + 1].max(0) - seq[:, :, i + 1].min(0))
+                print(f"   {nme:36s} {per_cta[0]:7.0f} {per_cta.min():7.0f} {per_cta.max():7.0f}   skew {skew:6.0f}")
+            print(f"   stage total {np.median(d.sum(2), axis=1)[0]:.0f} ns")
+            f = T[0, 1:-1, :]
+            md = lambda a_, b_: np.median(f[:, a_] - f[:, b_])
+            print("   detail CTA 0 (ns): stage top -> rows landed %.0f, -> operand written + signalled %.0f | BN1: reduce+stats+stores %.0f, operand+signal %.0f | "
+                  "BN2: reduce+stats+stores %.0f, slice stores %.0f, fence+barrier %.0f, multicast issue %.0f" % (
+                      md(10, 0), md(1, 10), md(15, 3), md(4, 15), md(11, 5), md(12, 11), md(13, 12), md(6, 13)))
             _lib.check(lib.dpi_flow_debug_timing(h, 0))
     if len(res) == 2:
         x1, l1 = res["1"]; x0, l0 = res["0"]
