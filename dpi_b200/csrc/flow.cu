@@ -296,6 +296,13 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
   bp.oGP2T = take((long long)H * LB);
   bp.oPART = take(std::max(32LL, max_part));
   bp.oRED = take((long long)S * std::max(bp.red_tiles, bp.tc_red_tiles) * 2);
+  if (!bp.small.ok && h->nar_clusters > 0) {
+    nar::make_plan(bp.nar, h->nar_clusters, D, H, B, S, h->has_bn);
+    if (bp.nar.ok) {
+      const long long base = take(nar::workspace_floats(bp.nar, D, H, B, S));
+      nar::place_workspace(bp.nar, base, D, H, B, S);
+    }
+  }
   bp.cl.ok = (h->cl_avail && bp.small.ok && fcl::shape_ok(D, H, B)) ? 1 : 0;
   if (bp.cl.ok) {
     o = (o + 255) / 256 * 256;                  // packed tiles are fetched with cp.async.bulk
@@ -655,6 +662,10 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
   h->use_tc = (tile && tile[0] == 't') ? 1 : 0;
   small_query(h.get());
   {
+    const char* ne = getenv("DPI_B200_NAR");                // 0: never use the sample-resident narrow-flow kernels
+    h->nar_clusters = (ne && ne[0] == '0') ? 0 : nar::query(device);
+  }
+  {
     // The cluster-resident tcgen05 pass (flow_cl.cu) is opt-in (DPI_B200_CL=1): parity-green, but measured at 585 us
     // per RealNVP(1024, 16) reverse pass against 501 us for the fp32 small-batch kernel (profiles/cl_fwd_r02.md)
     const char* cle = getenv("DPI_B200_CL");
@@ -930,6 +941,10 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
     return fcl::forward(a, bp->cl, h->S, (cudaStream_t)stream);
   }
   if (bp->small.ok) return small_launch(h, *bp, a, 0, (cudaStream_t)stream);
+  if (bp->nar.ok && direction == 0) {
+    a.tbuf = h->d_tbuf;
+    return nar::forward(a, bp->nar, (cudaStream_t)stream);
+  }
   if (bp->tc_ok) return tc_forward(h, *bp, a, (cudaStream_t)stream);
   return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
 }
@@ -958,6 +973,7 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
     return fcl::backward(a, bp->cl, h->S, (cudaStream_t)stream);
   }
   if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
+  if (bp->nar.ok && nar::has_backward()) return nar::backward(a, bp->nar, (cudaStream_t)stream);
   if (bp->tc_ok) return tc_backward(h, *bp, a, (cudaStream_t)stream, 0, h->S);
   return launch_program(h, bp->bwd[g_in ? 1 : 0], a, (cudaStream_t)stream);
 }
@@ -999,6 +1015,14 @@ int dpi_flow_cl_active(dpi_flow_t h, int batch) {
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
   return bp->cl.ok ? (1 | (fcl::has_backward() ? 2 : 0)) : 0;
+}
+
+int dpi_flow_nar_active(dpi_flow_t h, int batch) {
+  if (!handle_live(h, 1) || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  return bp->nar.ok ? (1 | (nar::has_backward() ? 2 : 0)) : 0;
 }
 
 int dpi_flow_tc_active(dpi_flow_t h, int batch) {

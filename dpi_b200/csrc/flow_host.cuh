@@ -10,6 +10,7 @@
 #include "flow_small.cuh"
 #include "flow_tc.cuh"
 #include "flow_cl.cuh"
+#include "flow_nar.cuh"
 
 namespace dpi {
 void* flow_kernel_ptr();
@@ -46,6 +47,8 @@ struct BatchPlan {
   long long oWPF = 0, oWPB = 0, oEA2 = 0, oEA3 = 0, oED1 = 0, oEDIN = 0;
   // cluster-resident tcgen05 pass (flow_cl.cu): reference-default shape, batch <= 64
   fcl::Plan cl;
+  // sample-resident pass for narrow flows (flow_nar.cu): ndim <= 32, hidden <= 160, batch > 64
+  nar::Plan nar;
 };
 
 }  // namespace dpi
@@ -54,6 +57,7 @@ struct dpi_flow_s {
   int device = 0, D = 0, Da = 0, Db = 0, Dout = 0, H = 0, n_flow = 0, S = 0, has_bn = 1;
   int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   int small_mode = 1;                         // 0: never use the small-batch kernel
+  int nar_clusters = 0;                       // co-resident clusters of 8 of the narrow-flow kernels (0: unavailable)
   int cl_avail = 0;                           // one 16-CTA cluster of the flow_cl kernels can be scheduled
   cudaStream_t side = nullptr;                // weight-gradient GEMMs of the tensor-core path run here, beside the dgrad chain
   std::vector<cudaEvent_t> ev;                // [4 S + 2] fork / join events (main <-> side)

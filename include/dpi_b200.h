@@ -112,6 +112,10 @@ int dpi_flow_tc_active(dpi_flow_t h, int batch);
  * DPI_interferometry.py:127); bit 1 is set when the backward pass runs there too. Opt-in: DPI_B200_CL=1 (it is
  * parity-green but not yet faster than the fp32 small-batch kernel). */
 int dpi_flow_cl_active(dpi_flow_t h, int batch);
+/* 1 when `batch` runs RealNVP.reverse as the sample-resident narrow-flow pass (flow_nar.cu: ndim <= 32, hidden <= 160 and a
+ * multiple of 4, batch > 64 and a multiple of 4 - the alpha-DPI parameter flow DPIx_interferometry.py:250 and the 2-D toy
+ * flow DPI_2Dtoydist.py:52); bit 1 is set when the backward pass runs there too. DPI_B200_NAR=0 disables it. */
+int dpi_flow_nar_active(dpi_flow_t h, int batch);
 
 /* Glow building block (generative_model/glow_model.py:260-268, ZeroConv2d :238-251), forward only: a k x k
  * convolution (k = 1, or k = 3 with one pixel of padding filled with pad_value: 0 for nn.Conv2d(padding=1), 1 for
