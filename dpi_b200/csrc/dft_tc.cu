@@ -1,5 +1,6 @@
 // dft_tc.cu - tcgen05 GEMM for the dense DFT and its adjoint (see dft_tc.cuh).
 #include <algorithm>
+#include <cstdlib>
 
 #include "dft_tc.cuh"
 #include "tile_cp.cuh"   // UMMA descriptors, mbarrier / tcgen05 wrappers (umma_desc, umma_idesc, umma_tf32, ...)
@@ -42,91 +43,125 @@ __global__ void pack_kernel(const float* __restrict__ src, long long s_r, long l
   }
 }
 
-__global__ void __launch_bounds__(128) dft_tc_kernel(Plan p, const float* __restrict__ Apack, const float* __restrict__ Bpack,
-                                                     float* __restrict__ part) {
+// The tensor core adds each MMA's products to the fp32 accumulator with truncation, not round-to-nearest: over one long
+// accumulation (K = npix^2 = 4096 -> 1536 MMAs) the bias reaches ~1e-4 of the running sum, which the closure quantities
+// of weak baselines (d phase / d V = 1 / |V|) amplify to percent-level gradient errors (measured at npix = 64, batch
+// 1024: image-gradient error 2.5e-2 against fp64, 3e-3 once the accumulation is chunked; profiles/dft_accuracy_r02.md).
+// So TMEM holds the sum of kChunkTiles k-tiles only (96 MMAs); the four drain warps add every finished chunk to fp32
+// registers (round-to-nearest) while the issuer fills the other TMEM buffer.
+constexpr int kChunkTiles = 8;
+constexpr int kDftThreads = 192;      // warps 0-3: drain / epilogue (TMEM lane quadrant = warp), 4: producer, 5: MMA issuer
+constexpr int kDftTmemCols = 128;     // two 64-column accumulators
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kDftThreads) dft_tc_kernel(Plan p, const float* __restrict__ Apack,
+                                                             const float* __restrict__ Bpack, float* __restrict__ part) {
   extern __shared__ unsigned char raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) unsigned long long bars[2 * kStagesTc + 1];
+  __shared__ __align__(8) unsigned long long bars[2 * kStagesTc + 4];
   __shared__ unsigned tmem_slot;
   unsigned long long* full = bars;
   unsigned long long* empty = bars + kStagesTc;
-  unsigned long long* accum = bars + 2 * kStagesTc;
+  unsigned long long* tfull = bars + 2 * kStagesTc;       // [2] chunk complete in TMEM buffer b
+  unsigned long long* tfree = tfull + 2;                  // [2] buffer b drained (one arrival per drain warp)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t = blockIdx.x;
   const int sp = t % p.splits; t /= p.splits;
   const int nt = t % p.n_tiles, mt = t / p.n_tiles;
   const int kt0 = sp * p.kt_per_split, kt1 = min(p.k_tiles, kt0 + p.kt_per_split), nk = max(0, kt1 - kt0);
+  const int n_chunks = (nk + kChunkTiles - 1) / kChunkTiles;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesTc; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    mbar_init(accum, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tfree + i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(&tmem_slot);
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kDftTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = tmem_slot;
-  if (warp == 0 && lane == 0) {
-    // ---- producer: two bulk copies per stage (A_hi|A_lo = 32 KB, B_hi|B_lo = 16 KB)
-    for (int i = 0; i < nk; ++i) {
-      const int s = i % kStagesTc;
-      if (i >= kStagesTc) mbar_wait(empty + s, ((i / kStagesTc) - 1) & 1);
-      mbar_expect_tx(full + s, kStageBytes);
-      unsigned char* st = sm + s * kStageBytes;
-      bulk_g2s(st, Apack + ((size_t)mt * p.k_tiles + kt0 + i) * (2 * kATileFloats), 2 * kATileFloats * 4, full + s);
-      bulk_g2s(st + 2 * kATileFloats * 4, Bpack + ((size_t)nt * p.k_tiles + kt0 + i) * (2 * kBTileFloats),
-               2 * kBTileFloats * 4, full + s);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---- MMA issuer: 4 k-steps x (a_lo b_hi + a_hi b_lo + a_hi b_hi) per stage, small terms first
-    const unsigned idesc = umma_idesc(kTN, 0, 0);
-    for (int i = 0; i < nk; ++i) {
-      const int s = i % kStagesTc;
-      mbar_wait(full + s, (i / kStagesTc) & 1);
-      tc_fence_after();
-      const unsigned a_hi = smem_u32(sm + s * kStageBytes), a_lo = a_hi + kATileFloats * 4;
-      const unsigned b_hi = a_hi + 2 * kATileFloats * 4, b_lo = b_hi + kBTileFloats * 4;
-#pragma unroll
-      for (int ks = 0; ks < kTK / 8; ++ks) {
-        const unsigned off = ks * 256;      // 8 k = two 16-byte chunks
-        const unsigned long long dah = umma_desc(a_hi + off, 128, 1024), dal = umma_desc(a_lo + off, 128, 1024);
-        const unsigned long long dbh = umma_desc(b_hi + off, 128, 1024), dbl = umma_desc(b_lo + off, 128, 1024);
-        umma_tf32(tmem, dal, dbh, idesc, (i | ks) ? 1u : 0u);
-        umma_tf32(tmem, dah, dbl, idesc, 1u);
-        umma_tf32(tmem, dah, dbh, idesc, 1u);
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- producer: two bulk copies per stage (A_hi|A_lo = 32 KB, B_hi|B_lo = 16 KB)
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % kStagesTc;
+        if (i >= kStagesTc) mbar_wait(empty + s, ((i / kStagesTc) - 1) & 1);
+        mbar_expect_tx(full + s, kStageBytes);
+        unsigned char* st = sm + s * kStageBytes;
+        bulk_g2s(st, Apack + ((size_t)mt * p.k_tiles + kt0 + i) * (2 * kATileFloats), 2 * kATileFloats * 4, full + s);
+        bulk_g2s(st + 2 * kATileFloats * 4, Bpack + ((size_t)nt * p.k_tiles + kt0 + i) * (2 * kBTileFloats),
+                 2 * kBTileFloats * 4, full + s);
       }
-      umma_commit(empty + s);               // stage reusable once these MMAs have read it
     }
-    umma_commit(accum);                     // accumulator complete
-  }
-  // ---- epilogue: TMEM (lane = tile row, column = tile column) -> partial tile [128][64] in global memory
-  if (nk > 0) {
-    mbar_wait(accum, 0);
-    tc_fence_after();
-  }
-  __syncwarp();
-  float* dst = part + (((size_t)sp * p.m_tiles + mt) * p.n_tiles + nt) * (size_t)(kTM * kTN) + (size_t)(warp * 32 + lane) * kTN;
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ---- MMA issuer: 4 k-steps x (a_lo b_hi + a_hi b_lo + a_hi b_hi) per stage, small terms first
+      const unsigned idesc = umma_idesc(kTN, 0, 0);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % kStagesTc, c = i / kChunkTiles, first = (i % kChunkTiles) == 0;
+        if (first && c >= 2) {              // the drain warps have taken chunk c - 2 out of this buffer
+          mbar_wait(tfree + (c & 1), ((c >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(full + s, (i / kStagesTc) & 1);
+        tc_fence_after();
+        const unsigned acc = tmem + (unsigned)(c & 1) * kTN;
+        const unsigned a_hi = smem_u32(sm + s * kStageBytes), a_lo = a_hi + kATileFloats * 4;
+        const unsigned b_hi = a_hi + 2 * kATileFloats * 4, b_lo = b_hi + kBTileFloats * 4;
 #pragma unroll
-  for (int c0 = 0; c0 < kTN; c0 += 16) {
-    unsigned v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = 0u;
-    if (nk > 0) {
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int ks = 0; ks < kTK / 8; ++ks) {
+          const unsigned off = ks * 256;      // 8 k = two 16-byte chunks
+          const unsigned long long dah = umma_desc(a_hi + off, 128, 1024), dal = umma_desc(a_lo + off, 128, 1024);
+          const unsigned long long dbh = umma_desc(b_hi + off, 128, 1024), dbl = umma_desc(b_lo + off, 128, 1024);
+          umma_tf32(acc, dal, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+          umma_tf32(acc, dah, dbl, idesc, 1u);
+          umma_tf32(acc, dah, dbh, idesc, 1u);
+        }
+        umma_commit(empty + s);               // stage reusable once these MMAs have read it
+        if ((i + 1) % kChunkTiles == 0 || i + 1 == nk) umma_commit(tfull + (c & 1));
+      }
     }
+  } else {
+    // ---- drain + epilogue: TMEM (lane = tile row, column = tile column) chunk by chunk into fp32 registers, then the
+    // partial tile [128][64] in global memory
+    float acc[kTN];
 #pragma unroll
-    for (int u = 0; u < 16; u += 4)
-      *reinterpret_cast<float4*>(dst + c0 + u) = make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]),
-                                                             __uint_as_float(v[u + 2]), __uint_as_float(v[u + 3]));
+    for (int u = 0; u < kTN; ++u) acc[u] = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      mbar_wait(tfull + (c & 1), (c >> 1) & 1);
+      tc_fence_after();
+      const unsigned src = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(c & 1) * kTN;
+#pragma unroll
+      for (int c0 = 0; c0 < kTN; c0 += 16) {
+        unsigned v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(src + (unsigned)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[c0 + u] += __uint_as_float(v[u]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree + (c & 1));
+    }
+    float* dst = part + (((size_t)sp * p.m_tiles + mt) * p.n_tiles + nt) * (size_t)(kTM * kTN) + (size_t)(warp * 32 + lane) * kTN;
+#pragma unroll
+    for (int u = 0; u < kTN; u += 4)
+      *reinterpret_cast<float4*>(dst + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem);
+  if (warp == 4)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kDftTmemCols) : "memory");
 }
 
 // out <- sum over the K splits (in split order) of the partial tiles
@@ -155,6 +190,7 @@ Plan make_plan(int M, int N, int K, int n_sm) {
   const int mn = p.m_tiles * p.n_tiles;
   int want = std::max(1, n_sm / std::max(1, mn));
   want = std::min(std::min(want, std::max(1, p.k_tiles / 2)), 16);
+  if (const char* e = getenv("DPI_B200_DFT_SPLITS")) want = std::max(1, std::min(atoi(e), p.k_tiles));
   p.kt_per_split = (p.k_tiles + want - 1) / want;
   p.splits = (p.k_tiles + p.kt_per_split - 1) / p.kt_per_split;
   return p;
@@ -183,7 +219,7 @@ int gemm(const Plan& p, const float* A, int lda, const float* Bpack, float* a_pa
   pack_kernel<kTM><<<(unsigned)std::min<long long>((total + 255) / 256, 8192), 256, 0, st>>>(A, lda, 1, p.M, p.K, p.m_tiles,
                                                                                              p.k_tiles, a_pack);
   DPI_LAUNCH_CHECK();
-  dft_tc_kernel<<<p.m_tiles * p.n_tiles * p.splits, 128, kSmemBytes, st>>>(p, a_pack, Bpack, part);
+  dft_tc_kernel<<<p.m_tiles * p.n_tiles * p.splits, kDftThreads, kSmemBytes, st>>>(p, a_pack, Bpack, part);
   DPI_LAUNCH_CHECK();
   const long long out_n = (long long)p.M * p.N;
   reduce_kernel<<<(unsigned)std::min<long long>((out_n + 255) / 256, 8192), 256, 0, st>>>(p, part, out, mode);

@@ -9,10 +9,11 @@
 // the canonical shared-memory layout of a K-major UMMA operand (no swizzle: core matrix = 8 rows x 16 bytes,
 // LBO = 128 B between the 4-k chunks, SBO = 1024 B between 8-row groups), so one cp.async.bulk per 64 x 32 tile
 // brings it into shared memory ready for tcgen05.mma. A is split and tiled the same way by a small pre-pass.
-// Kernel: 128 threads. Warp 0 / lane 0 = producer (cp.async.bulk + mbarrier expect_tx, 3-stage ring), warp 1 /
+// Kernel: 192 threads. Warp 4 / lane 0 = producer (cp.async.bulk + mbarrier expect_tx, 3-stage ring), warp 5 /
 // lane 0 = MMA issuer (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8; a_lo*b_hi + a_hi*b_lo +
-// a_hi*b_hi into one TMEM accumulator; tcgen05.commit releases the stage), all four warps = epilogue
-// (tcgen05.ld 32x32b -> registers -> partial tile in global memory). K is split over CTAs when M x N alone does
+// a_hi*b_hi; tcgen05.commit releases the stage). TMEM holds two 64-column accumulators: each takes the sum of 8
+// k-tiles (256 k), then warps 0-3 add it to fp32 registers (tcgen05.ld 32x32b) while the other one fills - the tensor
+// core's accumulate truncates, so long sums are kept out of it (dft_tc.cu). K is split over CTAs when M x N alone does
 // not fill the GPU; a second tiny kernel sums the split partials in order (deterministic) into the output layout.
 #pragma once
 #include "common.cuh"

@@ -507,6 +507,309 @@ __global__ void __launch_bounds__(kT, 1) nar_fwd_kernel(const __grid_constant__ 
   cluster_sync_all();      // no CTA leaves while its cluster leader may still read its shared memory
 }
 
+// =================================================================================================== backward chain
+// Gradient state GX [D][SP] (rows in the order of the current stage's output) walks the stages backwards; per stage the
+// rows g_pre / p2 / p1 (gradients at the outputs of net.6.fc / net.3 / net.0, after the LeakyReLU and BatchNorm
+// backward) are stored for nar_pgrad_kernel, and the BatchNorm gamma / beta gradients (the two batch sums the BatchNorm
+// backward needs anyway) are written directly.
+__global__ void __launch_bounds__(kT, 1) nar_bwd_kernel(const __grid_constant__ NArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ __align__(8) unsigned long long bars[3];     // stage blocks 0 / 1, W2
+  __shared__ float sRed[2 * (kT / 32)];
+  const KArgs& a = A.k;
+  const Plan& p = A.p;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int D = a.D, Da = a.Da, Db = a.Db, Dout = a.Dout, H = a.H, S = a.S, B = a.B, LB = a.ldb, SP = p.SPB;
+  const int s_base = blockIdx.x * SP;
+  const int nv = max(0, min(SP, B - s_base));
+  const int tq = SP >> 2;
+  float* Gb[2] = {sm + p.oX0, sm + p.oX1};
+  float* U1 = sm + p.oU1;
+  float* U2 = sm + p.oU2;
+  float* W2 = sm + p.oW2;
+  float* sGld = sm + p.oLd;
+  float* part = sm + p.oPart;
+  float* tot = sm + p.oTot;
+  float* GP = sm + p.oGP;
+  float* Act[2] = {sm + p.oAct0, sm + p.oAct1};
+  StageTab* stb = reinterpret_cast<StageTab*>(sm + p.oSt);
+  const float invB = 1.0f / (float)B;
+  unsigned bar = 0;
+
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.st);
+    int4* dst = reinterpret_cast<int4*>(stb);
+    for (int i = t; i < S * (int)(sizeof(StageTab) / 16); i += kT) dst[i] = __ldg(src + i);
+  }
+  if (t == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = t; i < SP; i += kT) sGld[i] = i < nv ? __ldg(a.g_ld + s_base + i) : 0.f;
+  __syncthreads();
+  // saved activations of stage e for this slab -> shared memory rows [y (D) | o (Dout) | b_prev (Db) | l1 (H) | l2 (H)]
+  auto issue_act = [&](float* dst, int e) {
+    const float* yprev = e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * D * LB;
+    for (RowQuad it(tq); it.r < p.actRows; it.next()) {
+      const int r = it.r;
+      const float* src;
+      if (r < D) src = a.W + a.oYT + ((size_t)e * D + r) * LB;
+      else if (r < D + Dout) src = a.W + a.oOT + ((size_t)e * Dout + (r - D)) * LB;
+      else if (r < D + Dout + Db) src = yprev + (size_t)__ldg(a.gmaps + (size_t)e * D + Da + (r - D - Dout)) * LB;
+      else if (r < D + Dout + Db + H) src = a.W + a.oL1T + ((size_t)e * H + (r - D - Dout - Db)) * LB;
+      else src = a.W + a.oL2T + ((size_t)e * H + (r - D - Dout - Db - H)) * LB;
+      cp_async16(dst + r * SP + 4 * it.q, src + s_base + 4 * it.q, 4 * it.q < nv ? 16 : 0);
+    }
+  };
+  issue_block(a, p, stb, blk_at(sm + p.oBlk0, p, Dout, H), S - 1, true, bars + 0);
+  issue_w2(W2, a.P + stb[S - 1].p[P_W2], H, bars + 2);
+  issue_act(Act[0], S - 1);
+  cp_async_commit();
+  // gradient wrt the flow output, g_out [B][D] sample-major -> GX [D][SP]
+  for (int i = t; i < D * SP; i += kT) {
+    const int s = i / D, f = i - s * D;
+    Gb[0][f * SP + s] = s < nv ? __ldg(a.g_out + (size_t)(s_base + s) * D + f) : 0.f;
+  }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int u = 0; u < S; ++u) {
+    const int e = S - 1 - u;
+    const StageTab& st = stb[e];
+    const Blk sv = blk_at(sm + ((u & 1) ? p.oBlk1 : p.oBlk0), p, Dout, H);
+    float* GX = Gb[u & 1];
+    float* GXn = Gb[(u + 1) & 1];
+    const float* act = Act[u & 1];
+    const float* Ys = act;
+    const float* Os = act + D * SP;
+    const float* BPs = Os + Dout * SP;
+    const float* L1s = BPs + Db * SP;
+    const float* L2s = L1s + H * SP;
+    cp_async_wait<0>();
+    mbar_wait(bars + (u & 1), (u >> 1) & 1);
+    __syncthreads();
+    if (u + 1 < S) {
+      issue_block(a, p, stb, blk_at(sm + ((u & 1) ? p.oBlk0 : p.oBlk1), p, Dout, H), e - 1, true, bars + ((u + 1) & 1));
+      issue_act(Act[(u + 1) & 1], e - 1);
+      cp_async_commit();
+    }
+    const float e_lsi = expf(sv.act[0]), loc = sv.act[1];
+    // ---- ActNorm.reverse + coupling tail, elementwise: g_pre, the b-half input gradient, ActNorm sums
+    float S1 = 0.f, S2 = 0.f;
+    for (RowQuad it(SP); it.r < Db; it.next()) {
+      const int j = it.r, s = it.q;
+      const float gb = GX[(Da + j) * SP + s];
+      S1 += gb;
+      S2 = fmaf(gb, Ys[(Da + j) * SP + s] + loc, S2);
+      const float gbp = gb * e_lsi;
+      const float ols = Os[j * SP + s];
+      const float ls = tanhf(ols), ei = expf(-ls);
+      const float g_t = -gbp;
+      const float g_ls = -gbp * BPs[j * SP + s] * ei - sGld[s];
+      const float g_ols = g_ls * (1.f - ls * ls);
+      const float v_ls = g_ols * expf(3.f * sv.scale[j]), v_t = g_t * expf(3.f * sv.scale[Db + j]);
+      GP[j * SP + s] = v_ls;
+      GP[(Db + j) * SP + s] = v_t;
+      GXn[sv.idx[Da + j] * SP + s] = gbp * ei;
+      if (s < nv) {
+        __stcg(a.W + p.oGPRE + ((size_t)e * Dout + j) * LB + s_base + s, v_ls);
+        __stcg(a.W + p.oGPRE + ((size_t)e * Dout + Db + j) * LB + s_base + s, v_t);
+      }
+    }
+    for (RowQuad it(SP); it.r < Da; it.next()) {
+      const float ga = GX[it.r * SP + it.q];
+      S1 += ga;
+      S2 = fmaf(ga, Ys[it.r * SP + it.q] + loc, S2);
+    }
+    S1 = warp_sum(S1); S2 = warp_sum(S2);
+    if (lane == 0) { sRed[warp] = S1; sRed[kT / 32 + warp] = S2; }
+    __syncthreads();
+    if (t == 0) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int w = 0; w < kT / 32; ++w) { t1 += sRed[w]; t2 += sRed[kT / 32 + w]; }
+      float* ap = a.W + p.oActPart + ((size_t)e * gridDim.x + blockIdx.x) * 2;
+      __stcg(ap, t1);
+      __stcg(ap + 1, t2);
+    }
+    // ---- through net.6.fc: g_n2[h][s] = sum_j W3[j][h] g_pre[j][s]
+    gemm_kn(U2, sv.W3, H, GP, nullptr, H, Dout, SP, nullptr, false);
+    __syncthreads();
+    for (int which = 2; which >= 1; --which) {
+      float* U = which == 2 ? U2 : U1;
+      const float* Ls = which == 2 ? L2s : L1s;
+      const float* vec = which == 2 ? sv.v2 : sv.v1;               // [bias | gamma | beta], stride Hp
+      const float* mean = sv.stat + (which - 1) * 2 * H;            // saved batch statistics [mean | rstd], stride H
+      const float* rstd = mean + H;
+      if (which == 1) {
+        // ---- through net.3: g_n1[k][s] = sum_n W2[n][k] p2[n][s]; W2 is free afterwards -> next stage's
+        mbar_wait(bars + 2, u & 1);
+        gemm_kn(U1, W2, H, U2, nullptr, H, H, SP, nullptr, false);
+        __syncthreads();
+        if (u + 1 < S) issue_w2(W2, a.P + stb[e - 1].p[P_W2], H, bars + 2);
+      }
+      if (a.has_bn) {
+        if (t < H) {                                       // this slab's sums of g and g * xhat for feature t
+          float s0 = 0.f, s1 = 0.f;
+          const float m = mean[t], r = rstd[t];
+          for (int s = 0; s < nv; ++s) {
+            const float g = U[t * SP + s];
+            s0 += g;
+            s1 = fmaf(g, (Ls[t * SP + s] - m) * r, s1);
+          }
+          part[t] = s0; part[kMaxH + t] = s1;
+        }
+        cross_reduce(A, part, tot, H, false, 0.f, (2 * u + (2 - which)) & 1, bar);
+        if (blockIdx.x == 0 && t < H) {                   // BatchNorm weight / bias gradients are exactly these sums
+          a.G[st.p[which == 2 ? P_G2 : P_G1] + t] = tot[kMaxH + t];
+          a.G[st.p[which == 2 ? P_BE2 : P_BE1] + t] = tot[t];
+        }
+      }
+      // BatchNorm + LeakyReLU backward in place; rows kept for the weight gradients
+      float* Pg = a.W + (which == 2 ? p.oGP2 : p.oGP1) + (size_t)e * H * LB + s_base;
+      for (RowQuad it(tq); it.r < H; it.next()) {
+        const int h = it.r, q = it.q;
+        const float4 g = ld4(U + h * SP + 4 * q), l = ld4(Ls + h * SP + 4 * q);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, lv[4] = {l.x, l.y, l.z, l.w};
+        float o[4];
+        if (a.has_bn) {
+          const float m = mean[h], r = rstd[h], gr = vec[p.Hp + h] * r;
+          const float gbeta = tot[h] * invB, ggamma = tot[kMaxH + h] * invB;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = gr * (gv[i] - gbeta - (lv[i] - m) * r * ggamma);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = gv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = (4 * q + i < nv) ? o[i] * (lv[i] > 0.f ? 1.f : kLreluSlope) : 0.f;
+        const float4 r4 = make_float4(o[0], o[1], o[2], o[3]);
+        st4(U + h * SP + 4 * q, r4);
+        if (4 * q < nv) stcg4(Pg + (size_t)h * LB + 4 * q, r4);
+      }
+      __syncthreads();
+    }
+    // ---- through net.0 (+ the direct path of the pass-through half through ActNorm): input gradient of the a rows
+    gemm_small(U2, sv.W1, 1, Da, U1, Da, H, SP, 2);       // W1 stored [h][k]: element (k, h) at k + h * Da
+    __syncthreads();
+    for (RowQuad it(tq); it.r < Da; it.next()) {
+      const int k = it.r, q = it.q;
+      const float4 n = ld4(U2 + k * SP + 4 * q), g = ld4(GX + k * SP + 4 * q);
+      st4(GXn + sv.idx[k] * SP + 4 * q, make_float4(fmaf(g.x, e_lsi, n.x), fmaf(g.y, e_lsi, n.y), fmaf(g.z, e_lsi, n.z), fmaf(g.w, e_lsi, n.w)));
+    }
+  }
+  __syncthreads();
+  if (a.g_in) {
+    const float* GX = Gb[S & 1];
+    for (int i = t; i < D * SP; i += kT) {
+      const int s = i / D, f = i - s * D;
+      if (s < nv) a.g_in[(size_t)(s_base + s) * D + f] = GX[f * SP + s];
+    }
+  }
+  cluster_sync_all();
+}
+
+// =================================================================================================== parameter gradients
+// One batched pass over the rows the chain stored: for every stage e
+//   gW3[j][h] = sum_s g_pre[j][s] n2[h][s]    gW2[n][k] = sum_s p2[n][s] n1[k][s]    gW1[h][k] = sum_s p1[h][s] a[k][s]
+//   gb3 = sum_s g_pre   gb2 = sum_s p2   gb1 = sum_s p1   gscale[j] = 3 sum_s g_pre[j][s] o[j][s] / exp(3 scale_j)
+//   g_loc = -sum S1     g_lsi = sum S2 + D sum_s g_ld[s]
+// Job = (stage, 64 x 64 tile of one weight gradient | a block of row sums); no cross-CTA dependencies.
+struct PJob { int e, kind, i0, j0; };
+
+__global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ NArgs A, int jobs_per_stage, int tiles2, int tiles3,
+                                                        int tiles1) {
+  __shared__ __align__(16) float Gs[32][68];
+  __shared__ __align__(16) float As[32][68];
+  const KArgs& a = A.k;
+  const Plan& p = A.p;
+  const int D = a.D, Da = a.Da, Db = a.Db, Dout = a.Dout, H = a.H, B = a.B, LB = a.ldb;
+  const int e = blockIdx.x / jobs_per_stage;
+  int job = blockIdx.x - e * jobs_per_stage;
+  const StageTab& st = a.st[e];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* yprev = e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * D * LB;
+  const int th = (H + 63) / 64;
+  // ---- decode the job
+  const float* Grows; const float* Arows; int I, J; float* out; const int* amap = nullptr; int ti, tj;
+  if (job < tiles2) { Grows = a.W + p.oGP2 + (size_t)e * H * LB; Arows = a.W + a.oN1T + (size_t)e * H * LB; I = H; J = H; out = a.G + st.p[P_W2]; ti = job / th; tj = job % th; }
+  else if ((job -= tiles2) < tiles3) { Grows = a.W + p.oGPRE + (size_t)e * Dout * LB; Arows = a.W + a.oN2T + (size_t)e * H * LB; I = Dout; J = H; out = a.G + st.p[P_W3]; ti = job / th; tj = job % th; }
+  else if ((job -= tiles3) < tiles1) { Grows = a.W + p.oGP1 + (size_t)e * H * LB; Arows = yprev; amap = a.gmaps + (size_t)e * D; I = H; J = Da; out = a.G + st.p[P_W1]; ti = job; tj = 0; }
+  else {
+    // ---- row sums: biases, ZeroFC scale, ActNorm; one warp per row, lanes stride the batch
+    job -= tiles1;                                         // 0..3: which quarter of the rows
+    const int rows = 2 * H + 2 * Dout;                     // [b1: H | b2: H | b3: Dout | scale: Dout]
+    for (int r = job * 8 + warp; r < rows; r += 32) {
+      const float* g; const float* o = nullptr; float* dst; float mul = 1.f;
+      if (r < H) { g = a.W + p.oGP1 + ((size_t)e * H + r) * LB; dst = a.G + st.p[P_B1] + r; }
+      else if (r < 2 * H) { g = a.W + p.oGP2 + ((size_t)e * H + r - H) * LB; dst = a.G + st.p[P_B2] + (r - H); }
+      else if (r < 2 * H + Dout) { g = a.W + p.oGPRE + ((size_t)e * Dout + r - 2 * H) * LB; dst = a.G + st.p[P_B3] + (r - 2 * H); }
+      else {
+        const int j = r - 2 * H - Dout;
+        g = a.W + p.oGPRE + ((size_t)e * Dout + j) * LB; o = a.W + a.oOT + ((size_t)e * Dout + j) * LB;
+        dst = a.G + st.p[P_SCALE] + j; mul = 3.f / expf(3.f * __ldg(a.P + st.p[P_SCALE] + j));
+      }
+      float acc = 0.f;
+      for (int s = lane; s < B; s += 32) acc = o ? fmaf(__ldcg(g + s), __ldcg(o + s), acc) : acc + __ldcg(g + s);
+      acc = warp_sum(acc);
+      if (lane == 0) *dst = acc * mul;
+    }
+    if (job == 0 && warp == 0) {
+      float s1 = 0.f, s2 = 0.f, gl = 0.f;
+      const float* ap = a.W + p.oActPart + (size_t)e * p.G * 2;
+      for (int c = lane; c < p.G; c += 32) { s1 += __ldcg(ap + 2 * c); s2 += __ldcg(ap + 2 * c + 1); }
+      for (int s = lane; s < B; s += 32) gl += __ldg(a.g_ld + s);
+      s1 = warp_sum(s1); s2 = warp_sum(s2); gl = warp_sum(gl);
+      if (lane == 0) {
+        a.G[st.loc] = -s1 + (__ldcg(a.ctrl + 2) ? __int_as_float(0x7fc00000) : 0.f);     // timed-out barrier -> NaN
+        a.G[st.lsi] = s2 + (float)D * gl;
+      }
+    }
+    return;
+  }
+  // ---- 64 x 64 tile of C[i][j] = sum_s G[i][s] Arow(j)[s]
+  const int i0 = ti * 64, j0 = tj * 64;
+  const int tr = t >> 4, tc = t & 15;                      // thread tile: rows 4 tr.., columns 4 tc..
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+  for (int s0 = 0; s0 < B; s0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {                    // 64 rows x 8 quads per operand, 512 quads, 2 per thread
+      const int id = t + rep * 256, r = id >> 3, q = id & 7;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), v = g;
+      if (s0 + 4 * q < B) {
+        if (i0 + r < I) g = __ldcg(reinterpret_cast<const float4*>(Grows + (size_t)(i0 + r) * LB + s0 + 4 * q));
+        if (j0 + r < J) {
+          const int row = amap ? __ldg(amap + j0 + r) : j0 + r;
+          v = __ldcg(reinterpret_cast<const float4*>(Arows + (size_t)row * LB + s0 + 4 * q));
+        }
+      }
+      Gs[4 * q + 0][r] = g.x; Gs[4 * q + 1][r] = g.y; Gs[4 * q + 2][r] = g.z; Gs[4 * q + 3][r] = g.w;
+      As[4 * q + 0][r] = v.x; As[4 * q + 1][r] = v.y; As[4 * q + 2][r] = v.z; As[4 * q + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int s = 0; s < 32; ++s) {
+      const float4 g = ld4(&Gs[s][4 * tr]), v = ld4(&As[s][4 * tc]);
+      const float gv[4] = {g.x, g.y, g.z, g.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(gv[x], vv[y], acc[x][y]);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int i = i0 + 4 * tr + x, j = j0 + 4 * tc + y;
+      if (i < I && j < J) out[(size_t)i * J + j] = acc[x][y];
+    }
+}
+
 // =================================================================================================== host side
 namespace {
 int g_dev = -1, g_max_clusters = 0;
@@ -525,13 +828,17 @@ cudaLaunchConfig_t make_cfg(cudaLaunchAttribute* at, int G, int smem, cudaStream
 inline int pad32i(int n) { return (n + 31) & ~31; }
 }  // namespace
 
-int has_backward() { return 0; }
+int has_backward() {
+  static const bool off = []() { const char* e = getenv("DPI_B200_NAR_BWD"); return e && e[0] == '0'; }();
+  return off ? 0 : 1;
+}
 
 int query(int device) {
   if (g_dev == device) return g_max_clusters;
   g_dev = device;
   g_max_clusters = 0;
-  if (cudaFuncSetAttribute((const void*)nar_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) {
+  if (cudaFuncSetAttribute((const void*)nar_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess ||
+      cudaFuncSetAttribute((const void*)nar_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -584,7 +891,7 @@ void make_plan(Plan& p, int max_clusters, int D, int H, int B, int S, int has_bn
   p.actRows = D + Dout + Db + 2 * H;
   p.oAct0 = take(p.actRows * SPB); p.oAct1 = take(p.actRows * SPB);
   p.smem_bwd = o * 4;
-  p.ok = (p.smem_fwd <= kSmemMax) ? 1 : 0;
+  p.ok = (p.smem_bwd <= kSmemMax) ? 1 : 0;
 }
 
 long long workspace_floats(const Plan& p, int D, int H, int B, int S) {
@@ -623,9 +930,21 @@ int forward(const KArgs& a, const Plan& p, cudaStream_t st) {
   return DPI_OK;
 }
 
-int backward(const KArgs&, const Plan&, cudaStream_t) {
-  set_error("flow_nar: backward kernel not built");
-  return DPI_ERR_UNSUPPORTED;
+int backward(const KArgs& a, const Plan& p, cudaStream_t st) {
+  NArgs A{};
+  A.k = a;
+  A.p = p;
+  DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), st));
+  cudaLaunchAttribute at[2];
+  cudaLaunchConfig_t cfg = make_cfg(at, p.G, p.smem_bwd, st, a.has_bn != 0);
+  DPI_CUDA(cudaLaunchKernelEx(&cfg, nar_bwd_kernel, A));
+  count_launch();
+  const int th = (a.H + 63) / 64;
+  const int tiles2 = th * th, tiles3 = ((a.Dout + 63) / 64) * th, tiles1 = th * ((a.Da + 63) / 64);
+  const int jobs = tiles2 + tiles3 + tiles1 + 4;
+  nar_pgrad_kernel<<<a.S * jobs, 256, 0, st>>>(A, jobs, tiles2, tiles3, tiles1);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
 }
 
 }  // namespace nar

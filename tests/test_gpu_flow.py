@@ -233,8 +233,10 @@ def test_tensor_core_path_beyond_fused_batchnorm_limit():
 def test_toy_2d_script_loop_body_at_its_own_sizes():
     """BASELINE configs[0]: DPI_2Dtoydist.py:62-76 (ndim 2, n_flow 16, seqfrac 1/128 -> H = 128, 512 samples) with the
     drop-in RealNVP in place of the reference class and the script's own torch code around it. ndim = 2 is the
-    narrowest flow there is (one input feature, one coupling column per stage) and 512 samples put it on the
-    tcgen05 path: loss, samples, log-determinant and every parameter gradient against the oracle's toy_loss."""
+    narrowest flow there is (one input feature, one coupling column per stage); narrow flows are routed BY SHAPE to the
+    sample-resident fp32 kernels (flow_nar.cu), so loss, samples, log-determinant and every parameter gradient meet
+    the fp32 bar against the oracle's toy_loss."""
+    from dpi_b200 import _lib
     from dpi_b200.generative_model.realnvpfc_model import RealNVP
     D, NF, B, seqfrac = 2, 16, 512, 1 / 128
     sd = O.init_state(D, NF, seqfrac=seqfrac, seed=31, randomize=True)
@@ -256,15 +258,12 @@ def test_toy_2d_script_loop_body_at_its_own_sizes():
     assert rel_err(xt, aux["x"]) < RTOL
     assert rel_err(logdet + det_sigmoid, aux["logdet_vec"]) < RTOL
     assert abs(float(loss.detach()) - float(loss_o.detach())) < RTOL * max(1.0, abs(float(loss_o.detach())))
-    # Gradients: the tensor-core tolerance, stated separately (BASELINE north_star). This net is the worst case for it:
-    # 128 hidden units feed ONE input feature, so the data gradient of every stage is a cancelling 128-term sum, the
-    # randomised weights make the 32-stage chain ill-conditioned, and 3xTF32 carries ~2^-21 per product against 2^-24
-    # for an fp32 FMA. tools/tf32_emulation.py reproduces the 2.0e-3 (which the mma.sync and the tcgen05 path share) on
-    # the CPU with an fp32 accumulator that rounds toward zero, and 2e-6 with exact accumulation: it is the truncating
-    # accumulation of the tensor cores, a bias that the cancelling sums amplify. The stage the
-    # backward visits first is at fp32 level (1e-6) and the error grows with depth to ~2e-3 at the last one; the same
-    # depth at ndim 8 / H 4 stays at 1e-6 on every path (tools/toy_diag.py). Batches <= 64 run plain fp32 FFMA.
-    TC_GRAD_TOL = 5e-3
+    # Gradients: fp32 FFMA end to end (round 1 ran this net on 3xTF32 tensor cores and needed a 5e-3 tolerance: the
+    # truncating accumulation of the tensor cores is a bias that the cancelling 128-term sums of this net amplify,
+    # tools/tf32_emulation.py). The randomised 32-stage chain is still ill-conditioned, hence 3x the bar as for every
+    # parameter-gradient comparison in this suite.
+    assert _lib.load().dpi_flow_nar_active(m._handle(torch.device("cuda", torch.cuda.current_device())), B) == 3
+    TC_GRAD_TOL = 3 * RTOL
     views = dict(m.named_grad_views())
     first = [rel_err(gv, sd[k].grad) for k, gv in views.items() if k.startswith("blocks.0.") and "actnorm" not in k]
     assert max(first) < RTOL, max(first)
