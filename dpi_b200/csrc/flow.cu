@@ -303,6 +303,13 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
       nar::place_workspace(bp.nar, base, D, H, B, S);
     }
   }
+  if (bp.small.ok && h->sr_avail) {
+    sr::make_plan(bp.sr, h->sr_avail, D, H, B, S);
+    if (bp.sr.ok) {
+      const long long base = take(sr::workspace_floats(bp.sr, D, H, B, S));
+      sr::place_workspace(bp.sr, base, D, H, B, S);
+    }
+  }
   bp.cl.ok = (h->cl_avail && bp.small.ok && fcl::shape_ok(D, H, B)) ? 1 : 0;
   if (bp.cl.ok) {
     o = (o + 255) / 256 * 256;                  // packed tiles are fetched with cp.async.bulk
@@ -666,6 +673,13 @@ int dpi_flow_create(dpi_flow_t* out, int device, int ndim, int n_flow, int hidde
     h->nar_clusters = (ne && ne[0] == '0') ? 0 : nar::query(device);
   }
   {
+    // The sample-resident small-batch pass (flow_sr.cu) is opt-in (DPI_B200_SR=1): parity-green, but measured at 664 us per
+    // RealNVP(1024, 16) reverse pass / 835 us backward against 508 / 675 us for the feature-split kernel
+    // (profiles/sr_r02.md: LDG.128 and FFMA issue add up instead of overlapping, 63 B/clk per SM in the micro-GEMM)
+    const char* se = getenv("DPI_B200_SR");
+    h->sr_avail = (se && se[0] == '1') ? sr::query(device) : 0;
+  }
+  {
     // The cluster-resident tcgen05 pass (flow_cl.cu) is opt-in (DPI_B200_CL=1): parity-green, but measured at 585 us
     // per RealNVP(1024, 16) reverse pass against 501 us for the fp32 small-batch kernel (profiles/cl_fwd_r02.md)
     const char* cle = getenv("DPI_B200_CL");
@@ -940,6 +954,10 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
     a.tbuf = h->d_tbuf;
     return fcl::forward(a, bp->cl, h->S, (cudaStream_t)stream);
   }
+  if (bp->sr.ok && direction == 0) {
+    a.tbuf = h->d_tbuf;
+    return sr::forward(a, bp->sr, (cudaStream_t)stream);
+  }
   if (bp->small.ok) return small_launch(h, *bp, a, 0, (cudaStream_t)stream);
   if (bp->nar.ok && direction == 0) {
     a.tbuf = h->d_tbuf;
@@ -971,6 +989,10 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
   if (bp->cl.ok && fcl::has_backward()) {
     a.tbuf = h->d_tbuf;
     return fcl::backward(a, bp->cl, h->S, (cudaStream_t)stream);
+  }
+  if (bp->sr.ok) {
+    a.tbuf = h->d_tbuf;
+    return sr::backward(a, bp->sr, (cudaStream_t)stream);
   }
   if (bp->small.ok) return small_launch(h, *bp, a, 1, (cudaStream_t)stream);
   if (bp->nar.ok && nar::has_backward()) return nar::backward(a, bp->nar, (cudaStream_t)stream);
@@ -1015,6 +1037,14 @@ int dpi_flow_cl_active(dpi_flow_t h, int batch) {
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
   return bp->cl.ok ? (1 | (fcl::has_backward() ? 2 : 0)) : 0;
+}
+
+int dpi_flow_sr_active(dpi_flow_t h, int batch) {
+  if (!handle_live(h, 1) || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  return (bp->sr.ok && !bp->cl.ok) ? 1 : 0;
 }
 
 int dpi_flow_nar_active(dpi_flow_t h, int batch) {

@@ -11,6 +11,7 @@
 #include "flow_tc.cuh"
 #include "flow_cl.cuh"
 #include "flow_nar.cuh"
+#include "flow_sr.cuh"
 
 namespace dpi {
 void* flow_kernel_ptr();
@@ -49,6 +50,8 @@ struct BatchPlan {
   fcl::Plan cl;
   // sample-resident pass for narrow flows (flow_nar.cu): ndim <= 32, hidden <= 160, batch > 64
   nar::Plan nar;
+  // sample-resident pass for batch <= 64 of a mid-sized flow (flow_sr.cu): weights streamed from L2, one cluster of 16
+  sr::Plan sr;
 };
 
 }  // namespace dpi
@@ -58,6 +61,7 @@ struct dpi_flow_s {
   int n_sm = 0, persistent = 0, ctas_per_sm = 1, coop_max_per_sm = 1, use_tc = 1;
   int small_mode = 1;                         // 0: never use the small-batch kernel
   int nar_clusters = 0;                       // co-resident clusters of 8 of the narrow-flow kernels (0: unavailable)
+  int sr_avail = 0;                           // one 16-CTA cluster of the flow_sr kernels can be scheduled
   int cl_avail = 0;                           // one 16-CTA cluster of the flow_cl kernels can be scheduled
   cudaStream_t side = nullptr;                // weight-gradient GEMMs of the tensor-core path run here, beside the dgrad chain
   std::vector<cudaEvent_t> ev;                // [4 S + 2] fork / join events (main <-> side)

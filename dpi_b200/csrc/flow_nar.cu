@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ 
   const float* Grows; const float* Arows; int I, J; float* out; const int* amap = nullptr; int ti, tj;
   if (job < tiles2) { Grows = a.W + p.oGP2 + (size_t)e * H * LB; Arows = a.W + a.oN1T + (size_t)e * H * LB; I = H; J = H; out = a.G + st.p[P_W2]; ti = job / th; tj = job % th; }
   else if ((job -= tiles2) < tiles3) { Grows = a.W + p.oGPRE + (size_t)e * Dout * LB; Arows = a.W + a.oN2T + (size_t)e * H * LB; I = Dout; J = H; out = a.G + st.p[P_W3]; ti = job / th; tj = job % th; }
-  else if ((job -= tiles3) < tiles1) { Grows = a.W + p.oGP1 + (size_t)e * H * LB; Arows = yprev; amap = a.gmaps + (size_t)e * D; I = H; J = Da; out = a.G + st.p[P_W1]; ti = job; tj = 0; }
+  else if ((job -= tiles3) < tiles1) { Grows = a.W + p.oGP1 + (size_t)e * H * LB; Arows = yprev; amap = a.gmaps + (size_t)e * D; I = H; J = Da; out = a.G + st.p[P_W1]; const int tda = (Da + 63) / 64; ti = job / tda; tj = job - ti * tda; }
   else {
     // ---- row sums: biases, ZeroFC scale, ActNorm; one warp per row, lanes stride the batch
     job -= tiles1;                                         // 0..3: which quarter of the rows
@@ -939,6 +939,15 @@ int backward(const KArgs& a, const Plan& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg = make_cfg(at, p.G, p.smem_bwd, st, a.has_bn != 0);
   DPI_CUDA(cudaLaunchKernelEx(&cfg, nar_bwd_kernel, A));
   count_launch();
+  return param_grads(a, p, st);
+}
+
+// Batched weight / bias / scale / ActNorm gradients from the rows a backward chain stored (p.oGPRE, oGP2, oGP1, oActPart
+// with p.G partial pairs per stage); also used by the sample-resident small-batch chain of flow_sr.cu.
+int param_grads(const KArgs& a, const Plan& p, cudaStream_t st) {
+  NArgs A{};
+  A.k = a;
+  A.p = p;
   const int th = (a.H + 63) / 64;
   const int tiles2 = th * th, tiles3 = ((a.Dout + 63) / 64) * th, tiles1 = th * ((a.Da + 63) / 64);
   const int jobs = tiles2 + tiles3 + tiles1 + 4;

@@ -34,6 +34,7 @@ void place_workspace(Plan& p, long long base, int D, int H, int B, int S);
 int forward(const KArgs& a, const Plan& p, cudaStream_t st);
 int backward(const KArgs& a, const Plan& p, cudaStream_t st);
 int has_backward();
+int param_grads(const KArgs& a, const Plan& p, cudaStream_t st);   // batched parameter gradients from stored rows
 
 }  // namespace nar
 }  // namespace dpi

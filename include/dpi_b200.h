@@ -116,6 +116,8 @@ int dpi_flow_cl_active(dpi_flow_t h, int batch);
  * multiple of 4, batch > 64 and a multiple of 4 - the alpha-DPI parameter flow DPIx_interferometry.py:250 and the 2-D toy
  * flow DPI_2Dtoydist.py:52); bit 1 is set when the backward pass runs there too. DPI_B200_NAR=0 disables it. */
 int dpi_flow_nar_active(dpi_flow_t h, int batch);
+/* 1 when batch `batch` runs the sample-resident small-batch kernels (flow_sr.cu: batch <= 64, weights streamed from L2). */
+int dpi_flow_sr_active(dpi_flow_t h, int batch);
 
 /* Glow building block (generative_model/glow_model.py:260-268, ZeroConv2d :238-251), forward only: a k x k
  * convolution (k = 1, or k = 3 with one pixel of padding filled with pad_value: 0 for nn.Conv2d(padding=1), 1 for

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _run(D, NF, B, seqfrac, env, persistent=True, bn=True, seed=11):
     from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    env = {"DPI_B200_SR": "0", **env}           # this file tests flow_small.cu; the sample-resident kernels have their own
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
