@@ -301,6 +301,9 @@ int build_plan(dpi_flow_s* h, int B, BatchPlan& bp) {
     if (bp.nar.ok) {
       const long long base = take(nar::workspace_floats(bp.nar, D, H, B, S));
       nar::place_workspace(bp.nar, base, D, H, B, S);
+    } else {
+      nar::make_plan_eval(bp.nar_eval, h->nar_clusters, D, H, B, S);
+      if (bp.nar_eval.ok) nar::place_workspace_eval(bp.nar_eval, take(nar::workspace_floats_eval(bp.nar_eval, D, H, S)));
     }
   }
   if (bp.small.ok && h->sr_avail) {
@@ -963,6 +966,7 @@ int dpi_flow_run(dpi_flow_t h, int direction, int train, int batch, const float*
     a.tbuf = h->d_tbuf;
     return nar::forward(a, bp->nar, (cudaStream_t)stream);
   }
+  if (bp->nar_eval.ok && direction == 0 && !a.train) return nar::forward(a, bp->nar_eval, (cudaStream_t)stream);
   if (bp->tc_ok) return tc_forward(h, *bp, a, (cudaStream_t)stream);
   return launch_program(h, bp->fwd[direction][a.train], a, (cudaStream_t)stream);
 }
@@ -1052,7 +1056,7 @@ int dpi_flow_nar_active(dpi_flow_t h, int batch) {
   DeviceGuard g(h->device);
   BatchPlan* bp = nullptr;
   if (get_plan(h, batch, &bp)) return 0;
-  return bp->nar.ok ? (1 | (nar::has_backward() ? 2 : 0)) : 0;
+  return bp->nar.ok ? (1 | (nar::has_backward() ? 2 : 0)) : (bp->nar_eval.ok ? 4 : 0);
 }
 
 int dpi_flow_tc_active(dpi_flow_t h, int batch) {

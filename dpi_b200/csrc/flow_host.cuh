@@ -50,6 +50,7 @@ struct BatchPlan {
   fcl::Plan cl;
   // sample-resident pass for narrow flows (flow_nar.cu): ndim <= 32, hidden <= 160, batch > 64
   nar::Plan nar;
+  nar::Plan nar_eval;    // forward-only plan for eval-mode passes of batches the training plan cannot take (sampling)
   // sample-resident pass for batch <= 64 of a mid-sized flow (flow_sr.cu): weights streamed from L2, one cluster of 16
   sr::Plan sr;
 };

@@ -713,30 +713,42 @@ __global__ void __launch_bounds__(kT, 1) nar_bwd_kernel(const __grid_constant__ 
 //   gW3[j][h] = sum_s g_pre[j][s] n2[h][s]    gW2[n][k] = sum_s p2[n][s] n1[k][s]    gW1[h][k] = sum_s p1[h][s] a[k][s]
 //   gb3 = sum_s g_pre   gb2 = sum_s p2   gb1 = sum_s p1   gscale[j] = 3 sum_s g_pre[j][s] o[j][s] / exp(3 scale_j)
 //   g_loc = -sum S1     g_lsi = sum S2 + D sum_s g_ld[s]
-// Job = (stage, 64 x 64 tile of one weight gradient | a block of row sums); no cross-CTA dependencies.
-struct PJob { int e, kind, i0, j0; };
+// Job = (stage, tile of one weight gradient | a block of row sums); no cross-CTA dependencies.
 
-__global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ NArgs A, int jobs_per_stage, int tiles2, int tiles3,
-                                                        int tiles1) {
+// Tile shapes follow the matrix: rows / columns per tile from {16, 32, 48, 64} with the least padding (hidden 144 -> 48,
+// 18 output rows -> 32, 9 input columns -> 16), 4 x 4 outputs per thread.
+struct PTiles {
+  int ti2, tj2, ti3, tj3, ti1, tj1;     // tile rows / columns of gW2 [H][H], gW3 [Dout][H], gW1 [H][Da]
+  int n2, n3, n1;                       // tiles per stage of each
+};
+__host__ __device__ inline int pg_tile_dim(int n) {
+  int best = 64, waste = ((n + 63) / 64) * 64 - n;
+  for (int t = 48; t >= 16; t -= 16) {
+    const int w = ((n + t - 1) / t) * t - n;
+    if (w < waste) { waste = w; best = t; }
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ NArgs A, int jobs_per_stage, const PTiles pt) {
   __shared__ __align__(16) float Gs[32][68];
   __shared__ __align__(16) float As[32][68];
   const KArgs& a = A.k;
   const Plan& p = A.p;
-  const int D = a.D, Da = a.Da, Db = a.Db, Dout = a.Dout, H = a.H, B = a.B, LB = a.ldb;
+  const int D = a.D, Da = a.Da, Dout = a.Dout, H = a.H, B = a.B, LB = a.ldb;
   const int e = blockIdx.x / jobs_per_stage;
   int job = blockIdx.x - e * jobs_per_stage;
   const StageTab& st = a.st[e];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const float* yprev = e == 0 ? a.W + a.oZT : a.W + a.oYT + (size_t)(e - 1) * D * LB;
-  const int th = (H + 63) / 64;
   // ---- decode the job
-  const float* Grows; const float* Arows; int I, J; float* out; const int* amap = nullptr; int ti, tj;
-  if (job < tiles2) { Grows = a.W + p.oGP2 + (size_t)e * H * LB; Arows = a.W + a.oN1T + (size_t)e * H * LB; I = H; J = H; out = a.G + st.p[P_W2]; ti = job / th; tj = job % th; }
-  else if ((job -= tiles2) < tiles3) { Grows = a.W + p.oGPRE + (size_t)e * Dout * LB; Arows = a.W + a.oN2T + (size_t)e * H * LB; I = Dout; J = H; out = a.G + st.p[P_W3]; ti = job / th; tj = job % th; }
-  else if ((job -= tiles3) < tiles1) { Grows = a.W + p.oGP1 + (size_t)e * H * LB; Arows = yprev; amap = a.gmaps + (size_t)e * D; I = H; J = Da; out = a.G + st.p[P_W1]; const int tda = (Da + 63) / 64; ti = job / tda; tj = job - ti * tda; }
+  const float* Grows; const float* Arows; int I, J, TI, TJ; float* out; const int* amap = nullptr;
+  if (job < pt.n2) { Grows = a.W + p.oGP2 + (size_t)e * H * LB; Arows = a.W + a.oN1T + (size_t)e * H * LB; I = H; J = H; TI = pt.ti2; TJ = pt.tj2; out = a.G + st.p[P_W2]; }
+  else if ((job -= pt.n2) < pt.n3) { Grows = a.W + p.oGPRE + (size_t)e * Dout * LB; Arows = a.W + a.oN2T + (size_t)e * H * LB; I = Dout; J = H; TI = pt.ti3; TJ = pt.tj3; out = a.G + st.p[P_W3]; }
+  else if ((job -= pt.n3) < pt.n1) { Grows = a.W + p.oGP1 + (size_t)e * H * LB; Arows = yprev; amap = a.gmaps + (size_t)e * D; I = H; J = Da; TI = pt.ti1; TJ = pt.tj1; out = a.G + st.p[P_W1]; }
   else {
     // ---- row sums: biases, ZeroFC scale, ActNorm; one warp per row, lanes stride the batch
-    job -= tiles1;                                         // 0..3: which quarter of the rows
+    job -= pt.n1;                                          // 0..3: which quarter of the rows
     const int rows = 2 * H + 2 * Dout;                     // [b1: H | b2: H | b3: Dout | scale: Dout]
     for (int r = job * 8 + warp; r < rows; r += 32) {
       const float* g; const float* o = nullptr; float* dst; float mul = 1.f;
@@ -766,9 +778,13 @@ __global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ 
     }
     return;
   }
-  // ---- 64 x 64 tile of C[i][j] = sum_s G[i][s] Arow(j)[s]
-  const int i0 = ti * 64, j0 = tj * 64;
-  const int tr = t >> 4, tc = t & 15;                      // thread tile: rows 4 tr.., columns 4 tc..
+  // ---- TI x TJ tile of C[i][j] = sum_s G[i][s] Arow(j)[s]
+  const int tjn = (J + TJ - 1) / TJ;
+  const int ti = job / tjn, tj = job - ti * tjn;
+  const int i0 = ti * TI, j0 = tj * TJ;
+  const int tcn = TJ >> 2;                                 // thread tile columns
+  const bool on = t < (TI >> 2) * tcn;
+  const int tr = on ? t / tcn : 0, tc = on ? t - tr * tcn : 0;   // thread tile: rows 4 tr.., columns 4 tc..
   float acc[4][4];
 #pragma unroll
   for (int x = 0; x < 4; ++x)
@@ -776,38 +792,44 @@ __global__ void __launch_bounds__(256) nar_pgrad_kernel(const __grid_constant__ 
     for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
   for (int s0 = 0; s0 < B; s0 += 32) {
     __syncthreads();
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {                    // 64 rows x 8 quads per operand, 512 quads, 2 per thread
-      const int id = t + rep * 256, r = id >> 3, q = id & 7;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), v = g;
+    for (int id = t; id < (TI + TJ) * 8; id += 256) {      // (TI + TJ) rows x 8 sample quads
+      const int rr = id >> 3, q = id & 7;
+      const bool isg = rr < TI;
+      const int r = isg ? rr : rr - TI;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s0 + 4 * q < B) {
-        if (i0 + r < I) g = __ldcg(reinterpret_cast<const float4*>(Grows + (size_t)(i0 + r) * LB + s0 + 4 * q));
-        if (j0 + r < J) {
+        if (isg) {
+          if (i0 + r < I) v = __ldcg(reinterpret_cast<const float4*>(Grows + (size_t)(i0 + r) * LB + s0 + 4 * q));
+        } else if (j0 + r < J) {
           const int row = amap ? __ldg(amap + j0 + r) : j0 + r;
           v = __ldcg(reinterpret_cast<const float4*>(Arows + (size_t)row * LB + s0 + 4 * q));
         }
       }
-      Gs[4 * q + 0][r] = g.x; Gs[4 * q + 1][r] = g.y; Gs[4 * q + 2][r] = g.z; Gs[4 * q + 3][r] = g.w;
-      As[4 * q + 0][r] = v.x; As[4 * q + 1][r] = v.y; As[4 * q + 2][r] = v.z; As[4 * q + 3][r] = v.w;
+      float (*dst)[68] = isg ? Gs : As;
+      dst[4 * q + 0][r] = v.x; dst[4 * q + 1][r] = v.y; dst[4 * q + 2][r] = v.z; dst[4 * q + 3][r] = v.w;
     }
     __syncthreads();
+    if (on) {
 #pragma unroll 8
-    for (int s = 0; s < 32; ++s) {
-      const float4 g = ld4(&Gs[s][4 * tr]), v = ld4(&As[s][4 * tc]);
-      const float gv[4] = {g.x, g.y, g.z, g.w}, vv[4] = {v.x, v.y, v.z, v.w};
+      for (int s = 0; s < 32; ++s) {
+        const float4 g = ld4(&Gs[s][4 * tr]), v = ld4(&As[s][4 * tc]);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 4; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(gv[x], vv[y], acc[x][y]);
+          for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(gv[x], vv[y], acc[x][y]);
+      }
     }
   }
+  if (on) {
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int i = i0 + 4 * tr + x, j = j0 + 4 * tc + y;
-      if (i < I && j < J) out[(size_t)i * J + j] = acc[x][y];
-    }
+      for (int y = 0; y < 4; ++y) {
+        const int i = i0 + 4 * tr + x, j = j0 + 4 * tc + y;
+        if (i < I && j < J) out[(size_t)i * J + j] = acc[x][y];
+      }
+  }
 }
 
 // =================================================================================================== host side
@@ -827,6 +849,13 @@ cudaLaunchConfig_t make_cfg(cudaLaunchAttribute* at, int G, int smem, cudaStream
 }
 inline int pad32i(int n) { return (n + 31) & ~31; }
 }  // namespace
+
+// DPI_B200_NAR_COOP=0: plain (non-cooperative) launches, for Nsight Compute, which cannot profile cooperative cluster
+// launches; the grid is sized to be co-resident either way.
+static bool coop_allowed() {
+  static const bool off = []() { const char* e = getenv("DPI_B200_NAR_COOP"); return e && e[0] == '0'; }();
+  return !off;
+}
 
 int has_backward() {
   static const bool off = []() { const char* e = getenv("DPI_B200_NAR_BWD"); return e && e[0] == '0'; }();
@@ -853,16 +882,10 @@ int query(int device) {
   return g_max_clusters;
 }
 
-void make_plan(Plan& p, int max_clusters, int D, int H, int B, int S, int has_bn) {
-  p = Plan{};
-  (void)has_bn;
-  if (max_clusters < 1 || D > kMaxD || D < 2 || H > kMaxH || (H & 3) || B < 8 || (B & 3) || S > 128) return;
+namespace {
+// block and shared-memory layout for slabs of SPB samples on G CTAs
+void fill_layout(Plan& p, int G, int SPB, int D, int H, int S) {
   const int Da = D - D / 2, Db = D / 2, Dout = 2 * Db;
-  const int cap = kClusterN * max_clusters;
-  int SPB = ((B + cap - 1) / cap + 3) & ~3;
-  SPB = std::max(SPB, 8);
-  if (SPB > kMaxSPB) return;
-  const int G = ((B + SPB - 1) / SPB + kClusterN - 1) / kClusterN * kClusterN;
   p.G = G; p.ncl = G / kClusterN; p.SPB = SPB;
   p.Da4 = (Da + 3) & ~3;
   p.Hp = pad32i(H);
@@ -891,8 +914,40 @@ void make_plan(Plan& p, int max_clusters, int D, int H, int B, int S, int has_bn
   p.actRows = D + Dout + Db + 2 * H;
   p.oAct0 = take(p.actRows * SPB); p.oAct1 = take(p.actRows * SPB);
   p.smem_bwd = o * 4;
+}
+bool shape_ok(int D, int H, int B, int S) { return !(D > kMaxD || D < 2 || H > kMaxH || (H & 3) || B < 8 || (B & 3) || S > 128); }
+}  // namespace
+
+void make_plan(Plan& p, int max_clusters, int D, int H, int B, int S, int has_bn) {
+  p = Plan{};
+  (void)has_bn;
+  if (max_clusters < 1 || !shape_ok(D, H, B, S)) return;
+  const int cap = kClusterN * max_clusters;
+  int SPB = ((B + cap - 1) / cap + 3) & ~3;
+  SPB = std::max(SPB, 8);
+  if (SPB > kMaxSPB) return;
+  const int G = ((B + SPB - 1) / SPB + kClusterN - 1) / kClusterN * kClusterN;
+  fill_layout(p, G, SPB, D, H, S);
   p.ok = (p.smem_bwd <= kSmemMax) ? 1 : 0;
 }
+
+// Forward-only plan for passes that need no cross-CTA exchange (eval mode: running statistics): the slabs are independent,
+// so the grid may exceed the co-resident CTAs - any batch, 32 samples per CTA (posterior sampling at 8192,
+// DPIx_interferometry.py:433). p.ok then means "the forward fits"; there is no backward for it.
+void make_plan_eval(Plan& p, int avail, int D, int H, int B, int S) {
+  p = Plan{};
+  if (avail < 1 || !shape_ok(D, H, B, S)) return;
+  const int SPB = 32;
+  const int G = ((B + SPB - 1) / SPB + kClusterN - 1) / kClusterN * kClusterN;
+  fill_layout(p, G, SPB, D, H, S);
+  p.ok = (p.smem_fwd <= kSmemMax) ? 1 : 0;
+}
+
+long long workspace_floats_eval(const Plan& p, int D, int H, int S) {
+  (void)D;
+  return (long long)S * (p.Da4 + H) * H + 256;
+}
+void place_workspace_eval(Plan& p, long long base) { p.oWT = base; }
 
 long long workspace_floats(const Plan& p, int D, int H, int B, int S) {
   const long long Dout = 2 * (D / 2);
@@ -923,7 +978,7 @@ int forward(const KArgs& a, const Plan& p, cudaStream_t st) {
   }
   cudaLaunchAttribute at[2];
   // batch statistics need every CTA co-resident (grid barrier): cooperative launch; eval / no-BatchNorm passes do not
-  const bool coop = a.has_bn && a.train;
+  const bool coop = a.has_bn && a.train && coop_allowed();
   cudaLaunchConfig_t cfg = make_cfg(at, p.G, p.smem_fwd, st, coop);
   DPI_CUDA(cudaLaunchKernelEx(&cfg, nar_fwd_kernel, A));
   count_launch();
@@ -936,7 +991,7 @@ int backward(const KArgs& a, const Plan& p, cudaStream_t st) {
   A.p = p;
   DPI_CUDA(cudaMemsetAsync(a.ctrl, 0, kCtrlWords * sizeof(unsigned), st));
   cudaLaunchAttribute at[2];
-  cudaLaunchConfig_t cfg = make_cfg(at, p.G, p.smem_bwd, st, a.has_bn != 0);
+  cudaLaunchConfig_t cfg = make_cfg(at, p.G, p.smem_bwd, st, a.has_bn != 0 && coop_allowed());
   DPI_CUDA(cudaLaunchKernelEx(&cfg, nar_bwd_kernel, A));
   count_launch();
   return param_grads(a, p, st);
@@ -948,10 +1003,16 @@ int param_grads(const KArgs& a, const Plan& p, cudaStream_t st) {
   NArgs A{};
   A.k = a;
   A.p = p;
-  const int th = (a.H + 63) / 64;
-  const int tiles2 = th * th, tiles3 = ((a.Dout + 63) / 64) * th, tiles1 = th * ((a.Da + 63) / 64);
-  const int jobs = tiles2 + tiles3 + tiles1 + 4;
-  nar_pgrad_kernel<<<a.S * jobs, 256, 0, st>>>(A, jobs, tiles2, tiles3, tiles1);
+  PTiles pt{};
+  pt.ti2 = pt.tj2 = pg_tile_dim(a.H);
+  pt.ti3 = pg_tile_dim(a.Dout); pt.tj3 = pg_tile_dim(a.H);
+  pt.ti1 = pg_tile_dim(a.H); pt.tj1 = pg_tile_dim(a.Da);
+  auto cnt = [](int n, int t) { return (n + t - 1) / t; };
+  pt.n2 = cnt(a.H, pt.ti2) * cnt(a.H, pt.tj2);
+  pt.n3 = cnt(a.Dout, pt.ti3) * cnt(a.H, pt.tj3);
+  pt.n1 = cnt(a.H, pt.ti1) * cnt(a.Da, pt.tj1);
+  const int jobs = pt.n2 + pt.n3 + pt.n1 + 4;
+  nar_pgrad_kernel<<<a.S * jobs, 256, 0, st>>>(A, jobs, pt);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

@@ -29,6 +29,9 @@ struct Plan {
 
 int query(int device);                                   // max co-resident clusters of 8 (0: unavailable)
 void make_plan(Plan& p, int max_clusters, int D, int H, int B, int S, int has_bn);
+void make_plan_eval(Plan& p, int avail, int D, int H, int B, int S);   // forward-only, eval mode, any batch
+long long workspace_floats_eval(const Plan& p, int D, int H, int S);
+void place_workspace_eval(Plan& p, long long base);
 long long workspace_floats(const Plan& p, int D, int H, int B, int S);
 void place_workspace(Plan& p, long long base, int D, int H, int B, int S);
 int forward(const KArgs& a, const Plan& p, cudaStream_t st);

@@ -180,6 +180,21 @@ __global__ void __launch_bounds__(256) step_terms_kernel(int B, TermArgs a, floa
   }
 }
 
+// interferometry_helpers.py torch_complex_mul :30-34: out[o][:, i] = x[o][:, i] * y[:, i] as complex numbers stored as
+// (real row, imaginary row); conj = 1 multiplies with conj(y) (the gradient wrt x).
+__global__ void complex_mul_kernel(long long outer, int n, int conj, const float* __restrict__ x, const float* __restrict__ y,
+                                   float* __restrict__ out) {
+  const long long total = outer * n;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+    const long long o = id / n;
+    const int i = (int)(id - o * n);
+    const float xr = x[(o * 2) * n + i], xi = x[(o * 2 + 1) * n + i];
+    const float yr = __ldg(y + i), yi = conj ? -__ldg(y + n + i) : __ldg(y + n + i);
+    out[(o * 2) * n + i] = xr * yr - xi * yi;
+    out[(o * 2 + 1) * n + i] = xr * yi + xi * yr;
+  }
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -250,6 +265,14 @@ int dpi_step_terms(int batch, const double* data64, float w64, const float* data
 int dpi_reduce_sum(int n, const float* in, float* out, double* sq_out, dpi_stream_t stream) {
   DPI_REQUIRE(n >= 1 && in, "dpi_reduce_sum: bad argument");
   reduce_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n, in, out, sq_out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_complex_mul(long long outer, int n, int conj, const float* x, const float* y, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(outer >= 1 && n >= 1 && x && y && out, "dpi_complex_mul: bad argument");
+  const long long total = outer * n;
+  complex_mul_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(outer, n, conj, x, y, out);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

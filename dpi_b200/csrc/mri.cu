@@ -140,6 +140,33 @@ int launch(int mode, int batch, int npix, const float* img, float* kspace, const
   return DPI_OK;
 }
 
+// MRI_helpers.py:18-26: loss[b] = mean_i |y_pred[b][i] - y_true[i]|^p / sigma^p, p = 1 (Loss_kspace_diff) or 2
+// (Loss_kspace_diff2); with g_loss also g_pred[b][i] = g_loss[b] p |d|^(p-1) sign(d) / (n sigma^p). One CTA per sample,
+// fixed-order block reduction.
+__global__ void __launch_bounds__(256) kspace_loss_kernel(int power, int n, float inv_sigma_p, const float* __restrict__ y_true,
+                                                          const float* __restrict__ y_pred, float* __restrict__ loss,
+                                                          const float* __restrict__ g_loss, float* __restrict__ g_pred) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* yp = y_pred + (size_t)b * n;
+  const float inv_n = 1.0f / (float)n;
+  const float gs = g_loss ? g_loss[b] * inv_sigma_p * inv_n : 0.f;
+  float acc = 0.f;
+  for (int i = t; i < n; i += 256) {
+    const float d = yp[i] - __ldg(y_true + i);
+    acc += power == 2 ? d * d : fabsf(d);
+    if (g_pred) g_pred[(size_t)b * n + i] = power == 2 ? 2.f * d * gs : (d > 0.f ? gs : (d < 0.f ? -gs : 0.f));
+  }
+  acc = warp_sum(acc);
+  if ((t & 31) == 0) red[t >> 5] = acc;
+  __syncthreads();
+  if (t == 0 && loss) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    loss[b] = tot * inv_n * inv_sigma_p;
+  }
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -165,6 +192,17 @@ int dpi_mri_data_loss(int batch, int npix, const float* img, const float* mask, 
   DPI_REQUIRE(!g_img || gw, "dpi_mri_data_loss: g_img requested without weights");
   return launch(2, batch, npix, img, nullptr, nullptr, mask, kspace_true, 1.0f / (sigma * sigma) / mean_mask, loss, gw,
                 g_img, (cudaStream_t)stream);
+}
+
+int dpi_kspace_loss(int power, int batch, int n, float sigma, const float* y_true, const float* y_pred, float* loss,
+                    const float* g_loss, float* g_pred, dpi_stream_t stream) {
+  DPI_REQUIRE((power == 1 || power == 2) && batch >= 1 && n >= 1 && sigma > 0.f && y_true && y_pred, "dpi_kspace_loss: bad argument");
+  DPI_REQUIRE(loss || (g_loss && g_pred), "dpi_kspace_loss: nothing to compute");
+  DPI_REQUIRE(!g_pred || g_loss, "dpi_kspace_loss: g_pred requested without g_loss");
+  const float isp = power == 2 ? 1.0f / (sigma * sigma) : 1.0f / sigma;
+  kspace_loss_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(power, n, isp, y_true, y_pred, loss, g_loss, g_pred);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
 }
 
 }  // extern "C"

@@ -32,13 +32,44 @@ def _need_cuda(t, what):
 
 
 # ------------------------------------------------------------------------------------------------
-# complex helpers kept for API completeness (torch ops; not on the fused path)
+# complex helpers (the reference uses torch_complex_mul only on its NUFFT branch, :267)
 # ------------------------------------------------------------------------------------------------
+class _ComplexMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib = _lib.load()
+        _need_cuda(x, "torch_complex_mul")
+        xc = x.contiguous().float()
+        yc = y.to(xc.device).contiguous().float()
+        n = xc.shape[-1]
+        if xc.dim() < 2 or xc.shape[-2] != 2 or tuple(yc.shape) != (2, n):
+            raise ValueError(f"torch_complex_mul: x [..., 2, n] and y [2, n] expected, got {tuple(x.shape)} and {tuple(y.shape)}")
+        out = torch.empty_like(xc)
+        ctx.save_for_backward(yc)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.dpi_complex_mul(xc.numel() // (2 * n), n, 0, xc.data_ptr(), yc.data_ptr(), out.data_ptr(),
+                                           _lib.stream_ptr()), "dpi_complex_mul")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("dpi_b200.torch_complex_mul: gradient wrt the second factor (a constant pulse "
+                                      "function in the reference, interferometry_helpers.py:267) is not implemented")
+        (yc,) = ctx.saved_tensors
+        gc = g.contiguous().float()
+        n = gc.shape[-1]
+        gx = torch.empty_like(gc)
+        with torch.cuda.device(gc.device):
+            _lib.check(lib.dpi_complex_mul(gc.numel() // (2 * n), n, 1, gc.data_ptr(), yc.data_ptr(), gx.data_ptr(),
+                                           _lib.stream_ptr()), "dpi_complex_mul")
+        return gx, None
+
+
 def torch_complex_mul(x, y):
-    """interferometry_helpers.py:30-34."""
-    xy_real = x[:, :, 0:1] * y[0:1] - x[:, :, 1::] * y[1::]
-    xy_imag = x[:, :, 0:1] * y[1::] + x[:, :, 1::] * y[0:1]
-    return torch.cat([xy_real, xy_imag], -2)
+    """interferometry_helpers.py:30-34: x [A, C, 2, n] times y [2, n] as complex numbers (real row, imaginary row)."""
+    return _ComplexMul.apply(x, y)
 
 
 def torch_complex_matmul(x, F):

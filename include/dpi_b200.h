@@ -114,7 +114,8 @@ int dpi_flow_tc_active(dpi_flow_t h, int batch);
 int dpi_flow_cl_active(dpi_flow_t h, int batch);
 /* 1 when `batch` runs RealNVP.reverse as the sample-resident narrow-flow pass (flow_nar.cu: ndim <= 32, hidden <= 160 and a
  * multiple of 4, batch > 64 and a multiple of 4 - the alpha-DPI parameter flow DPIx_interferometry.py:250 and the 2-D toy
- * flow DPI_2Dtoydist.py:52); bit 1 is set when the backward pass runs there too. DPI_B200_NAR=0 disables it. */
+ * flow DPI_2Dtoydist.py:52); bit 1 is set when the backward pass runs there too; 4 = only eval-mode passes run there (batches
+ * the training plan cannot take, e.g. posterior sampling at 8192). DPI_B200_NAR=0 disables it. */
 int dpi_flow_nar_active(dpi_flow_t h, int batch);
 /* 1 when batch `batch` runs the sample-resident small-batch kernels (flow_sr.cu: batch <= 64, weights streamed from L2). */
 int dpi_flow_sr_active(dpi_flow_t h, int batch);
@@ -305,6 +306,10 @@ int dpi_alpha_objective(int batch, int nparams, const float* z, const double* lo
                         float* gscale, float* g_logdet, float* terms /*[8]*/, float* stats /*[2]*/,
                         dpi_stream_t stream);
 
+/* interferometry_helpers.py torch_complex_mul :30-34. x, out: [outer][2][n] (real row, imaginary row), y: [2][n];
+ * out = x * y, or x * conj(y) when conj != 0 (the gradient wrt x of the former). */
+int dpi_complex_mul(long long outer, int n, int conj, const float* x, const float* y, float* out, dpi_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * MRI operator: DPI_MRI.py fft2c_torch :70-74 + MRI_helpers.py Loss_kspace_diff2 :23-26.
  * ------------------------------------------------------------------------------------------ */
@@ -312,6 +317,11 @@ int dpi_alpha_objective(int batch, int nparams, const float* z, const double* lo
 int dpi_fft2c_forward(int batch, int npix, const float* img, float* kspace, dpi_stream_t stream);
 /* g_img = adjoint applied to g_kspace (real part) */
 int dpi_fft2c_backward(int batch, int npix, const float* g_kspace, float* g_img, dpi_stream_t stream);
+/* MRI_helpers.py Loss_kspace_diff :18-21 (power 1) / Loss_kspace_diff2 :23-26 (power 2):
+ * loss[b] = mean_i |y_pred[b][i] - y_true[i]|^power / sigma^power over the n values of a sample (y_true broadcast over the
+ * batch). With g_loss [batch] and g_pred [batch][n] also the gradient wrt y_pred; loss may then be NULL. */
+int dpi_kspace_loss(int power, int batch, int n, float sigma, const float* y_true, const float* y_pred, float* loss,
+                    const float* g_loss, float* g_pred, dpi_stream_t stream);
 /* Fused data term of DPI_MRI.py:181-182: loss[b] = mean((fft2c(img)*mask - kspace_true)^2)/sigma^2/mean_mask
  * and, if g_img != NULL, g_img[b,:] = gw[b] * d loss[b]/d img. mask, kspace_true [npix,npix,2]. */
 int dpi_mri_data_loss(int batch, int npix, const float* img, const float* mask, const float* kspace_true,

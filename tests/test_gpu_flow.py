@@ -274,3 +274,21 @@ def test_toy_2d_script_loop_body_at_its_own_sizes():
         mine = torch.cat([views[k].reshape(-1).cpu() for k in ks])
         ref = torch.cat([sd[k].grad.reshape(-1) for k in ks])
         assert rel_err(mine, ref) < GRAD_TOL, (kind, rel_err(mine, ref))
+
+
+def test_narrow_flow_eval_pass_at_sampling_batch():
+    """Posterior sampling (DPIx_interferometry.py:433: 8192 samples through the alpha-DPI flow in eval mode): batches the
+    sample-resident training plan cannot take run its forward-only plan (independent slabs, running statistics)."""
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    D, NF, B, sf = 18, 4, 8192, 1 / 16
+    sd = O.init_state(D, NF, seqfrac=sf, seed=5, randomize=True)
+    m = RealNVP(D, NF, seqfrac=sf)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    assert _lib.load().dpi_flow_nar_active(m._handle(torch.device("cuda", torch.cuda.current_device())), B) == 4
+    torch.manual_seed(1)
+    z = torch.randn(B, D)
+    with torch.no_grad():
+        x, ld = m.reverse(z.cuda())
+        xo, ldo = O.realnvp_reverse({k: v for k, v in sd.items()}, z, train=False)
+    assert rel_err(x, xo) < RTOL and rel_err(ld, ldo) < RTOL

@@ -236,3 +236,20 @@ def test_positivity_roundtrip():
     _lib.check(lib.dpi_positivity_backward(B, npix, xg.data_ptr(), lsg.data_ptr(), im.data_ptr(), cig.data_ptr(), None,
                                            cdg.data_ptr(), gx.data_ptr(), gp.data_ptr(), st))
     assert rel_err(gx, x.grad) < RTOL and rel_err(gp.sum(), ls.grad.sum()) < RTOL
+
+
+def test_torch_complex_mul_matches_reference_definition():
+    """interferometry_helpers.py:30-34 (used on the reference's NUFFT branch, :267): value and gradient wrt the first factor."""
+    from dpi_b200 import interferometry_helpers as ih
+    torch.manual_seed(4)
+    x = torch.randn(3, 1, 2, 157, requires_grad=True)
+    y = torch.randn(2, 157)
+    c = torch.randn(3, 1, 2, 157)
+    ref = torch.cat([x[:, :, 0:1] * y[0:1] - x[:, :, 1::] * y[1::], x[:, :, 0:1] * y[1::] + x[:, :, 1::] * y[0:1]], -2)
+    (ref * c).sum().backward()
+    xg = x.detach().cuda().requires_grad_(True)
+    out = ih.torch_complex_mul(xg, y.cuda())
+    (out * c.cuda()).sum().backward()
+    assert out.shape == ref.shape and rel_err(out, ref) < 1e-6 and rel_err(xg.grad, x.grad) < 1e-6
+    with pytest.raises(RuntimeError):
+        ih.torch_complex_mul(x.detach(), y)          # CPU tensors: no fallback
