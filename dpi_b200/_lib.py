@@ -56,6 +56,7 @@ PROTOTYPES = {
     "dpi_flow_tc_active": (i32, [vp, i32]),
     "dpi_flow_cl_active": (i32, [vp, i32]),
     "dpi_flow_nar_active": (i32, [vp, i32]),
+    "dpi_flow_range_ok": (i32, [vp, i32]),
     "dpi_flow_sr_active": (i32, [vp, i32]),
     "dpi_flow_debug_timing": (i32, [vp, i32]),
     "dpi_flow_debug_read": (i32, [vp, vp, vp, i32]),

@@ -1017,9 +1017,10 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
   BatchPlan* bp = nullptr;
   int rc = get_plan(h, batch, &bp);
   if (rc) return rc;
-  if (!bp->tc_ok) {
-    set_error("dpi_flow_backward_range: partial stage ranges need the tcgen05 path (batch >= %d); batch %d runs one kernel per pass",
-              h->tc_min_batch, batch);
+  const bool small_path = bp->small.ok && !bp->sr.ok && !(bp->cl.ok && fcl::has_backward());
+  if (!bp->tc_ok && !small_path) {
+    set_error("dpi_flow_backward_range: partial stage ranges need the tcgen05 path (batch >= %d) or the small-batch kernel; batch %d "
+              "runs on a path with one launch per pass", h->tc_min_batch, batch);
     return DPI_ERR_UNSUPPORTED;
   }
   const size_t need = kCtrlWords * sizeof(unsigned) + (size_t)bp->total_floats * sizeof(float);
@@ -1032,7 +1033,17 @@ int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float*
   a.dir = 0; a.train = 1;
   a.P = params; a.G = grads; a.R = nullptr; a.in = in; a.out = nullptr; a.logdet = nullptr;
   a.g_out = g_out; a.g_ld = g_logdet; a.g_in = g_in;
+  if (small_path) return small_launch(h, *bp, a, 1, (cudaStream_t)stream, stage_lo, stage_hi);
   return tc_backward(h, *bp, a, (cudaStream_t)stream, stage_lo, stage_hi);
+}
+
+int dpi_flow_range_ok(dpi_flow_t h, int batch) {
+  if (!handle_live(h, 1) || batch < 1) return 0;
+  DeviceGuard g(h->device);
+  BatchPlan* bp = nullptr;
+  if (get_plan(h, batch, &bp)) return 0;
+  if (bp->tc_ok) return 1;
+  return (bp->small.ok && !bp->sr.ok && !(bp->cl.ok && fcl::has_backward())) ? 2 : 0;
 }
 
 int dpi_flow_cl_active(dpi_flow_t h, int batch) {

@@ -76,6 +76,7 @@ struct KArgs {
   int use_tc;                 // 1: tcgen05/TMEM tile core, 0: mma.sync tile core
   int fin_lo, fin_hi;         // OP_BWD_FINAL: stages whose ActNorm gradients are finalised ([0, S) unless the backward
                               // is run in stage ranges)
+  int bfin_phase;             // flow_small.cu backward: the phase index that finalises (the last one of the launch)
   const int* pmaps;           // flow_cl.cu: [S][D] consumer slot (cta * 64 + row slot) of every output row in the next stage
   int ldb;                    // row stride (floats) of the feature-major workspace matrices: B, or round_up4(B)
                               // for the small-batch kernel (every row 16-byte aligned)

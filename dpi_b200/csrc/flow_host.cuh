@@ -93,5 +93,5 @@ namespace dpi {
 // flow_small.cu
 int small_query(dpi_flow_s* h);                                        // fills small_clusters / small_cl
 void small_plan(const dpi_flow_s* h, BatchPlan& bp);                   // fills bp.small / small_fwd (ok = 0 if unsupported)
-int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream);
+int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream, int lo = 0, int hi = -1);
 }  // namespace dpi

@@ -1016,7 +1016,7 @@ __device__ __noinline__ void run_bwd_final(const SArgs& A, const Sm& s) {
   for (int m = threadIdx.x; m < a.B; m += kT) sacc += ldcg(a.g_ld + m);
   const float gld = block_sum(sacc, s.red);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int e = w; e < a.S; e += kT / 32) {
+  for (int e = a.fin_lo + w; e < a.fin_hi; e += kT / 32) {      // the stages this launch covered
     const float* red = a.W + a.oRED + (size_t)e * A.sp.red_tiles * 2;
     float s1 = 0.f, s2 = 0.f;
     for (int t = lane; t < A.sp.red_tiles; t += 32) { s1 += ldcg(red + 2 * t); s2 += ldcg(red + 2 * t + 1); }
@@ -1039,7 +1039,8 @@ __device__ __forceinline__ void decode(const SArgs& A, int p, int& kind, int& e)
     else if (p <= 3 * S) { e = (p - 1) / 3; kind = K_F1 + (p - 1) % 3; }
     else { kind = K_FFIN; e = S - 1; }
   } else {
-    if (p == 0) { kind = K_TIN; e = S - 1; }
+    if (p == A.k.bfin_phase) { kind = K_BFIN; e = 0; }       // last phase of the launch (stage-range launches end early)
+    else if (p == 0) { kind = K_TIN; e = S - 1; }
     else if (p <= 4 * S) { e = S - 1 - ((p - 1) >> 2); kind = K_B0 + ((p - 1) & 3); }
     else { kind = K_BFIN; e = 0; }
   }
@@ -1374,7 +1375,7 @@ void small_plan(const dpi_flow_s* h, BatchPlan& bp) {
   bp.small.ldp_tiles = std::max(bp.small.ldp_tiles, bp.small_fwd.ldp_tiles);
 }
 
-int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream) {
+int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStream_t stream, int lo, int hi) {
   const SmallPlan& plan = bwd ? bp.small : bp.small_fwd;
   SArgs A{};
   A.k = a;
@@ -1387,7 +1388,19 @@ int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStre
   A.k.ldp_tiles = plan.ldp_tiles;
   A.k.red_tiles = plan.red_tiles;
   const int n_phases = bwd ? 4 * h->S + 2 : 3 * h->S + 2;
-  if (h->d_tbuf && n_phases <= 4096) {
+  // Backward over the stages [lo, hi) only (hi - 1 first): phases [p0, p1) of the full sequence, then the finalising phase
+  // for exactly these stages (the input-gradient transpose belongs to the range that ends at stage 0). State between
+  // ranges lives in the workspace, as between the launches of the one-launch-per-phase mode.
+  const bool ranged = bwd && hi >= 0 && !(lo == 0 && hi == h->S);
+  int p0 = 0, p1 = n_phases;
+  A.k.fin_lo = 0; A.k.fin_hi = h->S; A.k.bfin_phase = bwd ? 4 * h->S + 1 : -1;
+  if (ranged) {
+    p0 = hi == h->S ? 0 : 1 + 4 * (h->S - hi);
+    p1 = 1 + 4 * (h->S - lo) + 1;
+    A.k.fin_lo = lo; A.k.fin_hi = hi; A.k.bfin_phase = p1 - 1;
+    if (lo > 0) A.k.g_in = nullptr;
+  }
+  if (h->d_tbuf && n_phases <= 4096 && !ranged) {
     A.k.tbuf = h->d_tbuf;
     h->tbuf_phases = n_phases;
     h->last_ops.assign(n_phases, 0);
@@ -1423,12 +1436,12 @@ int small_launch(dpi_flow_s* h, const BatchPlan& bp, KArgs& a, int bwd, cudaStre
   cfg.attrs = at;
   cfg.numAttrs = na;
   if (h->persistent) {
-    A.k.phase_begin = 0; A.k.phase_end = n_phases; A.k.persistent = 1;
+    A.k.phase_begin = p0; A.k.phase_end = p1; A.k.persistent = 1;
     DPI_CUDA(cudaLaunchKernelEx(&cfg, flow_small_kernel, A));
     count_launch();
   } else {
     A.k.persistent = 0;
-    for (int p = 0; p < n_phases; ++p) {
+    for (int p = p0; p < p1; ++p) {
       A.k.phase_begin = p; A.k.phase_end = p + 1;
       DPI_CUDA(cudaLaunchKernelEx(&cfg, flow_small_kernel, A));
       count_launch();

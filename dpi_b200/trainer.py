@@ -119,8 +119,12 @@ class _FusedTrainer:
         self.launches_per_step = None
 
     def _plan_buckets(self):
-        nb = int(os.environ.get("DPI_B200_BUCKETS", "4" if self.world > 1 else "0"))
-        if nb < 2 or not self.lib.dpi_flow_tc_active(self.handle, self.B):
+        # tcgen05 path: 4 ranges of a many-launch backward; small-batch kernel: 2 persistent launches (each costs a launch
+        # + pipeline fill, and half of the exchange hidden is what there is to win)
+        kind = int(self.lib.dpi_flow_range_ok(self.handle, self.B))
+        default = ("4" if kind == 1 else "2") if self.world > 1 else "0"
+        nb = int(os.environ.get("DPI_B200_BUCKETS", default))
+        if nb < 2 or kind == 0:
             return None
         from dpi_b200.dist import gradient_buckets
         nf = self.flow.n_flow

@@ -105,6 +105,9 @@ int dpi_flow_backward(dpi_flow_t h, int batch, const float* params, float* grads
 int dpi_flow_backward_range(dpi_flow_t h, int batch, const float* params, float* grads, const float* in,
                             const float* g_out, const float* g_logdet, float* g_in, void* workspace,
                             size_t workspace_bytes, int stage_lo, int stage_hi, dpi_stream_t stream);
+/* Can dpi_flow_backward_range split the backward at this batch size? 1: tcgen05 path, 2: small-batch kernel (one persistent
+ * launch per range), 0: no (sample-resident kernels, tiled program). */
+int dpi_flow_range_ok(dpi_flow_t h, int batch);
 /* 1 if a pass at this batch size runs on the tcgen05 path (one launch per operation), 0 if one kernel per pass. */
 int dpi_flow_tc_active(dpi_flow_t h, int batch);
 /* 1 when `batch` runs RealNVP.reverse (realnvpfc_model.py:594-603) as the cluster-resident tcgen05 pass (flow_cl.cu:

@@ -279,6 +279,7 @@ def test_toy_2d_script_loop_body_at_its_own_sizes():
 def test_narrow_flow_eval_pass_at_sampling_batch():
     """Posterior sampling (DPIx_interferometry.py:433: 8192 samples through the alpha-DPI flow in eval mode): batches the
     sample-resident training plan cannot take run its forward-only plan (independent slabs, running statistics)."""
+    from dpi_b200 import _lib
     from dpi_b200.generative_model.realnvpfc_model import RealNVP
     D, NF, B, sf = 18, 4, 8192, 1 / 16
     sd = O.init_state(D, NF, seqfrac=sf, seed=5, randomize=True)
