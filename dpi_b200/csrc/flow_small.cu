@@ -1152,12 +1152,13 @@ __global__ void __launch_bounds__(kT, 1) flow_small_kernel(const __grid_constant
       STAMP(6);
       // shadow of the barrier: weight gradients of this stage (inputs complete since the previous barrier)
       // net.6.fc.weight with DG2, net.3.weight with DG1; net.0.weight of stage e + 1 rides with B0 of stage e
-      // (B0 keeps only Db / 8 CTAs busy; DGIN keeps all of them busy), the first stage's with its own DGIN
+      // (B0 keeps only Db / 8 CTAs busy; DGIN keeps all of them busy), the last stage of the launch with its own DGIN
+      // (stage 0, or the lower end of a stage range: every gradient of the range is final when its launch ends)
       int which = 0, we = e;
       if (kind == K_DG2) which = 3;
       else if (kind == K_DG1) which = 2;
-      else if (kind == K_B0 && e + 1 < a.S) { which = 1; we = e + 1; }
-      else if (kind == K_DGIN && e == 0) which = 1;
+      else if (kind == K_B0 && e + 1 < a.fin_hi) { which = 1; we = e + 1; }
+      else if (kind == K_DGIN && e == a.fin_lo) which = 1;
       if (which) {
         // CTAs occupied by this phase's critical part
         const PD& dc = pd[p - a.phase_begin];

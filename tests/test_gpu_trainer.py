@@ -189,3 +189,38 @@ def test_bucketed_backward_equals_single_pass(use_graph, B, monkeypatch):
         assert torch.equal(a, b)
     assert torch.equal(t0.params, t3.params) and torch.equal(t0.grads_all, t3.grads_all)
     assert torch.equal(t0.log_scale, t3.log_scale)
+
+
+@pytest.mark.parametrize("B", [128, 32])
+def test_first_stage_range_leaves_its_gradient_slice_final(B, monkeypatch):
+    """What the overlapped data-parallel exchange relies on: when the launch(es) of the FIRST stage range return, every
+    gradient of that range's slice of the flat buffer is final (weight gradients deferred into the next stage's phases
+    included) - bit-identical to the same slice after a complete backward - so its all-reduce may start."""
+    from dpi_b200 import _lib
+    from dpi_b200.generative_model.realnvpfc_model import RealNVP
+    from dpi_b200.trainer import InterferometryTrainer
+    from dpi_b200.workloads import interferometry_workload
+    npix, NF = 8, 6
+    monkeypatch.setenv("DPI_B200_BUCKETS", "2")
+    wl = interferometry_workload(npix=npix, seed=3, n_stations=5, n_scans=8)
+    flow = RealNVP(npix * npix, NF)
+    flow.load_state_dict(O.init_state(npix * npix, NF, seed=8, randomize=True))
+    tr = InterferometryTrainer(flow, wl, B, lr=1e-4, clip=1e-3, device="cuda", use_graph=False)
+    assert tr._buckets is not None and len(tr._buckets) == 2
+    torch.manual_seed(5)
+    tr.loss_and_grad(torch.randn(B, npix * npix).cuda())
+    torch.cuda.synchronize()
+    full = tr.grads.clone()
+    tr.grads.fill_(float("nan"))
+    s_lo, s_hi, f_lo, f_hi = tr._buckets[0]
+    lib = _lib.load()
+    _lib.check(lib.dpi_flow_backward_range(tr.handle, B, tr.params.data_ptr(), tr.grads.data_ptr(), tr.z.data_ptr(),
+                                           tr.g_x.data_ptr(), tr.g_det.data_ptr(), None, tr.ws_flow.data_ptr(),
+                                           tr.ws_flow.numel(), s_lo, s_hi, _lib.stream_ptr()), "dpi_flow_backward_range")
+    torch.cuda.synchronize()
+    hi = min(f_hi, tr.P)
+    mask = torch.zeros_like(full)                      # tensor starts are padded to 32 floats: the gaps are never written
+    for _, view in tr.flow.named_grad_views(mask):
+        view.fill_(1.0)
+    got, ref, m = tr.grads[f_lo:hi], full[f_lo:hi], mask[f_lo:hi] > 0
+    assert int(m.sum()) > 0 and torch.equal(got[m], ref[m])
