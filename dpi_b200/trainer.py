@@ -123,6 +123,11 @@ class _FusedTrainer:
         # + pipeline fill, and half of the exchange hidden is what there is to win)
         kind = int(self.lib.dpi_flow_range_ok(self.handle, self.B))
         default = ("4" if kind == 1 else "2") if self.world > 1 else "0"
+        if kind == 2 and self.zero:
+            # measured at 8 ranks on C1: one reduce-scatter + shard Adam + all-gather 1.459 ms; two bucket all-reduces +
+            # shard Adam + all-gather 1.535 ms (half again the traffic); at 2 ranks the replicated optimiser with two
+            # overlapped buckets wins (1.387 vs 1.405 ms unbucketed)
+            default = "0"
         nb = int(os.environ.get("DPI_B200_BUCKETS", default))
         if nb < 2 or kind == 0:
             return None
