@@ -215,7 +215,7 @@ template <bool WK>
 __device__ __forceinline__ void act_mac(float (&acc)[4][4], const float* X_s, const float* W_s, int ldw, int knp, int sq,
                                         int fq, int kp, int KP) {
   if (WK) {
-#pragma unroll 2
+#pragma unroll 4
     for (int k4 = 4 * kp; k4 < knp; k4 += 4 * KP) {
       float4 x[4], w[4];
 #pragma unroll
