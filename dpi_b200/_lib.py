@@ -49,6 +49,14 @@ PROTOTYPES = {
     "dpi_glow_prior_forward": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp, vp]),
     "dpi_glow_squeeze": (i32, [i32, i32, i32, i32, vp, vp, vp]),
     "dpi_glow_row_affine": (i32, [i32, i64, vp, vp, vp, vp, vp]),
+    "dpi_glow_actnorm_reverse_bwd": (i32, [i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dpi_glow_affine_reverse_bwd": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp]),
+    "dpi_glow_zeroconv_bwd": (i32, [i32, i64, vp, vp, vp, vp, vp, vp]),
+    "dpi_glow_bn_lrelu_bwd": (i32, [i32, i64, vp, vp, vp, f32, f32, vp, vp, vp, vp]),
+    "dpi_glow_row_sum": (i32, [i32, i64, vp, f32, vp, vp]),
+    "dpi_glow_lu_bwd": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dpi_glow_prior_sample_bwd": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp]),
+    "dpi_glow_scaled_sum": (i32, [i32, vp, f32, vp, vp]),
     "dpi_glow_logdet_scalar": (i32, [i32, i32, i32, vp, f32, vp, f32, vp, vp]),
     "dpi_flow_run": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "dpi_flow_backward": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -238,6 +238,193 @@ __global__ void row_affine_kernel(int C, long long M, const float* __restrict__ 
   }
 }
 
+
+// ================================================================================= training backward (sampling direction)
+// Formulas: oracle/glow_backward_spec.py (each checked against autograd through the oracle, which is bit-identical to the
+// reference). All stacks are feature-major [channel][b * hw + p]; per-channel reductions are one CTA per row with a
+// fixed-order block reduction (bit-reproducible).
+
+// ActNorm.reverse x = v * si - loc (glow_model.py:132-148), given y = x: v = (y + loc) / si.
+// g_v = g * si; g_loc = -sum g; g_si = sum g v + hw_gld / si   (hw_gld = h w sum_b g_logdet[b])
+__global__ void __launch_bounds__(kT) actnorm_reverse_bwd_kernel(long long M, const float* __restrict__ y, const float* __restrict__ loc,
+                                                                const float* __restrict__ si, const float* __restrict__ g,
+                                                                const float* __restrict__ hw_gld, float* __restrict__ g_v,
+                                                                float* __restrict__ g_loc, float* __restrict__ g_si) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float l = loc[c], s = si[c], inv = 1.0f / s;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) {
+    const float gv = __ldcg(g + (long long)c * M + m);
+    a0 += gv;
+    a1 = fmaf(gv, (__ldcg(y + (long long)c * M + m) + l) * inv, a1);
+    g_v[(long long)c * M + m] = gv * s;
+  }
+  const float t0 = block_sum(a0, red);
+  const float t1 = block_sum(a1, red);
+  if (threadIdx.x == 0) { g_loc[c] = -t0; g_si[c] = t1 + hw_gld[0] * inv; }
+}
+
+// AffineCoupling.reverse tail (:299-320): x_b = b / exp(tanh(ls0)) - t, logdet -= sum tanh(ls0); out = [ls0 ; t], xm = x_b.
+// b exp(-ls) = x_b + t.  g_out[j] = (-g_b (x_b + t) - g_ld[b]) (1 - ls^2); g_out[half + j] = -g_b; g rows of the b half become
+// g_b exp(-ls) in place (the a half is left to the caller).
+__global__ void affine_reverse_bwd_kernel(int batch, int hw, int C, const float* __restrict__ net, long long ldn,
+                                          const float* __restrict__ xm, long long ldx, float* __restrict__ g, long long ldg,
+                                          const float* __restrict__ g_ld, float* __restrict__ g_out, long long ldo) {
+  const int half = C / 2;
+  const long long M = (long long)batch * hw, total = (long long)half * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / M);
+    const long long m = i - (long long)j * M;
+    const float ls = tanhf(__ldcg(net + (long long)j * ldn + m)), t = __ldcg(net + (long long)(half + j) * ldn + m);
+    const float gb = g[(long long)(half + j) * ldg + m];
+    const float xb = __ldcg(xm + (long long)(half + j) * ldx + m);
+    g_out[(long long)j * ldo + m] = (-gb * (xb + t) - __ldg(g_ld + m / hw)) * (1.f - ls * ls);
+    g_out[(long long)(half + j) * ldo + m] = -gb;
+    g[(long long)(half + j) * ldg + m] = gb * expf(-ls);
+  }
+}
+
+// ZeroConv2d epilogue out = zc * exp(3 scale) (:246-251): g_zc = g_out e3 (in place); g_scale = 3 sum g_out out; g_bias = sum g_zc
+__global__ void __launch_bounds__(kT) zeroconv_bwd_kernel(long long M, float* __restrict__ g, const float* __restrict__ out,
+                                                         const float* __restrict__ scale, float* __restrict__ g_scale,
+                                                         float* __restrict__ g_bias) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float e3 = expf(3.f * scale[c]);
+  float a0 = 0.f, a1 = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) {
+    const float gv = g[(long long)c * M + m];
+    a0 = fmaf(gv, __ldcg(out + (long long)c * M + m), a0);
+    const float gz = gv * e3;
+    a1 += gz;
+    g[(long long)c * M + m] = gz;
+  }
+  const float t0 = block_sum(a0, red);
+  const float t1 = block_sum(a1, red);
+  if (threadIdx.x == 0) { g_scale[c] = 3.f * t0; g_bias[c] = t1; }
+}
+
+// Conv -> LeakyReLU -> BatchNorm2d (training): l = LeakyReLU output (the BatchNorm input). In place on g:
+// g <- LeakyReLU'(l) * gamma rstd (g - mean(g) - xh mean(g xh)); g_gamma = sum g xh; g_beta = sum g; g_bias = sum of the result
+__global__ void __launch_bounds__(kT) bn_lrelu_bwd_kernel(long long M, float* __restrict__ g, const float* __restrict__ l,
+                                                         const float* __restrict__ gamma, float eps, float slope,
+                                                         float* __restrict__ g_gamma, float* __restrict__ g_beta,
+                                                         float* __restrict__ g_bias) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float* lr = l + (long long)c * M;
+  float* gr = g + (long long)c * M;
+  float a = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) a += __ldcg(lr + m);
+  const float mean = block_sum(a, red) / (float)M;
+  a = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) { const float d = __ldcg(lr + m) - mean; a = fmaf(d, d, a); }
+  const float rstd = 1.0f / sqrtf(block_sum(a, red) / (float)M + eps);
+  float a0 = 0.f, a1 = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) {
+    const float gv = gr[m];
+    a0 += gv;
+    a1 = fmaf(gv, (__ldcg(lr + m) - mean) * rstd, a1);
+  }
+  const float sb = block_sum(a0, red);
+  const float sg = block_sum(a1, red);
+  const float k = gamma[c] * rstd, mb = sb / (float)M, mg = sg / (float)M;
+  float ab = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) {
+    const float lv = __ldcg(lr + m);
+    const float o = k * (gr[m] - mb - (lv - mean) * rstd * mg) * (lv > 0.f ? 1.f : slope);
+    gr[m] = o;
+    ab += o;
+  }
+  const float tb = block_sum(ab, red);
+  if (threadIdx.x == 0) { g_gamma[c] = sg; g_beta[c] = sb; g_bias[c] = tb; }
+}
+
+// out[c] = coef * sum_m a[c][m]
+__global__ void __launch_bounds__(kT) row_sum_kernel(long long M, const float* __restrict__ a, float coef, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (long long m = threadIdx.x; m < M; m += kT) s += __ldcg(a + (long long)c * M + m);
+  const float t = block_sum(s, red);
+  if (threadIdx.x == 0) out[c] = coef * t;
+}
+
+// InvConv2dLU.reverse (:215-234): x = V u, V = W^-1, W = P Lm Um, Lm = w_l l_mask + I, Um = w_u u_mask + diag(d), d = s_sign exp(w_s).
+// Given G_V = sum_m g[c][m] u[c'][m]: G_W = -V^T G_V V^T; G_Lm = P^T G_W Um^T; G_Um = (P Lm)^T G_W;
+// g_wl = G_Lm l_mask; g_wu = G_Um u_mask; g_ws = diag(G_Um) d - hw_gld. One CTA, C <= kMaxC.
+__global__ void __launch_bounds__(kT) lu_bwd_kernel(int C, const float* __restrict__ w_p, const float* __restrict__ w_l,
+                                                   const float* __restrict__ w_s, const float* __restrict__ w_u,
+                                                   const float* __restrict__ l_mask, const float* __restrict__ u_mask,
+                                                   const float* __restrict__ s_sign, const float* __restrict__ l_eye,
+                                                   const float* __restrict__ V, const float* __restrict__ GV,
+                                                   const float* __restrict__ hw_gld, float* __restrict__ scratch,
+                                                   float* __restrict__ g_wl, float* __restrict__ g_wu, float* __restrict__ g_ws) {
+  // scratch: 4 C x C matrices in global memory (C <= 64: 64 KB, L2-resident): T1, GW, PL, T2
+  float* T1 = scratch;
+  float* GW = scratch + (size_t)C * C;
+  float* PL = GW + (size_t)C * C;
+  const int tid = threadIdx.x, n = C * C;
+  auto Lm = [&](int r, int c) { return w_l[r * C + c] * l_mask[r * C + c] + l_eye[r * C + c]; };
+  auto Um = [&](int r, int c) { return w_u[r * C + c] * u_mask[r * C + c] + (r == c ? s_sign[r] * expf(w_s[r]) : 0.f); };
+  for (int i = tid; i < n; i += kT) {          // T1 = V^T G_V ; PL = P Lm
+    const int r = i / C, c = i - r * C;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < C; ++k) { s = fmaf(V[k * C + r], GV[k * C + c], s); q = fmaf(w_p[r * C + k], Lm(k, c), q); }
+    T1[i] = s; PL[i] = q;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kT) {          // G_W = -T1 V^T
+    const int r = i / C, c = i - r * C;
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s = fmaf(T1[r * C + k], V[c * C + k], s);
+    GW[i] = -s;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kT) {          // T1 <- P^T G_W
+    const int r = i / C, c = i - r * C;
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s = fmaf(w_p[k * C + r], GW[k * C + c], s);
+    T1[i] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kT) {          // G_Lm = T1 Um^T ; G_Um = PL^T G_W
+    const int r = i / C, c = i - r * C;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < C; ++k) { s = fmaf(T1[r * C + k], Um(c, k), s); q = fmaf(PL[k * C + r], GW[k * C + c], q); }
+    g_wl[i] = s * l_mask[i];
+    g_wu[i] = q * u_mask[i];
+    if (r == c) g_ws[r] = q * s_sign[r] * expf(w_s[r]) - hw_gld[0];
+  }
+}
+
+// Split prior of Block.reverse (:436-452): z = mean + exp(lsd) eps, logdet += sum lsd; ml = [mean ; lsd].
+// g_ml = [g_z ; g_z exp(lsd) eps + g_ld[b]]; g_eps = g_z exp(lsd)
+__global__ void prior_sample_bwd_kernel(int batch, int hw, int C2, const float* __restrict__ ml, long long ldm,
+                                        const float* __restrict__ eps, long long lde, const float* __restrict__ g_z, long long ldz,
+                                        const float* __restrict__ g_ld, float* __restrict__ g_ml, long long ldo,
+                                        float* __restrict__ g_eps, long long ldge) {
+  const long long M = (long long)batch * hw, total = (long long)C2 * M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / M);
+    const long long m = i - (long long)j * M;
+    const float e = expf(__ldcg(ml + (long long)(C2 + j) * ldm + m)), gz = __ldcg(g_z + (long long)j * ldz + m);
+    g_ml[(long long)j * ldo + m] = gz;
+    g_ml[(long long)(C2 + j) * ldo + m] = fmaf(gz * e, __ldcg(eps + (long long)j * lde + m), __ldg(g_ld + m / hw));
+    g_eps[(long long)j * ldge + m] = gz * e;
+  }
+}
+
+// out[0] = coef * sum_b v[b]
+__global__ void __launch_bounds__(kT) scaled_sum_kernel(int n, const float* __restrict__ v, float coef, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += kT) s += v[i];
+  const float t = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = coef * t;
+}
+
 }  // namespace
 }  // namespace dpi
 
@@ -347,6 +534,84 @@ int dpi_glow_row_affine(int channels, int64_t positions, const float* x, const f
   const long long total = (long long)channels * positions;
   row_affine_kernel<<<(unsigned)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       channels, positions, x, add, div, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+
+int dpi_glow_actnorm_reverse_bwd(int channels, int64_t positions, const float* y, const float* loc, const float* scale_inv,
+                                 const float* g, const float* hw_gld, float* g_v, float* g_loc, float* g_scale_inv,
+                                 dpi_stream_t stream) {
+  DPI_REQUIRE(channels >= 1 && positions >= 1 && y && loc && scale_inv && g && hw_gld && g_v && g_loc && g_scale_inv,
+              "dpi_glow_actnorm_reverse_bwd: bad argument");
+  actnorm_reverse_bwd_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(positions, y, loc, scale_inv, g, hw_gld, g_v, g_loc, g_scale_inv);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_affine_reverse_bwd(int batch, int hw, int channels, const float* net_out, int64_t ld_net, const float* x_mid,
+                                int64_t ldx, float* g, int64_t ldg, const float* g_logdet, float* g_out, int64_t ldo,
+                                dpi_stream_t stream) {
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 2 && !(channels & 1) && net_out && x_mid && g && g_logdet && g_out,
+              "dpi_glow_affine_reverse_bwd: bad argument");
+  const long long total = (long long)(channels / 2) * batch * hw;
+  affine_reverse_bwd_kernel<<<(unsigned)std::min<long long>((total + kT - 1) / kT, 148 * 16), kT, 0, (cudaStream_t)stream>>>(
+      batch, hw, channels, net_out, ld_net, x_mid, ldx, g, ldg, g_logdet, g_out, ldo);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_zeroconv_bwd(int channels, int64_t positions, float* g, const float* out, const float* scale, float* g_scale,
+                          float* g_bias, dpi_stream_t stream) {
+  DPI_REQUIRE(channels >= 1 && positions >= 1 && g && out && scale && g_scale && g_bias, "dpi_glow_zeroconv_bwd: bad argument");
+  zeroconv_bwd_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(positions, g, out, scale, g_scale, g_bias);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_bn_lrelu_bwd(int channels, int64_t positions, float* g, const float* lrelu_out, const float* gamma, float eps,
+                          float slope, float* g_gamma, float* g_beta, float* g_bias, dpi_stream_t stream) {
+  DPI_REQUIRE(channels >= 1 && positions >= 2 && g && lrelu_out && gamma && g_gamma && g_beta && g_bias,
+              "dpi_glow_bn_lrelu_bwd: bad argument");
+  bn_lrelu_bwd_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(positions, g, lrelu_out, gamma, eps, slope, g_gamma, g_beta, g_bias);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_row_sum(int channels, int64_t positions, const float* a, float coef, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(channels >= 1 && positions >= 1 && a && out, "dpi_glow_row_sum: bad argument");
+  row_sum_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(positions, a, coef, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_lu_bwd(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u, const float* l_mask,
+                    const float* u_mask, const float* s_sign, const float* l_eye, const float* w_inv, const float* g_winv,
+                    const float* hw_gld, float* scratch, float* g_wl, float* g_wu, float* g_ws, dpi_stream_t stream) {
+  DPI_REQUIRE(channels >= 1 && channels <= kMaxC, "dpi_glow_lu_bwd: channels out of range");
+  DPI_REQUIRE(w_p && w_l && w_s && w_u && l_mask && u_mask && s_sign && l_eye && w_inv && g_winv && hw_gld && scratch && g_wl &&
+                  g_wu && g_ws, "dpi_glow_lu_bwd: null argument");
+  lu_bwd_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(channels, w_p, w_l, w_s, w_u, l_mask, u_mask, s_sign, l_eye, w_inv, g_winv,
+                                                     hw_gld, scratch, g_wl, g_wu, g_ws);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_prior_sample_bwd(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* eps,
+                              int64_t ld_eps, const float* g_z, int64_t ld_gz, const float* g_logdet, float* g_ml, int64_t ld_gml,
+                              float* g_eps, int64_t ld_geps, dpi_stream_t stream) {
+  DPI_REQUIRE(batch >= 1 && hw >= 1 && channels >= 1 && mean_logsd && eps && g_z && g_logdet && g_ml && g_eps,
+              "dpi_glow_prior_sample_bwd: bad argument");
+  const long long total = (long long)channels * batch * hw;
+  prior_sample_bwd_kernel<<<(unsigned)std::min<long long>((total + kT - 1) / kT, 148 * 16), kT, 0, (cudaStream_t)stream>>>(
+      batch, hw, channels, mean_logsd, ld_ml, eps, ld_eps, g_z, ld_gz, g_logdet, g_ml, ld_gml, g_eps, ld_geps);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_glow_scaled_sum(int n, const float* v, float coef, float* out, dpi_stream_t stream) {
+  DPI_REQUIRE(n >= 1 && v && out, "dpi_glow_scaled_sum: bad argument");
+  scaled_sum_kernel<<<1, kT, 0, (cudaStream_t)stream>>>(n, v, coef, out);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

@@ -216,7 +216,9 @@ class Glow(nn.Module):
         return glow_ops.conv2d_fm(x_fm, zc.conv.weight.detach(), zc.conv.bias.detach(), B, h, w, pad_value=1.0,
                                   scale=zc.scale.detach())
 
-    def _conv_lrelu_bn(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, x_fm, B, h, w):
+    def _conv_lrelu_bn(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, x_fm, B, h, w, rec=None):
+        """rec (a list): training pass that records what the backward needs - the LeakyReLU output is kept and the
+        BatchNorm writes into a second buffer instead of in place."""
         lib = _lib.load()
         wt = conv.weight.detach().contiguous()
         c_out, c_in, k, _ = wt.shape
@@ -227,20 +229,26 @@ class Glow(nn.Module):
         _lib.check(lib.dpi_conv2d_fm_lrelu(B, h, w, c_in, c_out, k, 0.0, x_fm.data_ptr(), x_fm.shape[1], wt.data_ptr(),
                                            conv.bias.detach().data_ptr(), LRELU_SLOPE, y.data_ptr(), M, ws.data_ptr(),
                                            ws.numel(), st), "dpi_conv2d_fm_lrelu")
+        n = torch.empty_like(y) if rec is not None else y
         _lib.check(lib.dpi_glow_bn_rows(c_out, M, M, y.data_ptr(), bn.weight.detach().data_ptr(), bn.bias.detach().data_ptr(),
                                         bn.running_mean.data_ptr(), bn.running_var.data_ptr(), int(self.training), BN_EPS,
-                                        y.data_ptr(), st), "dpi_glow_bn_rows")
+                                        n.data_ptr(), st), "dpi_glow_bn_rows")
         if self.training:
             bn.num_batches_tracked += 1
-        return y
+        if rec is not None:
+            rec.append(y)
+        return n
 
-    def _flow_reverse(self, fl: Flow, x_fm, logdet, B, h, w):
+    def _flow_reverse(self, fl: Flow, x_fm, logdet, B, h, w, tape=None):
         lib, st = _lib.load(), _lib.stream_ptr()
         C, M = x_fm.shape
         net = fl.coupling.net
+        if tape is not None:
+            x_fm = x_fm.clone()                                      # the producer's backward needs its output intact
+        saved = [] if tape is not None else None
         a = x_fm[: C // 2]                                           # rows of the a-half: a contiguous block
-        h1 = self._conv_lrelu_bn(net[0], net[2], a, B, h, w)
-        h2 = self._conv_lrelu_bn(net[3], net[5], h1, B, h, w)
+        h1 = self._conv_lrelu_bn(net[0], net[2], a, B, h, w, saved)
+        h2 = self._conv_lrelu_bn(net[3], net[5], h1, B, h, w, saved)
         out = self._zero_conv(net[6], h2, B, h, w)                   # rows [0, C/2): log_s0, rows [C/2, C): t
         _lib.check(lib.dpi_glow_affine_reverse(B, h * w, C, out.data_ptr(), M, x_fm.data_ptr(), M, logdet.data_ptr(), st),
                    "dpi_glow_affine_reverse")
@@ -264,15 +272,26 @@ class Glow(nn.Module):
         # InvConv2dLU.reverse: -h w sum w_s (:231); ActNorm.reverse: +h w sum log|scale_inv| (:141-143)
         _lib.check(lib.dpi_glow_logdet_scalar(B, h * w, C, ic.w_s.detach().data_ptr(), -1.0, an.scale_inv.detach().data_ptr(), 1.0,
                                               logdet.data_ptr(), st), "dpi_glow_logdet_scalar")
+        if tape is not None:
+            tape.append(dict(fl=fl, l1=saved[0], n1=h1, l2=saved[1], n2=h2, out=out, x_mid=x_fm, winv=winv, y=y))
         return y
 
     def reverse(self, z_list):
-        """z_list[i]: [B, c_i, h_i, w_i] as calc_z_shapes gives them -> (image [B, in_channel, npix, npix], logdet [B])."""
-        self._no_gradients_yet(list(z_list), "reverse")
+        """z_list[i]: [B, c_i, h_i, w_i] as calc_z_shapes gives them -> (image [B, in_channel, npix, npix], logdet [B]).
+        With gradients enabled (the training loop, DPI_interferometry.py:129-136 / :201-204 with --model_form glow) the call
+        is one autograd node whose backward runs the op-by-op backward kernels (training-mode BatchNorm only)."""
+        z_list = list(z_list)
+        params = [p for p in self.parameters() if p.requires_grad]
+        if torch.is_grad_enabled() and (params or any(z.requires_grad for z in z_list)):
+            if not self.training:
+                raise NotImplementedError("dpi_b200 Glow.reverse: gradients through an eval-mode pass (running BatchNorm "
+                                          "statistics) are not built; call .train() or wrap inference in torch.no_grad()")
+            out = _GlowReverse.apply(self, len(z_list), *z_list, *params)
+            return out[0], out[1]
         with torch.no_grad():
             return self._reverse(z_list)
 
-    def _reverse(self, z_list):
+    def _reverse(self, z_list, tape=None):
         z_list = [z.detach().to(torch.float32) for z in z_list]
         if not all(z.is_cuda for z in z_list):
             raise RuntimeError("dpi_b200 has no CPU path: Glow.reverse needs CUDA tensors")
@@ -289,22 +308,169 @@ class Glow(nn.Module):
                 st = _lib.stream_ptr()
                 eps_fm = glow_ops.to_feature_major(eps)
                 if blk.split:
+                    prior_in = x
                     ml = self._zero_conv(blk.prior, x, B, h, w)                     # [mean ; log_sd] of the dropped half
                     full = torch.empty(x.shape[0] + c_eps, M, dtype=torch.float32, device=dev)
                     full[: x.shape[0]].copy_(x)
                     z_rows = full[x.shape[0]:]
                 else:
-                    ml = self._zero_conv(blk.prior, torch.zeros(c_eps, M, dtype=torch.float32, device=dev), B, h, w)
+                    prior_in = torch.zeros(c_eps, M, dtype=torch.float32, device=dev)
+                    ml = self._zero_conv(blk.prior, prior_in, B, h, w)
                     full = torch.empty(c_eps, M, dtype=torch.float32, device=dev)
                     z_rows = full
+                flows_tape = [] if tape is not None else None
                 _lib.check(lib.dpi_glow_prior_sample(B, h * w, c_eps, ml.data_ptr(), M, eps_fm.data_ptr(), M, z_rows.data_ptr(), M,
                                                      logdet.data_ptr(), st), "dpi_glow_prior_sample")
                 x = full
                 for fl in reversed(blk.flows):
-                    x = self._flow_reverse(fl, x, logdet, B, h, w)
+                    x = self._flow_reverse(fl, x, logdet, B, h, w, flows_tape)
+                if tape is not None:
+                    tape.append(dict(blk=blk, B=B, h=h, w=w, prior_in=prior_in, ml=ml, eps=eps_fm, flows=flows_tape))
                 C = x.shape[0]
                 up = torch.empty(C // 4, 4 * M, dtype=torch.float32, device=dev)
                 _lib.check(lib.dpi_glow_unsqueeze(B, h, w, C, x.data_ptr(), up.data_ptr(), st), "dpi_glow_unsqueeze")
                 x = up
                 h, w = 2 * h, 2 * w
         return glow_ops.from_feature_major(x, B, h, w), logdet
+
+
+# ------------------------------------------------------------------------------------------------
+# training backward of the sampling direction (formulas: oracle/glow_backward_spec.py)
+# ------------------------------------------------------------------------------------------------
+def _acc(grads, p, g):
+    g = g.reshape(p.shape)
+    grads[p] = g if p not in grads else grads[p] + g
+
+
+def _zero_conv_backward(zc: "ZeroConv2d", x_in, out, g_out, B, h, w, grads, need_input_grad=True):
+    """ZeroConv2d (:246-251). g_out is the gradient of the scaled output and is consumed (scaled in place)."""
+    lib, st = _lib.load(), _lib.stream_ptr()
+    C, M = out.shape
+    g_scale = torch.empty(C, dtype=torch.float32, device=out.device)
+    g_bias = torch.empty(C, dtype=torch.float32, device=out.device)
+    _lib.check(lib.dpi_glow_zeroconv_bwd(C, M, g_out.data_ptr(), out.data_ptr(), zc.scale.detach().data_ptr(), g_scale.data_ptr(),
+                                         g_bias.data_ptr(), st), "dpi_glow_zeroconv_bwd")
+    _acc(grads, zc.scale, g_scale)
+    _acc(grads, zc.conv.bias, g_bias)
+    _acc(grads, zc.conv.weight, glow_ops.conv2d_fm_wgrad(x_in, g_out, 3, B, h, w, pad_value=1.0))
+    return glow_ops.conv2d_fm_dgrad(g_out, zc.conv.weight.detach(), B, h, w) if need_input_grad else None
+
+
+def _conv_bn_backward(conv: nn.Conv2d, bn: nn.BatchNorm2d, x_in, l, g, B, h, w, grads):
+    """Conv -> LeakyReLU -> BatchNorm2d (:260-268), training mode. g: gradient of the BatchNorm output (consumed)."""
+    lib, st = _lib.load(), _lib.stream_ptr()
+    C, M = l.shape
+    gg, gb, gbias = (torch.empty(C, dtype=torch.float32, device=l.device) for _ in range(3))
+    _lib.check(lib.dpi_glow_bn_lrelu_bwd(C, M, g.data_ptr(), l.data_ptr(), bn.weight.detach().data_ptr(), BN_EPS, LRELU_SLOPE,
+                                         gg.data_ptr(), gb.data_ptr(), gbias.data_ptr(), st), "dpi_glow_bn_lrelu_bwd")
+    _acc(grads, bn.weight, gg)
+    _acc(grads, bn.bias, gb)
+    _acc(grads, conv.bias, gbias)
+    k = conv.weight.shape[-1]
+    _acc(grads, conv.weight, glow_ops.conv2d_fm_wgrad(x_in, g, k, B, h, w, pad_value=0.0))
+    return glow_ops.conv2d_fm_dgrad(g, conv.weight.detach(), B, h, w)
+
+
+def _flow_reverse_backward(rec, g, g_ld, hw_gld, B, h, w, grads):
+    """Flow.reverse = coupling^-1 -> invconv^-1 -> actnorm^-1 (:349-358); g: gradient of the flow's output [C][M]."""
+    lib, st = _lib.load(), _lib.stream_ptr()
+    fl = rec["fl"]
+    C, M = g.shape
+    dev = g.device
+    an, ic, net = fl.actnorm, fl.invconv, fl.coupling.net
+    f32 = torch.float32
+    # ActNorm.reverse
+    g_v = torch.empty_like(g)
+    g_loc, g_si = torch.empty(C, dtype=f32, device=dev), torch.empty(C, dtype=f32, device=dev)
+    _lib.check(lib.dpi_glow_actnorm_reverse_bwd(C, M, rec["y"].data_ptr(), an.loc.detach().data_ptr(), an.scale_inv.detach().data_ptr(),
+                                                g.data_ptr(), hw_gld.data_ptr(), g_v.data_ptr(), g_loc.data_ptr(), g_si.data_ptr(),
+                                                st), "dpi_glow_actnorm_reverse_bwd")
+    _acc(grads, an.loc, g_loc)
+    _acc(grads, an.scale_inv, g_si)
+    # InvConv2dLU.reverse: x = V u
+    winv4 = rec["winv"].view(C, C, 1, 1)
+    g_u = glow_ops.conv2d_fm_dgrad(g_v, winv4, B, h, w)
+    G_V = glow_ops.conv2d_fm_wgrad(rec["x_mid"], g_v, 1, B, h, w).view(C, C).contiguous()
+    g_wl, g_wu = torch.empty(C, C, dtype=f32, device=dev), torch.empty(C, C, dtype=f32, device=dev)
+    g_ws = torch.empty(C, dtype=f32, device=dev)
+    scratch = torch.empty(3 * C * C, dtype=f32, device=dev)
+    _lib.check(lib.dpi_glow_lu_bwd(C, ic.w_p.data_ptr(), ic.w_l.detach().data_ptr(), ic.w_s.detach().data_ptr(),
+                                   ic.w_u.detach().data_ptr(), ic.l_mask.data_ptr(), ic.u_mask.data_ptr(), ic.s_sign.data_ptr(),
+                                   ic.l_eye.data_ptr(), rec["winv"].data_ptr(), G_V.data_ptr(), hw_gld.data_ptr(),
+                                   scratch.data_ptr(), g_wl.data_ptr(), g_wu.data_ptr(), g_ws.data_ptr(), st), "dpi_glow_lu_bwd")
+    _acc(grads, ic.w_l, g_wl)
+    _acc(grads, ic.w_u, g_wu)
+    _acc(grads, ic.w_s, g_ws)
+    # AffineCoupling.reverse
+    g_out = torch.empty(C, M, dtype=f32, device=dev)
+    _lib.check(lib.dpi_glow_affine_reverse_bwd(B, h * w, C, rec["out"].data_ptr(), M, rec["x_mid"].data_ptr(), M, g_u.data_ptr(), M,
+                                               g_ld.data_ptr(), g_out.data_ptr(), M, st), "dpi_glow_affine_reverse_bwd")
+    g_n2 = _zero_conv_backward(net[6], rec["n2"], rec["out"], g_out, B, h, w, grads)
+    g_n1 = _conv_bn_backward(net[3], net[5], rec["n1"], rec["l2"], g_n2, B, h, w, grads)
+    g_a = _conv_bn_backward(net[0], net[2], rec["x_mid"][: C // 2], rec["l1"], g_n1, B, h, w, grads)
+    g_u[: C // 2].add_(g_a)
+    return g_u
+
+
+def _reverse_backward(tape, g_img, g_ld):
+    """-> (gradients of z_list in its order, {parameter: gradient})."""
+    lib = _lib.load()
+    grads, g_z = {}, []
+    dev = g_img.device
+    f32 = torch.float32
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr()
+        g = glow_ops.to_feature_major(g_img.contiguous().float())
+        g_ld = g_ld.contiguous().float()
+        hw_gld = torch.empty(1, dtype=f32, device=dev)
+        for rec in reversed(tape):
+            B, h, w = rec["B"], rec["h"], rec["w"]
+            M = B * h * w
+            C = g.shape[0] * 4
+            gx = torch.empty(C, M, dtype=f32, device=dev)               # unsqueeze^T = squeeze
+            _lib.check(lib.dpi_glow_squeeze(B, h, w, C // 4, g.data_ptr(), gx.data_ptr(), st), "dpi_glow_squeeze")
+            g = gx
+            _lib.check(lib.dpi_glow_scaled_sum(B, g_ld.data_ptr(), float(h * w), hw_gld.data_ptr(), st), "dpi_glow_scaled_sum")
+            for frec in reversed(rec["flows"]):
+                g = _flow_reverse_backward(frec, g, g_ld, hw_gld, B, h, w, grads)
+            blk = rec["blk"]
+            c_eps = rec["eps"].shape[0]
+            c_x = C - c_eps
+            gz_rows = g[c_x:]
+            g_ml = torch.empty(2 * c_eps, M, dtype=f32, device=dev)
+            g_eps = torch.empty(c_eps, M, dtype=f32, device=dev)
+            _lib.check(lib.dpi_glow_prior_sample_bwd(B, h * w, c_eps, rec["ml"].data_ptr(), M, rec["eps"].data_ptr(), M,
+                                                     gz_rows.data_ptr(), M, g_ld.data_ptr(), g_ml.data_ptr(), M,
+                                                     g_eps.data_ptr(), M, st), "dpi_glow_prior_sample_bwd")
+            g_prior_in = _zero_conv_backward(blk.prior, rec["prior_in"], rec["ml"], g_ml, B, h, w, grads, need_input_grad=blk.split)
+            g_z.append(glow_ops.from_feature_major(g_eps, B, h, w))
+            if blk.split:
+                g = g[:c_x] + g_prior_in
+    return g_z, grads
+
+
+class _GlowReverse(torch.autograd.Function):
+    """Glow.reverse as ONE autograd node: inputs (z_0 .. z_{n-1}, trainable parameters), outputs (image, logdet)."""
+
+    @staticmethod
+    def forward(ctx, module, n_z, *args):
+        z_list, params = list(args[:n_z]), list(args[n_z:])
+        tape = []
+        with torch.no_grad():
+            x, ld = module._reverse(z_list, tape)
+        ctx.tape, ctx.params, ctx.n_z = tape, params, n_z
+        return x, ld
+
+    @staticmethod
+    def backward(ctx, g_x, g_ld):
+        tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("dpi_b200 Glow.reverse: backward called twice (the saved activations are released after one)")
+        ctx.tape = None
+        if g_ld is None:
+            g_ld = torch.zeros(tape[0]["B"], dtype=torch.float32, device=g_x.device)
+        g_z, grads = _reverse_backward(tape, g_x, g_ld)
+        out = [None, None]
+        out += [g_z[i] if ctx.needs_input_grad[2 + i] else None for i in range(ctx.n_z)]
+        out += [grads.get(p) for p in ctx.params]
+        return tuple(out)

@@ -186,6 +186,37 @@ int dpi_glow_squeeze(int batch, int h_out, int w_out, int channels_in, const flo
 int dpi_glow_row_affine(int channels, int64_t positions, const float* x, const float* add, const float* div, float* out,
                         dpi_stream_t stream);
 
+/* Training backward of the sampling direction (Glow.reverse, glow_model.py:526-539), op by op; stacks feature-major
+ * [channel][b * hw + p], per-channel reductions in a fixed order. hw_gld points at ONE device float = h w sum_b g_logdet[b]
+ * (dpi_glow_scaled_sum makes it).
+ *  actnorm_reverse_bwd : x = v si - loc (:132-148) given y = x: g_v = g si, g_loc = -sum g, g_si = sum g v + hw_gld / si
+ *  affine_reverse_bwd  : x_b = b / exp(tanh ls0) - t (:299-320); net_out = [ls0 ; t], x_mid = the flow's state after the
+ *                        coupling; g rows [C/2, C) become the gradient of b IN PLACE, g_out = gradient of net_out
+ *  zeroconv_bwd        : out = zc exp(3 scale) (:246-251); g <- g exp(3 scale) in place, g_scale = 3 sum g out, g_bias = sum
+ *  bn_lrelu_bwd        : Conv -> LeakyReLU -> BatchNorm2d in training mode (:260-268); lrelu_out = the BatchNorm input;
+ *                        g <- gradient of the conv output in place; g_gamma, g_beta, g_bias (the conv bias)
+ *  lu_bwd              : InvConv2dLU.reverse x = W^-1 u (:215-234) given g_winv = sum_m g[c][m] u[c'][m]: gradients of w_l,
+ *                        w_u, w_s (incl. the -h w sum w_s logdet term); scratch: 3 C^2 floats; C <= 64
+ *  prior_sample_bwd    : z = mean + exp(lsd) eps, logdet += sum lsd (:436-452): g_ml = gradient of [mean ; lsd], g_eps */
+int dpi_glow_actnorm_reverse_bwd(int channels, int64_t positions, const float* y, const float* loc, const float* scale_inv,
+                                 const float* g, const float* hw_gld, float* g_v, float* g_loc, float* g_scale_inv,
+                                 dpi_stream_t stream);
+int dpi_glow_affine_reverse_bwd(int batch, int hw, int channels, const float* net_out, int64_t ld_net, const float* x_mid,
+                                int64_t ldx, float* g, int64_t ldg, const float* g_logdet, float* g_out, int64_t ldo,
+                                dpi_stream_t stream);
+int dpi_glow_zeroconv_bwd(int channels, int64_t positions, float* g, const float* out, const float* scale, float* g_scale,
+                          float* g_bias, dpi_stream_t stream);
+int dpi_glow_bn_lrelu_bwd(int channels, int64_t positions, float* g, const float* lrelu_out, const float* gamma, float eps,
+                          float slope, float* g_gamma, float* g_beta, float* g_bias, dpi_stream_t stream);
+int dpi_glow_row_sum(int channels, int64_t positions, const float* a, float coef, float* out, dpi_stream_t stream);
+int dpi_glow_lu_bwd(int channels, const float* w_p, const float* w_l, const float* w_s, const float* w_u, const float* l_mask,
+                    const float* u_mask, const float* s_sign, const float* l_eye, const float* w_inv, const float* g_winv,
+                    const float* hw_gld, float* scratch, float* g_wl, float* g_wu, float* g_ws, dpi_stream_t stream);
+int dpi_glow_prior_sample_bwd(int batch, int hw, int channels, const float* mean_logsd, int64_t ld_ml, const float* eps,
+                              int64_t ld_eps, const float* g_z, int64_t ld_gz, const float* g_logdet, float* g_ml, int64_t ld_gml,
+                              float* g_eps, int64_t ld_geps, dpi_stream_t stream);
+int dpi_glow_scaled_sum(int n, const float* v, float coef, float* out, dpi_stream_t stream);
+
 /* Host-only: the tile plan the tcgen05 path (batch >= 96, flow_tc.cu) would use for one coupling-net GEMM
  * C[M, N] = A[M, K] B[N, K]^T on a GPU with n_sm SMs. out[0..9] = column tile TN, k-tile KT, accumulators per CTA
  * MH, 128-row tiles, column tiles, k tiles, K splits, k tiles per split, pipeline stages, dynamic shared-memory

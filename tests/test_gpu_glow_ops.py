@@ -68,8 +68,8 @@ def test_glow_reverse_matches_reference_fixture():
     g, sd, m = _glow_from_fixture()
     zs = [torch.from_numpy(g[f"z{i}"]).cuda() for i in range(int(g["n_block"]))]
     m.train()
-    with pytest.raises(NotImplementedError):        # a training loop must not get history-free tensors silently
-        m.reverse(zs)
+    with pytest.raises(NotImplementedError):        # the density direction has no backward: never history-free silently
+        m.forward(torch.from_numpy(g["x_rev"]).cuda())
     torch.set_grad_enabled(False)                   # inference is opt-in (the whole test runs under no_grad)
     x, ld = m.reverse(zs)
     assert rel_err(x, g["x_rev"]) < RTOL, rel_err(x, g["x_rev"])
@@ -160,3 +160,49 @@ def test_conv2d_gradients_match_torch_autograd(B, cin, cout, hw, k, pad):
     gw = G.conv2d_fm_wgrad(G.to_feature_major(x.detach().cuda()), g_fm, k, B, hw, hw, pad_value=pad).cpu()
     assert rel_err(gx, x.grad) < RTOL, rel_err(gx, x.grad)
     assert rel_err(gw, wt.grad) < RTOL, rel_err(gw, wt.grad)
+
+
+def test_glow_training_backward_matches_reference_fixture():
+    """SURVEY 8 a20, the training direction: Glow.reverse with gradients enabled is one autograd node; the gradients of the
+    reference's objective sum(x * c) + sum(logdet) with respect to the latents and to EVERY parameter (ActNorm, the P L U
+    factors of the invertible 1x1 convolutions, coupling-net convolutions, BatchNorm affine, ZeroConv2d weight / bias /
+    scale, split priors) match the ones the unmodified reference produced (tests/golden/make_golden.py glow_case). The
+    convolutions run 3xTF32 on the tensor cores: gradients are held to the suite's gradient bar, 3e-4 normwise."""
+    from oracle import glow_oracle as GO
+    g, sd, m = _glow_from_fixture()
+    m.train()
+    nb = int(g["n_block"])
+    zs = [torch.from_numpy(g[f"z{i}"]).cuda().requires_grad_(True) for i in range(nb)]
+    x, ld = m.reverse(zs)
+    assert x.requires_grad and ld.requires_grad
+    assert rel_err(x, g["x_rev"]) < RTOL and rel_err(ld, g["ld_rev"]) < RTOL
+    c = torch.from_numpy(g["c"]).cuda()
+    ((x * c).sum() + ld.sum()).backward()
+    for i in range(nb):
+        assert rel_err(zs[i].grad, g[f"g_z{i}"]) < 3 * RTOL, (i, rel_err(zs[i].grad, g[f"g_z{i}"]))
+    big = set(GO.big_weight_keys(m.state_dict().keys()))
+    worst = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        mine = p.grad.detach().reshape(-1)[::1021] if k in big else p.grad.detach()
+        worst.append((rel_err(mine.cpu().reshape(-1), torch.from_numpy(g["grad." + k]).reshape(-1)), k))
+    bad = [w for w in worst if not w[0] < 3 * RTOL]
+    assert not bad, sorted(bad, reverse=True)[:8]
+
+
+def test_glow_training_step_moves_every_parameter():
+    """A torch.optim.Adam step on the drop-in Glow (what DPI_interferometry.py --model_form glow does) changes every
+    parameter tensor and keeps everything finite."""
+    g, sd, m = _glow_from_fixture()
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    torch.manual_seed(0)
+    zs = [torch.randn(4, *s, device="cuda") for s in [tuple(g[f"z{i}"].shape[1:]) for i in range(int(g["n_block"]))]]
+    x, ld = m.reverse(zs)
+    loss = (x ** 2).mean() - ld.mean()
+    loss.backward()
+    opt.step()
+    for k, p in m.named_parameters():
+        assert torch.isfinite(p).all(), k
+        assert not torch.equal(p.detach(), before[k]), k

@@ -197,10 +197,14 @@ def test_glow_module_surface_and_reference_state_dict():
     assert calc_z_shapes(1, 32, 16, 4) == [(2, 16, 16), (4, 8, 8), (8, 4, 4), (32, 2, 2)]
     assert sum(p.numel() for p in Glow(1, 16, 4).parameters()) == 23677792
     zs = [torch.randn(2, *s) for s in calc_z_shapes(1, 8, 1, 2)]
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):                 # a training call on CPU tensors: no fallback
         m.reverse([z.clone().requires_grad_(True) for z in zs])
-    with pytest.raises(NotImplementedError, match="training backward"):    # grad enabled + trainable parameters
+    m.eval()
+    with pytest.raises(NotImplementedError, match="eval-mode"):            # gradients through running statistics: not built
         m.reverse(zs)
+    m.train()
+    with pytest.raises(NotImplementedError, match="training backward"):    # density direction: no backward, never silent
+        m.forward(torch.randn(2, 1, 8, 8))
     with torch.no_grad():
         with pytest.raises(RuntimeError, match="no CPU path"):
             m.reverse(zs)
