@@ -42,7 +42,7 @@ def _modules():
 class ReferenceStep:
     """One optimisation step of the reference loop body per call: step(z [B, D]) -> loss (python float)."""
 
-    def __init__(self, kind, wl, n_flow, lr, clip, device="cpu", modules=None):
+    def __init__(self, kind, wl, n_flow, lr, clip, device="cpu", modules=None, model_form="realnvp", n_block=4):
         """device="cuda": the same stock-PyTorch eager path on the GPU (`.to(device)`, DPI_interferometry.py:91-92,162-168)
         - the "reference on the same B200" context number; device="cpu": the CPU baseline.
         modules: dict(realnvp=, interferometry=, mri=) to run the SAME loop body over another implementation of the
@@ -54,7 +54,12 @@ class ReferenceStep:
         wl = {k: (v.to(dev) if torch.is_tensor(v) and k in ("prior", "cphase_true", "logcamp_true", "mask", "kspace_true")
                   else v) for k, v in wl.items()}
         self.kind, self.wl, self.npix, self.clip, self.device = kind, wl, npix, clip, dev
-        self.gen = R["realnvp"].RealNVP(npix * npix, n_flow).to(dev)      # DPI_interferometry.py:127,164 / DPI_MRI.py:118
+        self.model_form = model_form
+        if model_form == "glow":
+            self.gen = R["glow"].Glow(1, n_flow, n_block, affine=True, conv_lu=True).to(dev)      # :129-136
+            self.z_shapes = R["glow"].calc_z_shapes(1, npix, n_flow, n_block)
+        else:
+            self.gen = R["realnvp"].RealNVP(npix * npix, n_flow).to(dev)  # DPI_interferometry.py:127,164 / DPI_MRI.py:118
         self.log_scale = torch.nn.Parameter(torch.tensor([wl["log_scale_init"]], dtype=torch.float32, device=dev))
         self.params = list(self.gen.parameters()) + [self.log_scale]
         self.opt = torch.optim.Adam(self.params, lr=lr)                   # :172 / :146
@@ -75,8 +80,8 @@ class ReferenceStep:
     def step(self, z):
         """z: host tensor, as DPI_interferometry.py:193 draws it (`torch.randn(B, D).to(device)`)."""
         npix, w, wl = self.npix, self.wl["w"], self.wl
-        z = z.to(self.device)
-        img_samp, logdet = self.gen.reverse(z)                                     # :201
+        z = [zz.to(self.device) for zz in z] if self.model_form == "glow" else z.to(self.device)
+        img_samp, logdet = self.gen.reverse(z)                                     # :201 / :197-200
         img_samp = img_samp.reshape((-1, npix, npix))
         img = torch.nn.Softplus()(img_samp) * torch.exp(self.log_scale)            # :205-208
         det_softplus = torch.sum(img_samp - torch.nn.Softplus()(img_samp), (1, 2))

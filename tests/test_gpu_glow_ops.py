@@ -206,3 +206,49 @@ def test_glow_training_step_moves_every_parameter():
     for k, p in m.named_parameters():
         assert torch.isfinite(p).all(), k
         assert not torch.equal(p.detach(), before[k]), k
+
+
+def test_glow_training_trajectory_matches_reference_run():
+    """three optimisation steps of the DPI_interferometry.py loop body with --model_form glow (:129-136,
+    :193-235: Glow.reverse -> Softplus * exp(log_scale) -> closure quantities -> chi^2 + priors - logdet -> backward ->
+    clip_grad_norm_ -> Adam), once over the UNMODIFIED reference modules on the CPU (baseline/_ref, installed by
+    __graft_entry__.build()) and once over this package's drop-in modules on the GPU, same initial state, same latents."""
+    from baseline.ref_step import ReferenceStep, reference_root
+    if reference_root() is None:
+        pytest.skip("reference modules not installed (baseline/_ref)")
+    import dpi_b200.MRI_helpers as MH
+    import dpi_b200.interferometry_helpers as IH
+    import dpi_b200.generative_model.glow_model as GM
+    import dpi_b200.generative_model.realnvpfc_model as RN
+    from dpi_b200.workloads import interferometry_workload
+    npix, NF, NB, B, lr, clip = 8, 2, 2, 6, 1e-3, 1e-2
+    wl = interferometry_workload(npix=npix, seed=3, n_stations=5, n_scans=8)
+    torch.manual_seed(7)
+    import numpy as np
+    np.random.seed(7)
+    ref = ReferenceStep("interferometry", wl, NF, lr, clip, device="cpu", model_form="glow", n_block=NB)
+    with torch.no_grad():
+        for name, p in ref.gen.named_parameters():          # ZeroConv2d layers start at zero: make every term live
+            if ".net.6." in name or ".prior." in name:
+                p.normal_(0, 0.05)
+    mine = ReferenceStep("interferometry", wl, NF, lr, clip, device="cuda",
+                         modules=dict(realnvp=RN, interferometry=IH, mri=MH, glow=GM), model_form="glow", n_block=NB)
+    mine.gen.load_state_dict(ref.gen.state_dict(), strict=True)
+    p0 = {k: v.detach().clone() for k, v in ref.gen.named_parameters()}
+    losses = []
+    for k in range(3):
+        z = [torch.randn(B, *s) for s in ref.z_shapes]
+        losses.append((ref.step(z), mine.step(z)))
+    for k, (a, b) in enumerate(losses):
+        assert abs(a - b) < (RTOL if k == 0 else 10 * RTOL) * max(1.0, abs(a)), (k, a, b)
+    mine_p = dict(mine.gen.named_parameters())
+    for k, p in ref.gen.named_parameters():
+        up_ref = (p.detach() - p0[k]).double()
+        up_mine = (mine_p[k].detach().cpu() - p0[k]).double()
+        assert float(up_ref.norm()) > 0, k
+        # Adam normalises every element by its own |g| (an element whose gradient is at round-off level moves by +lr on one
+        # side and -lr on the other): judge the update vector per tensor in L2, as the full-size RealNVP trajectory test
+        # does, and bound every element by one such flip
+        assert float((up_mine - up_ref).norm() / up_ref.norm()) < 0.05, k
+        assert float((up_mine - up_ref).abs().max()) < 2.1 * lr, k
+    assert abs(float(mine.log_scale) - float(ref.log_scale)) < 1e-5

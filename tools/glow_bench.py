@@ -1,4 +1,5 @@
-"""Throughput of Glow.reverse (sampling direction) at the reference's `--model_form glow` shape: Glow(1, 16, 4), npix 32."""
+"""Throughput of Glow.reverse (sampling direction) and of a training step (reverse + backward + Adam) at the reference's
+`--model_form glow` shape: Glow(1, 16, 4), npix 32."""
 import os
 import sys
 import time
@@ -19,6 +20,7 @@ for B in (32, 64):
     zs = [torch.randn(B, *s, device="cuda") for s in calc_z_shapes(1, npix, n_flow, n_block)]
     for mode in ("train", "eval"):
         m.train(mode == "train")
+        torch.set_grad_enabled(False)
         for _ in range(2):
             x, ld = m.reverse(zs)
         torch.cuda.synchronize()
@@ -31,3 +33,28 @@ for B in (32, 64):
         dt = (time.perf_counter() - t0) / reps
         print(f"B={B} {mode}: {1e3 * dt:.2f} ms per reverse pass, {B / dt:.0f} samples/s, "
               f"{(_lib.launch_count() - n0) // reps} library launches, finite={bool(torch.isfinite(x).all())}")
+    # training step: the objective of the fixture, gradients of all 23.7 M parameters, torch.optim.Adam
+    torch.set_grad_enabled(True)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-7)
+    c = torch.randn(B, 1, npix, npix, device="cuda")
+
+    def step():
+        x, ld = m.reverse(zs)
+        loss = ((x - c) ** 2).mean() - 1e-3 * ld.mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        loss = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 5
+    print(f"B={B} training step: {1e3 * dt:.2f} ms, {B / dt:.0f} samples/s, {(_lib.launch_count() - n0) // 5} library launches, "
+          f"loss finite={bool(torch.isfinite(loss))}")
