@@ -58,3 +58,41 @@ for B in (32, 64):
     dt = (time.perf_counter() - t0) / 5
     print(f"B={B} training step: {1e3 * dt:.2f} ms, {B / dt:.0f} samples/s, {(_lib.launch_count() - n0) // 5} library launches, "
           f"loss finite={bool(torch.isfinite(loss))}")
+
+# the same step captured into ONE CUDA graph (static latents, Adam(capturable=True)): what is left is kernel time
+try:
+    B = 64
+    m2 = Glow(1, n_flow, n_block).cuda().train()
+    zs2 = [torch.randn(B, *s, device="cuda") for s in calc_z_shapes(1, npix, n_flow, n_block)]
+    c2 = torch.randn(B, 1, npix, npix, device="cuda")
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-7, capturable=True)
+
+    def step2():
+        x, ld = m2.reverse(zs2)
+        loss = ((x - c2) ** 2).mean() - 1e-3 * ld.mean()
+        opt2.zero_grad(set_to_none=False)
+        loss.backward()
+        opt2.step()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step2()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_static = step2()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        graph.replay()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 10
+    print(f"B={B} training step as one CUDA graph: {1e3 * dt:.2f} ms, {B / dt:.0f} samples/s, loss finite={bool(torch.isfinite(loss_static))}")
+except Exception as e:  # noqa: BLE001
+    print("graph capture of the training step failed:", type(e).__name__, str(e)[:300])
