@@ -734,3 +734,22 @@ class DPIxTrainer:
         res["img_mean"], res["img_std"] = res["img"].mean(0), res["img"].std(0)
         res["img_map"] = res["img"][torch.argmin(res["loss_data"])]
         return res
+
+    def sample_posterior2(self, n_concat=1, generator=None, z=None):
+        """`Gen_samples2` of DPIx_interferometry.py:665-709: the same pass without the rejection step - every sample is
+        kept and the posterior summaries are importance-weighted: per batch of n_batch samples w = softmax_i(-loss_orig),
+        img_mean = sum_i w_i img_i, img_std = sqrt(sum_i w_i (img_i - img_mean)^2), and the log importance weights
+        -loss_orig (:699-707). Returns dict(params, img, weights, log_weights, img_mean [n_concat, npix, npix], img_std,
+        img_map)."""
+        res = self.sample_posterior(n_concat=n_concat, rejsamp=False, generator=generator, z=z)
+        B, n = self.B, self.npix
+        w = res["weights"].view(-1, B, 1, 1)
+        img = res["img"].view(-1, B, n, n)
+        mean = (w * img).sum(1)
+        res["img_mean"] = mean
+        res["img_std"] = torch.sqrt((w * (img - mean[:, None]) ** 2).sum(1))
+        # softmax(-loss_orig) = exp(-loss_orig - logsumexp(-loss_orig)): the script keeps the un-normalised exponent; the
+        # normalised one differs by a per-batch constant
+        res["log_weights"] = torch.log(res["weights"].clamp_min(1e-45))
+        res.pop("accepted")
+        return res

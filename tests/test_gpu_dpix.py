@@ -141,6 +141,13 @@ def test_posterior_sampling_weights_vs_oracle():
     assert rel_err(res["weights"], w) < 5e-3          # exp() of O(1e2) exponents amplifies 1e-5 input differences
     assert bool(res["accepted"][torch.argmax(res["weights"])])
     assert res["img_mean"].shape == (32, 32) and res["img_std"].shape == (32, 32)
+    # Gen_samples2 (:665-709): no rejection, importance-weighted summaries
+    res2 = tr.sample_posterior2(z=z.cuda())
+    wm = (w.float().view(-1, 1, 1) * img).sum(0)
+    ws = torch.sqrt((w.float().view(-1, 1, 1) * (img - wm) ** 2).sum(0))
+    assert "accepted" not in res2 and res2["img_mean"].shape == (1, 32, 32)
+    assert rel_err(res2["img_mean"][0], wm) < 5e-3 and rel_err(res2["img_std"][0], ws) < 5e-3
+    assert abs(float(res2["weights"].sum()) - 1.0) < 1e-4
     conv = SimpleCrescentNuisanceFloor_Param2Img(32, n_gaussian=2, fov=160)
     feats = conv.compute_features(res["params"])
     assert len(feats) == 12 and feats[0].shape == (B, 1, 1)
