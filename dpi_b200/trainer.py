@@ -49,12 +49,12 @@ class _FusedTrainer:
         self.P = P
         # Data parallel, SURVEY 8(e): reduce-scatter the flat gradient -> per-shard ||g||^2 -> scalar all-reduce ->
         # clip + Adam on this rank's 1/world shard (optimizer state and traffic / world) -> all-gather the parameters.
-        # Three collectives instead of one: it pays when the optimizer pass is large against their launch latency
-        # or when there are many ranks (measured, C1 = 6.9 M parameters: 2 GPUs 1.428 ms sharded vs 1.407 ms all-reduce +
-        # replicated Adam; 8 GPUs 1.459 vs 1.517 ms), so the default is by size and rank count; DPI_B200_ZERO=1 / 0
-        # forces it on / off.
-        zenv = os.environ.get("DPI_B200_ZERO", "")
-        self.zero = self.world > 1 and (zenv == "1" or (zenv != "0" and (P >= (16 << 20) or self.world >= 4)))
+        # Three collectives instead of one and no overlap with the backward. Measured on C1 (6.9 M parameters), sharded vs
+        # all-reduce + replicated Adam: 2 GPUs 1.428 vs 1.407 ms, 8 GPUs 1.459 vs 1.517 ms - but the replicated optimiser
+        # with the gradient exchange overlapped in two stage ranges beats both (2 / 4 / 8 GPUs: 1.387 / 1.413 / 1.442 ms), and
+        # on C4 (218 M parameters, 8 GPUs) the bucketed all-reduce gives 21.3 ms against 21.6 ms sharded. So the sharded
+        # optimiser is opt-in (DPI_B200_ZERO=1): it is the memory-saving mode (Adam state / world), not the fast one.
+        self.zero = self.world > 1 and os.environ.get("DPI_B200_ZERO", "") == "1"
         if self.zero:
             from dpi_b200.dist import shard_layout
             self.rank = torch.distributed.get_rank(process_group)
@@ -125,8 +125,7 @@ class _FusedTrainer:
         default = ("4" if kind == 1 else "2") if self.world > 1 else "0"
         if kind == 2 and self.zero:
             # measured at 8 ranks on C1: one reduce-scatter + shard Adam + all-gather 1.459 ms; two bucket all-reduces +
-            # shard Adam + all-gather 1.535 ms (half again the traffic); at 2 ranks the replicated optimiser with two
-            # overlapped buckets wins (1.387 vs 1.405 ms unbucketed)
+            # shard Adam + all-gather 1.535 ms (half again the traffic)
             default = "0"
         nb = int(os.environ.get("DPI_B200_BUCKETS", default))
         if nb < 2 or kind == 0:
