@@ -88,6 +88,7 @@ PROTOTYPES = {
     "dpi_sigmoid_backward": (i32, [i32, i32, vp, vp, vp, vp, vp]),
     "dpi_alpha_objective": (i32, [i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "dpi_fft2c_forward": (i32, [i32, i32, vp, vp, vp]),
+    "dpi_row_scale_dot": (i32, [i32, i32, vp, vp, vp, vp, f32, vp, vp]),
     "dpi_complex_mul": (i32, [i64, i32, i32, vp, vp, vp, vp]),
     "dpi_kspace_loss": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "dpi_fft2c_backward": (i32, [i32, i32, vp, vp, vp]),

@@ -180,6 +180,32 @@ __global__ void __launch_bounds__(256) step_terms_kernel(int B, TermArgs a, floa
   }
 }
 
+// y[r][i] = s[r] * x[r][i] (y may be NULL) and dot[r] = coef * sum_i x[r][i] * b[r][i] (dot may be NULL); one CTA per row,
+// fixed-order reduction. Used by the flux_flag=True form of the crescent renderer (geometric_model.py:373-376).
+__global__ void __launch_bounds__(256) row_scale_dot_kernel(int n, const float* __restrict__ x, const float* __restrict__ s,
+                                                           float* __restrict__ y, const float* __restrict__ b, float coef,
+                                                           float* __restrict__ dot) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, t = threadIdx.x;
+  const float sc = s ? s[r] : 1.f;
+  float acc = 0.f;
+  for (int i = t; i < n; i += 256) {
+    const float v = x[(size_t)r * n + i];
+    if (y) y[(size_t)r * n + i] = sc * v;
+    if (dot) acc = fmaf(v, b[(size_t)r * n + i], acc);
+  }
+  if (dot) {
+    acc = warp_sum(acc);
+    if ((t & 31) == 0) red[t >> 5] = acc;
+    __syncthreads();
+    if (t == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      dot[r] = coef * tot;
+    }
+  }
+}
+
 // interferometry_helpers.py torch_complex_mul :30-34: out[o][:, i] = x[o][:, i] * y[:, i] as complex numbers stored as
 // (real row, imaginary row); conj = 1 multiplies with conj(y) (the gradient wrt x).
 __global__ void complex_mul_kernel(long long outer, int n, int conj, const float* __restrict__ x, const float* __restrict__ y,
@@ -273,6 +299,14 @@ int dpi_complex_mul(long long outer, int n, int conj, const float* x, const floa
   DPI_REQUIRE(outer >= 1 && n >= 1 && x && y && out, "dpi_complex_mul: bad argument");
   const long long total = outer * n;
   complex_mul_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(outer, n, conj, x, y, out);
+  DPI_LAUNCH_CHECK();
+  return DPI_OK;
+}
+
+int dpi_row_scale_dot(int rows, int n, const float* x, const float* s, float* y, const float* b, float coef, float* dot,
+                      dpi_stream_t stream) {
+  DPI_REQUIRE(rows >= 1 && n >= 1 && x && (y || dot) && (!dot || b), "dpi_row_scale_dot: bad argument");
+  row_scale_dot_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(n, x, s, y, b, coef, dot);
   DPI_LAUNCH_CHECK();
   return DPI_OK;
 }

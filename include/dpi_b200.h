@@ -340,6 +340,11 @@ int dpi_alpha_objective(int batch, int nparams, const float* z, const double* lo
                         float* gscale, float* g_logdet, float* terms /*[8]*/, float* stats /*[2]*/,
                         dpi_stream_t stream);
 
+/* y[r][i] = s[r] x[r][i] (s NULL: 1; y NULL: skipped) and dot[r] = coef sum_i x[r][i] b[r][i] (dot NULL: skipped) over rows of
+ * n floats: the total-flux factor of the crescent renderer with flux_flag=True (geometric_model.py:373-376) and its gradient. */
+int dpi_row_scale_dot(int rows, int n, const float* x, const float* s, float* y, const float* b, float coef, float* dot,
+                      dpi_stream_t stream);
+
 /* interferometry_helpers.py torch_complex_mul :30-34. x, out: [outer][2][n] (real row, imaginary row), y: [2][n];
  * out = x * y, or x * conj(y) when conj != 0 (the gradient wrt x of the former). */
 int dpi_complex_mul(long long outer, int n, int conj, const float* x, const float* y, float* out, dpi_stream_t stream);

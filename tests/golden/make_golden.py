@@ -351,8 +351,29 @@ def glow_case(name, npix, n_flow, n_block, B, seed):
     print(name, "ok", sum(v.nbytes for v in out.values() if hasattr(v, "nbytes")) // 1024, "KiB")
 
 
+def crescent_flux_case(name, npix, B, ng, seed, flux_range):
+    """SURVEY 8 a17 with flux_flag=True (geometric_model.py:253-256, :305-309, :373-376; the renderer DPIx_interferometry.py
+    builds for every data product except cphase_logcamp, :214-229): image, parameter gradient and the feature tuple."""
+    conv = R["geometric"].SimpleCrescentNuisanceFloor_Param2Img(npix, r_range=[10.0, 40.0], fov=160.0, n_gaussian=ng,
+                                                                flux_flag=True, flux_range=flux_range)
+    p0 = torch.rand(B, conv.nparams, generator=torch.Generator().manual_seed(seed)).requires_grad_(True)
+    cimg = torch.randn(B, npix, npix, generator=torch.Generator().manual_seed(seed + 1))
+    im0 = conv.forward(p0)
+    (im0 * cimg).sum().backward()
+    feats = conv.compute_features(p0.detach())
+    out = dict(npix=npix, B=B, ng=ng, nparams=conv.nparams, flux_lo=flux_range[0], flux_hi=flux_range[1],
+               render_params=p0.detach().numpy(), render_cimg=cimg.numpy(), render_img=im0.detach().numpy(),
+               render_gparams=p0.grad.numpy().copy(), feat_flux=feats[4].numpy(), feat_crescent_flux=feats[5].numpy(),
+               feat_floor=feats[6].numpy(), n_feats=len(feats))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", sum(v.nbytes for v in out.values() if hasattr(v, "nbytes")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "crescent_flux":      # add this fixture without regenerating the others
+        crescent_flux_case("crescent_flux", npix=16, B=9, ng=2, seed=33, flux_range=[0.8 * 0.6, 1.2 * 0.6])
+        sys.exit(0)
     flow_case("flow_even", D=20, NF=2, B=6, seqfrac=1, seed=11)          # H=10, one row tile
     flow_case("flow_odd", D=9, NF=2, B=5, seqfrac=0.25, seed=12)         # odd ndim: chunk gives 5 + 4, H=18
     flow_case("flow_bigbatch", D=12, NF=2, B=80, seqfrac=0.5, seed=13)   # batch spans two 64-row tiles, H=12

@@ -25,6 +25,26 @@ def test_renderer_matches_reference_fixture(name):
     assert rel_err(p.grad, g["render_gparams"]) < RTOL, rel_err(p.grad, g["render_gparams"])
 
 
+def test_renderer_with_total_flux_matches_reference_fixture():
+    """flux_flag=True (geometric_model.py:253-256, :305-309, :373-376): 7 + 6 g parameters, image = total flux x unit-flux
+    image; image, parameter gradient and the feature tuple against the unmodified reference (tests/golden/make_golden.py
+    crescent_flux_case)."""
+    from dpi_b200.geometric_model import SimpleCrescentNuisanceFloor_Param2Img
+    g = load_golden("crescent_flux")
+    conv = SimpleCrescentNuisanceFloor_Param2Img(int(g["npix"]), r_range=[10.0, 40.0], fov=160.0, n_gaussian=int(g["ng"]),
+                                                 flux_flag=True, flux_range=[float(g["flux_lo"]), float(g["flux_hi"])])
+    assert conv.nparams == int(g["nparams"]) == 19
+    p = torch.from_numpy(g["render_params"]).cuda().requires_grad_(True)
+    img = conv.forward(p)
+    (img * torch.from_numpy(g["render_cimg"]).cuda()).sum().backward()
+    assert rel_err(img, g["render_img"]) < RTOL, rel_err(img, g["render_img"])
+    assert rel_err(p.grad, g["render_gparams"]) < RTOL, rel_err(p.grad, g["render_gparams"])
+    feats = conv.compute_features(p.detach())
+    assert len(feats) == int(g["n_feats"]) == 13
+    assert rel_err(feats[4], g["feat_flux"]) < 1e-6 and rel_err(feats[5], g["feat_crescent_flux"]) < 1e-6
+    assert rel_err(feats[6], g["feat_floor"]) < 1e-6
+
+
 @pytest.mark.parametrize("npix,B,ng", [(64, 32, 2), (32, 7, 1), (24, 5, 0)])
 def test_renderer_vs_oracle(npix, B, ng):
     from dpi_b200.geometric_model import SimpleCrescentNuisanceFloor_Param2Img
