@@ -188,6 +188,7 @@ def test_glow_training_backward_matches_reference_fixture():
         worst.append((rel_err(mine.cpu().reshape(-1), torch.from_numpy(g["grad." + k]).reshape(-1)), k))
     bad = [w for w in worst if not w[0] < 3 * RTOL]
     assert not bad, sorted(bad, reverse=True)[:8]
+    assert max(w[0] for w in worst) < RTOL          # measured 1.1e-5: the fp32 bar holds for every Glow gradient on this fixture
 
 
 def test_glow_training_step_moves_every_parameter():
