@@ -19,6 +19,10 @@ constexpr float kEpsN = 1e-4f;           // geometric_model.py:263
 struct Feat {
   float r, sg, s, eta, fl, cf;
   float x0[kMaxG], y0[kMaxG], a[kMaxG], sx[kMaxG], sy[kMaxG], ct[kMaxG], st[kMaxG];
+  // per-image reciprocals of what every pixel would otherwise divide by (a division is ~8 instructions, and the pixel
+  // loops run 3 (forward) / 5 (backward) times over the image)
+  float i2s2, irs, isx2[kMaxG], isy2[kMaxG], gn[kMaxG];
+  float ce, se;   // cos / sin of eta: cos(theta - eta) = (gx ce + gy se) / r_grid without atan2 + sincos per pixel
 };
 struct FeatScale {   // d feature / d parameter
   float r, sg, s, eta, fl, cf, sh, a, sxy, th;
@@ -55,7 +59,13 @@ __device__ __forceinline__ Feat features(const float* p, int g, float fov) {   /
     } else {
       f.x0[q] = f.y0[q] = f.a[q] = 0.f; f.sx[q] = f.sy[q] = 1.f; f.ct[q] = 1.f; f.st[q] = 0.f;
     }
+    f.isx2[q] = 1.0f / (f.sx[q] * f.sx[q]);
+    f.isy2[q] = 1.0f / (f.sy[q] * f.sy[q]);
+    f.gn[q] = 1.0f / (6.28318530717958648f * f.sx[q] * f.sy[q]);
   }
+  f.ce = cosf(f.eta); f.se = sinf(f.eta);
+  f.i2s2 = 0.5f / (f.sg * f.sg);
+  f.irs = 1.0f / (1.41421356237309515f * f.sg);
   return f;
 }
 
@@ -75,19 +85,21 @@ __device__ __forceinline__ Pix pixel(int pix, int npix, const Feat& f, int g) { 
   Pix q;
   grid_at(pix, npix, q.gx, q.gy);
   q.rg = sqrtf(q.gx * q.gx + q.gy * q.gy);
-  q.th = atan2f(q.gy, q.gx);
+  q.th = 0.f;   // grid_theta (:272) only enters through cos / sin (theta - eta)
+  const float irg = q.rg > 0.f ? 1.0f / q.rg : 0.f;   // odd npix: the centre pixel sits on the origin (atan2(0, 0) = 0)
   const float d = q.rg - f.r;
-  q.ring = expf(-0.5f * d * d / (f.sg * f.sg));
-  q.cs = cosf(q.th - f.eta); q.sn = sinf(q.th - f.eta);
+  q.ring = expf(-d * d * f.i2s2);
+  q.cs = q.rg > 0.f ? (q.gx * f.ce + q.gy * f.se) * irg : f.ce;
+  q.sn = q.rg > 0.f ? (q.gy * f.ce - q.gx * f.se) * irg : -f.se;
   q.c = (1.0f + f.s * q.cs) * q.ring;
-  q.dk = 0.5f * (1.0f + erff((f.r - q.rg) / (1.41421356237309515f * f.sg)));
+  q.dk = 0.5f * (1.0f + erff((f.r - q.rg) * f.irs));
   for (int k = 0; k < kMaxG; ++k) {
     if (k < g) {
       const float xc = q.gx - f.x0[k], yc = q.gy - f.y0[k];
       q.xr[k] = xc * f.ct[k] + yc * f.st[k];
       q.yr[k] = -xc * f.st[k] + yc * f.ct[k];
-      const float delta = 0.5f * (q.xr[k] * q.xr[k] / (f.sx[k] * f.sx[k]) + q.yr[k] * q.yr[k] / (f.sy[k] * f.sy[k]));
-      q.n[k] = 1.0f / (6.28318530717958648f * f.sx[k] * f.sy[k]) * expf(-delta);
+      const float delta = 0.5f * (q.xr[k] * q.xr[k] * f.isx2[k] + q.yr[k] * q.yr[k] * f.isy2[k]);
+      q.n[k] = f.gn[k] * expf(-delta);
     } else {
       q.n[k] = 0.f; q.xr[k] = q.yr[k] = 0.f;
     }
@@ -149,13 +161,13 @@ __device__ __forceinline__ void block_sum_multi(float (&v)[K], float* sm /* >= 8
   }
 }
 
-struct Norms { float C, Dk, T, N[kMaxG]; };
+struct Norms { float C, Dk, T, N[kMaxG], iC, iDk, iT, iN[kMaxG]; };
 
 // total image before the final normalisation at one pixel
 __device__ __forceinline__ float tot_at(const Pix& q, const Feat& f, const Norms& nm, int g) {
-  float t = f.cf * ((1.0f - f.fl) * (q.c / nm.C) + f.fl * (q.dk / nm.Dk));
+  float t = f.cf * ((1.0f - f.fl) * (q.c * nm.iC) + f.fl * (q.dk * nm.iDk));
   for (int k = 0; k < kMaxG; ++k)
-    if (k < g) t += f.a[k] * (q.n[k] / nm.N[k]);
+    if (k < g) t += f.a[k] * (q.n[k] * nm.iN[k]);
   return t;
 }
 
@@ -174,12 +186,14 @@ __device__ __forceinline__ Norms compute_norms(int npix, const Feat& f, int g, f
   block_sum_multi<2 + kMaxG>(v, sm);
   Norms nm;
   nm.C = v[0] + kEpsN; nm.Dk = v[1] + kEpsN;
+  nm.iC = 1.0f / nm.C; nm.iDk = 1.0f / nm.Dk;
 #pragma unroll
-  for (int k = 0; k < kMaxG; ++k) nm.N[k] = v[2 + k] + kEpsN;
+  for (int k = 0; k < kMaxG; ++k) { nm.N[k] = v[2 + k] + kEpsN; nm.iN[k] = 1.0f / nm.N[k]; }
   float t[1] = {0.f};
   for (int pix = threadIdx.x; pix < P; pix += kCT) t[0] += tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g);
   block_sum_multi<1>(t, sm);
   nm.T = t[0] + kEpsN;
+  nm.iT = 1.0f / nm.T;
   return nm;
 }
 
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(kCT) crescent_fwd_kernel(int npix, int g, floa
   const Norms nm = compute_norms<CACHED>(npix, f, g, sm, cache);
   float* out = img + (size_t)b * P;
   for (int pix = threadIdx.x; pix < P; pix += kCT)
-    out[pix] = tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) / nm.T;
+    out[pix] = tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) * nm.iT;
 }
 
 // g_params[b, :] = gscale[b] * sum_p g_img[b, p] * d img[b, p] / d params[b, :]
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
   const float gs = gscale ? gscale[b] : 1.0f;
   // img = tot / T: u = d L / d tot = (G - sum(G * img)) / T
   float gi[1] = {0.f};
-  for (int pix = threadIdx.x; pix < P; pix += kCT) gi[0] += G[pix] * (tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) / nm.T);
+  for (int pix = threadIdx.x; pix < P; pix += kCT) gi[0] += G[pix] * (tot_at(get_pixel<CACHED>(pix, npix, P, f, g, cache, false), f, nm, g) * nm.iT);
   block_sum_multi<1>(gi, sm);
   const float GI = gi[0];
   // second-level sums: sum u c, sum u dk, sum u n_k
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
   for (int k = 0; k < 2 + kMaxG; ++k) u2[k] = 0.f;
   for (int pix = threadIdx.x; pix < P; pix += kCT) {
     const Pix q = get_pixel<CACHED>(pix, npix, P, f, g, cache, false);
-    const float u = gs * (G[pix] - GI) / nm.T;
+    const float u = gs * (G[pix] - GI) * nm.iT;
     u2[0] += u * q.c; u2[1] += u * q.dk;
 #pragma unroll
     for (int k = 0; k < kMaxG; ++k) u2[2 + k] += u * q.n[k];
@@ -237,13 +251,20 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
   float s[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) s[k] = 0.f;
-  const float kc = f.cf * (1.0f - f.fl) / nm.C, kd = f.cf * f.fl / nm.Dk;
+  const float kc = f.cf * (1.0f - f.fl) * nm.iC, kd = f.cf * f.fl * nm.iDk;
   const float inv_sg = 1.0f / f.sg;
+  const float UcC = Uc * nm.iC, UdD = Ud * nm.iDk;
+  float vnk[kMaxG], unk[kMaxG], isx[kMaxG], isy[kMaxG];
+#pragma unroll
+  for (int k = 0; k < kMaxG; ++k) {
+    vnk[k] = f.a[k] * nm.iN[k]; unk[k] = u2[2 + k] * nm.iN[k];
+    isx[k] = 1.0f / f.sx[k]; isy[k] = 1.0f / f.sy[k];
+  }
   for (int pix = threadIdx.x; pix < P; pix += kCT) {
     const Pix q = get_pixel<CACHED>(pix, npix, P, f, g, cache, false);
-    const float u = gs * (G[pix] - GI) / nm.T;
-    const float vc = kc * (u - Uc / nm.C);         // d L / d c (unnormalised crescent)
-    const float vd = kd * (u - Ud / nm.Dk);        // d L / d disk
+    const float u = gs * (G[pix] - GI) * nm.iT;
+    const float vc = kc * (u - UcC);               // d L / d c (unnormalised crescent)
+    const float vd = kd * (u - UdD);               // d L / d disk
     const float d = q.rg - f.r;
     const float Sx = 1.0f + f.s * q.cs;
     const float z = (f.r - q.rg) * inv_sg * 0.707106781186547524f;
@@ -254,14 +275,14 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
 #pragma unroll
     for (int k = 0; k < kMaxG; ++k) {
       if (k < g) {
-        const float vn = f.a[k] / nm.N[k] * (u - u2[2 + k] / nm.N[k]);   // d L / d n_k (unnormalised Gaussian)
+        const float vn = vnk[k] * (u - unk[k]);                           // d L / d n_k (unnormalised Gaussian)
         const float n = q.n[k], xr = q.xr[k], yr = q.yr[k];
-        const float ix2 = 1.0f / (f.sx[k] * f.sx[k]), iy2 = 1.0f / (f.sy[k] * f.sy[k]);
+        const float ix2 = f.isx2[k], iy2 = f.isy2[k];
         const float ddx = xr * ix2, ddy = yr * iy2;                       // d delta / d xr, d delta / d yr
         s[4 + 5 * k + 0] += vn * n * (ddx * f.ct[k] - ddy * f.st[k]);     // x0:  -n * (ddx * (-ct) + ddy * st)
         s[4 + 5 * k + 1] += vn * n * (ddx * f.st[k] + ddy * f.ct[k]);     // y0:  -n * (ddx * (-st) + ddy * (-ct))
-        s[4 + 5 * k + 2] += vn * n * (xr * xr * ix2 - 1.0f) / f.sx[k];    // sigma_x
-        s[4 + 5 * k + 3] += vn * n * (yr * yr * iy2 - 1.0f) / f.sy[k];    // sigma_y
+        s[4 + 5 * k + 2] += vn * n * (xr * xr * ix2 - 1.0f) * isx[k];     // sigma_x
+        s[4 + 5 * k + 3] += vn * n * (yr * yr * iy2 - 1.0f) * isy[k];     // sigma_y
         s[4 + 5 * k + 4] += -vn * n * (ddx * yr - ddy * xr);              // theta: d xr = yr, d yr = -xr
       }
     }
@@ -274,13 +295,13 @@ __global__ void __launch_bounds__(kCT) crescent_bwd_kernel(int npix, int g, floa
     for (int q = 0; q < g; ++q) {
       o[4 + 6 * q] = s[4 + 5 * q] * k.sh;
       o[5 + 6 * q] = s[4 + 5 * q + 1] * k.sh;
-      o[6 + 6 * q] = (u2[2 + q] / nm.N[q]) * k.a;
+      o[6 + 6 * q] = (u2[2 + q] * nm.iN[q]) * k.a;
       o[7 + 6 * q] = s[4 + 5 * q + 2] * k.sxy;
       o[8 + 6 * q] = s[4 + 5 * q + 3] * k.sxy;
       o[9 + 6 * q] = s[4 + 5 * q + 4] * k.th;
     }
-    o[4 + 6 * g] = f.cf * (Ud / nm.Dk - Uc / nm.C) * k.fl;                         // floor
-    o[5 + 6 * g] = ((1.0f - f.fl) * Uc / nm.C + f.fl * Ud / nm.Dk) * k.cf;         // crescent flux
+    o[4 + 6 * g] = f.cf * (UdD - UcC) * k.fl;                                      // floor
+    o[5 + 6 * g] = ((1.0f - f.fl) * UcC + f.fl * UdD) * k.cf;                      // crescent flux
   }
 }
 
